@@ -1,0 +1,123 @@
+// Shared declarations of the sm_100a quant path: launcher prototypes and small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SQ_MAXK 8             // k values per index (SQ_MAX_K_COUNT)
+#define SQ_CHUNK 256          // window-end positions handled by one sketch thread
+#define SQ_EMPTY 0xFFFFFFFFu  // empty marker in hash tables / bucket offsets
+#define SQ_LAST 0x80000000u   // flag on the last transcript id of a posting list
+
+namespace sq {
+
+// ---------- ntHash2 forward hash, 33-bit lane only ----------
+// The reference keeps (uint32_t)get_forward_hash() (src/sketch.cpp:33).  ntHash2's split rotation never
+// mixes bits 63..33 with bits 32..0, so those 32 bits depend only on the 33-bit low lane.  A lane value s
+// is held as two words: x = s[31:0], y = s[32:1]; rotating the lane left by one is then
+//   x' = funnelshift_l(y, x, 1), y' = x.
+__host__ __device__ inline uint64_t seed33(uint32_t code) {
+  // low 33 bits of ntHash2's SEED_A/C/G/T (0x3c8bfbb395c60474, 0x3193c18562a02b4c, 0x20323ed082572324,
+  // 0x295549f54be24456)
+  return code == 0 ? 0x195c60474ULL : code == 1 ? 0x162a02b4cULL : code == 2 ? 0x082572324ULL : 0x14be24456ULL;
+}
+__host__ __device__ inline uint64_t rol33(uint64_t s, uint32_t n) {
+  n %= 33;
+  if (n == 0) return s;
+  return ((s << n) | (s >> (33 - n))) & 0x1FFFFFFFFULL;
+}
+
+// per-k lookup table in the two-word form: entries 0..15 = seed[in] ^ rol33^k(seed[out]) indexed by
+// in*4+out, entries 16..19 = seed[in] alone (used while the first window is being filled)
+struct KLut {
+  uint2 e[20];
+};
+
+struct SketchParams {
+  const uint32_t* packed;      // 2-bit bases, 16 per word
+  uint64_t n_words;            // words readable at `packed` (padded to a multiple of 4)
+  const uint32_t* base_off;    // per read: first base; (base_off - bias) is relative to packed[0]
+  uint32_t bias;
+  const uint32_t* len;         // per read
+  const uint32_t* item_read;   // per item: read index
+  const uint32_t* item_start;  // per read: first item (exclusive scan of items per read), n_reads+1 entries
+  uint32_t n_reads;
+  uint32_t n_items_ub;         // launch bound; the true count is item_start[n_reads]
+  uint32_t nk;
+  uint32_t threshold;
+  uint32_t ks[SQ_MAXK];
+  uint32_t kmax;
+  uint32_t* sel;               // [nk][slot_stride] selected hashes; item slots start at base_off+chunk start
+  uint64_t slot_stride;
+  uint16_t* cnt;               // [nk][n_items_ub] selected count per item
+  KLut lut[SQ_MAXK];
+};
+
+// bucketed open-addressing table: bucket = 4 keys (uint4) + 4 posting offsets (uint4), 32 B, one sector
+struct IndexTable {
+  const uint4* buckets;     // 2*nb uint4
+  const uint32_t* postings; // transcript ids, last of each list flagged with SQ_LAST
+  uint32_t shift;           // 32 - log2(nb)
+  uint32_t mask;            // nb - 1
+  uint32_t present;         // 0: k-index has no map (sparse_chaining.cpp:51-53)
+};
+
+struct VoteParams {
+  const uint32_t* base_off;
+  uint32_t bias;
+  const uint32_t* len;
+  const uint32_t* item_start;
+  uint32_t n_reads;
+  uint32_t n_items_ub;
+  uint32_t nk;
+  double fraction;
+  const uint32_t* sel;
+  uint64_t slot_stride;
+  const uint16_t* cnt;
+  IndexTable tab[SQ_MAXK];
+  // staging output (batch local)
+  uint32_t* stage_tid;
+  int32_t* stage_score;
+  uint64_t stage_cap;
+  unsigned long long* stage_cursor;  // device counter
+  uint32_t* read_soff;               // per read: staging offset
+  uint32_t* read_cnt;                // per read: candidates
+  uint32_t* ovf_list;                // reads that overflowed the shared-memory tables
+  uint32_t* ovf_count;
+  uint32_t* flags;                   // bit0: staging overflow, bit1: large-table overflow
+  // large-table scratch (one region per worker block of the overflow kernel)
+  uint32_t* big_keys; uint32_t* big_cnt; uint32_t* big_list; uint32_t* big_set; unsigned long long* big_cand;
+  uint32_t big_cap_log2;     // table slots per worker
+  uint32_t big_set_log2;     // dedup-set slots per worker
+  uint32_t n_workers;
+};
+
+// ---------- launchers (definitions in the .cu files) ----------
+void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t* item_start, uint32_t* item_read,
+                  uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches);
+void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches);
+void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches);
+
+// exclusive scan of n u32 values; out[n] receives the total (out has n+1 entries); tmp holds >= n/2048+2 u32
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t s,
+                           uint64_t* launches);
+size_t scan_tmp_words(uint32_t n);
+
+// stable LSD radix sort of (key64, val32) pairs on bits [0, nbits); buffers are ping-ponged, the result
+// pointers are returned through *keys_out / *vals_out (one of the two buffers each)
+void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n,
+                       int nbits, uint32_t* hist_tmp, uint64_t** keys_out, uint32_t** vals_out, cudaStream_t s,
+                       uint64_t* launches);
+size_t radix_tmp_words(uint64_t n);
+
+}  // namespace sq
+
+// warp helpers
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, d);
+    if ((int)lane_id() >= d) v += t;
+  }
+  return v;
+}

@@ -1,0 +1,362 @@
+// Index-table construction, candidate compaction, and the EM / assignment kernels.
+//
+// EM follows estimate_isoform_abundance_em (reference src/isoform_assignment.cpp:9-68) and
+// assign_reads_to_isoforms (:70-97) on a flat CSR of (read -> candidates).  Every reduction has a fixed
+// order (no floating-point atomics): the E-step denominator is a per-read sequential sum in candidate
+// order; the per-transcript posterior sums run over a transcript-major copy of the pairs (stable radix
+// sort), split into fixed-size segments that are reduced by one warp each and then added in segment order.
+#include "sq_common.cuh"
+#include "sq_kernels.cuh"
+
+namespace sq {
+
+static constexpr uint32_t kHashMul = 0x9E3779B1u;
+
+// ------------------------------------------------------------------ index table
+__global__ void table_insert_kernel(const uint32_t* __restrict__ keys, const uint64_t* __restrict__ off,
+                                    uint64_t nkeys, uint4* buckets, uint32_t shift, uint32_t mask,
+                                    uint32_t* __restrict__ postings, uint32_t* fail) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nkeys) return;
+  const uint64_t b0 = off[i], b1 = off[i + 1];
+  if (b1 <= b0) return;  // a key without postings cannot vote
+  postings[b1 - 1] |= SQ_LAST;
+  const uint32_t key = keys[i];
+  uint32_t b = (key * kHashMul) >> shift;
+  for (uint32_t tries = 0; tries <= mask; ++tries) {
+    uint32_t* bk = reinterpret_cast<uint32_t*>(buckets + 2 * (size_t)b);
+    uint32_t* bo = bk + 4;
+    for (int s = 0; s < 4; ++s)
+      if (atomicCAS(&bo[s], SQ_EMPTY, (uint32_t)b0) == SQ_EMPTY) {
+        bk[s] = key;
+        return;
+      }
+    b = (b + 1) & mask;
+  }
+  atomicExch(fail, 1u);
+}
+
+void launch_table_build(const uint32_t* keys, const uint64_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
+                        uint32_t mask, uint32_t* postings, uint32_t* fail, cudaStream_t s, uint64_t* launches) {
+  launch_fill_u32(reinterpret_cast<uint32_t*>(buckets), (size_t)(mask + 1) * 8, SQ_EMPTY, s);
+  if (launches) ++*launches;
+  if (nkeys == 0) return;
+  const uint32_t grid = (uint32_t)((nkeys + 255) / 256);
+  table_insert_kernel<<<grid, 256, 0, s>>>(keys, off, nkeys, buckets, shift, mask, postings, fail);
+  if (launches) ++*launches;
+}
+
+// ------------------------------------------------------------------ candidate compaction
+// staging (arbitrary order) -> final CSR in read order
+__global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uint32_t* __restrict__ read_cnt,
+                               const uint32_t* __restrict__ batch_off, uint32_t n_reads,
+                               const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
+                               const unsigned long long* __restrict__ totals, uint64_t read_base, uint64_t cap,
+                               uint32_t* __restrict__ cand_tid, int32_t* __restrict__ cand_score,
+                               uint32_t* __restrict__ read_off, uint32_t* flags) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const unsigned long long pbase = totals[0];
+  const unsigned long long dst = pbase + batch_off[r];
+  read_off[read_base + r] = (uint32_t)dst;
+  const uint32_t c = read_cnt[r], so = read_soff[r];
+  if (dst + c > cap) {
+    atomicOr(flags, 4u);
+    return;
+  }
+  for (uint32_t i = 0; i < c; ++i) {
+    cand_tid[dst + i] = stage_tid[so + i];
+    cand_score[dst + i] = stage_score[so + i];
+  }
+}
+
+__global__ void advance_kernel(unsigned long long* totals, const uint32_t* batch_off, uint32_t n_reads,
+                               uint64_t read_base, uint32_t* read_off, unsigned long long* stage_cursor,
+                               uint32_t* ovf_count, unsigned long long* host_mirror) {
+  // single thread: publish the new pair total, close the CSR, reset the per-batch counters
+  const unsigned long long p = totals[0] + batch_off[n_reads];
+  totals[0] = p;
+  totals[1] += *ovf_count;
+  read_off[read_base + n_reads] = (uint32_t)p;
+  *stage_cursor = 0;
+  *ovf_count = 0;
+  if (host_mirror) { host_mirror[0] = p; host_mirror[1] = totals[1]; }
+}
+
+void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
+                    const uint32_t* stage_tid, const int32_t* stage_score, unsigned long long* totals,
+                    uint64_t read_base, uint64_t cap, uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off,
+                    uint32_t* flags, unsigned long long* stage_cursor, uint32_t* ovf_count,
+                    unsigned long long* host_mirror, cudaStream_t s, uint64_t* launches) {
+  if (n_reads) {
+    compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
+                                                         stage_score, totals, read_base, cap, cand_tid, cand_score,
+                                                         read_off, flags);
+    if (launches) ++*launches;
+  }
+  advance_kernel<<<1, 1, 0, s>>>(totals, batch_off, n_reads, read_base, read_off, stage_cursor, ovf_count,
+                                 host_mirror);
+  if (launches) ++*launches;
+}
+
+// number of selected hashes in a batch (stats): sum of the u16 counters
+__global__ void sum_u16_kernel(const uint16_t* __restrict__ cnt, uint64_t n, unsigned long long* out) {
+  unsigned long long s = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    s += cnt[i];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+  if (lane_id() == 0 && s) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------ transcript-major view
+__global__ void make_sort_keys_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                                      const uint32_t* __restrict__ cand_tid, uint64_t* __restrict__ keys) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t b = read_off[r], e = read_off[r + 1];
+  for (uint32_t j = b; j < e; ++j) keys[j] = ((uint64_t)r << 32) | cand_tid[j];
+}
+
+// keys sorted by transcript (low 32 bits): toff[t] = first pair of transcript t, toff[T] = P
+__global__ void seg_offsets_kernel(const uint64_t* __restrict__ keys, uint64_t P, uint32_t T,
+                                   uint32_t* __restrict__ toff) {
+  const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j > P) return;
+  const int64_t prev = j == 0 ? -1 : (int64_t)(uint32_t)keys[j - 1];
+  const int64_t cur = j == P ? (int64_t)T : (int64_t)(uint32_t)keys[j];
+  for (int64_t t = prev + 1; t <= cur; ++t) toff[t] = (uint32_t)j;
+}
+
+__global__ void split_keys_kernel(const uint64_t* __restrict__ keys, uint64_t P, uint32_t* __restrict__ tm_read) {
+  const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (j < P) tm_read[j] = (uint32_t)(keys[j] >> 32);
+}
+
+__global__ void seg_count_kernel(const uint32_t* __restrict__ toff, uint32_t T, uint32_t seg, uint32_t* nseg) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) nseg[t] = (toff[t + 1] - toff[t] + seg - 1) / seg;
+}
+
+__global__ void seg_expand_kernel(const uint32_t* __restrict__ toff, const uint32_t* __restrict__ seg_off,
+                                  uint32_t T, uint32_t seg, uint32_t* __restrict__ seg_tid,
+                                  uint32_t* __restrict__ seg_begin) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const uint32_t b = toff[t], e = toff[t + 1];
+  uint32_t s = seg_off[t];
+  for (uint32_t p = b; p < e; p += seg, ++s) {
+    seg_tid[s] = t;
+    seg_begin[s] = p;
+  }
+}
+
+// ------------------------------------------------------------------ EM
+__global__ void em_init_kernel(double* pi, uint32_t T, uint32_t* state) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) pi[t] = 1.0 / (double)T;  // isoform_assignment.cpp:17-20
+  if (t == 0) { state[0] = 0; state[1] = 0; }  // [0]=converged flag, [1]=iterations executed
+}
+
+// per read: den = sum_j pi[t_j]*s_j in candidate order; inv = 1/den when den > 1e-10 (:36-45), else 0
+__global__ void em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                              const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                              const double* __restrict__ pi, double* __restrict__ inv_den,
+                              const uint32_t* __restrict__ state) {
+  if (state[0]) return;
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t b = read_off[r], e = read_off[r + 1];
+  double den = 0.0;
+  for (uint32_t j = b; j < e; ++j) den += pi[cand_tid[j]] * (double)cand_score[j];
+  inv_den[r] = den > 1e-10 ? 1.0 / den : 0.0;
+}
+
+// one warp per segment of <= seg pairs of one transcript: partial posterior sum (:46-49)
+__global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
+                                  const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
+                                  const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
+                                  const double* __restrict__ inv_den, const double* __restrict__ pi,
+                                  double* __restrict__ partial, const uint32_t* __restrict__ state) {
+  if (state[0]) return;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_seg) return;
+  const uint32_t t = seg_tid[w];
+  const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
+  const double p = pi[t];
+  double acc = 0.0;
+  for (uint32_t j = b + lane_id(); j < e; j += 32)
+    acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+  if (lane_id() == 0) partial[w] = acc;
+}
+
+__global__ void seg_sum_kernel(const uint32_t* __restrict__ seg_off, uint32_t T,
+                               const double* __restrict__ partial, double* __restrict__ out,
+                               const uint32_t* __restrict__ state) {
+  if (state && state[0]) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double s = 0.0;
+  for (uint32_t i = seg_off[t]; i < seg_off[t + 1]; ++i) s += partial[i];
+  out[t] = s;
+}
+
+// M-step (:54-60): new = ps + (double)(0.01f/(float)R) + (double)0.01f, evaluated left to right
+__global__ void __launch_bounds__(256) em_update_kernel(const double* __restrict__ ps, double* __restrict__ pi,
+                                                        uint32_t T, double add_a, double add_b,
+                                                        double* __restrict__ block_change,
+                                                        const uint32_t* __restrict__ state) {
+  if (state[0]) return;
+  __shared__ double sh[256];
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  double ch = 0.0;
+  if (t < T) {
+    const double np = (ps[t] + add_a) + add_b;
+    ch = fabs(np - pi[t]);
+    pi[t] = np;
+  }
+  sh[threadIdx.x] = ch;
+  __syncthreads();
+  for (int d = 128; d; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_change[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(256) em_converge_kernel(const double* __restrict__ block_change, uint32_t nb,
+                                                          double tol, uint32_t* state, double* last_change) {
+  if (state[0]) return;
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (uint32_t i = threadIdx.x; i < nb; i += 256) s += block_change[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    state[1] += 1;
+    *last_change = sh[0];
+    if (sh[0] < tol) state[0] = 1;  // :62-64
+  }
+}
+
+// ------------------------------------------------------------------ assignment (:70-97)
+__global__ void as_tot_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                              const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                              const double* __restrict__ pi, double* __restrict__ tot) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t b = read_off[r], e = read_off[r + 1];
+  double s = 0.0;
+  for (uint32_t j = b; j < e; ++j) s += pi[cand_tid[j]] * (double)cand_score[j];
+  tot[r] = s;
+}
+
+__global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
+                                  const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
+                                  const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
+                                  const double* __restrict__ tot, const double* __restrict__ pi,
+                                  double* __restrict__ partial, uint32_t* __restrict__ present_u32) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_seg) return;
+  const uint32_t t = seg_tid[w];
+  const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
+  const double p = pi[t];
+  double acc = 0.0;
+  bool any = false;
+  for (uint32_t j = b + lane_id(); j < e; j += 32) {
+    const double tt = tot[tm_read[j]];
+    if (tt > 0.0) {
+      acc += (p * (double)(int32_t)tm_score[j]) / tt;  // :90 divides per term
+      any = true;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+  const uint32_t anyw = __ballot_sync(0xFFFFFFFFu, any);
+  if (lane_id() == 0) {
+    partial[w] = acc;
+    if (anyw) present_u32[t] = 1;  // benign race: all writers store 1
+  }
+}
+
+// ------------------------------------------------------------------ host-side launch helpers
+void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
+                           cudaStream_t s, uint64_t* launches) {
+  if (!n_reads) return;
+  make_sort_keys_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, keys);
+  if (launches) ++*launches;
+}
+
+void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, uint32_t* toff, uint32_t* tm_read,
+                   uint32_t* nseg, uint32_t* seg_off, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches) {
+  seg_offsets_kernel<<<(uint32_t)((P + 1 + 255) / 256), 256, 0, s>>>(keys, P, T, toff);
+  if (P) split_keys_kernel<<<(uint32_t)((P + 255) / 256), 256, 0, s>>>(keys, P, tm_read);
+  seg_count_kernel<<<(T + 255) / 256, 256, 0, s>>>(toff, T, seg, nseg);
+  if (launches) *launches += 3;
+  launch_exclusive_scan(nseg, seg_off, T, scan_tmp, s, launches);
+}
+
+void launch_seg_expand(const uint32_t* toff, const uint32_t* seg_off, uint32_t T, uint32_t seg, uint32_t* seg_tid,
+                       uint32_t* seg_begin, cudaStream_t s, uint64_t* launches) {
+  seg_expand_kernel<<<(T + 255) / 256, 256, 0, s>>>(toff, seg_off, T, seg, seg_tid, seg_begin);
+  if (launches) ++*launches;
+}
+
+void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uint64_t* launches) {
+  em_init_kernel<<<(T + 255) / 256, 256, 0, s>>>(pi, T, state);
+  if (launches) ++*launches;
+}
+
+void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches) {
+  if (v.n_reads) {
+    em_den_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
+                                                                      v.cand_score, v.pi, v.read_tmp, v.state);
+    if (launches) ++*launches;
+  }
+  if (v.n_seg) {
+    em_partial_kernel<<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
+        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+    if (launches) ++*launches;
+  }
+  seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, v.ps, v.state);
+  if (launches) ++*launches;
+}
+
+void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches) {
+  const uint32_t nb = (v.T + 255) / 256;
+  em_update_kernel<<<nb, 256, 0, s>>>(v.ps, v.pi, v.T, add_a, add_b, v.block_change, v.state);
+  em_converge_kernel<<<1, 256, 0, s>>>(v.block_change, nb, tol, v.state, v.last_change);
+  if (launches) *launches += 2;
+}
+
+void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches) {
+  cudaMemsetAsync(present_u32, 0, sizeof(uint32_t) * v.T, s);
+  if (v.n_reads) {
+    as_tot_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
+                                                                      v.cand_score, v.pi, v.read_tmp);
+    if (launches) ++*launches;
+  }
+  if (v.n_seg) {
+    as_partial_kernel<<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
+        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial,
+        present_u32);
+    if (launches) ++*launches;
+  }
+  seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, numreads, nullptr);
+  if (launches) ++*launches;
+}
+
+void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches) {
+  if (!n) return;
+  const uint32_t grid = (uint32_t)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+  sum_u16_kernel<<<grid, 256, 0, s>>>(cnt, n, out);
+  if (launches) ++*launches;
+}
+
+}  // namespace sq

@@ -1,0 +1,1087 @@
+// C ABI of the quant hot path (include/sketchquant.h): engine state, batch pipeline, EM driver, NCCL glue.
+// There is deliberately no CPU implementation behind these entry points: without a CUDA device every call
+// fails with SQ_ERR_NO_DEVICE.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sketchquant.h"
+#include "sq_common.cuh"
+#include "sq_kernels.cuh"
+#include "sq_tap.cuh"
+
+using namespace sq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T> T* as() const { return static_cast<T*>(p); }
+  // grow-only; contents are NOT preserved
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+  DevBuf packed, base_off, len;  // only used for host pushes
+  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, stage_tid, stage_score,
+      scan_tmp;
+  cudaEvent_t done = nullptr, copied = nullptr;
+  bool in_flight = false;
+  uint64_t stage_cap = 0;
+  void release() {
+    DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &sel, &read_soff, &read_cnt,
+                     &batch_off, &ovf_list, &stage_tid, &stage_score, &scan_tmp};
+    for (DevBuf* b : all) b->release();
+  }
+};
+
+struct KTab {
+  DevBuf buckets, postings;
+  uint32_t shift = 0, mask = 0;
+  bool present = false;
+  uint64_t nkeys = 0, npost = 0;
+};
+
+struct StageEvent { cudaEvent_t a, b; int stage; };
+
+// NCCL entry points resolved at run time (single-GPU use needs no NCCL at all)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string* err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct sq_engine {
+  int device = 0;
+  uint32_t nk = 0;
+  uint32_t ks[SQ_MAXK] = {0};
+  uint32_t kmax = 0, kmin = 0;
+  uint32_t threshold = 0;
+  double fraction = 0.9;
+  uint64_t T = 0;
+  KLut lut[SQ_MAXK];
+  cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+  bool profiling = false;
+  std::string err;
+  KTab tab[SQ_MAXK];
+  // options
+  uint64_t batch_bases = 1ull << 28;
+  uint32_t cand_per_read = 16;
+  uint32_t n_workers = 64;
+  uint32_t max_read_len = 1u << 20;
+  uint32_t em_seg = 1024;
+  // batch slots
+  Slot slot[2];
+  int next_slot = 0;
+  // device counters + pinned mirror
+  unsigned long long* d_totals = nullptr;        // [0] pairs, [1] overflow reads, [2] sketch hashes
+  unsigned long long* d_stage_cursor = nullptr;
+  uint32_t* d_ovf_count = nullptr;
+  uint32_t* d_flags = nullptr;
+  uint32_t* d_fail = nullptr;
+  unsigned long long* h_mirror = nullptr;        // [0] pairs, [1] overflow reads
+  uint64_t pairs_upper = 0;                       // host-side upper bound of pairs after all enqueued batches
+  // large-table scratch
+  DevBuf big_keys, big_cnt, big_list, big_set, big_cand;
+  uint32_t big_cap_log2 = 0, big_set_log2 = 0;
+  bool big_ready = false;
+  // candidate store (CSR over all pushed reads)
+  uint32_t* cand_tid = nullptr;
+  int32_t* cand_score = nullptr;
+  uint32_t* read_off = nullptr;
+  uint64_t cand_cap = 0, read_cap = 0;
+  uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;
+  // EM scratch
+  DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
+      read_tmp, partial, block_change, misc, numreads, present, scan_tmp;
+  int em_iterations = 0;
+  // sq_sketch / sq_build_postings scratch
+  Slot tap;
+  DevBuf tap_counts, tap_offs, tap_out, tap_tid, bp_newpair, bp_newkey, bp_ppos, bp_kpos, bp_keys, bp_off, bp_post;
+  uint64_t bp_nkeys = 0, bp_npost = 0;
+  int bp_kidx = -1;
+  const void* bp_sig = nullptr;
+  // profiling
+  std::vector<StageEvent> events;
+  float ms[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+  // NCCL
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+namespace {
+
+int fail(sq_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define SQ_CUDA(e, call)                                                                          \
+  do {                                                                                            \
+    cudaError_t _err = (call);                                                                    \
+    if (_err != cudaSuccess)                                                                      \
+      return fail((e), SQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_err), __FILE__, __LINE__); \
+  } while (0)
+
+#define SQ_TRY(call)              \
+  do {                            \
+    int _rc = (call);             \
+    if (_rc != SQ_OK) return _rc; \
+  } while (0)
+
+struct StageScope {
+  sq_engine* e;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageScope(sq_engine* e_, int s) : e(e_), stage(s) {
+    if (e->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~StageScope() {
+    if (e->profiling) {
+      cudaEventRecord(b, e->stream);
+      e->events.push_back({a, b, stage});
+    }
+  }
+};
+
+void resolve_events(sq_engine* e) {
+  for (auto& ev : e->events) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) e->ms[ev.stage] += ms;
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  e->events.clear();
+}
+
+uint32_t log2_ceil(uint64_t v) {
+  uint32_t l = 0;
+  while ((1ull << l) < v) ++l;
+  return l;
+}
+
+void make_lut(uint32_t k, KLut* out) {
+  for (uint32_t in = 0; in < 4; ++in) {
+    for (uint32_t o = 0; o < 4; ++o) {
+      const uint64_t s = seed33(in) ^ rol33(seed33(o), k);
+      out->e[in * 4 + o] = make_uint2((uint32_t)s, (uint32_t)(s >> 1));
+    }
+    const uint64_t s = seed33(in);
+    out->e[16 + in] = make_uint2((uint32_t)s, (uint32_t)(s >> 1));
+  }
+}
+
+int check_flags(sq_engine* e) {
+  uint32_t flags = 0;
+  SQ_CUDA(e, cudaMemcpyAsync(&flags, e->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  if (flags & 1u) return fail(e, SQ_ERR_CAPACITY, "candidate staging overflow: raise option cand_per_read (now %u)", e->cand_per_read);
+  if (flags & 2u) return fail(e, SQ_ERR_CAPACITY, "large-table overflow: a read is longer than option max_read_len (%u)", e->max_read_len);
+  if (flags & 4u) return fail(e, SQ_ERR_CAPACITY, "candidate store overflow (internal growth bound violated)");
+  return SQ_OK;
+}
+
+// make sure the CSR store can take `reads` more reads and `pairs` more pairs (contents preserved)
+int ensure_store(sq_engine* e, uint64_t reads, uint64_t pairs) {
+  const uint64_t need_reads = e->n_reads + reads + 1;
+  if (need_reads > e->read_cap) {
+    uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
+    uint32_t* p = nullptr;
+    SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
+    if (e->read_off) {
+      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (e->n_reads + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+      SQ_CUDA(e, cudaFree(e->read_off));
+    } else {
+      SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), e->stream));
+    }
+    e->read_off = p;
+    e->read_cap = cap;
+  }
+  const uint64_t need_pairs = e->pairs_upper + pairs;
+  if (need_pairs >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "more than 2^32 candidate pairs on one engine");
+  if (need_pairs > e->cand_cap) {
+    uint64_t cap = std::max<uint64_t>(need_pairs + need_pairs / 2, 1 << 20);
+    if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+    uint32_t* t = nullptr;
+    int32_t* s = nullptr;
+    SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint32_t)));
+    SQ_CUDA(e, cudaMalloc(&s, cap * sizeof(int32_t)));
+    if (e->cand_tid) {
+      // everything enqueued so far must land before the old arrays are copied
+      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+      const uint64_t p = e->h_mirror[0];
+      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, p * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(s, e->cand_score, p * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+      SQ_CUDA(e, cudaFree(e->cand_tid));
+      SQ_CUDA(e, cudaFree(e->cand_score));
+      e->pairs_upper = p;
+    }
+    e->cand_tid = t;
+    e->cand_score = s;
+    e->cand_cap = cap;
+  }
+  return SQ_OK;
+}
+
+int ensure_big_scratch(sq_engine* e) {
+  if (e->big_ready) return SQ_OK;
+  e->big_cap_log2 = std::max<uint32_t>(10, log2_ceil(e->T + e->T / 3 + 2));
+  e->big_set_log2 = std::max<uint32_t>(12, log2_ceil((uint64_t)e->max_read_len + e->max_read_len / 3 + 2));
+  const size_t tab = (size_t)1 << e->big_cap_log2, set = (size_t)1 << e->big_set_log2, w = e->n_workers;
+  SQ_CUDA(e, e->big_keys.ensure(w * tab * 4));
+  SQ_CUDA(e, e->big_cnt.ensure(w * tab * e->nk * 4));
+  SQ_CUDA(e, e->big_list.ensure(w * tab * 4));
+  SQ_CUDA(e, e->big_set.ensure(w * set * 4));
+  SQ_CUDA(e, e->big_cand.ensure(w * tab * 8));
+  launch_fill_u32(e->big_keys.as<uint32_t>(), w * tab, SQ_EMPTY, e->stream);
+  launch_fill_u32(e->big_set.as<uint32_t>(), w * set, SQ_EMPTY, e->stream);
+  SQ_CUDA(e, cudaMemsetAsync(e->big_cnt.p, 0, w * tab * e->nk * 4, e->stream));
+  e->launches += 2;
+  e->big_ready = true;
+  return SQ_OK;
+}
+
+// wait for the slot's previous batch, refresh the host-side pair bound
+int acquire_slot(sq_engine* e, Slot** out) {
+  Slot& s = e->slot[e->next_slot];
+  e->next_slot ^= 1;
+  if (!s.done) {
+    SQ_CUDA(e, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    SQ_CUDA(e, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+  }
+  if (s.in_flight) {
+    SQ_CUDA(e, cudaEventSynchronize(s.done));
+    s.in_flight = false;
+  }
+  *out = &s;
+  return SQ_OK;
+}
+
+// enqueue sketch + vote + compaction for one batch whose inputs are in device memory
+int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words, const uint32_t* d_boff, uint32_t bias,
+              const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases) {
+  if (n_reads == 0) return SQ_OK;
+  const uint64_t items_ub64 = (uint64_t)n_reads + n_bases / SQ_CHUNK + 1;
+  if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
+  const uint32_t items_ub = (uint32_t)items_ub64;
+  const uint64_t slot_stride = (n_bases + 3) & ~3ull;
+  s.stage_cap = std::max<uint64_t>((uint64_t)e->cand_per_read * n_reads, 4096);
+  SQ_CUDA(e, s.nit.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.item_start.ensure(((size_t)n_reads + 1) * 4));
+  SQ_CUDA(e, s.item_read.ensure((size_t)items_ub * 4));
+  SQ_CUDA(e, s.cnt.ensure((size_t)items_ub * e->nk * 2));
+  SQ_CUDA(e, s.sel.ensure((size_t)slot_stride * e->nk * 4));
+  SQ_CUDA(e, s.read_soff.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.read_cnt.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.batch_off.ensure(((size_t)n_reads + 1) * 4));
+  SQ_CUDA(e, s.ovf_list.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
+  SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
+  SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
+  SQ_TRY(ensure_big_scratch(e));
+  SQ_TRY(ensure_store(e, n_reads, s.stage_cap));
+
+  {
+    StageScope st(e, 0);
+    launch_items(d_len, n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(), s.item_read.as<uint32_t>(),
+                 items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches);
+    SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * e->nk * 2, e->stream));
+    SketchParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.packed = d_packed;
+    sp.n_words = n_words;
+    sp.base_off = d_boff;
+    sp.bias = bias;
+    sp.len = d_len;
+    sp.item_read = s.item_read.as<uint32_t>();
+    sp.item_start = s.item_start.as<uint32_t>();
+    sp.n_reads = n_reads;
+    sp.n_items_ub = items_ub;
+    sp.nk = e->nk;
+    sp.threshold = e->threshold;
+    for (uint32_t i = 0; i < e->nk; ++i) { sp.ks[i] = e->ks[i]; sp.lut[i] = e->lut[i]; }
+    sp.kmax = e->kmax;
+    sp.sel = s.sel.as<uint32_t>();
+    sp.slot_stride = slot_stride;
+    sp.cnt = s.cnt.as<uint16_t>();
+    launch_sketch(sp, e->stream, &e->launches);
+    launch_sum_u16(s.cnt.as<uint16_t>(), (uint64_t)items_ub * e->nk, e->d_totals + 2, e->stream, &e->launches);
+  }
+  {
+    StageScope st(e, 1);
+    VoteParams vp;
+    memset(&vp, 0, sizeof(vp));
+    vp.base_off = d_boff;
+    vp.bias = bias;
+    vp.len = d_len;
+    vp.item_start = s.item_start.as<uint32_t>();
+    vp.n_reads = n_reads;
+    vp.n_items_ub = items_ub;
+    vp.nk = e->nk;
+    vp.fraction = e->fraction;
+    vp.sel = s.sel.as<uint32_t>();
+    vp.slot_stride = slot_stride;
+    vp.cnt = s.cnt.as<uint16_t>();
+    for (uint32_t i = 0; i < e->nk; ++i) {
+      vp.tab[i].buckets = e->tab[i].buckets.as<uint4>();
+      vp.tab[i].postings = e->tab[i].postings.as<uint32_t>();
+      vp.tab[i].shift = e->tab[i].shift;
+      vp.tab[i].mask = e->tab[i].mask;
+      vp.tab[i].present = e->tab[i].present ? 1u : 0u;
+    }
+    vp.stage_tid = s.stage_tid.as<uint32_t>();
+    vp.stage_score = s.stage_score.as<int32_t>();
+    vp.stage_cap = s.stage_cap;
+    vp.stage_cursor = e->d_stage_cursor;
+    vp.read_soff = s.read_soff.as<uint32_t>();
+    vp.read_cnt = s.read_cnt.as<uint32_t>();
+    vp.ovf_list = s.ovf_list.as<uint32_t>();
+    vp.ovf_count = e->d_ovf_count;
+    vp.flags = e->d_flags;
+    vp.big_keys = e->big_keys.as<uint32_t>();
+    vp.big_cnt = e->big_cnt.as<uint32_t>();
+    vp.big_list = e->big_list.as<uint32_t>();
+    vp.big_set = e->big_set.as<uint32_t>();
+    vp.big_cand = e->big_cand.as<unsigned long long>();
+    vp.big_cap_log2 = e->big_cap_log2;
+    vp.big_set_log2 = e->big_set_log2;
+    vp.n_workers = e->n_workers;
+    launch_vote(vp, e->stream, &e->launches);
+  }
+  {
+    StageScope st(e, 2);
+    launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), n_reads, s.scan_tmp.as<uint32_t>(),
+                          e->stream, &e->launches);
+    launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), n_reads,
+                   s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->d_totals, e->n_reads, e->cand_cap,
+                   e->cand_tid, e->cand_score, e->read_off, e->d_flags, e->d_stage_cursor, e->d_ovf_count,
+                   e->h_mirror, e->stream, &e->launches);
+  }
+  SQ_CUDA(e, cudaGetLastError());
+  SQ_CUDA(e, cudaEventRecord(s.done, e->stream));
+  s.in_flight = true;
+  e->pairs_upper += s.stage_cap;
+  e->n_reads += n_reads;
+  e->n_bases += n_bases;
+  e->n_batches += 1;
+  return SQ_OK;
+}
+
+int require_index(sq_engine* e) {
+  if (!e) return SQ_ERR_ARG;
+  return SQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sq_version(void) { return "sketchquant-b200 0.1 (sm_100a)"; }
+
+int sq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return SQ_ERR_NO_DEVICE; }
+  return n;
+}
+
+const char* sq_last_error(const sq_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+uint32_t sq_threshold_from_fraction(double fraction) {
+  const uint32_t H = 0xFFFFFFFFu;
+  return static_cast<uint32_t>(H * fraction);
+}
+
+int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint32_t threshold, double chain_fraction,
+              uint64_t n_transcripts) {
+  if (!out) return fail(nullptr, SQ_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (nk == 0 || nk > SQ_MAXK || !ks) return fail(nullptr, SQ_ERR_ARG, "nk must be in 1..%d", SQ_MAXK);
+  for (uint32_t i = 0; i < nk; ++i)
+    if (ks[i] == 0 || ks[i] > 4096) return fail(nullptr, SQ_ERR_ARG, "k[%u]=%u out of range 1..4096", i, ks[i]);
+  if (n_transcripts == 0 || n_transcripts >= 0x7FFFFFFFull) return fail(nullptr, SQ_ERR_ARG, "n_transcripts out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return fail(nullptr, SQ_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, SQ_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+  sq_engine* e = new sq_engine();
+  e->device = device;
+  e->nk = nk;
+  e->kmin = 0xFFFFFFFFu;
+  for (uint32_t i = 0; i < nk; ++i) {
+    e->ks[i] = ks[i];
+    e->kmax = std::max(e->kmax, ks[i]);
+    e->kmin = std::min(e->kmin, ks[i]);
+    make_lut(ks[i], &e->lut[i]);
+  }
+  e->threshold = threshold;
+  e->fraction = chain_fraction;
+  e->T = n_transcripts;
+  auto bail = [&](cudaError_t ce, const char* what) {
+    fail(nullptr, SQ_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+    delete e;
+    return SQ_ERR_CUDA;
+  };
+  cudaError_t ce;
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
+  if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
+  if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
+  e->stream = e->own_stream;
+  void* ctr = nullptr;
+  if ((ce = cudaMalloc(&ctr, 64)) != cudaSuccess) return bail(ce, "cudaMalloc");
+  if ((ce = cudaMemset(ctr, 0, 64)) != cudaSuccess) return bail(ce, "cudaMemset");
+  e->d_totals = static_cast<unsigned long long*>(ctr);                 // 3 x u64
+  e->d_stage_cursor = e->d_totals + 4;                                 // byte 32
+  e->d_ovf_count = reinterpret_cast<uint32_t*>(e->d_totals + 5);       // byte 40
+  e->d_flags = e->d_ovf_count + 1;                                     // byte 44
+  e->d_fail = e->d_ovf_count + 2;                                      // byte 48
+  if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
+  memset(e->h_mirror, 0, 64);
+  *out = e;
+  return SQ_OK;
+}
+
+void sq_destroy(sq_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  resolve_events(e);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  for (auto& s : e->slot) {
+    s.release();
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.copied) cudaEventDestroy(s.copied);
+  }
+  for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); }
+  e->tap.release();
+  {
+    DevBuf* tb[] = {&e->tap_counts, &e->tap_offs, &e->tap_out, &e->tap_tid, &e->bp_newpair, &e->bp_newkey,
+                    &e->bp_ppos, &e->bp_kpos, &e->bp_keys, &e->bp_off, &e->bp_post};
+    for (DevBuf* b : tb) b->release();
+  }
+  DevBuf* all[] = {&e->big_keys, &e->big_cnt, &e->big_list, &e->big_set, &e->big_cand, &e->keys_a, &e->keys_b,
+                   &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
+                   &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
+                   &e->numreads, &e->present, &e->scan_tmp};
+  for (DevBuf* b : all) b->release();
+  if (e->cand_tid) cudaFree(e->cand_tid);
+  if (e->cand_score) cudaFree(e->cand_score);
+  if (e->read_off) cudaFree(e->read_off);
+  if (e->d_totals) cudaFree(e->d_totals);
+  if (e->h_mirror) cudaFreeHost(e->h_mirror);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  delete e;
+}
+
+int sq_set_stream(sq_engine* e, void* cuda_stream) {
+  if (!e) return SQ_ERR_ARG;
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return SQ_OK;
+}
+
+int sq_set_profiling(sq_engine* e, int enabled) {
+  if (!e) return SQ_ERR_ARG;
+  e->profiling = enabled != 0;
+  return SQ_OK;
+}
+
+int sq_set_option(sq_engine* e, const char* name, int64_t value) {
+  if (!e || !name) return SQ_ERR_ARG;
+  if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
+  const std::string n(name);
+  if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
+  if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
+  else if (n == "cand_per_read") e->cand_per_read = (uint32_t)value;
+  else if (n == "overflow_workers") { e->n_workers = (uint32_t)value; e->big_ready = false; }
+  else if (n == "max_read_len") { e->max_read_len = (uint32_t)value; e->big_ready = false; }
+  else if (n == "em_segment") e->em_seg = (uint32_t)value;
+  else return fail(e, SQ_ERR_ARG, "unknown option %s", name);
+  return SQ_OK;
+}
+
+int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* keys, const uint64_t* post_off,
+                  const uint32_t* post_tid) {
+  if (!e) return SQ_ERR_ARG;
+  if (kidx >= e->nk) return fail(e, SQ_ERR_ARG, "kidx %u out of range", kidx);
+  if (nkeys && (!keys || !post_off || !post_tid)) return fail(e, SQ_ERR_ARG, "NULL index array");
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  const uint64_t npost = nkeys ? post_off[nkeys] : 0;
+  if (npost >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "more than 2^32 postings for one k");
+  for (uint64_t i = 0; i < npost; ++i)
+    if (post_tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "posting %llu names transcript %u >= T", (unsigned long long)i, post_tid[i]);
+  KTab& t = e->tab[kidx];
+  const uint32_t nb_log2 = std::max<uint32_t>(1, log2_ceil((nkeys + 1) / 2 + 1));
+  const uint64_t nb = 1ull << nb_log2;
+  SQ_CUDA(e, t.buckets.ensure(nb * 32));
+  SQ_CUDA(e, t.postings.ensure((npost + 1) * 4));
+  t.shift = 32 - nb_log2;
+  t.mask = (uint32_t)(nb - 1);
+  t.nkeys = nkeys;
+  t.npost = npost;
+  DevBuf dkeys, doff;
+  SQ_CUDA(e, dkeys.ensure((nkeys + 1) * 4));
+  SQ_CUDA(e, doff.ensure((nkeys + 1) * 8));
+  if (nkeys) {
+    SQ_CUDA(e, cudaMemcpyAsync(dkeys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, e->stream));
+    SQ_CUDA(e, cudaMemcpyAsync(doff.p, post_off, (nkeys + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+    SQ_CUDA(e, cudaMemcpyAsync(t.postings.p, post_tid, npost * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  SQ_CUDA(e, cudaMemsetAsync(e->d_fail, 0, 4, e->stream));
+  launch_table_build(dkeys.as<uint32_t>(), doff.as<uint64_t>(), nkeys, t.buckets.as<uint4>(), t.shift, t.mask,
+                     t.postings.as<uint32_t>(), e->d_fail, e->stream, &e->launches);
+  uint32_t failed = 0;
+  SQ_CUDA(e, cudaMemcpyAsync(&failed, e->d_fail, 4, cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  SQ_CUDA(e, cudaGetLastError());
+  dkeys.release();
+  doff.release();
+  if (failed) return fail(e, SQ_ERR_CAPACITY, "index table build failed (table full)");
+  t.present = true;
+  return SQ_OK;
+}
+
+int sq_push_reads_device(sq_engine* e, const uint32_t* d_packed_words, uint64_t n_words, const uint32_t* d_base_off,
+                         const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases_hint) {
+  if (!e) return SQ_ERR_ARG;
+  if (n_reads == 0) return SQ_OK;
+  if (!d_packed_words || !d_base_off || !d_len) return fail(e, SQ_ERR_ARG, "NULL device pointer");
+  if ((reinterpret_cast<uintptr_t>(d_packed_words) & 15) != 0) return fail(e, SQ_ERR_ARG, "packed words must be 16-byte aligned");
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  const uint64_t n_bases = n_bases_hint ? n_bases_hint : n_words * 16;
+  Slot* s = nullptr;
+  SQ_TRY(acquire_slot(e, &s));
+  return run_batch(e, *s, d_packed_words, n_words, d_base_off, 0, d_len, n_reads, n_bases);
+}
+
+int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, const uint32_t* base_off,
+                  const uint32_t* len, uint32_t n_reads) {
+  if (!e) return SQ_ERR_ARG;
+  if (n_reads == 0) return SQ_OK;
+  if (!packed_words || !base_off || !len) return fail(e, SQ_ERR_ARG, "NULL host pointer");
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  uint32_t r0 = 0;
+  while (r0 < n_reads) {
+    // sub-batch [r0, r1): bases from word-aligned start of read r0, at most batch_bases
+    const uint64_t w0 = base_off[r0] >> 4;
+    const uint64_t limit = w0 * 16 + e->batch_bases;
+    uint32_t lo = r0 + 1, hi = n_reads;  // largest r1 with end(r1-1) <= limit (reads are laid out in order)
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      if ((uint64_t)base_off[mid - 1] + len[mid - 1] <= limit) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t r1 = lo;
+    const uint64_t end_base = (uint64_t)base_off[r1 - 1] + len[r1 - 1];
+    if (end_base < w0 * 16) return fail(e, SQ_ERR_ARG, "base_off must be non-decreasing");
+    const uint64_t w1 = std::min<uint64_t>((end_base + 15) >> 4, n_words);
+    if (((end_base + 15) >> 4) > n_words) return fail(e, SQ_ERR_ARG, "read %u extends beyond n_words", r1 - 1);
+    const uint64_t nw = w1 - w0, nb = end_base - w0 * 16;
+    const uint32_t nr = r1 - r0;
+    Slot* s = nullptr;
+    SQ_TRY(acquire_slot(e, &s));
+    SQ_CUDA(e, s->packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
+    SQ_CUDA(e, s->base_off.ensure((size_t)nr * 4));
+    SQ_CUDA(e, s->len.ensure((size_t)nr * 4));
+    SQ_CUDA(e, cudaMemcpyAsync(s->packed.p, packed_words + w0, nw * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaMemcpyAsync(s->base_off.p, base_off + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaMemcpyAsync(s->len.p, len + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
+    SQ_CUDA(e, cudaStreamWaitEvent(e->stream, s->copied, 0));
+    SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (nw + 3) & ~3ull, s->base_off.as<uint32_t>(), (uint32_t)(w0 * 16),
+                     s->len.as<uint32_t>(), nr, nb));
+    // the caller may reuse its buffers when we return: wait for the copies (not for the kernels)
+    SQ_CUDA(e, cudaEventSynchronize(s->copied));
+    r0 = r1;
+  }
+  return SQ_OK;
+}
+
+int sq_sync(sq_engine* e) {
+  if (!e) return SQ_ERR_ARG;
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  SQ_CUDA(e, cudaStreamSynchronize(e->copy_stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  for (auto& s : e->slot) s.in_flight = false;
+  resolve_events(e);
+  e->pairs_upper = e->h_mirror[0];
+  return check_flags(e);
+}
+
+int sq_reset_reads(sq_engine* e) {
+  if (!e) return SQ_ERR_ARG;
+  SQ_TRY(sq_sync(e));
+  SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 64, e->stream));
+  if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  memset(e->h_mirror, 0, 64);
+  e->pairs_upper = 0;
+  e->n_reads = e->n_bases = e->n_batches = 0;
+  return SQ_OK;
+}
+
+int sq_num_pairs(sq_engine* e, uint64_t* n_reads, uint64_t* n_pairs) {
+  if (!e) return SQ_ERR_ARG;
+  SQ_TRY(sq_sync(e));
+  if (n_reads) *n_reads = e->n_reads;
+  if (n_pairs) *n_pairs = e->h_mirror[0];
+  return SQ_OK;
+}
+
+int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* score) {
+  if (!e) return SQ_ERR_ARG;
+  SQ_TRY(sq_sync(e));
+  const uint64_t R = e->n_reads, P = e->h_mirror[0];
+  if (read_off) {
+    std::vector<uint32_t> tmp(R + 1, 0);
+    if (R) SQ_CUDA(e, cudaMemcpy(tmp.data(), e->read_off, (R + 1) * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i <= R; ++i) read_off[i] = tmp[i];
+  }
+  if (P && tid) SQ_CUDA(e, cudaMemcpy(tid, e->cand_tid, P * 4, cudaMemcpyDeviceToHost));
+  if (P && score) SQ_CUDA(e, cudaMemcpy(score, e->cand_score, P * 4, cudaMemcpyDeviceToHost));
+  return SQ_OK;
+}
+
+int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, const uint32_t* tid,
+                      const int32_t* score) {
+  if (!e) return SQ_ERR_ARG;
+  if (n_reads && !read_off) return fail(e, SQ_ERR_ARG, "NULL read_off");
+  SQ_TRY(sq_reset_reads(e));
+  const uint64_t P = n_reads ? read_off[n_reads] : 0;
+  if (P && (!tid || !score)) return fail(e, SQ_ERR_ARG, "NULL candidate array");
+  for (uint64_t i = 0; i < P; ++i)
+    if (tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "candidate %llu names transcript %u >= T", (unsigned long long)i, tid[i]);
+  e->pairs_upper = 0;
+  SQ_TRY(ensure_store(e, n_reads, P));
+  std::vector<uint32_t> off32(n_reads + 1, 0);
+  for (uint64_t i = 0; i <= n_reads && n_reads; ++i) {
+    if (i && read_off[i] < read_off[i - 1]) return fail(e, SQ_ERR_ARG, "read_off must be non-decreasing");
+    off32[i] = (uint32_t)read_off[i];
+  }
+  SQ_CUDA(e, cudaMemcpy(e->read_off, off32.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice));
+  if (P) {
+    SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
+    SQ_CUDA(e, cudaMemcpy(e->cand_score, score, P * 4, cudaMemcpyHostToDevice));
+  }
+  unsigned long long p64 = P;
+  SQ_CUDA(e, cudaMemcpy(e->d_totals, &p64, 8, cudaMemcpyHostToDevice));
+  e->h_mirror[0] = P;
+  e->pairs_upper = P;
+  e->n_reads = n_reads;
+  return SQ_OK;
+}
+
+static int allreduce(sq_engine* e, void* buf, size_t n, ncclDataType_t dt) {
+  if (!e->comm) return SQ_OK;
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, n, dt, ncclSum, e->comm, e->stream);
+  if (r != ncclSuccess) return fail(e, SQ_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  return SQ_OK;
+}
+
+int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, double* pi, double* numreads,
+              uint8_t* present, int* iters_done) {
+  if (!e) return SQ_ERR_ARG;
+  if (!pi || !numreads || !present) return fail(e, SQ_ERR_ARG, "NULL output array");
+  SQ_TRY(sq_sync(e));
+  const uint64_t R = e->n_reads, P = e->h_mirror[0];
+  const uint32_t T = (uint32_t)e->T;
+  cudaStream_t st = e->stream;
+  SQ_CUDA(e, e->misc.ensure(256));
+  uint32_t* state = e->misc.as<uint32_t>();                                // [0..1]
+  double* last_change = reinterpret_cast<double*>(e->misc.as<char>() + 16);
+  unsigned long long* d_R = reinterpret_cast<unsigned long long*>(e->misc.as<char>() + 32);
+
+  uint64_t R_all = R_total;
+  if (R_all == 0) {
+    R_all = R;
+    if (e->comm) {
+      unsigned long long v = R;
+      SQ_CUDA(e, cudaMemcpyAsync(d_R, &v, 8, cudaMemcpyHostToDevice, st));
+      SQ_TRY(allreduce(e, d_R, 1, ncclUint64));
+      SQ_CUDA(e, cudaMemcpyAsync(&v, d_R, 8, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaStreamSynchronize(st));
+      R_all = v;
+    }
+  }
+
+  // ---- transcript-major copy of the pairs: stable radix sort on the transcript id ----
+  uint64_t* keys = nullptr;
+  uint32_t* vals = nullptr;
+  uint32_t n_seg = 0;
+  {
+    StageScope sc(e, 3);
+    SQ_CUDA(e, e->toff.ensure(((size_t)T + 1) * 4));
+    SQ_CUDA(e, e->nseg.ensure((size_t)T * 4));
+    SQ_CUDA(e, e->seg_off.ensure(((size_t)T + 1) * 4));
+    SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words(T) * 4));
+    SQ_CUDA(e, e->keys_a.ensure((P + 1) * 8));
+    SQ_CUDA(e, e->keys_b.ensure((P + 1) * 8));
+    SQ_CUDA(e, e->vals_a.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->vals_b.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->tm_read.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(P) * 4));
+    if (P) {
+      launch_make_sort_keys(e->read_off, R, e->cand_tid, e->keys_a.as<uint64_t>(), st, &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->cand_score, P * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    const int nbits = (int)std::max<uint32_t>(1, log2_ceil(T));
+    launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
+                      e->vals_b.as<uint32_t>(), P, nbits, e->sort_tmp.as<uint32_t>(), &keys, &vals, st, &e->launches);
+    launch_tmajor(keys, P, T, e->em_seg, e->toff.as<uint32_t>(), e->tm_read.as<uint32_t>(), e->nseg.as<uint32_t>(),
+                  e->seg_off.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), st, &e->launches);
+    SQ_CUDA(e, cudaMemcpyAsync(&n_seg, e->seg_off.as<uint32_t>() + T, 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(e, cudaStreamSynchronize(st));
+    SQ_CUDA(e, e->seg_tid.ensure(((size_t)n_seg + 1) * 4));
+    SQ_CUDA(e, e->seg_begin.ensure(((size_t)n_seg + 1) * 4));
+    SQ_CUDA(e, e->partial.ensure(((size_t)n_seg + 1) * 8));
+    launch_seg_expand(e->toff.as<uint32_t>(), e->seg_off.as<uint32_t>(), T, e->em_seg, e->seg_tid.as<uint32_t>(),
+                      e->seg_begin.as<uint32_t>(), st, &e->launches);
+  }
+
+  SQ_CUDA(e, e->pi.ensure((size_t)T * 8));
+  SQ_CUDA(e, e->ps.ensure((size_t)T * 8));
+  SQ_CUDA(e, e->numreads.ensure((size_t)T * 8));
+  SQ_CUDA(e, e->present.ensure((size_t)T * 4));
+  SQ_CUDA(e, e->read_tmp.ensure((R + 1) * 8));
+  SQ_CUDA(e, e->block_change.ensure(((size_t)(T + 255) / 256 + 1) * 8));
+
+  EmView v;
+  v.read_off = e->read_off;
+  v.cand_tid = e->cand_tid;
+  v.cand_score = e->cand_score;
+  v.n_reads = R;
+  v.toff = e->toff.as<uint32_t>();
+  v.tm_read = e->tm_read.as<uint32_t>();
+  v.tm_score = vals;
+  v.seg_off = e->seg_off.as<uint32_t>();
+  v.seg_tid = e->seg_tid.as<uint32_t>();
+  v.seg_begin = e->seg_begin.as<uint32_t>();
+  v.n_seg = n_seg;
+  v.seg = e->em_seg;
+  v.T = T;
+  v.pi = e->pi.as<double>();
+  v.ps = e->ps.as<double>();
+  v.read_tmp = e->read_tmp.as<double>();
+  v.partial = e->partial.as<double>();
+  v.block_change = e->block_change.as<double>();
+  v.last_change = last_change;
+  v.state = state;
+
+  // M-step constants (isoform_assignment.cpp:54-57): float pseudocount, float division by R
+  const float pseudocount = 0.01f;
+  const double add_a = (double)(pseudocount / (float)R_all);
+  const double add_b = (double)pseudocount;
+  {
+    StageScope sc(e, 4);
+    launch_em_init(v.pi, T, state, st, &e->launches);
+    for (int it = 0; it < em_iters; ++it) {
+      launch_em_estep(v, st, &e->launches);
+      SQ_TRY(allreduce(e, v.ps, T, ncclDouble));
+      launch_em_mstep(v, add_a, add_b, em_tol, st, &e->launches);
+    }
+  }
+  {
+    StageScope sc(e, 5);
+    launch_assign(v, e->numreads.as<double>(), e->present.as<uint32_t>(), st, &e->launches);
+    SQ_TRY(allreduce(e, e->numreads.p, T, ncclDouble));
+    SQ_TRY(allreduce(e, e->present.p, T, ncclUint32));
+  }
+  std::vector<uint32_t> pres(T);
+  uint32_t st_host[2] = {0, 0};
+  SQ_CUDA(e, cudaMemcpyAsync(pi, v.pi, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(numreads, e->numreads.p, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(pres.data(), e->present.p, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(st_host, state, 8, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaStreamSynchronize(st));
+  SQ_CUDA(e, cudaGetLastError());
+  for (uint32_t t = 0; t < T; ++t) present[t] = pres[t] ? 1 : 0;
+  e->em_iterations = (int)st_host[1];
+  if (iters_done) *iters_done = e->em_iterations;
+  resolve_events(e);
+  return SQ_OK;
+}
+
+int sq_get_stats(sq_engine* e, sq_stats* out) {
+  if (!e || !out) return SQ_ERR_ARG;
+  SQ_TRY(sq_sync(e));
+  unsigned long long tot[3] = {0, 0, 0};
+  SQ_CUDA(e, cudaMemcpy(tot, e->d_totals, sizeof(tot), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->reads = e->n_reads;
+  out->bases = e->n_bases;
+  out->kmers = e->n_kmers_known;
+  out->sketch_hashes = tot[2];
+  out->pairs = tot[0];
+  out->overflow_reads = tot[1];
+  out->batches = e->n_batches;
+  out->em_iterations = e->em_iterations;
+  out->ms_sketch = e->ms[0]; out->ms_vote = e->ms[1]; out->ms_compact = e->ms[2];
+  out->ms_sort = e->ms[3]; out->ms_em = e->ms[4]; out->ms_assign = e->ms[5];
+  out->launches = e->launches;
+  return SQ_OK;
+}
+
+int sq_nccl_unique_id(uint8_t id[SQ_NCCL_ID_BYTES]) {
+  std::string err;
+  if (!g_nccl.load(&err)) return fail(nullptr, SQ_ERR_NCCL, "%s", err.c_str());
+  ncclUniqueId uid;
+  static_assert(sizeof(uid) == SQ_NCCL_ID_BYTES, "ncclUniqueId size");
+  ncclResult_t r = g_nccl.GetUniqueId(&uid);
+  if (r != ncclSuccess) return fail(nullptr, SQ_ERR_NCCL, "ncclGetUniqueId failed (%d)", (int)r);
+  memcpy(id, &uid, SQ_NCCL_ID_BYTES);
+  return SQ_OK;
+}
+
+int sq_comm_init(sq_engine* e, int nranks, int rank, const uint8_t id[SQ_NCCL_ID_BYTES]) {
+  if (!e) return SQ_ERR_ARG;
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(e, SQ_ERR_ARG, "bad rank %d of %d", rank, nranks);
+  if (nranks == 1) { e->nranks = 1; e->rank = 0; return SQ_OK; }
+  std::string err;
+  if (!g_nccl.load(&err)) return fail(e, SQ_ERR_NCCL, "%s", err.c_str());
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, SQ_NCCL_ID_BYTES);
+  ncclResult_t r = g_nccl.CommInitRank(&e->comm, nranks, uid, rank);
+  if (r != ncclSuccess) return fail(e, SQ_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
+  e->nranks = nranks;
+  e->rank = rank;
+  return SQ_OK;
+}
+
+}  // extern "C"
+
+// ---- sketch tap / postings build: run the sketch kernel on a host batch held in the engine's tap slot ----
+namespace {
+
+// uploads the batch and runs items + sketch for k-indices [k0, k0+nk); leaves counts per (read, k) in
+// e->tap_counts and their exclusive scan in e->tap_offs (total -> *total)
+int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_words, uint64_t n_words,
+               const uint32_t* base_off, const uint32_t* len, uint32_t n_reads, uint32_t* bias_out,
+               uint32_t* items_ub_out, uint64_t* stride_out, uint64_t* total) {
+  Slot& s = e->tap;
+  cudaStream_t st = e->stream;
+  const uint64_t w0 = base_off[0] >> 4;
+  uint64_t end_base = 0;
+  for (uint32_t r = 0; r < n_reads; ++r) end_base = std::max<uint64_t>(end_base, (uint64_t)base_off[r] + len[r]);
+  if (((end_base + 15) >> 4) > n_words) return fail(e, SQ_ERR_ARG, "a sequence extends beyond n_words");
+  if (end_base < w0 * 16) return fail(e, SQ_ERR_ARG, "base_off must be non-decreasing");
+  const uint64_t nw = ((end_base + 15) >> 4) - w0, nb = end_base - w0 * 16;
+  const uint64_t items_ub64 = (uint64_t)n_reads + nb / SQ_CHUNK + 1;
+  if (items_ub64 >= 0xFFFFFFFFull || nb >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
+  const uint32_t items_ub = (uint32_t)items_ub64;
+  const uint64_t stride = (nb + 3) & ~3ull;
+  SQ_CUDA(e, s.packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
+  SQ_CUDA(e, s.base_off.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.len.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.nit.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.item_start.ensure(((size_t)n_reads + 1) * 4));
+  SQ_CUDA(e, s.item_read.ensure((size_t)items_ub * 4));
+  SQ_CUDA(e, s.cnt.ensure((size_t)items_ub * nk * 2));
+  SQ_CUDA(e, s.sel.ensure((size_t)stride * nk * 4));
+  SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max<uint32_t>(items_ub, n_reads * nk)) * 4));
+  SQ_CUDA(e, e->tap_counts.ensure((size_t)n_reads * nk * 4));
+  SQ_CUDA(e, e->tap_offs.ensure(((size_t)n_reads * nk + 1) * 4));
+  SQ_CUDA(e, cudaMemcpyAsync(s.packed.p, packed_words + w0, nw * 4, cudaMemcpyHostToDevice, st));
+  SQ_CUDA(e, cudaMemcpyAsync(s.base_off.p, base_off, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  SQ_CUDA(e, cudaMemcpyAsync(s.len.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  launch_items(s.len.as<uint32_t>(), n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(),
+               s.item_read.as<uint32_t>(), items_ub, s.scan_tmp.as<uint32_t>(), st, &e->launches);
+  SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * nk * 2, st));
+  SketchParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.packed = s.packed.as<uint32_t>();
+  sp.n_words = (nw + 3) & ~3ull;
+  sp.base_off = s.base_off.as<uint32_t>();
+  sp.bias = (uint32_t)(w0 * 16);
+  sp.len = s.len.as<uint32_t>();
+  sp.item_read = s.item_read.as<uint32_t>();
+  sp.item_start = s.item_start.as<uint32_t>();
+  sp.n_reads = n_reads;
+  sp.n_items_ub = items_ub;
+  sp.nk = nk;
+  sp.threshold = e->threshold;
+  sp.kmax = 0;
+  for (uint32_t i = 0; i < nk; ++i) {
+    sp.ks[i] = e->ks[k0 + i];
+    sp.lut[i] = e->lut[k0 + i];
+    sp.kmax = std::max(sp.kmax, sp.ks[i]);
+  }
+  sp.sel = s.sel.as<uint32_t>();
+  sp.slot_stride = stride;
+  sp.cnt = s.cnt.as<uint16_t>();
+  launch_sketch(sp, st, &e->launches);
+  launch_tap_count(s.item_start.as<uint32_t>(), n_reads, nk, s.cnt.as<uint16_t>(), items_ub,
+                   e->tap_counts.as<uint32_t>(), st, &e->launches);
+  launch_exclusive_scan(e->tap_counts.as<uint32_t>(), e->tap_offs.as<uint32_t>(), n_reads * nk,
+                        s.scan_tmp.as<uint32_t>(), st, &e->launches);
+  uint32_t tot32 = 0;
+  SQ_CUDA(e, cudaMemcpyAsync(&tot32, e->tap_offs.as<uint32_t>() + (size_t)n_reads * nk, 4, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaStreamSynchronize(st));
+  SQ_CUDA(e, cudaGetLastError());
+  *bias_out = sp.bias;
+  *items_ub_out = items_ub;
+  *stride_out = stride;
+  *total = tot32;
+  return SQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sq_sketch(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, const uint32_t* base_off,
+              const uint32_t* len, uint32_t n_reads, uint32_t* counts, uint32_t* hashes, uint64_t cap,
+              uint64_t* total) {
+  if (!e) return SQ_ERR_ARG;
+  if (total) *total = 0;
+  if (n_reads == 0) return SQ_OK;
+  if (!packed_words || !base_off || !len || !counts) return fail(e, SQ_ERR_ARG, "NULL pointer");
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  uint32_t bias = 0, items_ub = 0;
+  uint64_t stride = 0, tot = 0;
+  SQ_TRY(tap_sketch(e, 0, e->nk, packed_words, n_words, base_off, len, n_reads, &bias, &items_ub, &stride, &tot));
+  Slot& s = e->tap;
+  cudaStream_t st = e->stream;
+  const uint64_t ncopy = std::min<uint64_t>(tot, cap);
+  SQ_CUDA(e, e->tap_out.ensure((ncopy + 1) * 4));
+  launch_tap_gather(s.item_start.as<uint32_t>(), s.base_off.as<uint32_t>(), bias, s.len.as<uint32_t>(), n_reads, e->nk,
+                    s.cnt.as<uint16_t>(), items_ub, s.sel.as<uint32_t>(), stride, e->tap_offs.as<uint32_t>(), ncopy,
+                    e->tap_out.as<uint32_t>(), nullptr, nullptr, 0, st, &e->launches);
+  SQ_CUDA(e, cudaMemcpyAsync(counts, e->tap_counts.p, (size_t)n_reads * e->nk * 4, cudaMemcpyDeviceToHost, st));
+  if (ncopy && hashes) SQ_CUDA(e, cudaMemcpyAsync(hashes, e->tap_out.p, ncopy * 4, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaStreamSynchronize(st));
+  SQ_CUDA(e, cudaGetLastError());
+  if (total) *total = tot;
+  return SQ_OK;
+}
+
+int sq_build_postings(sq_engine* e, uint32_t kidx, const uint32_t* packed_words, uint64_t n_words,
+                      const uint32_t* base_off, const uint32_t* len, const uint32_t* seq_tid, uint32_t n_seqs,
+                      uint64_t* nkeys, uint64_t* npost, uint32_t* keys, uint64_t* post_off, uint32_t* post_tid) {
+  if (!e) return SQ_ERR_ARG;
+  if (kidx >= e->nk) return fail(e, SQ_ERR_ARG, "kidx %u out of range", kidx);
+  if (!nkeys || !npost) return fail(e, SQ_ERR_ARG, "nkeys/npost must not be NULL");
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = e->stream;
+  if (!keys) {  // first call: compute and cache on the device
+    e->bp_kidx = -1;
+    e->bp_nkeys = e->bp_npost = 0;
+    if (n_seqs) {
+      if (!packed_words || !base_off || !len || !seq_tid) return fail(e, SQ_ERR_ARG, "NULL pointer");
+      for (uint32_t i = 0; i < n_seqs; ++i)
+        if (seq_tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "seq_tid[%u]=%u >= T", i, seq_tid[i]);
+      uint32_t bias = 0, items_ub = 0;
+      uint64_t stride = 0, tot = 0;
+      SQ_TRY(tap_sketch(e, kidx, 1, packed_words, n_words, base_off, len, n_seqs, &bias, &items_ub, &stride, &tot));
+      Slot& s = e->tap;
+      const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(e->T));
+      SQ_CUDA(e, e->tap_tid.ensure((size_t)n_seqs * 4));
+      SQ_CUDA(e, cudaMemcpyAsync(e->tap_tid.p, seq_tid, (size_t)n_seqs * 4, cudaMemcpyHostToDevice, st));
+      SQ_CUDA(e, e->keys_a.ensure((tot + 1) * 8));
+      SQ_CUDA(e, e->keys_b.ensure((tot + 1) * 8));
+      SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(tot) * 4));
+      launch_tap_gather(s.item_start.as<uint32_t>(), s.base_off.as<uint32_t>(), bias, s.len.as<uint32_t>(), n_seqs, 1,
+                        s.cnt.as<uint16_t>(), items_ub, s.sel.as<uint32_t>(), stride, e->tap_offs.as<uint32_t>(), tot,
+                        nullptr, e->keys_a.as<uint64_t>(), e->tap_tid.as<uint32_t>(), tbits, st, &e->launches);
+      uint64_t* sorted = nullptr;
+      uint32_t* dummy = nullptr;
+      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, tot, 32 + (int)tbits,
+                        e->sort_tmp.as<uint32_t>(), &sorted, &dummy, st, &e->launches);
+      SQ_CUDA(e, e->bp_newpair.ensure((tot + 1) * 4));
+      SQ_CUDA(e, e->bp_newkey.ensure((tot + 1) * 4));
+      SQ_CUDA(e, e->bp_ppos.ensure((tot + 2) * 4));
+      SQ_CUDA(e, e->bp_kpos.ensure((tot + 2) * 4));
+      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)tot + 1) * 4));
+      launch_post_flags(sorted, tot, tbits, e->bp_newpair.as<uint32_t>(), e->bp_newkey.as<uint32_t>(), st, &e->launches);
+      launch_exclusive_scan(e->bp_newpair.as<uint32_t>(), e->bp_ppos.as<uint32_t>(), (uint32_t)tot,
+                            e->scan_tmp.as<uint32_t>(), st, &e->launches);
+      launch_exclusive_scan(e->bp_newkey.as<uint32_t>(), e->bp_kpos.as<uint32_t>(), (uint32_t)tot,
+                            e->scan_tmp.as<uint32_t>(), st, &e->launches);
+      uint32_t np = 0, nkk = 0;
+      SQ_CUDA(e, cudaMemcpyAsync(&np, e->bp_ppos.as<uint32_t>() + tot, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaMemcpyAsync(&nkk, e->bp_kpos.as<uint32_t>() + tot, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaStreamSynchronize(st));
+      SQ_CUDA(e, e->bp_keys.ensure(((size_t)nkk + 1) * 4));
+      SQ_CUDA(e, e->bp_off.ensure(((size_t)nkk + 1) * 8));
+      SQ_CUDA(e, e->bp_post.ensure(((size_t)np + 1) * 4));
+      launch_post_scatter(sorted, tot, tbits, e->bp_newpair.as<uint32_t>(), e->bp_newkey.as<uint32_t>(),
+                          e->bp_ppos.as<uint32_t>(), e->bp_kpos.as<uint32_t>(), e->bp_keys.as<uint32_t>(),
+                          e->bp_off.as<unsigned long long>(), e->bp_post.as<uint32_t>(), st, &e->launches);
+      SQ_CUDA(e, cudaStreamSynchronize(st));
+      SQ_CUDA(e, cudaGetLastError());
+      e->bp_nkeys = nkk;
+      e->bp_npost = np;
+    }
+    e->bp_kidx = (int)kidx;
+    *nkeys = e->bp_nkeys;
+    *npost = e->bp_npost;
+    return SQ_OK;
+  }
+  // second call: copy the cached result out
+  if (e->bp_kidx != (int)kidx) return fail(e, SQ_ERR_STATE, "sq_build_postings: sizing call for kidx %u missing", kidx);
+  if (!post_off || !post_tid) return fail(e, SQ_ERR_ARG, "NULL output array");
+  if (e->bp_nkeys) {
+    SQ_CUDA(e, cudaMemcpyAsync(keys, e->bp_keys.p, e->bp_nkeys * 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(e, cudaMemcpyAsync(post_off, e->bp_off.p, (e->bp_nkeys + 1) * 8, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(e, cudaMemcpyAsync(post_tid, e->bp_post.p, e->bp_npost * 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(e, cudaStreamSynchronize(st));
+  } else {
+    post_off[0] = 0;
+  }
+  *nkeys = e->bp_nkeys;
+  *npost = e->bp_npost;
+  e->bp_kidx = -1;
+  return SQ_OK;
+}
+
+}  // extern "C"

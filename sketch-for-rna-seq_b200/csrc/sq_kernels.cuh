@@ -1,0 +1,57 @@
+// Launcher prototypes of sq_em.cu / sq_vote.cu helpers used by the engine.
+#pragma once
+#include "sq_common.cuh"
+
+namespace sq {
+
+struct EmView {
+  // read-major CSR
+  const uint32_t* read_off;
+  const uint32_t* cand_tid;
+  const int32_t* cand_score;
+  uint64_t n_reads;
+  // transcript-major copy, split into segments of <= seg pairs
+  const uint32_t* toff;
+  const uint32_t* tm_read;
+  const uint32_t* tm_score;
+  const uint32_t* seg_off;    // per transcript: first segment (T+1 entries)
+  const uint32_t* seg_tid;
+  const uint32_t* seg_begin;
+  uint32_t n_seg;
+  uint32_t seg;
+  uint32_t T;
+  // state
+  double* pi;
+  double* ps;
+  double* read_tmp;      // per read: 1/den (E-step) or tot (assignment)
+  double* partial;       // per segment
+  double* block_change;  // per 256-transcript block
+  double* last_change;
+  uint32_t* state;       // [0] converged, [1] iterations executed
+};
+
+void launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
+size_t vote_smem_bytes(uint32_t nk);
+
+void launch_table_build(const uint32_t* keys, const uint64_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
+                        uint32_t mask, uint32_t* postings, uint32_t* fail, cudaStream_t s, uint64_t* launches);
+
+void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
+                    const uint32_t* stage_tid, const int32_t* stage_score, unsigned long long* totals,
+                    uint64_t read_base, uint64_t cap, uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off,
+                    uint32_t* flags, unsigned long long* stage_cursor, uint32_t* ovf_count,
+                    unsigned long long* host_mirror, cudaStream_t s, uint64_t* launches);
+void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
+
+void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
+                           cudaStream_t s, uint64_t* launches);
+void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, uint32_t* toff, uint32_t* tm_read,
+                   uint32_t* nseg, uint32_t* seg_off, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches);
+void launch_seg_expand(const uint32_t* toff, const uint32_t* seg_off, uint32_t T, uint32_t seg, uint32_t* seg_tid,
+                       uint32_t* seg_begin, cudaStream_t s, uint64_t* launches);
+void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uint64_t* launches);
+void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches);
+void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches);
+void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches);
+
+}  // namespace sq

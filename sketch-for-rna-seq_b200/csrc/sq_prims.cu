@@ -1,0 +1,236 @@
+// Device primitives used by the quant path: exclusive scan (u32) and a stable LSD radix sort of
+// (key64, val32) pairs.  Hand-written for sm_100a; no CUB/Thrust.
+#include "sq_common.cuh"
+
+namespace sq {
+
+// ------------------------------------------------------------------ scan
+static constexpr int kScanThreads = 256;
+static constexpr int kScanItems = 8;
+static constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+  // exclusive scan of one value per thread over a 256-thread block
+  __shared__ uint32_t wsum[kScanThreads / 32];
+  __shared__ uint32_t wtot;
+  const uint32_t incl = warp_incl_scan(v);
+  if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = threadIdx.x < kScanThreads / 32 ? wsum[threadIdx.x] : 0;
+    const uint32_t wi = warp_incl_scan(w);
+    if (threadIdx.x < kScanThreads / 32) wsum[threadIdx.x] = wi - w;
+    if (threadIdx.x == kScanThreads / 32 - 1) wtot = wi;
+  }
+  __syncthreads();
+  const uint32_t r = wsum[threadIdx.x >> 5] + incl - v;
+  *total = wtot;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
+                                                               uint32_t* __restrict__ bsum) {
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i)
+    if (base + i < n) s += in[base + i];
+  uint32_t tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_bsums(uint32_t* __restrict__ bsum, uint32_t nb) {
+  // single block: exclusive scan of bsum[0..nb) in place, bsum[nb] = total
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += kScanThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? bsum[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(v, &tot);
+    if (i < nb) bsum[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) bsum[nb] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in, uint32_t n,
+                                                           const uint32_t* __restrict__ bsum, uint32_t nb,
+                                                           uint32_t* __restrict__ out) {
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    s += v[i];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan(s, &tot) + bsum[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < n) out[base + i] = ex;
+    ex += v[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
+}
+
+size_t scan_tmp_words(uint32_t n) { return (size_t)(n / kScanTile) + 4; }
+
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t s,
+                           uint64_t* launches) {
+  if (n == 0) {
+    cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
+    return;
+  }
+  const uint32_t nb = (n + kScanTile - 1) / kScanTile;
+  scan_tile_sums<<<nb, kScanThreads, 0, s>>>(in, n, tmp);
+  scan_bsums<<<1, kScanThreads, 0, s>>>(tmp, nb);
+  scan_apply<<<nb, kScanThreads, 0, s>>>(in, n, tmp, nb, out);
+  if (launches) *launches += 3;
+}
+
+// ------------------------------------------------------------------ radix sort
+// 8-bit digits, least significant first.  One upfront pass builds the per-tile digit histograms of every
+// pass; each pass then scans its histogram (digit-major) and scatters tile by tile.  Inside a tile keys are
+// ranked stably (warp match + per-warp digit counters), staged in shared memory in digit order and written
+// out in runs, so global writes are coalesced per digit.
+static constexpr int kSortThreads = 256;
+static constexpr int kSortItems = 8;
+static constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
+static constexpr int kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
+                                                                  int npass, uint32_t ntiles,
+                                                                  uint32_t* __restrict__ hist) {
+  // hist layout: [pass][digit][tile]
+  __shared__ uint32_t h[8][256];
+  for (int i = threadIdx.x; i < npass * 256; i += kSortThreads) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
+    if (idx < n) {
+      const uint64_t k = keys[idx];
+      for (int p = 0; p < npass; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * 256; i += kSortThreads) {
+    const int p = i >> 8, d = i & 255;
+    hist[((uint64_t)p * 256 + d) * ntiles + blockIdx.x] = h[p][d];
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ kin,
+                                                                     const uint32_t* __restrict__ vin,
+                                                                     uint64_t* __restrict__ kout,
+                                                                     uint32_t* __restrict__ vout, uint64_t n,
+                                                                     int shift, uint32_t ntiles,
+                                                                     const uint32_t* __restrict__ offs) {
+  // offs: exclusive scan of this pass's [digit][tile] histogram
+  __shared__ uint32_t wcnt[kSortWarps][256];  // per-warp digit counters -> exclusive over warps
+  __shared__ uint32_t dstart[256];            // tile-local start of each digit
+  __shared__ uint32_t gbase[256];             // global start of this tile's run of each digit
+  __shared__ uint64_t skey[kSortTile];
+  __shared__ uint32_t sval[kSortTile];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const uint64_t tbase = (uint64_t)blockIdx.x * kSortTile;
+  // element order inside the tile: warp-major, then round, then lane (this defines stability)
+  uint64_t key[kSortItems];
+  uint32_t val[kSortItems];
+  uint32_t rank[kSortItems];
+  const uint64_t wbase = tbase + (uint64_t)warp * (kSortItems * 32);
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint64_t idx = wbase + i * 32 + lane;
+    const bool ok = idx < n;
+    key[i] = ok ? kin[idx] : ~0ull;
+    val[i] = ok && vin ? vin[idx] : 0u;
+    const uint32_t d = ok ? (uint32_t)(key[i] >> shift) & 255u : 256u;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+    const uint32_t before = __popc(peers & ((1u << lane) - 1));
+    uint32_t old = 0;
+    if (ok && before == 0) {  // lowest lane of the group owns the counter update
+      old = wcnt[warp][d];
+      wcnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(0xFFFFFFFFu, old, __ffs(peers) - 1);
+    rank[i] = old + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // thread d: exclusive prefix over warps, tile totals
+    const uint32_t d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = wcnt[w][d];
+      wcnt[w][d] = run;
+      run += c;
+    }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(run, &tot);
+    dstart[d] = ex;
+    gbase[d] = offs[(uint64_t)d * ntiles + blockIdx.x];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint64_t idx = wbase + i * 32 + lane;
+    if (idx < n) {
+      const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+      const uint32_t pos = dstart[d] + wcnt[warp][d] + rank[i];
+      skey[pos] = key[i];
+      sval[pos] = val[i];
+    }
+  }
+  __syncthreads();
+  const uint32_t cnt = (uint32_t)min((uint64_t)kSortTile, n - tbase);
+  for (uint32_t i = threadIdx.x; i < cnt; i += kSortThreads) {
+    const uint64_t k = skey[i];
+    const uint32_t d = (uint32_t)(k >> shift) & 255u;
+    const uint64_t dst = (uint64_t)gbase[d] + (i - dstart[d]);
+    kout[dst] = k;
+    if (vout) vout[dst] = sval[i];
+  }
+}
+
+size_t radix_tmp_words(uint64_t n) {
+  const uint64_t ntiles = (n + kSortTile - 1) / kSortTile;
+  // histograms of up to 8 passes + scan output (+1) + scan scratch
+  return (size_t)(8 * 256 * ntiles) + (size_t)(256 * ntiles + 1) + scan_tmp_words((uint32_t)(256 * ntiles)) + 16;
+}
+
+void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n, int nbits,
+                       uint32_t* tmp, uint64_t** keys_out, uint32_t** vals_out, cudaStream_t s,
+                       uint64_t* launches) {
+  *keys_out = keys_a;
+  *vals_out = vals_a;
+  if (n == 0 || nbits <= 0) return;
+  const int npass = (nbits + 7) / 8;
+  const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
+  uint32_t* hist = tmp;
+  uint32_t* offs = hist + (size_t)8 * 256 * ntiles;
+  uint32_t* scan_tmp = offs + (size_t)256 * ntiles + 1;
+  radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(keys_a, n, npass, ntiles, hist);
+  if (launches) ++*launches;
+  uint64_t* kin = keys_a;
+  uint64_t* kout = keys_b;
+  uint32_t* vin = vals_a;
+  uint32_t* vout = vals_b;
+  for (int p = 0; p < npass; ++p) {
+    launch_exclusive_scan(hist + (size_t)p * 256 * ntiles, offs, 256 * ntiles, scan_tmp, s, launches);
+    radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, 8 * p, ntiles, offs);
+    if (launches) ++*launches;
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+  }
+  *keys_out = kin;
+  *vals_out = vin;
+}
+
+}  // namespace sq

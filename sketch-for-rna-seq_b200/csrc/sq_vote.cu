@@ -1,0 +1,378 @@
+// Seed lookup + per-read transcript vote (the reference's "sparse chaining", src/sparse_chaining.cpp:29-115).
+//
+// One warp per read.  For every k-index the warp walks the read's selected hashes (written by the sketch
+// kernel), removes duplicates (the sketch is a SET, include/sketch.h:15), probes the GPU-resident bucketed
+// hash table (one 32-byte sector per probe), walks the posting list of every hit and counts
+// (transcript, k-index) votes in a per-warp shared-memory table.  Then: per-k maximum over the transcripts
+// seen (shuffle reduction), the double-precision `count < fraction*max` filter for every k, integer score =
+// sum of counts, candidates ordered by (score desc, transcript asc) and appended to the batch staging area.
+// Reads whose tables do not fit in shared memory are queued for the large-table kernel, which runs the same
+// code on a per-worker global-memory scratch sized for the worst case (every transcript of the index).
+#include "sq_common.cuh"
+
+namespace sq {
+
+static constexpr int kVoteWarps = 8;
+static constexpr uint32_t kTabLog2 = 8;      // 256 transcript slots per warp
+static constexpr uint32_t kTabMaxFill = 192;
+static constexpr uint32_t kSetLog2 = 10;     // 1024 dedup-set slots per warp (aliased with the candidate buffer)
+static constexpr uint32_t kSetMaxFill = 768;
+static constexpr uint32_t kHashMul = 0x9E3779B1u;
+
+struct Scratch {
+  uint32_t* tkeys;  // transcript id per slot, SQ_EMPTY when free
+  uint32_t* tcnt;   // [slot][nk] votes
+  uint32_t* tlist;  // occupied slots in insertion order
+  uint32_t* dset;   // per-(read,k) set of hashes already looked up
+  unsigned long long* cand;  // sort buffer: (0x7FFFFFFF-score)<<32 | tid
+  uint32_t* ctr;    // [0]=occupied slots, [1]=overflow flag, [2]=set fill, [3]=0xFFFFFFFF seen
+  uint32_t tab_log2, tab_maxfill, set_log2, set_maxfill;
+};
+
+__device__ __forceinline__ bool set_insert(const Scratch& S, uint32_t h) {
+  if (h == SQ_EMPTY) return atomicExch(&S.ctr[3], 1u) == 0u;
+  const uint32_t mask = (1u << S.set_log2) - 1;
+  uint32_t s = (h * kHashMul) >> (32 - S.set_log2);
+  for (uint32_t tries = 0; tries <= mask; ++tries) {
+    const uint32_t old = atomicCAS(&S.dset[s], SQ_EMPTY, h);
+    if (old == SQ_EMPTY) {
+      if (atomicAdd(&S.ctr[2], 1u) >= S.set_maxfill) S.ctr[1] = 1;
+      return true;
+    }
+    if (old == h) return false;
+    s = (s + 1) & mask;
+  }
+  S.ctr[1] = 1;
+  return false;
+}
+
+__device__ __forceinline__ void table_vote(const Scratch& S, uint32_t t, uint32_t ki, uint32_t nk) {
+  const uint32_t mask = (1u << S.tab_log2) - 1;
+  uint32_t s = (t * kHashMul) >> (32 - S.tab_log2);
+  for (uint32_t tries = 0; tries <= mask; ++tries) {
+    const uint32_t old = atomicCAS(&S.tkeys[s], SQ_EMPTY, t);
+    if (old == SQ_EMPTY) {
+      const uint32_t n = atomicAdd(&S.ctr[0], 1u);
+      if (n < S.tab_maxfill) S.tlist[n] = s; else S.ctr[1] = 1;
+    }
+    if (old == SQ_EMPTY || old == t) {
+      atomicAdd(&S.tcnt[s * nk + ki], 1u);
+      return;
+    }
+    s = (s + 1) & mask;
+  }
+  S.ctr[1] = 1;
+}
+
+// look h up in the bucketed table; returns the posting offset or SQ_EMPTY
+__device__ __forceinline__ uint32_t probe(const IndexTable& tb, uint32_t h) {
+  uint32_t b = (h * kHashMul) >> tb.shift;
+  for (uint32_t tries = 0; tries <= tb.mask; ++tries) {
+    const uint4 kk = __ldg(tb.buckets + 2 * (size_t)b);
+    const uint4 oo = __ldg(tb.buckets + 2 * (size_t)b + 1);
+    if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
+    if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
+    if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
+    if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
+    if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
+    b = (b + 1) & tb.mask;
+  }
+  return SQ_EMPTY;
+}
+
+__device__ __forceinline__ uint32_t items_of(uint32_t L) { return L == 0 ? 1u : (L + SQ_CHUNK - 1) / SQ_CHUNK; }
+
+// warp-cooperative bitonic sort of cand[0..m), m a power of two >= 32
+__device__ void warp_bitonic(unsigned long long* a, uint32_t m) {
+  const uint32_t lane = lane_id();
+  for (uint32_t k = 2; k <= m; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = lane; i < m; i += 32) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = a[i], y = a[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+// Vote for read r.  Returns 0 = done, 1 = scratch overflow (nothing emitted; scratch is clean again).
+__device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r) {
+  const uint32_t lane = lane_id();
+  const uint32_t nk = P.nk;
+  const uint32_t item0 = P.item_start[r];
+  const uint32_t n_it = P.item_start[r + 1] - item0;
+  const uint32_t L = P.len[r], boff = P.base_off[r] - P.bias;
+  const uint32_t clen = (L + n_it - 1) / (n_it ? n_it : 1);
+  if (lane == 0) { S.ctr[0] = 0; S.ctr[1] = 0; }
+  __syncwarp();
+
+  for (uint32_t ki = 0; ki < nk; ++ki) {
+    const IndexTable& tb = P.tab[ki];
+    if (!tb.present) continue;
+    bool use_set = n_it > 1;
+    if (lane == 0) { S.ctr[2] = 0; S.ctr[3] = 0; }
+    __syncwarp();
+    bool set_used = false;
+    for (uint32_t g = 0; g < n_it; g += 32) {
+      const uint32_t it = g + lane;
+      const uint32_t c = it < n_it ? P.cnt[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+      const uint32_t incl = warp_incl_scan(c);
+      const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      const uint32_t excl = incl - c;
+      if (tot > 32) use_set = true;
+      for (uint32_t f = 0; f < tot; f += 32) {
+        const uint32_t idx = f + lane;
+        const bool v = idx < tot;
+        uint32_t j = 0;  // item (within this group) holding entry idx: number of lanes with incl <= idx
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (j + step - 1) & 31);
+          if (t <= idx) j += step;
+        }
+        const uint32_t exj = __shfl_sync(0xFFFFFFFFu, excl, j & 31);
+        uint32_t h = 0;
+        if (v) h = P.sel[(uint64_t)ki * P.slot_stride + boff + (uint64_t)(g + j) * clen + (idx - exj)];
+        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, v);
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h) & vm;
+        bool first = v && (peers & ((1u << lane) - 1)) == 0;
+        if (use_set) {
+          set_used = true;
+          if (first) first = set_insert(S, h);
+        }
+        if (first) {
+          uint32_t off = probe(tb, h);
+          if (off != SQ_EMPTY) {
+            uint32_t t;
+            do {
+              t = __ldg(tb.postings + off++);
+              table_vote(S, t & ~SQ_LAST, ki, nk);
+            } while (!(t & SQ_LAST));
+          }
+        }
+        __syncwarp();
+        if (*(volatile uint32_t*)&S.ctr[1]) break;
+      }
+      if (*(volatile uint32_t*)&S.ctr[1]) break;
+    }
+    if (set_used) {  // leave the set empty for the next k / read
+      const uint32_t n = 1u << S.set_log2;
+      for (uint32_t i = lane; i < n; i += 32) S.dset[i] = SQ_EMPTY;
+    }
+    __syncwarp();
+    if (*(volatile uint32_t*)&S.ctr[1]) break;
+  }
+  __syncwarp();
+
+  if (*(volatile uint32_t*)&S.ctr[1]) {  // overflow: wipe the table completely, emit nothing
+    const uint32_t n = 1u << S.tab_log2;
+    for (uint32_t i = lane; i < n; i += 32) S.tkeys[i] = SQ_EMPTY;
+    for (uint32_t i = lane; i < n * nk; i += 32) S.tcnt[i] = 0;
+    const uint32_t ns = 1u << S.set_log2;
+    for (uint32_t i = lane; i < ns; i += 32) S.dset[i] = SQ_EMPTY;
+    __syncwarp();
+    return 1;
+  }
+
+  // per-k maximum over the transcripts seen (sparse_chaining.cpp:76-82)
+  const uint32_t n = S.ctr[0];
+  uint32_t maxc[SQ_MAXK];
+#pragma unroll
+  for (int ki = 0; ki < SQ_MAXK; ++ki) maxc[ki] = 0;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t s = S.tlist[i];
+#pragma unroll
+    for (int ki = 0; ki < SQ_MAXK; ++ki)
+      if (ki < (int)nk) maxc[ki] = max(maxc[ki], S.tcnt[s * nk + ki]);
+  }
+  double thr[SQ_MAXK];
+#pragma unroll
+  for (int ki = 0; ki < SQ_MAXK; ++ki) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) maxc[ki] = max(maxc[ki], __shfl_xor_sync(0xFFFFFFFFu, maxc[ki], d));
+    thr[ki] = P.fraction * (double)(int)maxc[ki];  // thresholds[i] = fraction * max_counts[i], :84-87
+  }
+  // filter + score (:90-105), collect sort keys, and clean the table slots as they are consumed.
+  // The candidate buffer may alias the (now empty) dedup set, so it is re-emptied at the end.
+  uint32_t nc = 0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    bool ok = false;
+    uint32_t t = 0;
+    int score = 0;
+    if (i < n) {
+      const uint32_t s = S.tlist[i];
+      t = S.tkeys[s];
+      ok = true;
+#pragma unroll
+      for (int ki = 0; ki < SQ_MAXK; ++ki)
+        if (ki < (int)nk) {
+          const int c = (int)S.tcnt[s * nk + ki];
+          if ((double)c < thr[ki]) ok = false;  // counts_vec[i] < thresholds[i], :95
+          score += c;
+          S.tcnt[s * nk + ki] = 0;
+        }
+      S.tkeys[s] = SQ_EMPTY;
+    }
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+    if (ok) {
+      const uint32_t pos = nc + __popc(bal & ((1u << lane) - 1));
+      S.cand[pos] = ((unsigned long long)(0x7FFFFFFFu - (uint32_t)score) << 32) | t;
+    }
+    nc += __popc(bal);
+  }
+  __syncwarp();
+  // order: score descending (:108-109), ties by transcript id ascending (unspecified upstream)
+  uint32_t padded = nc;
+  if (nc > 1) {
+    if (nc <= 32) {
+      unsigned long long x = lane < nc ? S.cand[lane] : ~0ull;
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, x, j);
+          const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+          x = (lower == up) ? (x < y ? x : y) : (x < y ? y : x);
+        }
+      if (lane < nc) S.cand[lane] = x;
+    } else {
+      padded = 64;
+      while (padded < nc) padded <<= 1;
+      for (uint32_t i = nc + lane; i < padded; i += 32) S.cand[i] = ~0ull;
+      __syncwarp();
+      warp_bitonic(S.cand, padded);
+    }
+    __syncwarp();
+  }
+  // append to the batch staging area
+  unsigned long long sbase = 0;
+  if (lane == 0) {
+    sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
+    uint32_t kept = nc;
+    if (sbase + nc > P.stage_cap) { atomicOr(P.flags, 1u); kept = 0; }
+    P.read_soff[r] = (uint32_t)sbase;
+    P.read_cnt[r] = kept;
+  }
+  sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
+  if (sbase + nc <= P.stage_cap)
+    for (uint32_t i = lane; i < nc; i += 32) {
+      const unsigned long long key = S.cand[i];
+      P.stage_tid[sbase + i] = (uint32_t)key;
+      P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32));
+    }
+  __syncwarp();
+  // the candidate buffer aliases the dedup set in the shared-memory tier: restore the empty pattern
+  {
+    uint32_t* w = reinterpret_cast<uint32_t*>(S.cand);
+    for (uint32_t i = lane; i < 2 * padded; i += 32) w[i] = SQ_EMPTY;
+  }
+  __syncwarp();
+  return 0;
+}
+
+__global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_constant__ VoteParams P) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t nk = P.nk;
+  const uint32_t tab = 1u << kTabLog2, set = 1u << kSetLog2;
+  const uint32_t per_warp = tab + tab * nk + tab + set + 4;
+  uint32_t* base = smem + warp * per_warp;
+  Scratch S;
+  S.dset = base;                                   // first: 8-byte aligned for the aliased u64 view
+  S.cand = reinterpret_cast<unsigned long long*>(base);
+  S.tkeys = base + set;
+  S.tcnt = S.tkeys + tab;
+  S.tlist = S.tcnt + tab * nk;
+  S.ctr = S.tlist + tab;
+  S.tab_log2 = kTabLog2; S.tab_maxfill = kTabMaxFill; S.set_log2 = kSetLog2; S.set_maxfill = kSetMaxFill;
+  for (uint32_t i = lane; i < set; i += 32) S.dset[i] = SQ_EMPTY;
+  for (uint32_t i = lane; i < tab; i += 32) S.tkeys[i] = SQ_EMPTY;
+  for (uint32_t i = lane; i < tab * nk; i += 32) S.tcnt[i] = 0;
+  __syncwarp();
+  const uint32_t nwarps = gridDim.x * kVoteWarps;
+  for (uint32_t r = blockIdx.x * kVoteWarps + warp; r < P.n_reads; r += nwarps) {
+    if (vote_read(P, S, r)) {
+      if (lane == 0) {
+        const uint32_t pos = atomicAdd(P.ovf_count, 1u);
+        P.ovf_list[pos] = r;
+        P.read_cnt[r] = 0;
+        P.read_soff[r] = 0;
+      }
+    }
+  }
+}
+
+// large-table path: one warp per worker, scratch in global memory
+__global__ void __launch_bounds__(32) vote_overflow_kernel(const __grid_constant__ VoteParams P) {
+  const uint32_t w = blockIdx.x;
+  const uint32_t n = *P.ovf_count;
+  if (w >= n) return;
+  __shared__ uint32_t ctr[4];
+  Scratch S;
+  const size_t tab = (size_t)1 << P.big_cap_log2, set = (size_t)1 << P.big_set_log2;
+  S.tkeys = P.big_keys + w * tab;
+  S.tcnt = P.big_cnt + w * tab * P.nk;
+  S.tlist = P.big_list + w * tab;
+  S.dset = P.big_set + w * set;
+  S.cand = P.big_cand + w * tab;
+  S.ctr = ctr;
+  S.tab_log2 = P.big_cap_log2;
+  S.tab_maxfill = (uint32_t)tab;  // the table is sized so that every transcript fits
+  S.set_log2 = P.big_set_log2;
+  S.set_maxfill = (uint32_t)set;
+  for (uint32_t i = w; i < n; i += gridDim.x) {
+    const uint32_t r = P.ovf_list[i];
+    if (vote_read(P, S, r)) {
+      if (lane_id() == 0) {
+        atomicOr(P.flags, 2u);
+        P.read_cnt[r] = 0;
+        P.read_soff[r] = 0;
+      }
+    }
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+void launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s) {
+  if (n == 0) return;
+  const uint32_t grid = (uint32_t)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256);
+  fill_u32_kernel<<<grid, 256, 0, s>>>(p, n, v);
+}
+
+size_t vote_smem_bytes(uint32_t nk) {
+  const uint32_t tab = 1u << kTabLog2, set = 1u << kSetLog2;
+  return (size_t)kVoteWarps * (tab + tab * nk + tab + set + 4) * sizeof(uint32_t);
+}
+
+void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches) {
+  if (p.n_reads == 0) return;
+  static int sm_count = 0, configured_nk = -1;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const size_t smem = vote_smem_bytes(p.nk);
+  if (configured_nk != (int)p.nk) {
+    cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured_nk = (int)p.nk;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_kernel, kVoteWarps * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  uint32_t grid = (uint32_t)(sm_count * per_sm);
+  const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
+  if (grid > need) grid = need;
+  vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
+  vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
+  if (launches) *launches += 2;
+}
+
+}  // namespace sq

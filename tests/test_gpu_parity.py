@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle: bit-exact hashes / sketches /
+candidate sets / scores, and pi / NumReads within 1e-9 relative (the reference itself is only defined up to
+floating-point re-association; north_star asks 1e-6)."""
+import numpy as np
+import pytest
+
+import oracle_py
+from datasets import SKETCH, csr_to_lists, dataset
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _sketch_multisets(sqb, seqs, ks, fraction=SKETCH, threshold=None):
+    words, off, ln = sqb.packing.pack_reads(seqs)
+    with sqb.Engine(ks, 1, sketch_fraction=fraction, threshold=threshold) as e:
+        counts, hashes = e.sketch(words, off, ln)
+    out, p = [], 0
+    for r in range(len(seqs)):
+        row = []
+        for i in range(len(ks)):
+            c = int(counts[r, i])
+            row.append(np.sort(hashes[p:p + c]))
+            p += c
+        out.append(row)
+    assert p == hashes.shape[0]
+    return out
+
+
+@pytest.mark.parametrize("ks", [[31], [21, 25, 31], [5], [33, 67], [16, 32, 48]])
+def test_sketch_multiset_bit_exact(gpu_lib, sqb, port, ks):
+    d = dataset()
+    seqs = [s for s in d["reads"][:200] + d["tseqs"][:30] if len(s) >= max(ks)]
+    thr = port.threshold(SKETCH)
+    got = _sketch_multisets(sqb, seqs, ks)
+    for r, s in enumerate(seqs):
+        for i, k in enumerate(ks):
+            want = np.sort(port.selected(s, k, thr))
+            assert got[r][i].tolist() == want.tolist(), (r, k, len(s))
+
+
+def test_all_hashes_bit_exact_threshold_max(gpu_lib, sqb, port):
+    """threshold 0xFFFFFFFF keeps every k-mer: the whole hash stream must match, including ragged lengths"""
+    rng = np.random.default_rng(3)
+    seqs = [bytes(rng.choice(list(b"ACGT"), n).tolist()) for n in
+            [31, 32, 33, 47, 48, 49, 63, 64, 65, 150, 255, 256, 257, 511, 512, 513, 1000, 5000, 12345]]
+    for ks in ([31], [21, 25, 31], [1], [81]):
+        ss = [s for s in seqs if len(s) >= max(ks)]
+        got = _sketch_multisets(sqb, ss, ks, threshold=0xFFFFFFFF)
+        for r, s in enumerate(ss):
+            for i, k in enumerate(ks):
+                want = np.sort(port.hash32_windows(s, k))
+                assert got[r][i].shape[0] == len(s) - k + 1
+                assert got[r][i].tolist() == want.tolist(), (len(s), k)
+
+
+def test_unaligned_read_starts(gpu_lib, sqb, port):
+    """reads may start at any base of the packed stream"""
+    d = dataset()
+    seqs = d["reads"][:64]
+    thr = port.threshold(SKETCH)
+    for align in (1, 4, 16):
+        words, off, ln = sqb.packing.pack_reads(seqs, align=align)
+        with sqb.Engine([21, 31], 1) as e:
+            counts, hashes = e.sketch(words, off, ln)
+        p = 0
+        for r, s in enumerate(seqs):
+            for i, k in enumerate((21, 31)):
+                c = int(counts[r, i])
+                assert np.sort(hashes[p:p + c]).tolist() == np.sort(port.selected(s, k, thr)).tolist()
+                p += c
+
+
+def _gpu_quant(sqb, d, ks, postings, fraction=0.9, iters=20, tol=0.01, options=None, sketch=SKETCH, chunks=1):
+    e = sqb.Engine(ks, len(d["names"]), sketch_fraction=sketch, chain_fraction=fraction)
+    for name, val in (options or {}).items():
+        e.set_option(name, val)
+    for i, k in enumerate(ks):
+        if k in postings:
+            e.load_index(i, *postings[k])
+    reads = d["reads"]
+    step = (len(reads) + chunks - 1) // chunks
+    for c in range(0, len(reads), step):
+        words, off, ln = sqb.packing.pack_reads(reads[c:c + step])
+        e.push_reads(words, off, ln)
+    off, tid, score = e.candidates()
+    pi, nr, present, it = e.finish(0, iters, tol)
+    st = e.stats()
+    e.close()
+    return off, tid, score, pi, nr, present, it, st
+
+
+@pytest.mark.parametrize("ks,kw", [([31], {}), ([21, 25, 31], {}), ([31], dict(chunks=3)),
+                                   ([25, 31], dict(options={"batch_bases": 4096})),
+                                   ([31, 31], {})])
+def test_quant_parity_short_reads(gpu_lib, sqb, port, ks, kw):
+    d = dataset()
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], sorted(set(ks)), thr)
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, d, ks, postings, **kw)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, d["reads"])
+    assert st["reads"] == R == len(d["reads"])
+    assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+    # ordering contract of the tap: score descending, then transcript id
+    assert tid.tolist() == otid.tolist() and score.tolist() == oscore.tolist()
+    T = len(d["names"])
+    opi, oit = port.em(ooff, otid, oscore, R, T)
+    onr, opres = port.assign(ooff, otid, oscore, T, opi)
+    assert it == oit
+    np.testing.assert_allclose(pi, opi, rtol=RTOL, atol=0)
+    assert present.tolist() == opres.tolist()
+    np.testing.assert_allclose(nr, onr, rtol=RTOL, atol=1e-12)
+
+
+def test_quant_parity_long_reads(gpu_lib, sqb, port):
+    """ONT-like reads (1-10 kb, 5% substitutions): multi-item reads, cross-chunk duplicate removal"""
+    d = dataset(n_genes=60, n_reads=150, long_reads=(1000, 10000), err=0.05, exon_median=400, seed=9)
+    ks = [21, 31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, d, ks, postings)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, d["reads"])
+    assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+    T = len(d["names"])
+    opi, _ = port.em(ooff, otid, oscore, R, T)
+    onr, opres = port.assign(ooff, otid, oscore, T, opi)
+    np.testing.assert_allclose(pi, opi, rtol=RTOL)
+    np.testing.assert_allclose(nr, onr, rtol=RTOL, atol=1e-12)
+    assert max(len(s) for s in d["reads"]) > 2000
+
+
+def test_overflow_path_many_transcripts(gpu_lib, sqb, port):
+    """a k-mer shared by hundreds of transcripts overflows the shared-memory vote table: the large-table
+    kernel must give the same answer"""
+    rng = np.random.default_rng(11)
+    core = bytes(rng.choice(list(b"ACGT"), 120).tolist())
+    tseqs = [bytes(rng.choice(list(b"ACGT"), 60).tolist()) + core + bytes(rng.choice(list(b"ACGT"), 60).tolist())
+             for _ in range(700)]
+    names = ["T%d" % i for i in range(len(tseqs))]
+    reads = [core, tseqs[3][:150], tseqs[5][40:200], core[:100]] * 5
+    d = {"tseqs": tseqs, "names": names, "reads": reads}
+    ks = [31]
+    thr = port.threshold(float(np.float32(0.2)))
+    sk = float(np.float32(0.2))
+    postings = port.postings_from_sequences(tseqs, ks, thr)
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, d, ks, postings, sketch=sk)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, reads)
+    assert st["overflow_reads"] > 0
+    assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+    assert tid.tolist() == otid.tolist()
+    opi, _ = port.em(ooff, otid, oscore, R, len(names))
+    np.testing.assert_allclose(pi, opi, rtol=RTOL)
+
+
+def test_edge_cases(gpu_lib, sqb, port):
+    thr = port.threshold(SKETCH)
+    d = dataset()
+    ks = [31]
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    T = len(d["names"])
+    # no reads at all: pi = 1/T + pseudocounts with R = 0 -> inf like the reference (0.01f/0 in float)
+    with sqb.Engine(ks, T) as e:
+        e.load_index(0, *postings[31])
+        pi, nr, present, it = e.finish(0, 20, 0.01)
+        assert present.sum() == 0 and nr.sum() == 0
+    # reads that match nothing still count in R (sparse_chaining.cpp:111)
+    junk = [b"A" * 150, b"ACGT" * 40, d["reads"][0]]
+    dd = dict(d, reads=junk)
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, dd, ks, postings)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, junk)
+    assert R == 3 and csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+    opi, _ = port.em(ooff, otid, oscore, R, T)
+    np.testing.assert_allclose(pi, opi, rtol=RTOL)
+    # a k-index without a map contributes nothing (sparse_chaining.cpp:51-53)
+    ks2 = [25, 31]
+    off, tid, score, *_ = _gpu_quant(sqb, d, ks2, {31: postings[31]})
+    _, ooff, otid, oscore, _ = port.chain_batch(ks2, thr, 0.9, {31: postings[31]}, d["reads"])
+    assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+    # read exactly k long, duplicate reads, read made of one repeated k-mer
+    reads = [d["tseqs"][0][:31], d["reads"][1], d["reads"][1], (d["tseqs"][2][:31] * 6)[:150]]
+    dd = dict(d, reads=reads)
+    off, tid, score, *_ = _gpu_quant(sqb, dd, ks, postings, sketch=1.0)
+    p1 = port.postings_from_sequences(d["tseqs"], ks, 0xFFFFFFFF)
+    off, tid, score, *_ = _gpu_quant(sqb, dd, ks, p1, sketch=1.0)
+    _, ooff, otid, oscore, _ = port.chain_batch(ks, 0xFFFFFFFF, 0.9, p1, reads)
+    assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
+
+
+def test_em_from_candidates_and_convergence(gpu_lib, sqb, port):
+    """EM/assign kernels on hand-made homologous_segments, including the early-exit branch
+    (total_change < tol, isoform_assignment.cpp:62) and heavy transcripts spanning many segments"""
+    rng = np.random.default_rng(2)
+    T, R = 50, 6000
+    ncand = rng.integers(0, 5, R)
+    off = np.zeros(R + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(ncand)
+    tid = np.concatenate([rng.choice(T, n, replace=False) for n in ncand] + [np.zeros(0, int)]).astype(np.uint32)
+    hot = rng.random(tid.shape[0]) < 0.5
+    score = rng.integers(1, 9, tid.shape[0]).astype(np.int32)
+    with sqb.Engine([31], T) as e:
+        e.set_option("em_segment", 64)
+        e.set_candidates(off, tid, score)
+        for iters, tol in ((20, 0.01), (3, 0.01), (20, 1e9), (50, 1.0)):
+            pi, nr, present, it = e.finish(R, iters, tol)
+            opi, oit = port.em(off, tid, score, R, T, iters, tol)
+            onr, opres = port.assign(off, tid, score, T, opi)
+            assert it == oit
+            np.testing.assert_allclose(pi, opi, rtol=RTOL)
+            np.testing.assert_allclose(nr, onr, rtol=RTOL, atol=1e-12)
+            assert present.tolist() == opres.tolist()
+
+
+def test_build_postings_matches_oracle(gpu_lib, sqb, port):
+    d = dataset()
+    ks = [21, 31]
+    thr = port.threshold(SKETCH)
+    want = port.postings_from_sequences(d["tseqs"], ks, thr)
+    got = sqb.api.build_kmer_to_transcript_map(d["tseqs"], ks)
+    for k in ks:
+        for a, b in zip(got[k], want[k]):
+            assert a.tolist() == b.tolist()
+
+
+def test_api_mirror(gpu_lib, sqb, port):
+    d = dataset()
+    thr = port.threshold(SKETCH)
+    s = d["tseqs"][0]
+    assert sorted(sqb.api.createSketch_FracMinhash_direct(s, 31)) == port.sketch(s, 31, thr).tolist()
+    with pytest.raises(ValueError):
+        sqb.api.createSketch_FracMinhash_direct("ACGT", 31)
+
+
+@pytest.mark.skipif(not oracle_py.have_ref(), reason="oracle/_ref not present")
+def test_against_reference_code_directly(gpu_lib, sqb, port):
+    """same inputs through the reference's own translation units (oracle/_ref/libref_oracle.so)"""
+    d = dataset(seed=21, n_reads=300)
+    ks = [21, 25, 31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    r = oracle_py.RefOracle(ks)
+    r.set_transcripts(d["names"])
+    for k in ks:
+        r.set_postings(k, *postings[k])
+    for i, s in enumerate(d["reads"]):
+        r.add_read(b"r%d" % i, s, SKETCH)
+    r.chain(0.9)
+    r.em(20, 0.01)
+    r.assign()
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, d, ks, postings)
+    mine = csr_to_lists(off, tid, score)
+    for i in range(len(d["reads"])):
+        rt, rs = r.read_candidates(b"r%d" % i)
+        assert sorted(zip(rt.tolist(), rs.tolist())) == mine[i]
+    np.testing.assert_allclose(pi, r.pi(), rtol=RTOL)
+    rc, rp = r.counts()
+    assert present.tolist() == rp.tolist()
+    np.testing.assert_allclose(nr, rc, rtol=RTOL, atol=1e-12)
