@@ -47,55 +47,31 @@ void launch_table_build(const uint32_t* keys, const uint64_t* off, uint64_t nkey
 }
 
 // ------------------------------------------------------------------ candidate compaction
-// staging (arbitrary order) -> final CSR in read order
+// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store
 __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uint32_t* __restrict__ read_cnt,
                                const uint32_t* __restrict__ batch_off, uint32_t n_reads,
                                const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
-                               const unsigned long long* __restrict__ totals, uint64_t read_base, uint64_t cap,
-                               uint32_t* __restrict__ cand_tid, int32_t* __restrict__ cand_score,
-                               uint32_t* __restrict__ read_off, uint32_t* flags) {
+                               uint64_t pbase, uint64_t read_base, uint32_t* __restrict__ cand_tid,
+                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
-  const unsigned long long pbase = totals[0];
-  const unsigned long long dst = pbase + batch_off[r];
+  const uint64_t dst = pbase + batch_off[r];
   read_off[read_base + r] = (uint32_t)dst;
+  if (r == n_reads - 1) read_off[read_base + n_reads] = (uint32_t)(pbase + batch_off[n_reads]);
   const uint32_t c = read_cnt[r], so = read_soff[r];
-  if (dst + c > cap) {
-    atomicOr(flags, 4u);
-    return;
-  }
   for (uint32_t i = 0; i < c; ++i) {
     cand_tid[dst + i] = stage_tid[so + i];
     cand_score[dst + i] = stage_score[so + i];
   }
 }
 
-__global__ void advance_kernel(unsigned long long* totals, const uint32_t* batch_off, uint32_t n_reads,
-                               uint64_t read_base, uint32_t* read_off, unsigned long long* stage_cursor,
-                               uint32_t* ovf_count, unsigned long long* host_mirror) {
-  // single thread: publish the new pair total, close the CSR, reset the per-batch counters
-  const unsigned long long p = totals[0] + batch_off[n_reads];
-  totals[0] = p;
-  totals[1] += *ovf_count;
-  read_off[read_base + n_reads] = (uint32_t)p;
-  *stage_cursor = 0;
-  *ovf_count = 0;
-  if (host_mirror) { host_mirror[0] = p; host_mirror[1] = totals[1]; }
-}
-
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
-                    const uint32_t* stage_tid, const int32_t* stage_score, unsigned long long* totals,
-                    uint64_t read_base, uint64_t cap, uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off,
-                    uint32_t* flags, unsigned long long* stage_cursor, uint32_t* ovf_count,
-                    unsigned long long* host_mirror, cudaStream_t s, uint64_t* launches) {
-  if (n_reads) {
-    compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
-                                                         stage_score, totals, read_base, cap, cand_tid, cand_score,
-                                                         read_off, flags);
-    if (launches) ++*launches;
-  }
-  advance_kernel<<<1, 1, 0, s>>>(totals, batch_off, n_reads, read_base, read_off, stage_cursor, ovf_count,
-                                 host_mirror);
+                    const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s,
+                    uint64_t* launches) {
+  if (!n_reads) return;
+  compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
+                                                       stage_score, pbase, read_base, cand_tid, cand_score, read_off);
   if (launches) ++*launches;
 }
 

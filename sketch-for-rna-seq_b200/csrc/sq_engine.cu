@@ -42,9 +42,14 @@ struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
   DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, stage_tid, stage_score,
       scan_tmp;
-  cudaEvent_t done = nullptr, copied = nullptr;
-  bool in_flight = false;
+  cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr;
+  bool in_flight = false;   // compaction enqueued, `done` recorded
+  bool pending = false;     // vote enqueued, compaction not yet (needs the exact candidate count)
   uint64_t stage_cap = 0;
+  uint32_t n_reads = 0;
+  uint64_t read_base = 0;
+  VoteParams vp;
+  int id = 0;
   void release() {
     DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &sel, &read_soff, &read_cnt,
                      &batch_off, &ovf_list, &stage_tid, &stage_score, &scan_tmp};
@@ -110,13 +115,13 @@ struct sq_engine {
   Slot slot[2];
   int next_slot = 0;
   // device counters + pinned mirror
-  unsigned long long* d_totals = nullptr;        // [0] pairs, [1] overflow reads, [2] sketch hashes
-  unsigned long long* d_stage_cursor = nullptr;
-  uint32_t* d_ovf_count = nullptr;
+  unsigned long long* d_totals = nullptr;        // [0] sketch hashes (stats)
+  unsigned long long* d_slot_ctr = nullptr;      // per slot: [2*i] staging cursor, [2*i+1] low word = overflow reads
   uint32_t* d_flags = nullptr;
   uint32_t* d_fail = nullptr;
-  unsigned long long* h_mirror = nullptr;        // [0] pairs, [1] overflow reads
-  uint64_t pairs_upper = 0;                       // host-side upper bound of pairs after all enqueued batches
+  unsigned long long* h_mirror = nullptr;        // pinned copy of d_slot_ctr after each vote
+  uint64_t P = 0;                                 // candidate pairs of all finalized batches (exact)
+  uint64_t ovf_total = 0;
   // large-table scratch
   DevBuf big_keys, big_cnt, big_list, big_set, big_cand;
   uint32_t big_cap_log2 = 0, big_set_log2 = 0;
@@ -126,7 +131,7 @@ struct sq_engine {
   int32_t* cand_score = nullptr;
   uint32_t* read_off = nullptr;
   uint64_t cand_cap = 0, read_cap = 0;
-  uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;
+  uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
       read_tmp, partial, block_change, misc, numreads, present, scan_tmp;
@@ -221,21 +226,21 @@ int check_flags(sq_engine* e) {
   uint32_t flags = 0;
   SQ_CUDA(e, cudaMemcpyAsync(&flags, e->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
-  if (flags & 1u) return fail(e, SQ_ERR_CAPACITY, "candidate staging overflow: raise option cand_per_read (now %u)", e->cand_per_read);
   if (flags & 2u) return fail(e, SQ_ERR_CAPACITY, "large-table overflow: a read is longer than option max_read_len (%u)", e->max_read_len);
   if (flags & 4u) return fail(e, SQ_ERR_CAPACITY, "candidate store overflow (internal growth bound violated)");
   return SQ_OK;
 }
 
-// make sure the CSR store can take `reads` more reads and `pairs` more pairs (contents preserved)
-int ensure_store(sq_engine* e, uint64_t reads, uint64_t pairs) {
-  const uint64_t need_reads = e->n_reads + reads + 1;
+// make sure the CSR store can take `reads` more reads (beyond read_base) and `pairs` more pairs (beyond P);
+// contents are preserved
+int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pairs) {
+  const uint64_t need_reads = read_base + reads + 1;
   if (need_reads > e->read_cap) {
     uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
     uint32_t* p = nullptr;
     SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
     if (e->read_off) {
-      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (e->n_reads + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
       SQ_CUDA(e, cudaStreamSynchronize(e->stream));
       SQ_CUDA(e, cudaFree(e->read_off));
     } else {
@@ -244,28 +249,24 @@ int ensure_store(sq_engine* e, uint64_t reads, uint64_t pairs) {
     e->read_off = p;
     e->read_cap = cap;
   }
-  const uint64_t need_pairs = e->pairs_upper + pairs;
+  const uint64_t need_pairs = e->P + pairs;
   if (need_pairs >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "more than 2^32 candidate pairs on one engine");
   if (need_pairs > e->cand_cap) {
     uint64_t cap = std::max<uint64_t>(need_pairs + need_pairs / 2, 1 << 20);
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
     uint32_t* t = nullptr;
-    int32_t* s = nullptr;
+    int32_t* sc = nullptr;
     SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint32_t)));
-    SQ_CUDA(e, cudaMalloc(&s, cap * sizeof(int32_t)));
+    SQ_CUDA(e, cudaMalloc(&sc, cap * sizeof(int32_t)));
     if (e->cand_tid) {
-      // everything enqueued so far must land before the old arrays are copied
-      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
-      const uint64_t p = e->h_mirror[0];
-      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, p * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaMemcpyAsync(s, e->cand_score, p * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, e->P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(sc, e->cand_score, e->P * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
       SQ_CUDA(e, cudaStreamSynchronize(e->stream));
       SQ_CUDA(e, cudaFree(e->cand_tid));
       SQ_CUDA(e, cudaFree(e->cand_score));
-      e->pairs_upper = p;
     }
     e->cand_tid = t;
-    e->cand_score = s;
+    e->cand_score = sc;
     e->cand_cap = cap;
   }
   return SQ_OK;
@@ -289,14 +290,67 @@ int ensure_big_scratch(sq_engine* e) {
   return SQ_OK;
 }
 
-// wait for the slot's previous batch, refresh the host-side pair bound
+int enqueue_vote(sq_engine* e, Slot& s) {
+  unsigned long long* ctr = e->d_slot_ctr + 2 * s.id;
+  SQ_CUDA(e, cudaMemsetAsync(ctr, 0, 16, e->stream));
+  {
+    StageScope st(e, 1);
+    launch_vote(s.vp, e->stream, &e->launches);
+  }
+  SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 2 * s.id, ctr, 16, cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaGetLastError());
+  SQ_CUDA(e, cudaEventRecord(s.voted, e->stream));
+  return SQ_OK;
+}
+
+// The vote of a batch reports the exact number of candidate pairs; only then can they be moved into the
+// CSR store (grown exactly) in read order.  If the staging area was too small the vote is simply re-run
+// with a staging area of the reported size (the batch inputs are still in the slot).
+int finalize_slot(sq_engine* e, Slot& s) {
+  if (!s.pending) return SQ_OK;
+  SQ_CUDA(e, cudaEventSynchronize(s.voted));
+  uint64_t needed = e->h_mirror[2 * s.id];
+  while (needed > s.stage_cap) {
+    s.stage_cap = needed + needed / 8;
+    SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
+    SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
+    s.vp.stage_tid = s.stage_tid.as<uint32_t>();
+    s.vp.stage_score = s.stage_score.as<int32_t>();
+    s.vp.stage_cap = s.stage_cap;
+    SQ_TRY(enqueue_vote(e, s));
+    SQ_CUDA(e, cudaEventSynchronize(s.voted));
+    needed = e->h_mirror[2 * s.id];
+  }
+  const uint64_t ovf = e->h_mirror[2 * s.id + 1] & 0xFFFFFFFFull;
+  SQ_TRY(ensure_store(e, s.read_base, s.n_reads, needed));
+  {
+    StageScope st(e, 2);
+    launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads, s.scan_tmp.as<uint32_t>(),
+                          e->stream, &e->launches);
+    launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
+                   s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
+                   e->cand_score, e->read_off, e->stream, &e->launches);
+  }
+  SQ_CUDA(e, cudaGetLastError());
+  SQ_CUDA(e, cudaEventRecord(s.done, e->stream));
+  s.in_flight = true;
+  s.pending = false;
+  e->P += needed;
+  e->ovf_total += ovf;
+  return SQ_OK;
+}
+
+// next slot, free of its previous batch
 int acquire_slot(sq_engine* e, Slot** out) {
   Slot& s = e->slot[e->next_slot];
+  s.id = e->next_slot;
   e->next_slot ^= 1;
   if (!s.done) {
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    SQ_CUDA(e, cudaEventCreateWithFlags(&s.voted, cudaEventDisableTiming));
   }
+  SQ_TRY(finalize_slot(e, s));
   if (s.in_flight) {
     SQ_CUDA(e, cudaEventSynchronize(s.done));
     s.in_flight = false;
@@ -307,7 +361,7 @@ int acquire_slot(sq_engine* e, Slot** out) {
 
 // enqueue sketch + vote + compaction for one batch whose inputs are in device memory
 int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words, const uint32_t* d_boff, uint32_t bias,
-              const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases) {
+              const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases, cudaEvent_t inputs_ready) {
   if (n_reads == 0) return SQ_OK;
   const uint64_t items_ub64 = (uint64_t)n_reads + n_bases / SQ_CHUNK + 1;
   if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
@@ -327,7 +381,9 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
   SQ_TRY(ensure_big_scratch(e));
-  SQ_TRY(ensure_store(e, n_reads, s.stage_cap));
+  // the batch before this one (other slot) can now be finalized: its vote overlaps our copies
+  SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
+  if (inputs_ready) SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
 
   {
     StageScope st(e, 0);
@@ -353,11 +409,10 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     sp.slot_stride = slot_stride;
     sp.cnt = s.cnt.as<uint16_t>();
     launch_sketch(sp, e->stream, &e->launches);
-    launch_sum_u16(s.cnt.as<uint16_t>(), (uint64_t)items_ub * e->nk, e->d_totals + 2, e->stream, &e->launches);
+    launch_sum_u16(s.cnt.as<uint16_t>(), (uint64_t)items_ub * e->nk, e->d_totals, e->stream, &e->launches);
   }
   {
-    StageScope st(e, 1);
-    VoteParams vp;
+    VoteParams& vp = s.vp;
     memset(&vp, 0, sizeof(vp));
     vp.base_off = d_boff;
     vp.bias = bias;
@@ -380,11 +435,11 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.stage_tid = s.stage_tid.as<uint32_t>();
     vp.stage_score = s.stage_score.as<int32_t>();
     vp.stage_cap = s.stage_cap;
-    vp.stage_cursor = e->d_stage_cursor;
+    vp.stage_cursor = e->d_slot_ctr + 2 * s.id;
     vp.read_soff = s.read_soff.as<uint32_t>();
     vp.read_cnt = s.read_cnt.as<uint32_t>();
     vp.ovf_list = s.ovf_list.as<uint32_t>();
-    vp.ovf_count = e->d_ovf_count;
+    vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 2 * s.id + 1);
     vp.flags = e->d_flags;
     vp.big_keys = e->big_keys.as<uint32_t>();
     vp.big_cnt = e->big_cnt.as<uint32_t>();
@@ -394,21 +449,11 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.big_cap_log2 = e->big_cap_log2;
     vp.big_set_log2 = e->big_set_log2;
     vp.n_workers = e->n_workers;
-    launch_vote(vp, e->stream, &e->launches);
+    s.n_reads = n_reads;
+    s.read_base = e->n_reads;
+    SQ_TRY(enqueue_vote(e, s));
+    s.pending = true;
   }
-  {
-    StageScope st(e, 2);
-    launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), n_reads, s.scan_tmp.as<uint32_t>(),
-                          e->stream, &e->launches);
-    launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), n_reads,
-                   s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->d_totals, e->n_reads, e->cand_cap,
-                   e->cand_tid, e->cand_score, e->read_off, e->d_flags, e->d_stage_cursor, e->d_ovf_count,
-                   e->h_mirror, e->stream, &e->launches);
-  }
-  SQ_CUDA(e, cudaGetLastError());
-  SQ_CUDA(e, cudaEventRecord(s.done, e->stream));
-  s.in_flight = true;
-  e->pairs_upper += s.stage_cap;
   e->n_reads += n_reads;
   e->n_bases += n_bases;
   e->n_batches += 1;
@@ -479,11 +524,10 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   void* ctr = nullptr;
   if ((ce = cudaMalloc(&ctr, 64)) != cudaSuccess) return bail(ce, "cudaMalloc");
   if ((ce = cudaMemset(ctr, 0, 64)) != cudaSuccess) return bail(ce, "cudaMemset");
-  e->d_totals = static_cast<unsigned long long*>(ctr);                 // 3 x u64
-  e->d_stage_cursor = e->d_totals + 4;                                 // byte 32
-  e->d_ovf_count = reinterpret_cast<uint32_t*>(e->d_totals + 5);       // byte 40
-  e->d_flags = e->d_ovf_count + 1;                                     // byte 44
-  e->d_fail = e->d_ovf_count + 2;                                      // byte 48
+  e->d_totals = static_cast<unsigned long long*>(ctr);                 // byte 0
+  e->d_slot_ctr = e->d_totals + 2;                                     // bytes 16..47 (2 slots x 16 B)
+  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 6);           // byte 48
+  e->d_fail = e->d_flags + 1;                                          // byte 52
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 64);
   *out = e;
@@ -500,6 +544,7 @@ void sq_destroy(sq_engine* e) {
     s.release();
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
+    if (s.voted) cudaEventDestroy(s.voted);
   }
   for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); }
   e->tap.release();
@@ -602,7 +647,7 @@ int sq_push_reads_device(sq_engine* e, const uint32_t* d_packed_words, uint64_t 
   const uint64_t n_bases = n_bases_hint ? n_bases_hint : n_words * 16;
   Slot* s = nullptr;
   SQ_TRY(acquire_slot(e, &s));
-  return run_batch(e, *s, d_packed_words, n_words, d_base_off, 0, d_len, n_reads, n_bases);
+  return run_batch(e, *s, d_packed_words, n_words, d_base_off, 0, d_len, n_reads, n_bases, nullptr);
 }
 
 int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, const uint32_t* base_off,
@@ -637,9 +682,8 @@ int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, 
     SQ_CUDA(e, cudaMemcpyAsync(s->base_off.p, base_off + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, e->copy_stream));
     SQ_CUDA(e, cudaMemcpyAsync(s->len.p, len + r0, (size_t)nr * 4, cudaMemcpyHostToDevice, e->copy_stream));
     SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
-    SQ_CUDA(e, cudaStreamWaitEvent(e->stream, s->copied, 0));
     SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (nw + 3) & ~3ull, s->base_off.as<uint32_t>(), (uint32_t)(w0 * 16),
-                     s->len.as<uint32_t>(), nr, nb));
+                     s->len.as<uint32_t>(), nr, nb, s->copied));
     // the caller may reuse its buffers when we return: wait for the copies (not for the kernels)
     SQ_CUDA(e, cudaEventSynchronize(s->copied));
     r0 = r1;
@@ -651,10 +695,12 @@ int sq_sync(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_CUDA(e, cudaSetDevice(e->device));
   SQ_CUDA(e, cudaStreamSynchronize(e->copy_stream));
+  // at most one batch is waiting for its compaction; finalize in age order anyway
+  SQ_TRY(finalize_slot(e, e->slot[e->next_slot]));
+  SQ_TRY(finalize_slot(e, e->slot[e->next_slot ^ 1]));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   for (auto& s : e->slot) s.in_flight = false;
   resolve_events(e);
-  e->pairs_upper = e->h_mirror[0];
   return check_flags(e);
 }
 
@@ -665,7 +711,8 @@ int sq_reset_reads(sq_engine* e) {
   if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   memset(e->h_mirror, 0, 64);
-  e->pairs_upper = 0;
+  e->P = 0;
+  e->ovf_total = 0;
   e->n_reads = e->n_bases = e->n_batches = 0;
   return SQ_OK;
 }
@@ -674,14 +721,14 @@ int sq_num_pairs(sq_engine* e, uint64_t* n_reads, uint64_t* n_pairs) {
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
   if (n_reads) *n_reads = e->n_reads;
-  if (n_pairs) *n_pairs = e->h_mirror[0];
+  if (n_pairs) *n_pairs = e->P;
   return SQ_OK;
 }
 
 int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* score) {
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  const uint64_t R = e->n_reads, P = e->h_mirror[0];
+  const uint64_t R = e->n_reads, P = e->P;
   if (read_off) {
     std::vector<uint32_t> tmp(R + 1, 0);
     if (R) SQ_CUDA(e, cudaMemcpy(tmp.data(), e->read_off, (R + 1) * 4, cudaMemcpyDeviceToHost));
@@ -701,8 +748,7 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
   if (P && (!tid || !score)) return fail(e, SQ_ERR_ARG, "NULL candidate array");
   for (uint64_t i = 0; i < P; ++i)
     if (tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "candidate %llu names transcript %u >= T", (unsigned long long)i, tid[i]);
-  e->pairs_upper = 0;
-  SQ_TRY(ensure_store(e, n_reads, P));
+  SQ_TRY(ensure_store(e, 0, n_reads, P));
   std::vector<uint32_t> off32(n_reads + 1, 0);
   for (uint64_t i = 0; i <= n_reads && n_reads; ++i) {
     if (i && read_off[i] < read_off[i - 1]) return fail(e, SQ_ERR_ARG, "read_off must be non-decreasing");
@@ -713,10 +759,7 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
     SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
     SQ_CUDA(e, cudaMemcpy(e->cand_score, score, P * 4, cudaMemcpyHostToDevice));
   }
-  unsigned long long p64 = P;
-  SQ_CUDA(e, cudaMemcpy(e->d_totals, &p64, 8, cudaMemcpyHostToDevice));
-  e->h_mirror[0] = P;
-  e->pairs_upper = P;
+  e->P = P;
   e->n_reads = n_reads;
   return SQ_OK;
 }
@@ -733,7 +776,7 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   if (!e) return SQ_ERR_ARG;
   if (!pi || !numreads || !present) return fail(e, SQ_ERR_ARG, "NULL output array");
   SQ_TRY(sq_sync(e));
-  const uint64_t R = e->n_reads, P = e->h_mirror[0];
+  const uint64_t R = e->n_reads, P = e->P;
   const uint32_t T = (uint32_t)e->T;
   cudaStream_t st = e->stream;
   SQ_CUDA(e, e->misc.ensure(256));
@@ -854,15 +897,15 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
 int sq_get_stats(sq_engine* e, sq_stats* out) {
   if (!e || !out) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  unsigned long long tot[3] = {0, 0, 0};
+  unsigned long long tot[1] = {0};
   SQ_CUDA(e, cudaMemcpy(tot, e->d_totals, sizeof(tot), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->reads = e->n_reads;
   out->bases = e->n_bases;
   out->kmers = e->n_kmers_known;
-  out->sketch_hashes = tot[2];
-  out->pairs = tot[0];
-  out->overflow_reads = tot[1];
+  out->sketch_hashes = tot[0];
+  out->pairs = e->P;
+  out->overflow_reads = e->ovf_total;
   out->batches = e->n_batches;
   out->em_iterations = e->em_iterations;
   out->ms_sketch = e->ms[0]; out->ms_vote = e->ms[1]; out->ms_compact = e->ms[2];

@@ -37,10 +37,8 @@ void launch_table_build(const uint32_t* keys, const uint64_t* off, uint64_t nkey
                         uint32_t mask, uint32_t* postings, uint32_t* fail, cudaStream_t s, uint64_t* launches);
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
-                    const uint32_t* stage_tid, const int32_t* stage_score, unsigned long long* totals,
-                    uint64_t read_base, uint64_t cap, uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off,
-                    uint32_t* flags, unsigned long long* stage_cursor, uint32_t* ovf_count,
-                    unsigned long long* host_mirror, cudaStream_t s, uint64_t* launches);
+                    const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s, uint64_t* launches);
 void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
 void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,

@@ -92,8 +92,8 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32
 }
 
 // ------------------------------------------------------------------ radix sort
-// 8-bit digits, least significant first.  One upfront pass builds the per-tile digit histograms of every
-// pass; each pass then scans its histogram (digit-major) and scatters tile by tile.  Inside a tile keys are
+// 8-bit digits, least significant first.  Each pass builds per-tile digit histograms, scans them
+// (digit-major) and scatters tile by tile.  Inside a tile keys are
 // ranked stably (warp match + per-warp digit counters), staged in shared memory in digit order and written
 // out in runs, so global writes are coalesced per digit.
 static constexpr int kSortThreads = 256;
@@ -102,25 +102,20 @@ static constexpr int kSortTile = kSortThreads * kSortItems;  // 2048
 static constexpr int kSortWarps = kSortThreads / 32;
 
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n,
-                                                                  int npass, uint32_t ntiles,
+                                                                  int shift, uint32_t ntiles,
                                                                   uint32_t* __restrict__ hist) {
-  // hist layout: [pass][digit][tile]
-  __shared__ uint32_t h[8][256];
-  for (int i = threadIdx.x; i < npass * 256; i += kSortThreads) (&h[0][0])[i] = 0;
+  // per-tile digit histogram of the CURRENT key order (tiles change content after every pass);
+  // hist layout: [digit][tile]
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
   for (int i = 0; i < kSortItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-    if (idx < n) {
-      const uint64_t k = keys[idx];
-      for (int p = 0; p < npass; ++p) atomicAdd(&h[p][(k >> (8 * p)) & 255], 1u);
-    }
+    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npass * 256; i += kSortThreads) {
-    const int p = i >> 8, d = i & 255;
-    hist[((uint64_t)p * 256 + d) * ntiles + blockIdx.x] = h[p][d];
-  }
+  hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ kin,
@@ -201,8 +196,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 
 size_t radix_tmp_words(uint64_t n) {
   const uint64_t ntiles = (n + kSortTile - 1) / kSortTile;
-  // histograms of up to 8 passes + scan output (+1) + scan scratch
-  return (size_t)(8 * 256 * ntiles) + (size_t)(256 * ntiles + 1) + scan_tmp_words((uint32_t)(256 * ntiles)) + 16;
+  // one pass's histogram + its scan (+1) + scan scratch
+  return (size_t)(256 * ntiles) + (size_t)(256 * ntiles + 1) + scan_tmp_words((uint32_t)(256 * ntiles)) + 16;
 }
 
 void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n, int nbits,
@@ -214,16 +209,16 @@ void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uin
   const int npass = (nbits + 7) / 8;
   const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
   uint32_t* hist = tmp;
-  uint32_t* offs = hist + (size_t)8 * 256 * ntiles;
+  uint32_t* offs = hist + (size_t)256 * ntiles;
   uint32_t* scan_tmp = offs + (size_t)256 * ntiles + 1;
-  radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(keys_a, n, npass, ntiles, hist);
-  if (launches) ++*launches;
   uint64_t* kin = keys_a;
   uint64_t* kout = keys_b;
   uint32_t* vin = vals_a;
   uint32_t* vout = vals_b;
   for (int p = 0; p < npass; ++p) {
-    launch_exclusive_scan(hist + (size_t)p * 256 * ntiles, offs, 256 * ntiles, scan_tmp, s, launches);
+    radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, n, 8 * p, ntiles, hist);
+    if (launches) ++*launches;
+    launch_exclusive_scan(hist, offs, 256 * ntiles, scan_tmp, s, launches);
     radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, 8 * p, ntiles, offs);
     if (launches) ++*launches;
     uint64_t* tk = kin; kin = kout; kout = tk;

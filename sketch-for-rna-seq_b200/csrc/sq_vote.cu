@@ -253,7 +253,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r) {
   if (lane == 0) {
     sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
     uint32_t kept = nc;
-    if (sbase + nc > P.stage_cap) { atomicOr(P.flags, 1u); kept = 0; }
+    if (sbase + nc > P.stage_cap) kept = 0;  // the host re-runs the vote with a staging area of the reported size
     P.read_soff[r] = (uint32_t)sbase;
     P.read_cnt[r] = kept;
   }
