@@ -53,6 +53,12 @@ typedef struct sq_stats {
    * only filled when profiling was enabled with sq_set_profiling) */
   float ms_sketch, ms_vote, ms_compact, ms_sort, ms_em, ms_assign;
   uint64_t launches;       /* kernels launched by this engine so far */
+  /* vote-kernel work counters (for the roofline's algorithmic bytes) */
+  uint64_t queries;        /* distinct (read, k, hash) looked up in the index table */
+  uint64_t hits;           /* of which found */
+  uint64_t postings;       /* posting-list entries walked */
+  float ms_items;          /* item split + counters (everything of the sketch stage except the sketch kernel) */
+  uint32_t sketch_launches, vote_launches; /* launches of the two named kernels while profiling was on */
 } sq_stats;
 
 const char* sq_version(void);

@@ -63,6 +63,23 @@ class PortOracle:
                                       C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_uint64]
 
+    def build_postings(self, blob, soff, k, min_len, threshold):
+        """inverted map of one k over many sequences, in C (blob: ASCII bytes, soff: uint64 offsets)"""
+        L = self.lib
+        L.orc_build_postings.restype = None
+        L.orc_build_postings.argtypes = [C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        soff = np.ascontiguousarray(soff, dtype=np.uint64)
+        nk, npost = C.c_uint64(), C.c_uint64()
+        L.orc_build_postings(soff.shape[0] - 1, blob, _p(soff), k, min_len, threshold, C.byref(nk), C.byref(npost),
+                             None, None, None)
+        keys = np.zeros(nk.value, dtype=np.uint32)
+        off = np.zeros(nk.value + 1, dtype=np.uint64)
+        tids = np.zeros(npost.value, dtype=np.uint32)
+        L.orc_build_postings(soff.shape[0] - 1, blob, _p(soff), k, min_len, threshold, C.byref(nk), C.byref(npost),
+                             _p(keys), _p(off), _p(tids))
+        return keys, off, tids
+
     def fwd_hash64(self, s):
         return int(self.lib.orc_fwd_hash64(s, len(s)))
 

@@ -285,3 +285,51 @@ uint64_t orc_chain_batch(uint32_t nk, const uint32_t* ks, uint32_t threshold, do
   free(sk); free(nsk);
   return total;
 }
+
+/* ---- inverted map for one k from a set of sequences (main.cpp:66-85 + sketch.cpp:51-74) ----
+ * seq: ASCII bases concatenated, sequence s = seq[soff[s] .. soff[s+1]) with dense transcript id s.
+ * Sequences shorter than min_len (the largest k of the index, main.cpp:67-75) get no sketch.
+ * Two calls: with keys == NULL returns sizes through nkeys/npost; then fills keys (ascending),
+ * off[nkeys+1], tids (ascending inside a key). */
+typedef struct { uint32_t h; uint32_t t; } ht_t;
+static int cmp_ht(const void* a, const void* b) {
+  const ht_t* x = (const ht_t*)a; const ht_t* y = (const ht_t*)b;
+  if (x->h != y->h) return x->h < y->h ? -1 : 1;
+  return x->t < y->t ? -1 : x->t > y->t;
+}
+static ht_t* g_pairs = NULL;
+static uint64_t g_npairs = 0;
+
+void orc_build_postings(uint64_t nseq, const char* seq, const uint64_t* soff, uint32_t k, uint32_t min_len,
+                        uint32_t threshold, uint64_t* nkeys, uint64_t* npost, uint32_t* keys, uint64_t* off,
+                        uint32_t* tids) {
+  if (!keys) {
+    free(g_pairs); g_pairs = NULL; g_npairs = 0;
+    uint64_t cap = 1 << 20, n = 0;
+    ht_t* pr = (ht_t*)malloc(sizeof(ht_t) * cap);
+    uint32_t* tmp = NULL; uint64_t tmpcap = 0;
+    for (uint64_t s = 0; s < nseq; ++s) {
+      uint64_t len = soff[s + 1] - soff[s];
+      if (len < min_len || len < k) continue;
+      if (len > tmpcap) { tmpcap = len * 2; tmp = (uint32_t*)realloc(tmp, sizeof(uint32_t) * tmpcap); }
+      uint64_t m = orc_sketch(seq + soff[s], len, k, threshold, tmp, len);
+      if (n + m > cap) { while (n + m > cap) cap *= 2; pr = (ht_t*)realloc(pr, sizeof(ht_t) * cap); }
+      for (uint64_t i = 0; i < m; ++i) { pr[n].h = tmp[i]; pr[n].t = (uint32_t)s; ++n; }
+    }
+    free(tmp);
+    qsort(pr, n, sizeof(ht_t), cmp_ht);
+    uint64_t nk = 0;
+    for (uint64_t i = 0; i < n; ++i) if (i == 0 || pr[i].h != pr[i - 1].h) ++nk;
+    g_pairs = pr; g_npairs = n;
+    *nkeys = nk; *npost = n;
+    return;
+  }
+  uint64_t kpos = 0;
+  for (uint64_t i = 0; i < g_npairs; ++i) {
+    if (i == 0 || g_pairs[i].h != g_pairs[i - 1].h) { keys[kpos] = g_pairs[i].h; off[kpos] = i; ++kpos; }
+    tids[i] = g_pairs[i].t;
+  }
+  off[kpos] = g_npairs;
+  *nkeys = kpos; *npost = g_npairs;
+  free(g_pairs); g_pairs = NULL; g_npairs = 0;
+}

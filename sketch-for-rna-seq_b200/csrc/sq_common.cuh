@@ -83,7 +83,8 @@ struct VoteParams {
   uint32_t* read_cnt;                // per read: candidates
   uint32_t* ovf_list;                // reads that overflowed the shared-memory tables
   uint32_t* ovf_count;
-  uint32_t* flags;                   // bit0: staging overflow, bit1: large-table overflow
+  uint32_t* flags;                   // bit1: large-table overflow
+  unsigned long long* work;          // [0] queries, [1] hits, [2] postings walked (stats)
   // large-table scratch (one region per worker block of the overflow kernel)
   uint32_t* big_keys; uint32_t* big_cnt; uint32_t* big_list; uint32_t* big_set; unsigned long long* big_cand;
   uint32_t big_cap_log2;     // table slots per worker

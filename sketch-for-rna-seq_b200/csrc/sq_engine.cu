@@ -144,7 +144,8 @@ struct sq_engine {
   const void* bp_sig = nullptr;
   // profiling
   std::vector<StageEvent> events;
-  float ms[6] = {0, 0, 0, 0, 0, 0};
+  float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // sketch, vote, compact, sort, em, assign, items
+  uint32_t n_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   // NCCL
   ncclComm_t comm = nullptr;
@@ -198,7 +199,7 @@ struct StageScope {
 void resolve_events(sq_engine* e) {
   for (auto& ev : e->events) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) e->ms[ev.stage] += ms;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { e->ms[ev.stage] += ms; e->n_stage[ev.stage]++; }
     cudaEventDestroy(ev.a);
     cudaEventDestroy(ev.b);
   }
@@ -386,10 +387,12 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   if (inputs_ready) SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
 
   {
-    StageScope st(e, 0);
+    StageScope st(e, 6);
     launch_items(d_len, n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(), s.item_read.as<uint32_t>(),
                  items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches);
     SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * e->nk * 2, e->stream));
+  }
+  {
     SketchParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.packed = d_packed;
@@ -408,7 +411,11 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     sp.sel = s.sel.as<uint32_t>();
     sp.slot_stride = slot_stride;
     sp.cnt = s.cnt.as<uint16_t>();
-    launch_sketch(sp, e->stream, &e->launches);
+    {
+      StageScope st(e, 0);  // the sketch kernel alone
+      launch_sketch(sp, e->stream, &e->launches);
+    }
+    StageScope st2(e, 6);
     launch_sum_u16(s.cnt.as<uint16_t>(), (uint64_t)items_ub * e->nk, e->d_totals, e->stream, &e->launches);
   }
   {
@@ -441,6 +448,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.ovf_list = s.ovf_list.as<uint32_t>();
     vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 2 * s.id + 1);
     vp.flags = e->d_flags;
+    vp.work = e->d_totals + 1;
     vp.big_keys = e->big_keys.as<uint32_t>();
     vp.big_cnt = e->big_cnt.as<uint32_t>();
     vp.big_list = e->big_list.as<uint32_t>();
@@ -522,12 +530,12 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   e->stream = e->own_stream;
   void* ctr = nullptr;
-  if ((ce = cudaMalloc(&ctr, 64)) != cudaSuccess) return bail(ce, "cudaMalloc");
-  if ((ce = cudaMemset(ctr, 0, 64)) != cudaSuccess) return bail(ce, "cudaMemset");
+  if ((ce = cudaMalloc(&ctr, 128)) != cudaSuccess) return bail(ce, "cudaMalloc");
+  if ((ce = cudaMemset(ctr, 0, 128)) != cudaSuccess) return bail(ce, "cudaMemset");
   e->d_totals = static_cast<unsigned long long*>(ctr);                 // byte 0
-  e->d_slot_ctr = e->d_totals + 2;                                     // bytes 16..47 (2 slots x 16 B)
-  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 6);           // byte 48
-  e->d_fail = e->d_flags + 1;                                          // byte 52
+  e->d_slot_ctr = e->d_totals + 4;                                     // bytes 32..63 (2 slots x 16 B)
+  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 8);           // byte 64
+  e->d_fail = e->d_flags + 1;                                          // byte 68
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 64);
   *out = e;
@@ -707,13 +715,14 @@ int sq_sync(sq_engine* e) {
 int sq_reset_reads(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 64, e->stream));
+  SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 128, e->stream));
   if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   memset(e->h_mirror, 0, 64);
   e->P = 0;
   e->ovf_total = 0;
   e->n_reads = e->n_bases = e->n_batches = 0;
+  for (int i = 0; i < 8; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
   return SQ_OK;
 }
 
@@ -897,7 +906,7 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
 int sq_get_stats(sq_engine* e, sq_stats* out) {
   if (!e || !out) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  unsigned long long tot[1] = {0};
+  unsigned long long tot[4] = {0, 0, 0, 0};
   SQ_CUDA(e, cudaMemcpy(tot, e->d_totals, sizeof(tot), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->reads = e->n_reads;
@@ -911,6 +920,9 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->ms_sketch = e->ms[0]; out->ms_vote = e->ms[1]; out->ms_compact = e->ms[2];
   out->ms_sort = e->ms[3]; out->ms_em = e->ms[4]; out->ms_assign = e->ms[5];
   out->launches = e->launches;
+  out->queries = tot[1]; out->hits = tot[2]; out->postings = tot[3];
+  out->ms_items = e->ms[6];
+  out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
   return SQ_OK;
 }
 

@@ -100,7 +100,7 @@ __device__ void warp_bitonic(unsigned long long* a, uint32_t m) {
 }
 
 // Vote for read r.  Returns 0 = done, 1 = scratch overflow (nothing emitted; scratch is clean again).
-__device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r) {
+__device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint32_t (&work)[3]) {
   const uint32_t lane = lane_id();
   const uint32_t nk = P.nk;
   const uint32_t item0 = P.item_start[r];
@@ -145,11 +145,14 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r) {
         }
         if (first) {
           uint32_t off = probe(tb, h);
+          ++work[0];
           if (off != SQ_EMPTY) {
+            ++work[1];
             uint32_t t;
             do {
               t = __ldg(tb.postings + off++);
               table_vote(S, t & ~SQ_LAST, ki, nk);
+              ++work[2];
             } while (!(t & SQ_LAST));
           }
         }
@@ -294,8 +297,9 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
   for (uint32_t i = lane; i < tab * nk; i += 32) S.tcnt[i] = 0;
   __syncwarp();
   const uint32_t nwarps = gridDim.x * kVoteWarps;
+  uint32_t work[3] = {0, 0, 0};
   for (uint32_t r = blockIdx.x * kVoteWarps + warp; r < P.n_reads; r += nwarps) {
-    if (vote_read(P, S, r)) {
+    if (vote_read(P, S, r, work)) {
       if (lane == 0) {
         const uint32_t pos = atomicAdd(P.ovf_count, 1u);
         P.ovf_list[pos] = r;
@@ -303,6 +307,13 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
         P.read_soff[r] = 0;
       }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    uint32_t v = work[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if (lane == 0 && v) atomicAdd(P.work + i, (unsigned long long)v);
   }
 }
 
@@ -324,9 +335,10 @@ __global__ void __launch_bounds__(32) vote_overflow_kernel(const __grid_constant
   S.tab_maxfill = (uint32_t)tab;  // the table is sized so that every transcript fits
   S.set_log2 = P.big_set_log2;
   S.set_maxfill = (uint32_t)set;
+  uint32_t work[3] = {0, 0, 0};
   for (uint32_t i = w; i < n; i += gridDim.x) {
     const uint32_t r = P.ovf_list[i];
-    if (vote_read(P, S, r)) {
+    if (vote_read(P, S, r, work)) {
       if (lane_id() == 0) {
         atomicOr(P.flags, 2u);
         P.read_cnt[r] = 0;
