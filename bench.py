@@ -368,6 +368,8 @@ def run_ours(args):
                 "input": "2-bit packed reads in pinned host memory (sq_push_reads)"},
         "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps,
         "clocks": clk, "roofline": roofline, "em_iterations": iters,
+        "work": {k2: int(st[k2]) for k2 in ("reads", "sketch_hashes", "queries", "hits", "postings", "pairs",
+                                            "slow_reads", "overflow_reads", "batches")},
     }
 
     if rank == 0 and not args.no_cpu_baseline:

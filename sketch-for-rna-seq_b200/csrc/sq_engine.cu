@@ -40,8 +40,8 @@ struct DevBuf {
 
 struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
-  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, stage_tid, stage_score,
-      scan_tmp;
+  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, slow_list, stage_tid,
+      stage_score, scan_tmp;
   cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr;
   bool in_flight = false;   // compaction enqueued, `done` recorded
   bool pending = false;     // vote enqueued, compaction not yet (needs the exact candidate count)
@@ -52,7 +52,7 @@ struct Slot {
   int id = 0;
   void release() {
     DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &sel, &read_soff, &read_cnt,
-                     &batch_off, &ovf_list, &stage_tid, &stage_score, &scan_tmp};
+                     &batch_off, &ovf_list, &slow_list, &stage_tid, &stage_score, &scan_tmp};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -116,12 +116,12 @@ struct sq_engine {
   int next_slot = 0;
   // device counters + pinned mirror
   unsigned long long* d_totals = nullptr;        // [0] sketch hashes (stats)
-  unsigned long long* d_slot_ctr = nullptr;      // per slot: [2*i] staging cursor, [2*i+1] low word = overflow reads
+  unsigned long long* d_slot_ctr = nullptr;      // per slot: [2*i] staging cursor, [2*i+1] = overflow reads (low u32) | slow-path reads (high u32)
   uint32_t* d_flags = nullptr;
   uint32_t* d_fail = nullptr;
   unsigned long long* h_mirror = nullptr;        // pinned copy of d_slot_ctr after each vote
   uint64_t P = 0;                                 // candidate pairs of all finalized batches (exact)
-  uint64_t ovf_total = 0;
+  uint64_t ovf_total = 0, slow_total = 0;
   // large-table scratch
   DevBuf big_keys, big_cnt, big_list, big_set, big_cand;
   uint32_t big_cap_log2 = 0, big_set_log2 = 0;
@@ -338,6 +338,7 @@ int finalize_slot(sq_engine* e, Slot& s) {
   s.pending = false;
   e->P += needed;
   e->ovf_total += ovf;
+  e->slow_total += e->h_mirror[2 * s.id + 1] >> 32;
   return SQ_OK;
 }
 
@@ -378,6 +379,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.read_cnt.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.batch_off.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.ovf_list.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.slow_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
@@ -447,6 +449,8 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.read_cnt = s.read_cnt.as<uint32_t>();
     vp.ovf_list = s.ovf_list.as<uint32_t>();
     vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 2 * s.id + 1);
+    vp.slow_list = s.slow_list.as<uint32_t>();
+    vp.slow_count = vp.ovf_count + 1;
     vp.flags = e->d_flags;
     vp.work = e->d_totals + 1;
     vp.big_keys = e->big_keys.as<uint32_t>();
@@ -721,6 +725,7 @@ int sq_reset_reads(sq_engine* e) {
   memset(e->h_mirror, 0, 64);
   e->P = 0;
   e->ovf_total = 0;
+  e->slow_total = 0;
   e->n_reads = e->n_bases = e->n_batches = 0;
   for (int i = 0; i < 8; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
   return SQ_OK;
@@ -923,6 +928,7 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->queries = tot[1]; out->hits = tot[2]; out->postings = tot[3];
   out->ms_items = e->ms[6];
   out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
+  out->slow_reads = e->slow_total;
   return SQ_OK;
 }
 

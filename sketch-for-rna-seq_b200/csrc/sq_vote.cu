@@ -279,6 +279,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
 
 __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_constant__ VoteParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
+  if (*P.slow_count == 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t nk = P.nk;
   const uint32_t tab = 1u << kTabLog2, set = 1u << kSetLog2;
@@ -297,8 +298,10 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
   for (uint32_t i = lane; i < tab * nk; i += 32) S.tcnt[i] = 0;
   __syncwarp();
   const uint32_t nwarps = gridDim.x * kVoteWarps;
+  const uint32_t n_slow = *P.slow_count;
   uint32_t work[3] = {0, 0, 0};
-  for (uint32_t r = blockIdx.x * kVoteWarps + warp; r < P.n_reads; r += nwarps) {
+  for (uint32_t i = blockIdx.x * kVoteWarps + warp; i < n_slow; i += nwarps) {
+    const uint32_t r = P.slow_list[i];
     if (vote_read(P, S, r, work)) {
       if (lane == 0) {
         const uint32_t pos = atomicAdd(P.ovf_count, 1u);
@@ -313,7 +316,161 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
     uint32_t v = work[i];
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-    if (lane == 0 && v) atomicAdd(P.work + i, (unsigned long long)v);
+    if (lane == 0 && v && P.work) atomicAdd(P.work + i, (unsigned long long)v);
+  }
+}
+
+
+// ------------------------------------------------------------------ thread-per-read path (short reads)
+// A short read has one item and a handful of selected hashes, so one THREAD votes for it: duplicates are
+// removed by comparing with the earlier hashes of the same (read, k), every distinct hash is probed, the
+// posting list is walked and (transcript -> per-k counts packed 8 bits each) is kept in a kFastCap-entry
+// table.  The table lives in shared memory, entry-major ([entry][thread]) so a warp's accesses to entry i are
+// bank-conflict free and nothing spills to local memory.  Reads with more than one item, more than
+// kFastMaxHashes hashes for some k or more than kFastCap distinct transcripts are handed to the
+// warp-per-read kernel through slow_list.
+static constexpr int kFastBlock = 256;
+static constexpr int kFastCap = 16;
+static constexpr uint32_t kFastMaxHashes = 32;
+
+template <typename CT>  // packed per-k counters: uint32_t for nk <= 4, unsigned long long for nk <= 8
+__global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_constant__ VoteParams P) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  CT* tc = reinterpret_cast<CT*>(fast_smem);                                   // [kFastCap][kFastBlock]
+  uint32_t* tt = reinterpret_cast<uint32_t*>(tc + kFastCap * kFastBlock);      // [kFastCap][kFastBlock]
+  __shared__ uint32_t s_warp[kFastBlock / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_work[3];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tx = threadIdx.x;
+  const uint32_t r = blockIdx.x * kFastBlock + tx;
+  const bool valid = r < P.n_reads;
+  const uint32_t nk = P.nk;
+  if (tx < 3) s_work[tx] = 0;
+
+  uint32_t ntab = 0;
+  bool defer = false;
+  uint32_t wq = 0, wh = 0, wp = 0;
+  if (valid) {
+    const uint32_t item0 = P.item_start[r];
+    if (P.item_start[r + 1] - item0 != 1) defer = true;
+    const uint32_t boff = P.base_off[r] - P.bias;
+    for (uint32_t ki = 0; ki < nk && !defer; ++ki) {
+      const IndexTable& tb = P.tab[ki];
+      if (!tb.present) continue;
+      const uint32_t n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
+      if (n > kFastMaxHashes) { defer = true; break; }
+      const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
+      const CT one = (CT)1 << (8 * ki);
+      for (uint32_t j = 0; j < n && !defer; ++j) {
+        const uint32_t h = hs[j];
+        bool dup = false;
+        for (uint32_t jj = 0; jj < j; ++jj) dup |= hs[jj] == h;
+        if (dup) continue;
+        uint32_t off = probe(tb, h);
+        ++wq;
+        if (off == SQ_EMPTY) continue;
+        ++wh;
+        uint32_t t;
+        do {
+          t = __ldg(tb.postings + off++);
+          const uint32_t tid = t & ~SQ_LAST;
+          uint32_t idx = ntab;
+          for (uint32_t i = 0; i < ntab; ++i)
+            if (tt[i * kFastBlock + tx] == tid) idx = i;
+          if (idx == ntab) {
+            if (ntab == kFastCap) { defer = true; break; }
+            ++ntab;
+            tt[idx * kFastBlock + tx] = tid;
+            tc[idx * kFastBlock + tx] = 0;
+          }
+          tc[idx * kFastBlock + tx] += one;
+          ++wp;
+        } while (!(t & SQ_LAST));
+      }
+    }
+  }
+  // hand complicated reads to the warp-per-read kernel (their work counters are recounted there)
+  const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
+  if (dmask) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.slow_count, (uint32_t)__popc(dmask));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (valid && defer) {
+      P.slow_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+      wq = wh = wp = 0;
+    }
+  }
+  // per-k maximum (bytes of the packed word), threshold, filter, score; the surviving entries are sorted in
+  // place (entry i is consumed before any slot <= i is overwritten): tc := 0x7FFFFFFF-score, tt := transcript
+  uint32_t nc = 0;
+  if (valid && !defer && ntab) {
+    CT mx = 0;
+    for (uint32_t i = 0; i < ntab; ++i) {
+      const CT c = tc[i * kFastBlock + tx];
+      CT m2 = 0;
+      for (uint32_t ki = 0; ki < nk; ++ki) {
+        const CT a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
+        m2 |= (a > b ? a : b) << (8 * ki);
+      }
+      mx = m2;
+    }
+    for (uint32_t i = 0; i < ntab; ++i) {
+      const CT c = tc[i * kFastBlock + tx];
+      const uint32_t tid = tt[i * kFastBlock + tx];
+      bool ok = true;
+      uint32_t score = 0;
+      for (uint32_t ki = 0; ki < nk; ++ki) {
+        const int cc = (int)((c >> (8 * ki)) & 255), mm = (int)((mx >> (8 * ki)) & 255);
+        if ((double)cc < P.fraction * (double)mm) ok = false;  // sparse_chaining.cpp:84-98
+        score += (uint32_t)cc;
+      }
+      if (ok) {
+        // insertion sort: score descending, transcript ascending
+        const uint32_t inv = 0x7FFFFFFFu - score;
+        uint32_t pos = nc++;
+        while (pos > 0) {
+          const uint32_t pi = (uint32_t)tc[(pos - 1) * kFastBlock + tx], pt = tt[(pos - 1) * kFastBlock + tx];
+          if (pi < inv || (pi == inv && pt < tid)) break;
+          tc[pos * kFastBlock + tx] = (CT)pi;
+          tt[pos * kFastBlock + tx] = pt;
+          --pos;
+        }
+        tc[pos * kFastBlock + tx] = (CT)inv;
+        tt[pos * kFastBlock + tx] = tid;
+      }
+    }
+  }
+  // one staging allocation per block
+  const uint32_t incl = warp_incl_scan(nc);
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (tx == 0) {
+    uint32_t tot = 0;
+    for (int w = 0; w < kFastBlock / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+    s_base = tot ? atomicAdd(P.stage_cursor, (unsigned long long)tot) : 0ull;
+  }
+  __syncthreads();
+  if (valid) {
+    const unsigned long long sbase = s_base + s_warp[warp] + (incl - nc);
+    const bool fits = sbase + nc <= P.stage_cap;
+    P.read_soff[r] = (uint32_t)sbase;
+    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the warp kernel
+    if (fits)
+      for (uint32_t i = 0; i < nc; ++i) {
+        P.stage_tid[sbase + i] = tt[i * kFastBlock + tx];
+        P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)tc[i * kFastBlock + tx]);
+      }
+  }
+  if (P.work) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
+      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
+      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
+    }
+    if (lane == 0) { atomicAdd(&s_work[0], wq); atomicAdd(&s_work[1], wh); atomicAdd(&s_work[2], wp); }
+    __syncthreads();
+    if (tx < 3 && s_work[tx]) atomicAdd(P.work + tx, (unsigned long long)s_work[tx]);
   }
 }
 
@@ -382,9 +539,24 @@ void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches) {
   uint32_t grid = (uint32_t)(sm_count * per_sm);
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
+  {
+    const uint32_t fgrid = (p.n_reads + kFastBlock - 1) / kFastBlock;
+    if (p.nk <= 4) {
+      const size_t fsm = (size_t)kFastCap * kFastBlock * 8;
+      vote_fast_kernel<uint32_t><<<fgrid, kFastBlock, fsm, s>>>(p);
+    } else {
+      const size_t fsm = (size_t)kFastCap * kFastBlock * 12;
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(vote_fast_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
+        attr = true;
+      }
+      vote_fast_kernel<unsigned long long><<<fgrid, kFastBlock, fsm, s>>>(p);
+    }
+  }
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
   vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
-  if (launches) *launches += 2;
+  if (launches) *launches += 3;
 }
 
 }  // namespace sq

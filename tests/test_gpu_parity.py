@@ -92,7 +92,7 @@ def _gpu_quant(sqb, d, ks, postings, fraction=0.9, iters=20, tol=0.01, options=N
 
 @pytest.mark.parametrize("ks,kw", [([31], {}), ([21, 25, 31], {}), ([31], dict(chunks=3)),
                                    ([25, 31], dict(options={"batch_bases": 4096})),
-                                   ([31, 31], {})])
+                                   ([31, 31], {}), ([15, 17, 19, 21, 23], {})])
 def test_quant_parity_short_reads(gpu_lib, sqb, port, ks, kw):
     d = dataset()
     thr = port.threshold(SKETCH)
