@@ -59,7 +59,8 @@ typedef struct sq_stats {
   uint64_t postings;       /* posting-list entries walked */
   float ms_items;          /* item split + counters (everything of the sketch stage except the sketch kernel) */
   uint32_t sketch_launches, vote_launches; /* launches of the two named kernels while profiling was on */
-  uint64_t slow_reads;     /* reads voted by the warp-per-read kernel instead of the thread-per-read kernel */
+  uint64_t slow_reads;     /* reads voted by the warp-per-read kernel instead of a thread-per-read kernel */
+  uint64_t mid_reads;      /* reads voted by the 48-entry thread-per-read kernel (second tier) or later */
 } sq_stats;
 
 const char* sq_version(void);

@@ -33,7 +33,8 @@ class Stats(C.Structure):
                 ("ms_sketch", C.c_float), ("ms_vote", C.c_float), ("ms_compact", C.c_float), ("ms_sort", C.c_float),
                 ("ms_em", C.c_float), ("ms_assign", C.c_float), ("launches", C.c_uint64),
                 ("queries", C.c_uint64), ("hits", C.c_uint64), ("postings", C.c_uint64), ("ms_items", C.c_float),
-                ("sketch_launches", C.c_uint32), ("vote_launches", C.c_uint32), ("slow_reads", C.c_uint64)]
+                ("sketch_launches", C.c_uint32), ("vote_launches", C.c_uint32), ("slow_reads", C.c_uint64),
+                ("mid_reads", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

@@ -81,7 +81,9 @@ struct VoteParams {
   unsigned long long* stage_cursor;  // device counter
   uint32_t* read_soff;               // per read: staging offset
   uint32_t* read_cnt;                // per read: candidates
-  uint32_t* slow_list;               // reads the thread-per-read kernel hands to the warp-per-read kernel
+  uint32_t* mid_list;                // reads the 16-entry thread kernel hands to the 48-entry thread kernel
+  uint32_t* mid_count;
+  uint32_t* slow_list;               // reads the thread-per-read kernels hand to the warp-per-read kernel
   uint32_t* slow_count;
   uint32_t* ovf_list;                // reads that overflowed the shared-memory tables
   uint32_t* ovf_count;

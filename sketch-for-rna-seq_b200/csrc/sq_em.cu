@@ -13,21 +13,19 @@ namespace sq {
 static constexpr uint32_t kHashMul = 0x9E3779B1u;
 
 // ------------------------------------------------------------------ index table
-__global__ void table_insert_kernel(const uint32_t* __restrict__ keys, const uint64_t* __restrict__ off,
-                                    uint64_t nkeys, uint4* buckets, uint32_t shift, uint32_t mask,
-                                    uint32_t* __restrict__ postings, uint32_t* fail) {
+__global__ void table_insert_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ off,
+                                    uint64_t nkeys, uint4* buckets, uint32_t shift, uint32_t mask, uint32_t* fail) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= nkeys) return;
-  const uint64_t b0 = off[i], b1 = off[i + 1];
-  if (b1 <= b0) return;  // a key without postings cannot vote
-  postings[b1 - 1] |= SQ_LAST;
+  const uint32_t o = off[i];
+  if (o == SQ_EMPTY) return;  // a key without postings cannot vote
   const uint32_t key = keys[i];
   uint32_t b = (key * kHashMul) >> shift;
   for (uint32_t tries = 0; tries <= mask; ++tries) {
     uint32_t* bk = reinterpret_cast<uint32_t*>(buckets + 2 * (size_t)b);
     uint32_t* bo = bk + 4;
     for (int s = 0; s < 4; ++s)
-      if (atomicCAS(&bo[s], SQ_EMPTY, (uint32_t)b0) == SQ_EMPTY) {
+      if (atomicCAS(&bo[s], SQ_EMPTY, o) == SQ_EMPTY) {
         bk[s] = key;
         return;
       }
@@ -36,13 +34,14 @@ __global__ void table_insert_kernel(const uint32_t* __restrict__ keys, const uin
   atomicExch(fail, 1u);
 }
 
-void launch_table_build(const uint32_t* keys, const uint64_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
-                        uint32_t mask, uint32_t* postings, uint32_t* fail, cudaStream_t s, uint64_t* launches) {
+// keys[i] -> posting offset off[i] (SQ_EMPTY: no list); lists are already flagged with SQ_LAST
+void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
+                        uint32_t mask, uint32_t* fail, cudaStream_t s, uint64_t* launches) {
   launch_fill_u32(reinterpret_cast<uint32_t*>(buckets), (size_t)(mask + 1) * 8, SQ_EMPTY, s);
   if (launches) ++*launches;
   if (nkeys == 0) return;
   const uint32_t grid = (uint32_t)((nkeys + 255) / 256);
-  table_insert_kernel<<<grid, 256, 0, s>>>(keys, off, nkeys, buckets, shift, mask, postings, fail);
+  table_insert_kernel<<<grid, 256, 0, s>>>(keys, off, nkeys, buckets, shift, mask, fail);
   if (launches) ++*launches;
 }
 

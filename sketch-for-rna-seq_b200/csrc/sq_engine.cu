@@ -40,8 +40,8 @@ struct DevBuf {
 
 struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
-  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, slow_list, stage_tid,
-      stage_score, scan_tmp;
+  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, slow_list, mid_list,
+      stage_tid, stage_score, scan_tmp;
   cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr;
   bool in_flight = false;   // compaction enqueued, `done` recorded
   bool pending = false;     // vote enqueued, compaction not yet (needs the exact candidate count)
@@ -52,7 +52,7 @@ struct Slot {
   int id = 0;
   void release() {
     DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &sel, &read_soff, &read_cnt,
-                     &batch_off, &ovf_list, &slow_list, &stage_tid, &stage_score, &scan_tmp};
+                     &batch_off, &ovf_list, &slow_list, &mid_list, &stage_tid, &stage_score, &scan_tmp};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -61,7 +61,7 @@ struct KTab {
   DevBuf buckets, postings;
   uint32_t shift = 0, mask = 0;
   bool present = false;
-  uint64_t nkeys = 0, npost = 0;
+  uint64_t nkeys = 0, npost = 0, npost_stored = 0;
 };
 
 struct StageEvent { cudaEvent_t a, b; int stage; };
@@ -121,7 +121,7 @@ struct sq_engine {
   uint32_t* d_fail = nullptr;
   unsigned long long* h_mirror = nullptr;        // pinned copy of d_slot_ctr after each vote
   uint64_t P = 0;                                 // candidate pairs of all finalized batches (exact)
-  uint64_t ovf_total = 0, slow_total = 0;
+  uint64_t ovf_total = 0, slow_total = 0, mid_total = 0;
   // large-table scratch
   DevBuf big_keys, big_cnt, big_list, big_set, big_cand;
   uint32_t big_cap_log2 = 0, big_set_log2 = 0;
@@ -292,13 +292,13 @@ int ensure_big_scratch(sq_engine* e) {
 }
 
 int enqueue_vote(sq_engine* e, Slot& s) {
-  unsigned long long* ctr = e->d_slot_ctr + 2 * s.id;
-  SQ_CUDA(e, cudaMemsetAsync(ctr, 0, 16, e->stream));
+  unsigned long long* ctr = e->d_slot_ctr + 4 * s.id;
+  SQ_CUDA(e, cudaMemsetAsync(ctr, 0, 32, e->stream));
   {
     StageScope st(e, 1);
     launch_vote(s.vp, e->stream, &e->launches);
   }
-  SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 2 * s.id, ctr, 16, cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 4 * s.id, ctr, 32, cudaMemcpyDeviceToHost, e->stream));
   SQ_CUDA(e, cudaGetLastError());
   SQ_CUDA(e, cudaEventRecord(s.voted, e->stream));
   return SQ_OK;
@@ -310,7 +310,7 @@ int enqueue_vote(sq_engine* e, Slot& s) {
 int finalize_slot(sq_engine* e, Slot& s) {
   if (!s.pending) return SQ_OK;
   SQ_CUDA(e, cudaEventSynchronize(s.voted));
-  uint64_t needed = e->h_mirror[2 * s.id];
+  uint64_t needed = e->h_mirror[4 * s.id];
   while (needed > s.stage_cap) {
     s.stage_cap = needed + needed / 8;
     SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
@@ -320,9 +320,9 @@ int finalize_slot(sq_engine* e, Slot& s) {
     s.vp.stage_cap = s.stage_cap;
     SQ_TRY(enqueue_vote(e, s));
     SQ_CUDA(e, cudaEventSynchronize(s.voted));
-    needed = e->h_mirror[2 * s.id];
+    needed = e->h_mirror[4 * s.id];
   }
-  const uint64_t ovf = e->h_mirror[2 * s.id + 1] & 0xFFFFFFFFull;
+  const uint64_t ovf = e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull;
   SQ_TRY(ensure_store(e, s.read_base, s.n_reads, needed));
   {
     StageScope st(e, 2);
@@ -338,7 +338,8 @@ int finalize_slot(sq_engine* e, Slot& s) {
   s.pending = false;
   e->P += needed;
   e->ovf_total += ovf;
-  e->slow_total += e->h_mirror[2 * s.id + 1] >> 32;
+  e->slow_total += e->h_mirror[4 * s.id + 1] >> 32;
+  e->mid_total += e->h_mirror[4 * s.id + 2] & 0xFFFFFFFFull;
   return SQ_OK;
 }
 
@@ -380,6 +381,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.batch_off.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.ovf_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.slow_list.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, s.mid_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
@@ -444,13 +446,15 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.stage_tid = s.stage_tid.as<uint32_t>();
     vp.stage_score = s.stage_score.as<int32_t>();
     vp.stage_cap = s.stage_cap;
-    vp.stage_cursor = e->d_slot_ctr + 2 * s.id;
+    vp.stage_cursor = e->d_slot_ctr + 4 * s.id;
     vp.read_soff = s.read_soff.as<uint32_t>();
     vp.read_cnt = s.read_cnt.as<uint32_t>();
     vp.ovf_list = s.ovf_list.as<uint32_t>();
-    vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 2 * s.id + 1);
+    vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 4 * s.id + 1);
     vp.slow_list = s.slow_list.as<uint32_t>();
     vp.slow_count = vp.ovf_count + 1;
+    vp.mid_list = s.mid_list.as<uint32_t>();
+    vp.mid_count = vp.ovf_count + 2;
     vp.flags = e->d_flags;
     vp.work = e->d_totals + 1;
     vp.big_keys = e->big_keys.as<uint32_t>();
@@ -537,9 +541,9 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   if ((ce = cudaMalloc(&ctr, 128)) != cudaSuccess) return bail(ce, "cudaMalloc");
   if ((ce = cudaMemset(ctr, 0, 128)) != cudaSuccess) return bail(ce, "cudaMemset");
   e->d_totals = static_cast<unsigned long long*>(ctr);                 // byte 0
-  e->d_slot_ctr = e->d_totals + 4;                                     // bytes 32..63 (2 slots x 16 B)
-  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 8);           // byte 64
-  e->d_fail = e->d_flags + 1;                                          // byte 68
+  e->d_slot_ctr = e->d_totals + 4;                                     // bytes 32..95 (2 slots x 32 B)
+  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 12);          // byte 96
+  e->d_fail = e->d_flags + 1;                                          // byte 100
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 64);
   *out = e;
@@ -619,25 +623,80 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   for (uint64_t i = 0; i < npost; ++i)
     if (post_tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "posting %llu names transcript %u >= T", (unsigned long long)i, post_tid[i]);
   KTab& t = e->tab[kidx];
+  // Posting lists with identical content are stored once (all k-mers of an exon shared by the same isoforms
+  // have the same list), so the postings array shrinks to the distinct isoform sets and a read whose hits
+  // share a list can walk it once with a weight.  Open-addressing table on a 64-bit content hash, verified
+  // by comparing the content.
+  std::vector<uint32_t> off32(nkeys + 1, SQ_EMPTY);
+  std::vector<uint32_t> dpost;
+  dpost.reserve(npost / 4 + 16);
+  {
+    uint64_t cap = 16;
+    while (cap < nkeys * 2 + 2) cap <<= 1;
+    std::vector<uint64_t> hkey(cap, 0);
+    std::vector<uint32_t> hval(cap, SQ_EMPTY);
+    std::vector<uint32_t> sorted_list;
+    for (uint64_t i = 0; i < nkeys; ++i) {
+      uint64_t b0 = post_off[i], b1 = post_off[i + 1];
+      if (b1 <= b0) continue;
+      // the kernels merge lists assuming ascending transcript ids; the reference's file order is arbitrary
+      const uint32_t* post_tid_i = post_tid;
+      if (!std::is_sorted(post_tid + b0, post_tid + b1)) {
+        sorted_list.assign(post_tid + b0, post_tid + b1);
+        std::sort(sorted_list.begin(), sorted_list.end());
+        post_tid_i = sorted_list.data();
+        b1 -= b0;
+        b0 = 0;
+      }
+      const uint32_t* post_tid = post_tid_i;  // shadow: this key's (sorted) list lives at [b0, b1) of this array
+      uint64_t h = 0xcbf29ce484222325ull ^ (b1 - b0);
+      for (uint64_t j = b0; j < b1; ++j) { h ^= post_tid[j]; h *= 0x100000001b3ull; h ^= h >> 29; }
+      if (h == 0) h = 1;
+      uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
+      for (;;) {
+        if (hval[slot] == SQ_EMPTY) {
+          hkey[slot] = h;
+          hval[slot] = (uint32_t)dpost.size();
+          off32[i] = hval[slot];
+          for (uint64_t j = b0; j < b1; ++j) dpost.push_back(post_tid[j] | (j + 1 == b1 ? SQ_LAST : 0u));
+          break;
+        }
+        if (hkey[slot] == h) {  // same hash: verify content
+          const uint32_t o = hval[slot];
+          bool same = true;
+          uint64_t j = b0;
+          for (uint32_t q = o;; ++q, ++j) {
+            const uint32_t v = dpost[q];
+            if (j >= b1 || (v & ~SQ_LAST) != post_tid[j]) { same = false; break; }
+            if (v & SQ_LAST) { same = (j + 1 == b1); break; }
+          }
+          if (same) { off32[i] = o; break; }
+        }
+        slot = (slot + 1) & (cap - 1);
+      }
+    }
+  }
+  const uint64_t ndp = dpost.size();
   const uint32_t nb_log2 = std::max<uint32_t>(1, log2_ceil((nkeys + 1) / 2 + 1));
   const uint64_t nb = 1ull << nb_log2;
   SQ_CUDA(e, t.buckets.ensure(nb * 32));
-  SQ_CUDA(e, t.postings.ensure((npost + 1) * 4));
+  SQ_CUDA(e, t.postings.ensure((ndp + 1) * 4));
   t.shift = 32 - nb_log2;
   t.mask = (uint32_t)(nb - 1);
   t.nkeys = nkeys;
   t.npost = npost;
+  t.npost_stored = ndp;
   DevBuf dkeys, doff;
   SQ_CUDA(e, dkeys.ensure((nkeys + 1) * 4));
-  SQ_CUDA(e, doff.ensure((nkeys + 1) * 8));
+  SQ_CUDA(e, doff.ensure((nkeys + 1) * 4));
   if (nkeys) {
     SQ_CUDA(e, cudaMemcpyAsync(dkeys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, e->stream));
-    SQ_CUDA(e, cudaMemcpyAsync(doff.p, post_off, (nkeys + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-    SQ_CUDA(e, cudaMemcpyAsync(t.postings.p, post_tid, npost * 4, cudaMemcpyHostToDevice, e->stream));
+    SQ_CUDA(e, cudaMemcpyAsync(doff.p, off32.data(), nkeys * 4, cudaMemcpyHostToDevice, e->stream));
+    if (ndp) SQ_CUDA(e, cudaMemcpyAsync(t.postings.p, dpost.data(), ndp * 4, cudaMemcpyHostToDevice, e->stream));
   }
   SQ_CUDA(e, cudaMemsetAsync(e->d_fail, 0, 4, e->stream));
-  launch_table_build(dkeys.as<uint32_t>(), doff.as<uint64_t>(), nkeys, t.buckets.as<uint4>(), t.shift, t.mask,
-                     t.postings.as<uint32_t>(), e->d_fail, e->stream, &e->launches);
+  launch_table_build(dkeys.as<uint32_t>(), doff.as<uint32_t>(), nkeys, t.buckets.as<uint4>(), t.shift, t.mask,
+                     e->d_fail, e->stream, &e->launches);
   uint32_t failed = 0;
   SQ_CUDA(e, cudaMemcpyAsync(&failed, e->d_fail, 4, cudaMemcpyDeviceToHost, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -726,6 +785,7 @@ int sq_reset_reads(sq_engine* e) {
   e->P = 0;
   e->ovf_total = 0;
   e->slow_total = 0;
+  e->mid_total = 0;
   e->n_reads = e->n_bases = e->n_batches = 0;
   for (int i = 0; i < 8; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
   return SQ_OK;
@@ -929,6 +989,7 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->ms_items = e->ms[6];
   out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
   out->slow_reads = e->slow_total;
+  out->mid_reads = e->mid_total;
   return SQ_OK;
 }
 

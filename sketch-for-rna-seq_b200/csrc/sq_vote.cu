@@ -323,33 +323,58 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
 
 // ------------------------------------------------------------------ thread-per-read path (short reads)
 // A short read has one item and a handful of selected hashes, so one THREAD votes for it: duplicates are
-// removed by comparing with the earlier hashes of the same (read, k), every distinct hash is probed, the
-// posting list is walked and (transcript -> per-k counts packed 8 bits each) is kept in a kFastCap-entry
-// table.  The table lives in shared memory, entry-major ([entry][thread]) so a warp's accesses to entry i are
-// bank-conflict free and nothing spills to local memory.  Reads with more than one item, more than
-// kFastMaxHashes hashes for some k or more than kFastCap distinct transcripts are handed to the
-// warp-per-read kernel through slow_list.
-static constexpr int kFastBlock = 256;
-static constexpr int kFastCap = 16;
+// removed by comparing with the earlier hashes of the same (read, k), every distinct hash is probed, and the
+// posting lists of the hits are merged into a table (transcript -> per-k counts packed 8 bits each) that is
+// kept sorted by transcript id.  Identical posting lists are stored once in the index, so hits with the same
+// offset are walked once with a weight.  The table lives in shared memory, entry-major ([entry][thread]):
+// a warp's accesses are bank-conflict free whatever entry each lane touches, and nothing spills to local
+// memory.  Two instantiations run back to back: CAP=16 entries for every read, then CAP=48 for the reads
+// that did not fit; what still does not fit (or has several items / more than kFastMaxHashes hashes for a
+// k) goes to the warp-per-read kernel through slow_list.
 static constexpr uint32_t kFastMaxHashes = 32;
 
-template <typename CT>  // packed per-k counters: uint32_t for nk <= 4, unsigned long long for nk <= 8
-__global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_constant__ VoteParams P) {
+template <typename CT, int CAP, int BLOCK, bool LISTED>  // CT: uint32_t for nk <= 4, unsigned long long for nk <= 8
+__global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant__ VoteParams P) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
-  CT* tc = reinterpret_cast<CT*>(fast_smem);                                   // [kFastCap][kFastBlock]
-  uint32_t* tt = reinterpret_cast<uint32_t*>(tc + kFastCap * kFastBlock);      // [kFastCap][kFastBlock]
-  __shared__ uint32_t s_warp[kFastBlock / 32];
+  CT* tc = reinterpret_cast<CT*>(fast_smem);                       // [CAP][BLOCK]
+  uint32_t* tt = reinterpret_cast<uint32_t*>(tc + CAP * BLOCK);    // [CAP][BLOCK]
+  __shared__ uint32_t s_warp[BLOCK / 32];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_work[3];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tx = threadIdx.x;
-  const uint32_t r = blockIdx.x * kFastBlock + tx;
-  const bool valid = r < P.n_reads;
+  const uint32_t gi = blockIdx.x * BLOCK + tx;
+  const uint32_t n_in = LISTED ? *P.mid_count : P.n_reads;
+  if (blockIdx.x * BLOCK >= n_in) return;
+  const bool valid = gi < n_in;
+  const uint32_t r = valid ? (LISTED ? P.mid_list[gi] : gi) : 0u;
   const uint32_t nk = P.nk;
   if (tx < 3) s_work[tx] = 0;
 
   uint32_t ntab = 0;
   bool defer = false;
   uint32_t wq = 0, wh = 0, wp = 0;
+  // merge one posting list (ascending transcript ids) into the sorted table with weight `add`
+  auto merge_list = [&](const IndexTable& tb, uint32_t off, CT add, uint32_t w, uint32_t room) {
+    uint32_t p = 0, t;
+    do {
+      t = __ldg(tb.postings + off++);
+      const uint32_t tid = t & ~SQ_LAST;
+      while (p < ntab && tt[p * BLOCK + tx] < tid) ++p;
+      if (p < ntab && tt[p * BLOCK + tx] == tid) {
+        tc[p * BLOCK + tx] += add;
+      } else {
+        if (ntab >= room) { defer = true; return; }
+        for (uint32_t q = ntab; q > p; --q) {
+          tt[q * BLOCK + tx] = tt[(q - 1) * BLOCK + tx];
+          tc[q * BLOCK + tx] = tc[(q - 1) * BLOCK + tx];
+        }
+        tt[p * BLOCK + tx] = tid;
+        tc[p * BLOCK + tx] = add;
+        ++ntab;
+      }
+      wp += w;
+    } while (!(t & SQ_LAST));
+  };
   if (valid) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
@@ -360,44 +385,60 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
       const uint32_t n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
       if (n > kFastMaxHashes) { defer = true; break; }
       const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
-      const CT one = (CT)1 << (8 * ki);
+      // (1) probe every distinct hash; park the posting offsets of the hits in this thread's column of the
+      //     still unused top rows of the table (row CAP-1 downwards).  Without room the list is merged at once.
+      uint32_t nh = 0;
+      uint32_t* hit = tt + (CAP - 1) * BLOCK + tx;
       for (uint32_t j = 0; j < n && !defer; ++j) {
         const uint32_t h = hs[j];
         bool dup = false;
         for (uint32_t jj = 0; jj < j; ++jj) dup |= hs[jj] == h;
         if (dup) continue;
-        uint32_t off = probe(tb, h);
+        const uint32_t off = probe(tb, h);
         ++wq;
         if (off == SQ_EMPTY) continue;
         ++wh;
-        uint32_t t;
-        do {
-          t = __ldg(tb.postings + off++);
-          const uint32_t tid = t & ~SQ_LAST;
-          uint32_t idx = ntab;
-          for (uint32_t i = 0; i < ntab; ++i)
-            if (tt[i * kFastBlock + tx] == tid) idx = i;
-          if (idx == ntab) {
-            if (ntab == kFastCap) { defer = true; break; }
-            ++ntab;
-            tt[idx * kFastBlock + tx] = tid;
-            tc[idx * kFastBlock + tx] = 0;
-          }
-          tc[idx * kFastBlock + tx] += one;
-          ++wp;
-        } while (!(t & SQ_LAST));
+        if (nh + ntab + 1 < (uint32_t)CAP) {
+          hit[-(int)(nh * BLOCK)] = off;
+          ++nh;
+        } else {
+          merge_list(tb, off, (CT)1 << (8 * ki), 1, (uint32_t)CAP - nh);
+        }
+      }
+      // (2) group the parked offsets: equal offsets are the same list (weight = how many hits share it);
+      //     the distinct ones are compacted to the first rows, their weights kept in the same rows of tc
+      uint32_t nd = 0;
+      CT* wgt = tc + (CAP - 1) * BLOCK + tx;
+      for (uint32_t a = 0; a < nh; ++a) {
+        const uint32_t off = hit[-(int)(a * BLOCK)];
+        if (off == SQ_EMPTY) continue;
+        uint32_t w = 1;
+        for (uint32_t b = a + 1; b < nh; ++b)
+          if (hit[-(int)(b * BLOCK)] == off) { ++w; hit[-(int)(b * BLOCK)] = SQ_EMPTY; }
+        hit[-(int)(nd * BLOCK)] = off;
+        wgt[-(int)(nd * BLOCK)] = (CT)w;
+        ++nd;
+      }
+      // (3) merge each distinct list once, last parked first, so the rows they occupy free up as the table grows
+      for (uint32_t a = nd; a-- > 0 && !defer;) {
+        const uint32_t w = (uint32_t)wgt[-(int)(a * BLOCK)];
+        merge_list(tb, hit[-(int)(a * BLOCK)], (CT)w << (8 * ki), w, (uint32_t)CAP - a);
       }
     }
   }
-  // hand complicated reads to the warp-per-read kernel (their work counters are recounted there)
-  const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
-  if (dmask) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(P.slow_count, (uint32_t)__popc(dmask));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (valid && defer) {
-      P.slow_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
-      wq = wh = wp = 0;
+  // hand reads that did not fit to the next tier (their work counters are recounted there)
+  {
+    uint32_t* list = LISTED ? P.slow_list : P.mid_list;
+    uint32_t* count = LISTED ? P.slow_count : P.mid_count;
+    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
+    if (dmask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(dmask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (valid && defer) {
+        list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+        wq = wh = wp = 0;
+      }
     }
   }
   // per-k maximum (bytes of the packed word), threshold, filter, score; the surviving entries are sorted in
@@ -406,7 +447,7 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
   if (valid && !defer && ntab) {
     CT mx = 0;
     for (uint32_t i = 0; i < ntab; ++i) {
-      const CT c = tc[i * kFastBlock + tx];
+      const CT c = tc[i * BLOCK + tx];
       CT m2 = 0;
       for (uint32_t ki = 0; ki < nk; ++ki) {
         const CT a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
@@ -415,8 +456,8 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
       mx = m2;
     }
     for (uint32_t i = 0; i < ntab; ++i) {
-      const CT c = tc[i * kFastBlock + tx];
-      const uint32_t tid = tt[i * kFastBlock + tx];
+      const CT c = tc[i * BLOCK + tx];
+      const uint32_t tid = tt[i * BLOCK + tx];
       bool ok = true;
       uint32_t score = 0;
       for (uint32_t ki = 0; ki < nk; ++ki) {
@@ -429,14 +470,14 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
         const uint32_t inv = 0x7FFFFFFFu - score;
         uint32_t pos = nc++;
         while (pos > 0) {
-          const uint32_t pi = (uint32_t)tc[(pos - 1) * kFastBlock + tx], pt = tt[(pos - 1) * kFastBlock + tx];
+          const uint32_t pi = (uint32_t)tc[(pos - 1) * BLOCK + tx], pt = tt[(pos - 1) * BLOCK + tx];
           if (pi < inv || (pi == inv && pt < tid)) break;
-          tc[pos * kFastBlock + tx] = (CT)pi;
-          tt[pos * kFastBlock + tx] = pt;
+          tc[pos * BLOCK + tx] = (CT)pi;
+          tt[pos * BLOCK + tx] = pt;
           --pos;
         }
-        tc[pos * kFastBlock + tx] = (CT)inv;
-        tt[pos * kFastBlock + tx] = tid;
+        tc[pos * BLOCK + tx] = (CT)inv;
+        tt[pos * BLOCK + tx] = tid;
       }
     }
   }
@@ -446,7 +487,7 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
   __syncthreads();
   if (tx == 0) {
     uint32_t tot = 0;
-    for (int w = 0; w < kFastBlock / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+    for (int w = 0; w < BLOCK / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
     s_base = tot ? atomicAdd(P.stage_cursor, (unsigned long long)tot) : 0ull;
   }
   __syncthreads();
@@ -454,11 +495,11 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
     const unsigned long long sbase = s_base + s_warp[warp] + (incl - nc);
     const bool fits = sbase + nc <= P.stage_cap;
     P.read_soff[r] = (uint32_t)sbase;
-    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the warp kernel
+    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next tier
     if (fits)
       for (uint32_t i = 0; i < nc; ++i) {
-        P.stage_tid[sbase + i] = tt[i * kFastBlock + tx];
-        P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)tc[i * kFastBlock + tx]);
+        P.stage_tid[sbase + i] = tt[i * BLOCK + tx];
+        P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)tc[i * BLOCK + tx]);
       }
   }
   if (P.work) {
@@ -472,6 +513,20 @@ __global__ void __launch_bounds__(kFastBlock) vote_fast_kernel(const __grid_cons
     __syncthreads();
     if (tx < 3 && s_work[tx]) atomicAdd(P.work + tx, (unsigned long long)s_work[tx]);
   }
+}
+
+template <typename CT>
+static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
+  constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
+  constexpr size_t smA = (size_t)capA * blkA * (4 + sizeof(CT)), smB = (size_t)capB * blkB * (4 + sizeof(CT));
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(vote_fast_kernel<CT, capA, blkA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+    cudaFuncSetAttribute(vote_fast_kernel<CT, capB, blkB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
+    attr = true;
+  }
+  vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
+  vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
 }
 
 // large-table path: one warp per worker, scratch in global memory
@@ -539,24 +594,10 @@ void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches) {
   uint32_t grid = (uint32_t)(sm_count * per_sm);
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
-  {
-    const uint32_t fgrid = (p.n_reads + kFastBlock - 1) / kFastBlock;
-    if (p.nk <= 4) {
-      const size_t fsm = (size_t)kFastCap * kFastBlock * 8;
-      vote_fast_kernel<uint32_t><<<fgrid, kFastBlock, fsm, s>>>(p);
-    } else {
-      const size_t fsm = (size_t)kFastCap * kFastBlock * 12;
-      static bool attr = false;
-      if (!attr) {
-        cudaFuncSetAttribute(vote_fast_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
-        attr = true;
-      }
-      vote_fast_kernel<unsigned long long><<<fgrid, kFastBlock, fsm, s>>>(p);
-    }
-  }
+  if (p.nk <= 4) launch_fast_tiers<uint32_t>(p, s); else launch_fast_tiers<unsigned long long>(p, s);
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
   vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
-  if (launches) *launches += 3;
+  if (launches) *launches += 4;
 }
 
 }  // namespace sq

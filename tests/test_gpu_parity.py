@@ -152,6 +152,24 @@ def test_overflow_path_many_transcripts(gpu_lib, sqb, port):
     np.testing.assert_allclose(pi, opi, rtol=RTOL)
 
 
+def test_unsorted_posting_lists(gpu_lib, sqb, port):
+    """the reference's index file lists transcripts under a hash in arbitrary order"""
+    d = dataset()
+    ks = [31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    keys, off, tids = postings[31]
+    rng = np.random.default_rng(0)
+    shuffled = tids.copy()
+    for i in range(len(keys)):
+        seg = shuffled[int(off[i]):int(off[i + 1])]
+        rng.shuffle(seg)
+    off1, tid1, score1, pi1, *_ = _gpu_quant(sqb, d, ks, {31: (keys, off, shuffled)})
+    off0, tid0, score0, pi0, *_ = _gpu_quant(sqb, d, ks, postings)
+    assert off1.tolist() == off0.tolist() and tid1.tolist() == tid0.tolist() and score1.tolist() == score0.tolist()
+    assert pi1.tolist() == pi0.tolist()
+
+
 def test_edge_cases(gpu_lib, sqb, port):
     thr = port.threshold(SKETCH)
     d = dataset()
