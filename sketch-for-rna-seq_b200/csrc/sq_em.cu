@@ -84,6 +84,59 @@ __global__ void sum_u16_kernel(const uint16_t* __restrict__ cnt, uint64_t n, uns
   if (lane_id() == 0 && s) atomicAdd(out, s);
 }
 
+// ------------------------------------------------------------------ EM read order
+// EM does not care which read is which, so reads are renumbered by their best candidate (the first one:
+// highest score, lowest id).  Reads of one gene then sit next to each other and the transcript-major pass
+// gathers 1/den from a narrow, almost sequentially visited range instead of all over a 160 MB array.
+__global__ void top_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                               const uint32_t* __restrict__ cand_tid, uint32_t T, uint64_t* __restrict__ keys) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const uint32_t b = read_off[r], e = read_off[r + 1];
+  keys[r] = (r << 32) | (b < e ? cand_tid[b] : T);  // reads without candidates go last
+}
+
+__global__ void order_counts_kernel(const uint64_t* __restrict__ sorted, uint64_t n_reads,
+                                    const uint32_t* __restrict__ read_off, uint32_t* __restrict__ cnt) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  const uint32_t r = (uint32_t)(sorted[i] >> 32);
+  cnt[i] = read_off[r + 1] - read_off[r];
+}
+
+__global__ void permute_pairs_kernel(const uint64_t* __restrict__ sorted, uint64_t n_reads,
+                                     const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ new_off,
+                                     const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                     uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  const uint32_t r = (uint32_t)(sorted[i] >> 32);
+  const uint32_t b = read_off[r], n = read_off[r + 1] - b, d = new_off[i];
+  for (uint32_t j = 0; j < n; ++j) {
+    out_tid[d + j] = cand_tid[b + j];
+    out_score[d + j] = cand_score[b + j];
+  }
+}
+
+void launch_top_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint32_t T, uint64_t* keys,
+                     cudaStream_t s, uint64_t* launches) {
+  if (!n_reads) return;
+  top_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, T, keys);
+  if (launches) ++*launches;
+}
+
+void launch_permute(const uint64_t* sorted, uint64_t n_reads, const uint32_t* read_off, uint32_t* cnt,
+                    uint32_t* new_off, uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score,
+                    uint32_t* out_tid, int32_t* out_score, cudaStream_t s, uint64_t* launches) {
+  if (!n_reads) return;
+  const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
+  order_counts_kernel<<<grid, 256, 0, s>>>(sorted, n_reads, read_off, cnt);
+  launch_exclusive_scan(cnt, new_off, (uint32_t)n_reads, scan_tmp, s, launches);
+  permute_pairs_kernel<<<grid, 256, 0, s>>>(sorted, n_reads, read_off, new_off, cand_tid, cand_score, out_tid,
+                                            out_score);
+  if (launches) *launches += 2;
+}
+
 // ------------------------------------------------------------------ transcript-major view
 __global__ void make_sort_keys_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                                       const uint32_t* __restrict__ cand_tid, uint64_t* __restrict__ keys) {

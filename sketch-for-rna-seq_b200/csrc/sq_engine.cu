@@ -134,7 +134,7 @@ struct sq_engine {
   uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
-      read_tmp, partial, block_change, misc, numreads, present, scan_tmp;
+      read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score;
   int em_iterations = 0;
   // sq_sketch / sq_build_postings scratch
   Slot tap;
@@ -572,7 +572,7 @@ void sq_destroy(sq_engine* e) {
   DevBuf* all[] = {&e->big_keys, &e->big_cnt, &e->big_list, &e->big_set, &e->big_cand, &e->keys_a, &e->keys_b,
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
-                   &e->numreads, &e->present, &e->scan_tmp};
+                   &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
@@ -887,9 +887,32 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_CUDA(e, e->vals_b.ensure((P + 1) * 4));
     SQ_CUDA(e, e->tm_read.ensure((P + 1) * 4));
     SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(P) * 4));
+    // EM read order: renumber reads by best candidate (locality of the 1/den gathers, see sq_em.cu)
+    SQ_CUDA(e, e->em_off.ensure((R + 2) * 4));
+    SQ_CUDA(e, e->em_cnt.ensure((R + 1) * 4));
+    SQ_CUDA(e, e->em_tid.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
+    if (R) {
+      SQ_CUDA(e, e->keys_a.ensure((std::max(P, R) + 1) * 8));
+      SQ_CUDA(e, e->keys_b.ensure((std::max(P, R) + 1) * 8));
+      SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(std::max(P, R)) * 4));
+      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R)) * 4));
+      launch_top_keys(e->read_off, R, e->cand_tid, T, e->keys_a.as<uint64_t>(), st, &e->launches);
+      uint64_t* sorted = nullptr;
+      uint32_t* dummy = nullptr;
+      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
+                        (int)std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1)), e->sort_tmp.as<uint32_t>(), &sorted,
+                        &dummy, st, &e->launches);
+      launch_permute(sorted, R, e->read_off, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(),
+                     e->scan_tmp.as<uint32_t>(), e->cand_tid, e->cand_score, e->em_tid.as<uint32_t>(),
+                     e->em_score.as<int32_t>(), st, &e->launches);
+    } else {
+      SQ_CUDA(e, cudaMemsetAsync(e->em_off.p, 0, 4, st));
+    }
     if (P) {
-      launch_make_sort_keys(e->read_off, R, e->cand_tid, e->keys_a.as<uint64_t>(), st, &e->launches);
-      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->cand_score, P * 4, cudaMemcpyDeviceToDevice, st));
+      launch_make_sort_keys(e->em_off.as<uint32_t>(), R, e->em_tid.as<uint32_t>(), e->keys_a.as<uint64_t>(), st,
+                            &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->em_score.p, P * 4, cudaMemcpyDeviceToDevice, st));
     }
     const int nbits = (int)std::max<uint32_t>(1, log2_ceil(T));
     launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
@@ -913,9 +936,9 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   SQ_CUDA(e, e->block_change.ensure(((size_t)(T + 255) / 256 + 1) * 8));
 
   EmView v;
-  v.read_off = e->read_off;
-  v.cand_tid = e->cand_tid;
-  v.cand_score = e->cand_score;
+  v.read_off = e->em_off.as<uint32_t>();
+  v.cand_tid = e->em_tid.as<uint32_t>();
+  v.cand_score = e->em_score.as<int32_t>();
   v.n_reads = R;
   v.toff = e->toff.as<uint32_t>();
   v.tm_read = e->tm_read.as<uint32_t>();

@@ -41,6 +41,11 @@ void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const u
                     uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s, uint64_t* launches);
 void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
+void launch_top_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint32_t T, uint64_t* keys,
+                     cudaStream_t s, uint64_t* launches);
+void launch_permute(const uint64_t* sorted, uint64_t n_reads, const uint32_t* read_off, uint32_t* cnt,
+                    uint32_t* new_off, uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score,
+                    uint32_t* out_tid, int32_t* out_score, cudaStream_t s, uint64_t* launches);
 void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
                            cudaStream_t s, uint64_t* launches);
 void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, uint32_t* toff, uint32_t* tm_read,
