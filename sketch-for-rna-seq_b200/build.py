@@ -66,5 +66,27 @@ def build(verbose=False, force=False):
     return LIB
 
 
+HOST_SOURCES = ["main.cpp", "index_file.cpp", "fastx.cpp"]
+HOST_BIN = os.path.join(ROOT, "build", "test")  # the reference's executable name (build.sh:29)
+
+
+def build_host():
+    """C++17 command-line host (drop-in for the reference's ./build/test), linked against libsketchquant.so"""
+    hdir = os.path.join(HERE, "host")
+    srcs = [os.path.join(hdir, f) for f in HOST_SOURCES]
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".hpp")] + \
+        [os.path.join(ROOT, "include", "sketchquant.h"), LIB]
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    if not _newer(deps, HOST_BIN):
+        return HOST_BIN
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-pthread", "-Wall"] + srcs + \
+        ["-L" + HERE, "-lsketchquant", "-Wl,-rpath,$ORIGIN/../sketch-for-rna-seq_b200", "-o", HOST_BIN]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        raise RuntimeError("host build failed:\n%s\n%s" % (p.stdout, p.stderr))
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_host())

@@ -1,0 +1,82 @@
+"""End to end through the drop-in command line on the GPU: `build/test -o index` + `-o quant` against the
+reference PROGRAM (oracle/_ref/ref_test) on the same FASTA/FASTQ, including index files exchanged both ways."""
+import os
+import subprocess
+
+import pytest
+
+import oracle_py
+from datasets import dataset
+from test_cli_host import TRICKY_FASTQ
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "build", "test")
+REF = oracle_py.REF_BIN
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists(REF)), reason="binaries not built")]
+
+MARKERS = ["Index loaded from", "Loading index completed", "Loading read completed", "Sparse chaining completed",
+           "EM estimation completed", "Read assignment completed", "Output written to"]
+
+
+def read_csv(path):
+    lines = open(path).read().splitlines()
+    assert lines[0] == "Name,NumReads,EM_Abundance"
+    return {l.split(",")[0]: (float(l.split(",")[1]), float(l.split(",")[2])) for l in lines[1:]}
+
+
+def assert_csv_equal(a, b):
+    assert set(a) == set(b)
+    for k in a:
+        # both programs print 6 significant digits
+        assert a[k][0] == pytest.approx(b[k][0], rel=2e-5), k
+        assert a[k][1] == pytest.approx(b[k][1], rel=2e-5), k
+
+
+def write_inputs(tmp_path, d, extra_fastq=b""):
+    fa, fq = str(tmp_path / "t.fa"), str(tmp_path / "r.fq")
+    with open(fa, "wb") as f:
+        for nm, s in zip(d["names"], d["tseqs"]):
+            f.write(b">" + nm.encode() + b" gene\n")
+            for i in range(0, len(s), 70):
+                f.write(s[i:i + 70] + b"\n")
+    with open(fq, "wb") as f:
+        for i, s in enumerate(d["reads"]):
+            f.write(b"@q%d/1\n" % i + s + b"\n+\n" + b"F" * len(s) + b"\n")
+        f.write(extra_fastq)
+    return fa, fq
+
+
+@pytest.mark.parametrize("klist", ["31", "21,25,31"])
+def test_cli_matches_reference_program(gpu_lib, tmp_path, klist):
+    d = dataset(n_genes=60, n_reads=1500, seed=13)
+    fa, fq = write_inputs(tmp_path, d, TRICKY_FASTQ)
+    p = {n: str(tmp_path / n) for n in ("ours.idx", "ref.idx", "oo.csv", "rr.csv", "or.csv", "ro.csv")}
+    o = subprocess.run([OURS, "-k", klist, "-o", "index", fa, p["ours.idx"]], capture_output=True, text=True)
+    assert o.returncode == 0 and "Index built in" in o.stdout and "Index saved to " + p["ours.idx"] in o.stdout
+    subprocess.run([REF, "-k", klist, "-o", "index", fa, p["ref.idx"]], check=True, capture_output=True)
+    # quant ignores -k (main.cpp:174): pass a wrong one on purpose
+    runs = [(OURS, "ours.idx", "oo.csv"), (REF, "ref.idx", "rr.csv"), (OURS, "ref.idx", "or.csv"), (REF, "ours.idx", "ro.csv")]
+    for exe, idx, csv in runs:
+        r = subprocess.run([exe, "-k", "99", "-o", "quant", p[idx], fq, p[csv]], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        pos = [r.stdout.find(m) for m in MARKERS]
+        assert all(x >= 0 for x in pos) and pos == sorted(pos), r.stdout
+    ref = read_csv(p["rr.csv"])
+    assert len(ref) > 20
+    for csv in ("oo.csv", "or.csv", "ro.csv"):
+        assert_csv_equal(read_csv(p[csv]), ref)
+
+
+def test_cli_report_and_default_mode(gpu_lib, tmp_path):
+    d = dataset(n_genes=30, n_reads=400, seed=5)
+    fa, fq = write_inputs(tmp_path, d)
+    idx, csv, rep = str(tmp_path / "i.idx"), str(tmp_path / "o.csv"), str(tmp_path / "rep.json")
+    subprocess.run([OURS, "-o", "index", fa, idx], check=True, capture_output=True)
+    # default mode is quant (main.cpp:214)
+    r = subprocess.run([OURS, "--report", rep, idx, fq, csv], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import json
+    j = json.load(open(rep))
+    assert j["reads_admitted"] == 400 and j["kernel_launches"] > 0 and j["transcripts"] == len(d["names"])
