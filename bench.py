@@ -234,6 +234,7 @@ def run_ours(args):
         uid = torch.from_numpy(eng.nccl_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
         dist.broadcast(uid, 0)
         eng.comm_init(world, rank, uid.cpu().numpy())
+        log("[bench] rank %d: NCCL communicator ready" % rank)
     n_reads = sum(c["n"] for c in chunks)
     n_bases = sum(c["bases"] for c in chunks)
     pi = torch.empty(T, dtype=torch.float64, pin_memory=True)
@@ -311,7 +312,9 @@ def run_ours(args):
     clocks.start()
     ms, wall, launches, stage = timed(step_device, args.steps, args.warmup, profile=True)
     clk = clocks.stop()
+    log("[bench] rank %d: device-resident %.2f ms/step" % (rank, ms / args.steps))
     ms_e2e, wall_e2e, _, _ = timed(step_host, args.steps, max(args.warmup, 1))
+    log("[bench] rank %d: host-buffer e2e %.2f ms/step" % (rank, ms_e2e / args.steps))
     total_reads = n_reads * world
     value = total_reads * args.steps / (ms / 1e3)
     e2e_value = total_reads * args.steps / (max(ms_e2e, 0.0) / 1e3)
@@ -429,7 +432,13 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_ours(a)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
