@@ -372,7 +372,7 @@ def run_ours(args):
         "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps,
         "clocks": clk, "roofline": roofline, "em_iterations": iters,
         "work": {k2: int(st[k2]) for k2 in ("reads", "sketch_hashes", "queries", "hits", "postings", "pairs",
-                                            "mid_reads", "slow_reads", "overflow_reads", "batches")},
+                                            "mid_reads", "slow_reads", "overflow_reads", "batches", "em_classes", "em_class_pairs")},
     }
 
     if rank == 0 and not args.no_cpu_baseline:

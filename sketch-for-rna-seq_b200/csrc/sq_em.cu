@@ -84,57 +84,111 @@ __global__ void sum_u16_kernel(const uint16_t* __restrict__ cnt, uint64_t n, uns
   if (lane_id() == 0 && s) atomicAdd(out, s);
 }
 
-// ------------------------------------------------------------------ EM read order
-// EM does not care which read is which, so reads are renumbered by their best candidate (the first one:
-// highest score, lowest id).  Reads of one gene then sit next to each other and the transcript-major pass
-// gathers 1/den from a narrow, almost sequentially visited range instead of all over a 160 MB array.
-__global__ void top_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
-                               const uint32_t* __restrict__ cand_tid, uint32_t T, uint64_t* __restrict__ keys) {
+// ------------------------------------------------------------------ EM equivalence classes
+// EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
+// contribute identical terms, so they are collapsed into one class with a weight.  Reads are
+// sorted by (best candidate, hash of the list); a read starts a class when its list differs from its
+// predecessor's (lists are compared, the hash only brings equal lists together).  Sorting by best candidate
+// first also keeps the classes of one gene adjacent, which makes the 1/den gathers of the transcript-major
+// pass local.  Summing w identical terms becomes one multiplication by w: a re-association only.
+__global__ void class_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                                 const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                 uint32_t T, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = read_off[r], e = read_off[r + 1];
-  keys[r] = (r << 32) | (b < e ? cand_tid[b] : T);  // reads without candidates go last
+  uint64_t h = 0xcbf29ce484222325ull ^ (e - b);
+  for (uint32_t j = b; j < e; ++j) {
+    h ^= ((uint64_t)cand_tid[j] << 32) | (uint32_t)cand_score[j];
+    h *= 0x100000001b3ull;
+    h ^= h >> 31;
+  }
+  const uint64_t top = b < e ? cand_tid[b] : T;  // reads without candidates go last (one empty class)
+  keys[r] = (top << 32) | (uint32_t)(h ^ (h >> 32));
+  vals[r] = (uint32_t)r;
 }
 
-__global__ void order_counts_kernel(const uint64_t* __restrict__ sorted, uint64_t n_reads,
-                                    const uint32_t* __restrict__ read_off, uint32_t* __restrict__ cnt) {
+__global__ void class_head_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ order,
+                                  uint64_t n_reads, const uint32_t* __restrict__ read_off,
+                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                  uint32_t* __restrict__ head) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
-  const uint32_t r = (uint32_t)(sorted[i] >> 32);
-  cnt[i] = read_off[r + 1] - read_off[r];
+  uint32_t h = 1;
+  if (i > 0 && keys[i] == keys[i - 1]) {
+    const uint32_t r = order[i], q = order[i - 1];
+    const uint32_t b = read_off[r], n = read_off[r + 1] - b, bq = read_off[q];
+    if (read_off[q + 1] - bq == n) {
+      h = 0;
+      for (uint32_t j = 0; j < n; ++j)
+        if (cand_tid[b + j] != cand_tid[bq + j] || cand_score[b + j] != cand_score[bq + j]) { h = 1; break; }
+    }
+  }
+  head[i] = h;
 }
 
-__global__ void permute_pairs_kernel(const uint64_t* __restrict__ sorted, uint64_t n_reads,
-                                     const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ new_off,
-                                     const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                     uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score) {
+// class c = run of sorted positions starting at a head: its list is the head's, its weight the run length
+__global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ cid,
+                                  const uint32_t* __restrict__ order, uint64_t n_reads,
+                                  const uint32_t* __restrict__ read_off, uint32_t* __restrict__ class_read,
+                                  uint32_t* __restrict__ class_pos, uint32_t* __restrict__ class_cnt) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
-  const uint32_t r = (uint32_t)(sorted[i] >> 32);
-  const uint32_t b = read_off[r], n = read_off[r + 1] - b, d = new_off[i];
+  if (head[i]) {
+    const uint32_t c = cid[i], r = order[i];
+    class_read[c] = r;
+    class_pos[c] = (uint32_t)i;
+    class_cnt[c] = read_off[r + 1] - read_off[r];
+  }
+  if (i == n_reads - 1) class_pos[cid[n_reads]] = (uint32_t)n_reads;  // cid[n_reads] = number of classes
+}
+
+__global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, const uint32_t* __restrict__ class_pos,
+                                    const uint32_t* __restrict__ class_off, uint32_t n_classes,
+                                    const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ cand_tid,
+                                    const int32_t* __restrict__ cand_score, uint32_t* __restrict__ out_tid,
+                                    int32_t* __restrict__ out_score, double* __restrict__ weight) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  const uint32_t r = class_read[c];
+  const uint32_t b = read_off[r], n = read_off[r + 1] - b, d = class_off[c];
   for (uint32_t j = 0; j < n; ++j) {
     out_tid[d + j] = cand_tid[b + j];
     out_score[d + j] = cand_score[b + j];
   }
+  weight[c] = (double)(class_pos[c + 1] - class_pos[c]);
 }
 
-void launch_top_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint32_t T, uint64_t* keys,
-                     cudaStream_t s, uint64_t* launches) {
+void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
+                       uint32_t T, uint64_t* keys, uint32_t* vals, cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
-  top_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, T, keys);
+  class_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, cand_score, T, keys,
+                                                                     vals);
   if (launches) ++*launches;
 }
 
-void launch_permute(const uint64_t* sorted, uint64_t n_reads, const uint32_t* read_off, uint32_t* cnt,
-                    uint32_t* new_off, uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score,
-                    uint32_t* out_tid, int32_t* out_score, cudaStream_t s, uint64_t* launches) {
+// heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + class table (read, position, count)
+void launch_class_heads(const uint64_t* keys, const uint32_t* order, uint64_t n_reads, const uint32_t* read_off,
+                        const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* head, uint32_t* cid,
+                        uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
+                        cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  order_counts_kernel<<<grid, 256, 0, s>>>(sorted, n_reads, read_off, cnt);
-  launch_exclusive_scan(cnt, new_off, (uint32_t)n_reads, scan_tmp, s, launches);
-  permute_pairs_kernel<<<grid, 256, 0, s>>>(sorted, n_reads, read_off, new_off, cand_tid, cand_score, out_tid,
-                                            out_score);
+  class_head_kernel<<<grid, 256, 0, s>>>(keys, order, n_reads, read_off, cand_tid, cand_score, head);
+  launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
+  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, order, n_reads, read_off, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;
+}
+
+void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
+                         const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
+                         double* weight, cudaStream_t s, uint64_t* launches) {
+  launch_exclusive_scan(class_cnt, class_off, n_classes, scan_tmp, s, launches);
+  if (!n_classes) return;
+  class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, read_off,
+                                                              cand_tid, cand_score, out_tid, out_score, weight);
+  if (launches) ++*launches;
 }
 
 // ------------------------------------------------------------------ transcript-major view
@@ -189,15 +243,16 @@ __global__ void em_init_kernel(double* pi, uint32_t T, uint32_t* state) {
 // per read: den = sum_j pi[t_j]*s_j in candidate order; inv = 1/den when den > 1e-10 (:36-45), else 0
 __global__ void em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                               const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                              const double* __restrict__ pi, double* __restrict__ inv_den,
-                              const uint32_t* __restrict__ state) {
+                              const double* __restrict__ pi, const double* __restrict__ weight,
+                              double* __restrict__ inv_den, const uint32_t* __restrict__ state) {
   if (state[0]) return;
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = read_off[r], e = read_off[r + 1];
   double den = 0.0;
   for (uint32_t j = b; j < e; ++j) den += pi[cand_tid[j]] * (double)cand_score[j];
-  inv_den[r] = den > 1e-10 ? 1.0 / den : 0.0;
+  // a class of w identical reads adds w identical posteriors: fold w into the reciprocal (exact for w = 1)
+  inv_den[r] = den > 1e-10 ? (1.0 / den) * weight[r] : 0.0;
 }
 
 // one warp per segment of <= seg pairs of one transcript: partial posterior sum (:46-49)
@@ -288,8 +343,9 @@ __global__ void as_tot_kernel(const uint32_t* __restrict__ read_off, uint64_t n_
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
-                                  const double* __restrict__ tot, const double* __restrict__ pi,
-                                  double* __restrict__ partial, uint32_t* __restrict__ present_u32) {
+                                  const double* __restrict__ tot, const double* __restrict__ weight,
+                                  const double* __restrict__ pi, double* __restrict__ partial,
+                                  uint32_t* __restrict__ present_u32) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= n_seg) return;
   const uint32_t t = seg_tid[w];
@@ -298,9 +354,10 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
   double acc = 0.0;
   bool any = false;
   for (uint32_t j = b + lane_id(); j < e; j += 32) {
-    const double tt = tot[tm_read[j]];
+    const uint32_t c = tm_read[j];
+    const double tt = tot[c];
     if (tt > 0.0) {
-      acc += (p * (double)(int32_t)tm_score[j]) / tt;  // :90 divides per term
+      acc += ((p * (double)(int32_t)tm_score[j]) / tt) * weight[c];  // :90 divides per term; w identical reads
       any = true;
     }
   }
@@ -344,7 +401,7 @@ void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uin
 void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches) {
   if (v.n_reads) {
     em_den_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
-                                                                      v.cand_score, v.pi, v.read_tmp, v.state);
+                                                                      v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
@@ -372,7 +429,7 @@ void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cud
   }
   if (v.n_seg) {
     as_partial_kernel<<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial,
+        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
         present_u32);
     if (launches) ++*launches;
   }

@@ -134,7 +134,9 @@ struct sq_engine {
   uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
-      read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score;
+      read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score,
+      cls_head, cls_id, cls_read, cls_pos, cls_weight;
+  uint64_t n_classes_last = 0, n_cpairs_last = 0;
   int em_iterations = 0;
   // sq_sketch / sq_build_postings scratch
   Slot tap;
@@ -572,7 +574,8 @@ void sq_destroy(sq_engine* e) {
   DevBuf* all[] = {&e->big_keys, &e->big_cnt, &e->big_list, &e->big_set, &e->big_cand, &e->keys_a, &e->keys_b,
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
-                   &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score};
+                   &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score,
+                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
@@ -874,7 +877,7 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   // ---- transcript-major copy of the pairs: stable radix sort on the transcript id ----
   uint64_t* keys = nullptr;
   uint32_t* vals = nullptr;
-  uint32_t n_seg = 0;
+  uint32_t n_seg = 0, n_classes = 0, n_cpairs = 0;
   {
     StageScope sc(e, 3);
     SQ_CUDA(e, e->toff.ensure(((size_t)T + 1) * 4));
@@ -887,38 +890,55 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_CUDA(e, e->vals_b.ensure((P + 1) * 4));
     SQ_CUDA(e, e->tm_read.ensure((P + 1) * 4));
     SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(P) * 4));
-    // EM read order: renumber reads by best candidate (locality of the 1/den gathers, see sq_em.cu)
+    // equivalence classes of reads (identical candidate lists), ordered by best candidate (see sq_em.cu)
     SQ_CUDA(e, e->em_off.ensure((R + 2) * 4));
-    SQ_CUDA(e, e->em_cnt.ensure((R + 1) * 4));
+    SQ_CUDA(e, e->em_cnt.ensure((R + 2) * 4));
     SQ_CUDA(e, e->em_tid.ensure((P + 1) * 4));
     SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->cls_head.ensure((R + 2) * 4));
+    SQ_CUDA(e, e->cls_id.ensure((R + 2) * 4));
+    SQ_CUDA(e, e->cls_read.ensure((R + 2) * 4));
+    SQ_CUDA(e, e->cls_pos.ensure((R + 2) * 4));
+    SQ_CUDA(e, e->cls_weight.ensure((R + 2) * 8));
     if (R) {
       SQ_CUDA(e, e->keys_a.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->keys_b.ensure((std::max(P, R) + 1) * 8));
+      SQ_CUDA(e, e->vals_a.ensure((std::max(P, R) + 1) * 4));
+      SQ_CUDA(e, e->vals_b.ensure((std::max(P, R) + 1) * 4));
       SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(std::max(P, R)) * 4));
-      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R)) * 4));
-      launch_top_keys(e->read_off, R, e->cand_tid, T, e->keys_a.as<uint64_t>(), st, &e->launches);
-      uint64_t* sorted = nullptr;
-      uint32_t* dummy = nullptr;
-      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
-                        (int)std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1)), e->sort_tmp.as<uint32_t>(), &sorted,
-                        &dummy, st, &e->launches);
-      launch_permute(sorted, R, e->read_off, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(),
-                     e->scan_tmp.as<uint32_t>(), e->cand_tid, e->cand_score, e->em_tid.as<uint32_t>(),
-                     e->em_score.as<int32_t>(), st, &e->launches);
+      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R + 1)) * 4));
+      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, e->keys_a.as<uint64_t>(),
+                        e->vals_a.as<uint32_t>(), st, &e->launches);
+      uint64_t* skeys = nullptr;
+      uint32_t* order = nullptr;
+      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
+                        e->vals_b.as<uint32_t>(), R, 32 + (int)std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1)),
+                        e->sort_tmp.as<uint32_t>(), &skeys, &order, st, &e->launches);
+      launch_class_heads(skeys, order, R, e->read_off, e->cand_tid, e->cand_score, e->cls_head.as<uint32_t>(),
+                         e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
+                         e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaStreamSynchronize(st));
+      launch_class_gather(e->cls_read.as<uint32_t>(), e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(),
+                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid,
+                          e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(),
+                          e->cls_weight.as<double>(), st, &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(&n_cpairs, e->em_off.as<uint32_t>() + n_classes, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaStreamSynchronize(st));
     } else {
       SQ_CUDA(e, cudaMemsetAsync(e->em_off.p, 0, 4, st));
     }
-    if (P) {
-      launch_make_sort_keys(e->em_off.as<uint32_t>(), R, e->em_tid.as<uint32_t>(), e->keys_a.as<uint64_t>(), st,
-                            &e->launches);
-      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->em_score.p, P * 4, cudaMemcpyDeviceToDevice, st));
+    if (n_cpairs) {
+      launch_make_sort_keys(e->em_off.as<uint32_t>(), n_classes, e->em_tid.as<uint32_t>(), e->keys_a.as<uint64_t>(),
+                            st, &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->em_score.p, (size_t)n_cpairs * 4, cudaMemcpyDeviceToDevice, st));
     }
     const int nbits = (int)std::max<uint32_t>(1, log2_ceil(T));
     launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
-                      e->vals_b.as<uint32_t>(), P, nbits, e->sort_tmp.as<uint32_t>(), &keys, &vals, st, &e->launches);
-    launch_tmajor(keys, P, T, e->em_seg, e->toff.as<uint32_t>(), e->tm_read.as<uint32_t>(), e->nseg.as<uint32_t>(),
-                  e->seg_off.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), st, &e->launches);
+                      e->vals_b.as<uint32_t>(), n_cpairs, nbits, e->sort_tmp.as<uint32_t>(), &keys, &vals, st,
+                      &e->launches);
+    launch_tmajor(keys, n_cpairs, T, e->em_seg, e->toff.as<uint32_t>(), e->tm_read.as<uint32_t>(),
+                  e->nseg.as<uint32_t>(), e->seg_off.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), st, &e->launches);
     SQ_CUDA(e, cudaMemcpyAsync(&n_seg, e->seg_off.as<uint32_t>() + T, 4, cudaMemcpyDeviceToHost, st));
     SQ_CUDA(e, cudaStreamSynchronize(st));
     SQ_CUDA(e, e->seg_tid.ensure(((size_t)n_seg + 1) * 4));
@@ -933,13 +953,16 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   SQ_CUDA(e, e->numreads.ensure((size_t)T * 8));
   SQ_CUDA(e, e->present.ensure((size_t)T * 4));
   SQ_CUDA(e, e->read_tmp.ensure((R + 1) * 8));
+  e->n_classes_last = n_classes;
+  e->n_cpairs_last = n_cpairs;
   SQ_CUDA(e, e->block_change.ensure(((size_t)(T + 255) / 256 + 1) * 8));
 
   EmView v;
   v.read_off = e->em_off.as<uint32_t>();
   v.cand_tid = e->em_tid.as<uint32_t>();
   v.cand_score = e->em_score.as<int32_t>();
-  v.n_reads = R;
+  v.n_reads = n_classes;
+  v.weight = e->cls_weight.as<double>();
   v.toff = e->toff.as<uint32_t>();
   v.tm_read = e->tm_read.as<uint32_t>();
   v.tm_score = vals;
@@ -1012,6 +1035,8 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->ms_items = e->ms[6];
   out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
   out->slow_reads = e->slow_total;
+  out->em_classes = e->n_classes_last;
+  out->em_class_pairs = e->n_cpairs_last;
   out->mid_reads = e->mid_total;
   return SQ_OK;
 }

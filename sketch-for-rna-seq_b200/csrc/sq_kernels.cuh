@@ -9,7 +9,8 @@ struct EmView {
   const uint32_t* read_off;
   const uint32_t* cand_tid;
   const int32_t* cand_score;
-  uint64_t n_reads;
+  uint64_t n_reads;           // rows of the CSR = equivalence classes of reads
+  const double* weight;       // reads per class
   // transcript-major copy, split into segments of <= seg pairs
   const uint32_t* toff;
   const uint32_t* tm_read;
@@ -41,11 +42,16 @@ void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const u
                     uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s, uint64_t* launches);
 void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
-void launch_top_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint32_t T, uint64_t* keys,
-                     cudaStream_t s, uint64_t* launches);
-void launch_permute(const uint64_t* sorted, uint64_t n_reads, const uint32_t* read_off, uint32_t* cnt,
-                    uint32_t* new_off, uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score,
-                    uint32_t* out_tid, int32_t* out_score, cudaStream_t s, uint64_t* launches);
+void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
+                       uint32_t T, uint64_t* keys, uint32_t* vals, cudaStream_t s, uint64_t* launches);
+void launch_class_heads(const uint64_t* keys, const uint32_t* order, uint64_t n_reads, const uint32_t* read_off,
+                        const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* head, uint32_t* cid,
+                        uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
+                        cudaStream_t s, uint64_t* launches);
+void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
+                         const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
+                         double* weight, cudaStream_t s, uint64_t* launches);
 void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
                            cudaStream_t s, uint64_t* launches);
 void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, uint32_t* toff, uint32_t* tm_read,

@@ -389,6 +389,12 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
       //     still unused top rows of the table (row CAP-1 downwards).  Without room the list is merged at once.
       uint32_t nh = 0;
       uint32_t* hit = tt + (CAP - 1) * BLOCK + tx;
+      // the probes of one read are independent: pull every bucket towards L2/L1 before the dependent loop, so
+      // the DRAM latencies overlap instead of adding up
+      for (uint32_t j = 0; j < n; ++j) {
+        const uint32_t b = (hs[j] * kHashMul) >> tb.shift;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.buckets + 2 * (size_t)b));
+      }
       for (uint32_t j = 0; j < n && !defer; ++j) {
         const uint32_t h = hs[j];
         bool dup = false;
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
         hit[-(int)(nd * BLOCK)] = off;
         wgt[-(int)(nd * BLOCK)] = (CT)w;
         ++nd;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.postings + off));
       }
       // (3) merge each distinct list once, last parked first, so the rows they occupy free up as the table grows
       for (uint32_t a = nd; a-- > 0 && !defer;) {
