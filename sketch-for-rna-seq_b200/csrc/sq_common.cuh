@@ -55,7 +55,7 @@ struct SketchParams {
 // bucketed open-addressing table: bucket = 4 keys (uint4) + 4 posting offsets (uint4), 32 B, one sector
 struct IndexTable {
   const uint4* buckets;     // 2*nb uint4
-  const uint32_t* postings; // transcript ids, last of each list flagged with SQ_LAST
+  const uint32_t* postings; // per list: length, then transcript ids ascending, the last one flagged with SQ_LAST
   uint32_t shift;           // 32 - log2(nb)
   uint32_t mask;            // nb - 1
   uint32_t present;         // 0: k-index has no map (sparse_chaining.cpp:51-53)

@@ -661,6 +661,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
           hkey[slot] = h;
           hval[slot] = (uint32_t)dpost.size();
           off32[i] = hval[slot];
+          dpost.push_back((uint32_t)(b1 - b0));  // header: list length, then the ids (last one flagged)
           for (uint64_t j = b0; j < b1; ++j) dpost.push_back(post_tid[j] | (j + 1 == b1 ? SQ_LAST : 0u));
           break;
         }
@@ -668,7 +669,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
           const uint32_t o = hval[slot];
           bool same = true;
           uint64_t j = b0;
-          for (uint32_t q = o;; ++q, ++j) {
+          for (uint32_t q = o + 1;; ++q, ++j) {
             const uint32_t v = dpost[q];
             if (j >= b1 || (v & ~SQ_LAST) != post_tid[j]) { same = false; break; }
             if (v & SQ_LAST) { same = (j + 1 == b1); break; }

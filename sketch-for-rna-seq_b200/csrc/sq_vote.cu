@@ -148,6 +148,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
           ++work[0];
           if (off != SQ_EMPTY) {
             ++work[1];
+            ++off;  // skip the length header
             uint32_t t;
             do {
               t = __ldg(tb.postings + off++);
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
   // merge one posting list (ascending transcript ids) into the sorted table with weight `add`
   auto merge_list = [&](const IndexTable& tb, uint32_t off, CT add, uint32_t w, uint32_t room) {
     uint32_t p = 0, t;
+    ++off;  // skip the length header
     do {
       t = __ldg(tb.postings + off++);
       const uint32_t tid = t & ~SQ_LAST;
@@ -522,6 +524,251 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ warp-per-32-reads path (short reads)
+// Thread-per-read voting wastes most issue slots on divergence: reads differ in their number of hashes,
+// posting lists differ in length, candidate lists differ in size, and a warp always runs to the longest.
+// Here a warp owns a TILE of 32 consecutive reads and every data-dependent loop is FLATTENED over the tile:
+// the hashes of all 32 reads are dealt out to the lanes evenly for the table probes, then the posting
+// elements of all 32 reads (prefix sum of the list lengths, which the index stores in a header word) for the
+// vote into per-read shared-memory hash tables (atomics), then the surviving candidates for the ranking that
+// orders each read's list (score desc, transcript asc).  Only short bookkeeping stays "lane = read".
+// Tables are slot-major ([slot][read]), so lane=read accesses are bank-conflict free.
+// Reads with several items, more than kTileMaxHashes hashes for a k, more than kTileMaxLists distinct posting
+// lists or more than kTileMaxFill distinct transcripts go to the thread-per-read tier through mid_list.
+// Counts are packed 8 bits per k (nk <= 4).
+static constexpr int kTileWarps = 4;
+static constexpr uint32_t kTileSlots = 32;      // hash-table slots per read
+static constexpr uint32_t kTileMaxFill = 24;
+static constexpr uint32_t kTileMaxHashes = 16;  // selected hashes per (read, k)
+static constexpr uint32_t kTileMaxLists = 8;    // distinct posting lists per (read, k)
+
+struct TileSmem {
+  uint32_t key[kTileSlots][32];        // transcript id per slot, later the ordered candidate ids
+  uint32_t cnt[kTileSlots][32];        // packed votes, later 0x7FFFFFFF-score of the candidates
+  uint32_t ho[kTileMaxHashes][32];     // posting offset per hash; rows < kTileMaxLists are reused for the distinct lists
+  uint32_t llw[kTileMaxLists][32];     // list length (low 16 bits) | weight (high 16 bits)
+  uint16_t hh[kTileMaxHashes][32];     // low 16 bits of each hash (duplicate pre-filter)
+  uint32_t fill[32];
+};
+
+// owner of flattened element e: number of lanes whose inclusive prefix is <= e
+__device__ __forceinline__ uint32_t tile_owner(uint32_t incl, uint32_t e) {
+  uint32_t q = 0;
+#pragma unroll
+  for (int step = 16; step; step >>= 1) {
+    const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (q + step - 1) & 31);
+    if (t <= e) q += step;
+  }
+  return q;
+}
+
+__global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid_constant__ VoteParams P) {
+  extern __shared__ __align__(16) unsigned char tile_smem_raw[];
+  TileSmem& S = reinterpret_cast<TileSmem*>(tile_smem_raw)[threadIdx.x >> 5];
+  const uint32_t lane = lane_id();
+  const uint32_t nk = P.nk;
+  const uint32_t n_tiles = (P.n_reads + 31) / 32;
+  uint32_t wq = 0, wh = 0, wp = 0;
+
+  for (uint32_t tile = blockIdx.x * kTileWarps + (threadIdx.x >> 5); tile < n_tiles; tile += gridDim.x * kTileWarps) {
+    const uint32_t r = tile * 32 + lane;
+    const bool valid = r < P.n_reads;
+#pragma unroll
+    for (uint32_t sl = 0; sl < kTileSlots; ++sl) { S.key[sl][lane] = SQ_EMPTY; S.cnt[sl][lane] = 0; }
+    S.fill[lane] = 0;
+    bool defer = false;
+    uint32_t item0 = 0, boff = 0, tq = 0, th = 0;
+    if (valid) {
+      item0 = P.item_start[r];
+      if (P.item_start[r + 1] - item0 != 1) defer = true;
+      boff = P.base_off[r] - P.bias;
+    }
+    for (uint32_t ki = 0; ki < nk; ++ki) {
+      const IndexTable& tb = P.tab[ki];
+      if (!tb.present) continue;
+      uint32_t n = 0;
+      if (valid && !defer) {
+        n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
+        if (n > kTileMaxHashes) { defer = true; n = 0; }
+      }
+      // ---- flattened over the tile's hashes: probe the index table
+      {
+        const uint32_t incl = warp_incl_scan(n);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t* sel = P.sel + (uint64_t)ki * P.slot_stride;
+        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+          const uint32_t e = e0 + lane;
+          const uint32_t q = tile_owner(incl, e);
+          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - n, q & 31);
+          const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, boff, q & 31);
+          if (e < total) {
+            const uint32_t j = e - base;
+            const uint32_t h = sel[qoff + j];
+            S.hh[j][q] = (uint16_t)h;
+            S.ho[j][q] = probe(tb, h);
+          }
+        }
+      }
+      __syncwarp();
+      // ---- lane = read: drop duplicate hashes (the sketch is a set), group hits that share a posting list
+      uint32_t nd = 0, nel = 0;
+      if (n) {
+        const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
+        for (uint32_t j = 0; j < n; ++j) {
+          const uint32_t off = S.ho[j][lane];
+          const uint16_t h16 = S.hh[j][lane];
+          bool dup = false;
+          for (uint32_t jj = 0; jj < j; ++jj)
+            if (S.hh[jj][lane] == h16) dup |= hs[jj] == hs[j];  // exact check only when 16 bits agree
+          if (dup) continue;
+          ++tq;
+          if (off == SQ_EMPTY) continue;
+          ++th;
+          uint32_t i = 0;
+          for (; i < nd; ++i)
+            if (S.ho[i][lane] == off) break;  // rows [0, nd) of ho hold the distinct lists (nd <= j)
+          if (i < nd) {
+            S.llw[i][lane] += 1u << 16;
+          } else if (nd < kTileMaxLists) {
+            S.ho[nd][lane] = off;
+            S.llw[nd][lane] = 1u << 16;
+            ++nd;
+          } else {
+            defer = true;
+            break;
+          }
+        }
+        if (defer) nd = 0;
+        for (uint32_t i = 0; i < nd; ++i) {  // list lengths from the header words (independent loads)
+          const uint32_t len = __ldg(tb.postings + S.ho[i][lane]);
+          if (len > 0xFFFFu) { defer = true; break; }
+          S.llw[i][lane] |= len;
+          nel += len;
+        }
+        if (defer) { nd = 0; nel = 0; }
+      }
+      __syncwarp();
+      // ---- flattened over the tile's posting elements: vote into the owner's table
+      {
+        const uint32_t incl = warp_incl_scan(nel);
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+          const uint32_t e = e0 + lane;
+          const uint32_t q = tile_owner(incl, e);
+          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - nel, q & 31);
+          if (e < total) {
+            uint32_t idx = e - base, i = 0, lw = S.llw[0][q];
+            while (idx >= (lw & 0xFFFFu)) { idx -= lw & 0xFFFFu; lw = S.llw[++i][q]; }
+            const uint32_t tid = __ldg(tb.postings + S.ho[i][q] + 1 + idx) & ~SQ_LAST;
+            const uint32_t add = (lw >> 16) << (8 * ki);
+            uint32_t sl = (tid * kHashMul) >> 27;
+            for (uint32_t tries = 0; tries < kTileSlots; ++tries) {
+              const uint32_t old = atomicCAS(&S.key[sl][q], SQ_EMPTY, tid);
+              if (old == SQ_EMPTY) atomicAdd(&S.fill[q], 1u);
+              if (old == SQ_EMPTY || old == tid) { atomicAdd(&S.cnt[sl][q], add); break; }
+              sl = (sl + 1) & (kTileSlots - 1);
+            }
+            wp += lw >> 16;
+          }
+        }
+      }
+      __syncwarp();
+      if (S.fill[lane] > kTileMaxFill) defer = true;
+    }
+    // ---- lane = read: per-k maximum, threshold filter, score; survivors compacted to slots [0, nc)
+    uint32_t nc = 0;
+    if (valid && !defer) {
+      uint32_t mx = 0;
+#pragma unroll 4
+      for (uint32_t sl = 0; sl < kTileSlots; ++sl) {
+        const uint32_t c = S.cnt[sl][lane];
+        uint32_t m2 = 0;
+        for (uint32_t ki = 0; ki < nk; ++ki) {
+          const uint32_t a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
+          m2 |= (a > b ? a : b) << (8 * ki);
+        }
+        mx = m2;
+      }
+      double thr[4];
+#pragma unroll
+      for (int ki = 0; ki < 4; ++ki) thr[ki] = P.fraction * (double)(int)((mx >> (8 * ki)) & 255);  // :84-87
+#pragma unroll 4
+      for (uint32_t sl = 0; sl < kTileSlots; ++sl) {
+        const uint32_t tid = S.key[sl][lane];
+        const uint32_t c = S.cnt[sl][lane];
+        bool ok = tid != SQ_EMPTY;
+        uint32_t score = 0;
+#pragma unroll
+        for (int ki = 0; ki < 4; ++ki)
+          if (ki < (int)nk) {
+            const int cc = (int)((c >> (8 * ki)) & 255);
+            if ((double)cc < thr[ki]) ok = false;  // counts_vec[i] < thresholds[i], :95
+            score += (uint32_t)cc;
+          }
+        if (ok) {  // nc <= sl: the slot written has already been consumed
+          S.key[nc][lane] = tid;
+          S.cnt[nc][lane] = 0x7FFFFFFFu - score;
+          ++nc;
+        }
+      }
+    }
+    if (valid && !defer) { wq += tq; wh += th; }  // deferred reads are recounted by the next tier
+    // hand reads that did not fit to the thread-per-read tier
+    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
+    if (dmask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(P.mid_count, (uint32_t)__popc(dmask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (valid && defer) P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+    }
+    // one staging allocation per tile
+    const uint32_t cincl = warp_incl_scan(nc);
+    const uint32_t ctot = __shfl_sync(0xFFFFFFFFu, cincl, 31);
+    unsigned long long tbase = 0;
+    if (lane == 0 && ctot) tbase = atomicAdd(P.stage_cursor, (unsigned long long)ctot);
+    tbase = __shfl_sync(0xFFFFFFFFu, tbase, 0);
+    const bool fits = tbase + ctot <= P.stage_cap;
+    if (valid) {
+      P.read_soff[r] = (uint32_t)(tbase + (cincl - nc));
+      P.read_cnt[r] = (fits && !defer) ? nc : 0u;
+    }
+    __syncwarp();
+    // ---- flattened over the tile's candidates: rank inside the owner's list = position in the ordered output
+    if (fits)
+      for (uint32_t e0 = 0; e0 < ctot; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const uint32_t q = tile_owner(cincl, e);
+        const uint32_t base = __shfl_sync(0xFFFFFFFFu, cincl - nc, q & 31);
+        const uint32_t qn = __shfl_sync(0xFFFFFFFFu, nc, q & 31);
+        if (e < ctot) {
+          const uint32_t idx = e - base;
+          const uint32_t inv = S.cnt[idx][q], tid = S.key[idx][q];
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < qn; ++j) {
+            const uint32_t pi = S.cnt[j][q], pt = S.key[j][q];
+            rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
+          }
+          P.stage_tid[tbase + base + rank] = tid;
+          P.stage_score[tbase + base + rank] = (int32_t)(0x7FFFFFFFu - inv);
+        }
+      }
+    __syncwarp();
+  }
+  if (P.work) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
+      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
+      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
+    }
+    if (lane == 0) {
+      if (wq) atomicAdd(P.work + 0, (unsigned long long)wq);
+      if (wh) atomicAdd(P.work + 1, (unsigned long long)wh);
+      if (wp) atomicAdd(P.work + 2, (unsigned long long)wp);
+    }
+  }
+}
+
 template <typename CT>
 static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
   constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
@@ -532,9 +779,26 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
     cudaFuncSetAttribute(vote_fast_kernel<CT, capB, blkB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
     attr = true;
   }
-  vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
+  if (p.nk <= 4) {
+    // warp-per-32-reads tile kernel first (persistent grid), what does not fit goes to the CAP=48 thread tier
+    static int tile_grid = 0;
+    if (!tile_grid) {
+      int dev = 0, sms = 0, per_sm = 1;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(vote_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) * kTileWarps));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_tile_kernel, kTileWarps * 32, sizeof(TileSmem) * kTileWarps);
+      tile_grid = sms * (per_sm < 1 ? 1 : per_sm);
+    }
+    const uint32_t need = ((p.n_reads + 31) / 32 + kTileWarps - 1) / kTileWarps;
+    vote_tile_kernel<<<need < (uint32_t)tile_grid ? need : (uint32_t)tile_grid, kTileWarps * 32,
+                       sizeof(TileSmem) * kTileWarps, s>>>(p);
+  } else {
+    vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
+  }
   vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
 }
+
 
 // large-table path: one warp per worker, scratch in global memory
 __global__ void __launch_bounds__(32) vote_overflow_kernel(const __grid_constant__ VoteParams P) {
