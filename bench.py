@@ -36,6 +36,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def apply_workload(args):
+    """non-default configs of BASELINE.json (parity-test / sweep cases, not the headline line)"""
+    global K_LIST, READ_LEN, SKETCH
+    SKETCH = float(np.float32(args.sketch))
+    if args.workload == "long":
+        READ_LEN = None
+        if args.fragments == 10_000_000:
+            args.fragments = 500_000  # config 4: 1 M long reads
+        args.chunk = min(args.chunk, 1 << 16)
+    elif args.workload == "multik":
+        K_LIST = [21, 25, 31]
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -48,6 +61,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=1 << 21, help="reads per pushed batch")
     ap.add_argument("--trace", action="store_true", help="print host wall time of every C-ABI call of one step")
+    ap.add_argument("--workload", default="short", choices=["short", "long", "multik"],
+                    help="short = config 2 (the headline line); long = config 4 (ONT-like 1-10 kb, 5%% error); "
+                         "multik = config 5 (-k 21,25,31)")
+    ap.add_argument("--sketch", type=float, default=0.05, help="FracMinHash scale factor (config 5 sweep)")
     return ap.parse_args()
 
 
@@ -114,7 +131,8 @@ def make_workload(args, device, rank, want_host=True):
     n_reads = 2 * args.fragments
     chunks = []
     t0 = time.time()
-    for ch in syn.simulate_reads(tx, n_reads, READ_LEN, seed=1000 + rank, err=0.005, chunk=args.chunk):
+    sim = dict(read_len=READ_LEN, err=0.005) if READ_LEN else dict(long_reads=(1000, 10000), err=0.05)
+    for ch in syn.simulate_reads(tx, n_reads, seed=1000 + rank, chunk=args.chunk, **sim):
         words, boff, ln = syn.pack_ragged(ch["codes"], ch["r_off"], align=4)
         c = {"words": words, "boff": boff, "len": ln, "n": ln.numel(), "bases": int(ch["r_off"][-1])}
         if want_host:
@@ -229,7 +247,8 @@ def run_ours(args):
     eng.set_stream(stream.cuda_stream)
     t0 = time.time()
     postings = build_index_gpu(eng, tx, T)
-    log("[bench] index: %d keys, %d postings (%.1fs)" % (postings[31][0].shape[0], postings[31][2].shape[0], time.time() - t0))
+    log("[bench] index: %s keys, %s postings (%.1fs)" % ([int(postings[k][0].shape[0]) for k in K_LIST],
+                                                         [int(postings[k][2].shape[0]) for k in K_LIST], time.time() - t0))
     if world > 1:
         uid = torch.from_numpy(eng.nccl_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
         dist.broadcast(uid, 0)
@@ -328,6 +347,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
     nk = len(K_LIST)
+    n_kmers = sum(n_bases - n_reads * (k - 1) for k in K_LIST)
     b_sketch = n_bases / 4 + 12 * n_reads + 4 * st["sketch_hashes"] + 4 * n_reads * nk
     b_vote = (12 + 2 * nk) * n_reads + 4 * st["sketch_hashes"] + (4 + 8) * st["queries"] + 4 * st["postings"] \
         + 8 * st["pairs"] + 8 * n_reads
@@ -349,7 +369,7 @@ def run_ours(args):
                 "kernels": {n: {"ms_per_step": round(v["ms"], 4), "GBps": v["gbs"] and round(v["gbs"], 1),
                                 "frac": v["frac"] and round(v["frac"], 4)} for n, v in kern.items()},
                 "stage_ms_per_step": {k2: round(v / S, 4) for k2, v in stage.items() if k2.startswith("ms_")},
-                "sketch_gkmers_per_s": (n_bases - n_reads * (K_LIST[0] - 1)) / (kern["sketch_kernel"]["ms"] / 1e3) / 1e9
+                "sketch_gkmers_per_s": n_kmers / (kern["sketch_kernel"]["ms"] / 1e3) / 1e9
                 if kern["sketch_kernel"]["ms"] > 0 else None}
 
     out = {
@@ -357,15 +377,20 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 hash / f64 EM",
         "data": "synthetic",
-        "config": {"workload": "config 2: synthetic human-scale transcriptome, 10M simulated 2x150 bp fragments per GPU "
-                               "(both mates as forward-strand records), k=31, scale 0.05, chain 0.9, EM 20 iterations",
+        "config": {"workload": {"short": "config 2: synthetic human-scale transcriptome, 10M simulated 2x150 bp fragments per GPU "
+                                         "(both mates as forward-strand records), k=31, scale 0.05, chain 0.9, EM 20 iterations",
+                                "long": "config 4: same transcriptome, ONT-like forward-strand reads 1-10 kb (log-uniform, clipped to "
+                                        "the transcript), 5% substitutions, k=31",
+                                "multik": "config 5: same transcriptome and short reads, index -k 21,25,31, scale %g" % args.sketch}[args.workload],
                    "transcripts": T, "transcriptome_mbp": round(float(tx["t_off"][-1]) / 1e6, 1),
-                   "reads_per_gpu": n_reads, "read_len": READ_LEN, "k": K_LIST, "index_keys": int(postings[31][0].shape[0]),
-                   "index_postings": int(postings[31][2].shape[0]), "candidate_pairs": int(st["pairs"]),
+                   "reads_per_gpu": n_reads, "read_len": READ_LEN or "1000-10000", "bases_per_gpu": n_bases, "k": K_LIST,
+                   "sketch_scale": args.sketch,
+                   "index_keys": [int(postings[k][0].shape[0]) for k in K_LIST],
+                   "index_postings": [int(postings[k][2].shape[0]) for k in K_LIST], "candidate_pairs": int(st["pairs"]),
                    "l2_policy": "inputs (%.0f MB packed reads + %.0f MB index table) larger than the 126 MB L2"
-                                % (n_bases / 4 / 1e6, 32 * (1 << int(np.ceil(np.log2(max(postings[31][0].shape[0] / 2, 2))))) / 1e6),
+                                % (n_bases / 4 / 1e6, sum(32 * (1 << int(np.ceil(np.log2(max(postings[k][0].shape[0] / 2, 2))))) for k in K_LIST) / 1e6),
                    "parallelism": "reads sharded across %d GPU(s), index replicated, NCCL all-reduce of T-vectors" % world},
-        "gkmers_per_s": (n_bases - n_reads * (K_LIST[0] - 1)) * world * args.steps / (ms / 1e3) / 1e9,
+        "gkmers_per_s": n_kmers * world * args.steps / (ms / 1e3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(sum(c["h_words"].numel() * 4 + 8 * c["n"] for c in chunks)),
                 "d2h_bytes_per_step": int(T * 17), "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
                 "input": "2-bit packed reads in pinned host memory (sq_push_reads)"},
@@ -407,7 +432,7 @@ def run_reference(args):
     blob = sqb.synth.codes_to_ascii(tx["codes"])
     soff = tx["t_off"].cpu().numpy().astype(np.uint64)
     postings = {k: port.build_postings(blob, soff, k, max(K_LIST), port.threshold(SKETCH)) for k in K_LIST}
-    log("[bench] CPU index build: %d keys (%.1fs)" % (postings[31][0].shape[0], time.time() - t0))
+    log("[bench] CPU index build: %s keys (%.1fs)" % ([int(postings[k][0].shape[0]) for k in K_LIST], time.time() - t0))
     tmp = tempfile.mkdtemp(prefix="sqbench")
     fq = os.path.join(tmp, "sample.fq")
     ns = write_sample_fastq(chunks[0], args.cpu_sample, fq)
@@ -432,6 +457,7 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    apply_workload(a)
     try:
         if a.impl == "reference":
             run_reference(a)
