@@ -107,11 +107,11 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32
                            uint64_t* launches);
 size_t scan_tmp_words(uint32_t n);
 
-// stable LSD radix sort of (key64, val32) pairs on bits [0, nbits); buffers are ping-ponged, the result
-// pointers are returned through *keys_out / *vals_out (one of the two buffers each)
+// stable LSD radix sort of (key64, val32) pairs (vals may be NULL) on bits [bit_lo, bit_lo+nbits); buffers are
+// ping-ponged, the result pointers are returned through *keys_out / *vals_out (one of the two buffers each)
 void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n,
                        int nbits, uint32_t* hist_tmp, uint64_t** keys_out, uint32_t** vals_out, cudaStream_t s,
-                       uint64_t* launches);
+                       uint64_t* launches, int bit_lo = 0);
 size_t radix_tmp_words(uint64_t n);
 
 }  // namespace sq

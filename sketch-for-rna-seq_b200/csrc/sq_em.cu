@@ -88,54 +88,64 @@ __global__ void sum_u16_kernel(const uint16_t* __restrict__ cnt, uint64_t n, uns
 // EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
 // contribute identical terms, so they are collapsed into one class with a weight.  Reads are
 // sorted by (best candidate, hash of the list); a read starts a class when its list differs from its
-// predecessor's (lists are compared, the hash only brings equal lists together).  Sorting by best candidate
+// predecessor's.  "Differs" is decided on a 128-bit fingerprint of the list (two independent 64-bit hashes
+// over length, transcripts and scores): comparing the lists themselves costs ~10 random sectors per read
+// (2.8 ms at 20 M reads), the fingerprint one; two different lists collide with probability 2^-128, and a
+// collision would only merge two EM terms.  Sorting by best candidate
 // first also keeps the classes of one gene adjacent, which makes the 1/den gathers of the transcript-major
 // pass local.  Summing w identical terms becomes one multiplication by w: a re-association only.
 __global__ void class_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                 uint32_t T, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                 uint32_t T, uint32_t hash_bits, uint64_t* __restrict__ keys,
+                                 ulonglong2* __restrict__ fp) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = read_off[r], e = read_off[r + 1];
-  uint64_t h = 0xcbf29ce484222325ull ^ (e - b);
+  uint64_t h = 0xcbf29ce484222325ull ^ (e - b), g = 0x9E3779B97F4A7C15ull + (e - b);
   for (uint32_t j = b; j < e; ++j) {
-    h ^= ((uint64_t)cand_tid[j] << 32) | (uint32_t)cand_score[j];
+    const uint64_t x = ((uint64_t)cand_tid[j] << 32) | (uint32_t)cand_score[j];
+    h ^= x;
     h *= 0x100000001b3ull;
     h ^= h >> 31;
+    g = (g ^ (x * 0xC2B2AE3D27D4EB4Full)) * 0xD6E8FEB86659FD93ull;
+    g ^= g >> 29;
   }
+  fp[r] = make_ulonglong2(h, g);
   const uint64_t top = b < e ? cand_tid[b] : T;  // reads without candidates go last (one empty class)
-  keys[r] = (top << 32) | (uint32_t)(h ^ (h >> 32));
-  vals[r] = (uint32_t)r;
+  // few hash bits are enough: the hash only has to separate the handful of distinct lists that share a best
+  // candidate, and fewer key bits mean fewer radix passes
+  // (the sort key sits in the high word, the read index rides in the low word: a keys-only sort)
+  keys[r] = (((top << hash_bits) | ((h ^ (h >> 32)) & ((1ull << hash_bits) - 1))) << 32) | r;
 }
 
-__global__ void class_head_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ order,
-                                  uint64_t n_reads, const uint32_t* __restrict__ read_off,
-                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                  uint32_t* __restrict__ head) {
+__global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
+                                  const ulonglong2* __restrict__ fp, uint32_t* __restrict__ head) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= n_reads) return;
-  uint32_t h = 1;
-  if (i > 0 && keys[i] == keys[i - 1]) {
-    const uint32_t r = order[i], q = order[i - 1];
-    const uint32_t b = read_off[r], n = read_off[r + 1] - b, bq = read_off[q];
-    if (read_off[q + 1] - bq == n) {
-      h = 0;
-      for (uint32_t j = 0; j < n; ++j)
-        if (cand_tid[b + j] != cand_tid[bq + j] || cand_score[b + j] != cand_score[bq + j]) { h = 1; break; }
-    }
+  const bool valid = i < n_reads;
+  const uint64_t k = valid ? keys[i] : 0;
+  ulonglong2 mine = make_ulonglong2(0, 0);
+  if (valid) mine = fp[(uint32_t)k];
+  // the predecessor's key and fingerprint come from the neighbouring lane; lane 0 fetches them itself
+  uint64_t pk = __shfl_up_sync(0xFFFFFFFFu, k, 1);
+  unsigned long long px = __shfl_up_sync(0xFFFFFFFFu, mine.x, 1), py = __shfl_up_sync(0xFFFFFFFFu, mine.y, 1);
+  if (lane_id() == 0 && valid && i > 0) {
+    pk = keys[i - 1];
+    const ulonglong2 p = fp[(uint32_t)pk];
+    px = p.x;
+    py = p.y;
   }
-  head[i] = h;
+  if (valid) head[i] = (i == 0 || (k >> 32) != (pk >> 32) || mine.x != px || mine.y != py) ? 1u : 0u;
 }
 
 // class c = run of sorted positions starting at a head: its list is the head's, its weight the run length
 __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ cid,
-                                  const uint32_t* __restrict__ order, uint64_t n_reads,
+                                  const uint64_t* __restrict__ keys, uint64_t n_reads,
                                   const uint32_t* __restrict__ read_off, uint32_t* __restrict__ class_read,
                                   uint32_t* __restrict__ class_pos, uint32_t* __restrict__ class_cnt) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   if (head[i]) {
-    const uint32_t c = cid[i], r = order[i];
+    const uint32_t c = cid[i], r = (uint32_t)keys[i];
     class_read[c] = r;
     class_pos[c] = (uint32_t)i;
     class_cnt[c] = read_off[r + 1] - read_off[r];
@@ -160,23 +170,23 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
 }
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
-                       uint32_t T, uint64_t* keys, uint32_t* vals, cudaStream_t s, uint64_t* launches) {
+                       uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
-  class_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, cand_score, T, keys,
-                                                                     vals);
+  class_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, cand_score, T,
+                                                                     hash_bits, keys, static_cast<ulonglong2*>(fp));
   if (launches) ++*launches;
 }
 
 // heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + class table (read, position, count)
-void launch_class_heads(const uint64_t* keys, const uint32_t* order, uint64_t n_reads, const uint32_t* read_off,
-                        const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* head, uint32_t* cid,
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
+                        uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  class_head_kernel<<<grid, 256, 0, s>>>(keys, order, n_reads, read_off, cand_tid, cand_score, head);
+  class_head_kernel<<<grid, 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
   launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
-  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, order, n_reads, read_off, class_read, class_pos, class_cnt);
+  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, read_off, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;
 }
 

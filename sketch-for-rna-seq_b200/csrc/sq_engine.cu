@@ -135,7 +135,7 @@ struct sq_engine {
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
       read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score,
-      cls_head, cls_id, cls_read, cls_pos, cls_weight;
+      cls_head, cls_id, cls_read, cls_pos, cls_weight, cls_fp;
   uint64_t n_classes_last = 0, n_cpairs_last = 0;
   int em_iterations = 0;
   // sq_sketch / sq_build_postings scratch
@@ -575,7 +575,7 @@ void sq_destroy(sq_engine* e) {
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
                    &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score,
-                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight};
+                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->cls_fp};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
@@ -908,14 +908,17 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, e->vals_b.ensure((std::max(P, R) + 1) * 4));
       SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(std::max(P, R)) * 4));
       SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R + 1)) * 4));
-      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, e->keys_a.as<uint64_t>(),
-                        e->vals_a.as<uint32_t>(), st, &e->launches);
+      const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1));
+      const uint32_t hash_bits = top_bits <= 18 ? 32 - top_bits : 32 - top_bits >= 8 ? 32 - top_bits : 0;
+      if (hash_bits == 0) return fail(e, SQ_ERR_CAPACITY, "more than 2^24 transcripts are not supported");
+      SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
+      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
+                        e->cls_fp.p, st, &e->launches);
       uint64_t* skeys = nullptr;
-      uint32_t* order = nullptr;
-      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
-                        e->vals_b.as<uint32_t>(), R, 32 + (int)std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1)),
-                        e->sort_tmp.as<uint32_t>(), &skeys, &order, st, &e->launches);
-      launch_class_heads(skeys, order, R, e->read_off, e->cand_tid, e->cand_score, e->cls_head.as<uint32_t>(),
+      uint32_t* dummy = nullptr;
+      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
+                        (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
+      launch_class_heads(skeys, R, e->read_off, e->cls_fp.p, e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));

@@ -43,9 +43,9 @@ void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const u
 void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
-                       uint32_t T, uint64_t* keys, uint32_t* vals, cudaStream_t s, uint64_t* launches);
-void launch_class_heads(const uint64_t* keys, const uint32_t* order, uint64_t n_reads, const uint32_t* read_off,
-                        const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* head, uint32_t* cid,
+                       uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
+                        uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches);
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,

@@ -202,7 +202,7 @@ size_t radix_tmp_words(uint64_t n) {
 
 void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n, int nbits,
                        uint32_t* tmp, uint64_t** keys_out, uint32_t** vals_out, cudaStream_t s,
-                       uint64_t* launches) {
+                       uint64_t* launches, int bit_lo) {
   *keys_out = keys_a;
   *vals_out = vals_a;
   if (n == 0 || nbits <= 0) return;
@@ -216,10 +216,10 @@ void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uin
   uint32_t* vin = vals_a;
   uint32_t* vout = vals_b;
   for (int p = 0; p < npass; ++p) {
-    radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, n, 8 * p, ntiles, hist);
+    radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, n, bit_lo + 8 * p, ntiles, hist);
     if (launches) ++*launches;
     launch_exclusive_scan(hist, offs, 256 * ntiles, scan_tmp, s, launches);
-    radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, 8 * p, ntiles, offs);
+    radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, bit_lo + 8 * p, ntiles, offs);
     if (launches) ++*launches;
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;

@@ -608,19 +608,31 @@ __global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid
             S.ho[j][q] = probe(tb, h);
           }
         }
+        __syncwarp();
+        // the sketch is a set: a hash that already occurred earlier in the same read is marked (bit 31 of the
+        // offset; posting offsets stay below 2^31).  16 bits in shared memory pre-filter, exact check on a match.
+        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
+          const uint32_t e = e0 + lane;
+          const uint32_t q = tile_owner(incl, e);
+          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - n, q & 31);
+          const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, boff, q & 31);
+          if (e < total) {
+            const uint32_t j = e - base;
+            const uint16_t h16 = S.hh[j][q];
+            bool dup = false;
+            for (uint32_t jj = 0; jj < j; ++jj)
+              if (S.hh[jj][q] == h16) dup |= sel[qoff + jj] == sel[qoff + j];
+            if (dup) S.ho[j][q] = 0xFFFFFFFEu;
+          }
+        }
       }
       __syncwarp();
       // ---- lane = read: drop duplicate hashes (the sketch is a set), group hits that share a posting list
       uint32_t nd = 0, nel = 0;
       if (n) {
-        const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
         for (uint32_t j = 0; j < n; ++j) {
           const uint32_t off = S.ho[j][lane];
-          const uint16_t h16 = S.hh[j][lane];
-          bool dup = false;
-          for (uint32_t jj = 0; jj < j; ++jj)
-            if (S.hh[jj][lane] == h16) dup |= hs[jj] == hs[j];  // exact check only when 16 bits agree
-          if (dup) continue;
+          if (off == 0xFFFFFFFEu) continue;  // duplicate hash
           ++tq;
           if (off == SQ_EMPTY) continue;
           ++th;
@@ -689,9 +701,14 @@ __global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid
         }
         mx = m2;
       }
-      double thr[4];
+      // thresholds[i] = fraction * max_counts[i] (:84-87) and the test (double)count < threshold (:95).  For an
+      // integer count, count < x  <=>  count < ceil(x): one double multiply per k, integer compares per slot.
+      uint32_t ithr[4];
 #pragma unroll
-      for (int ki = 0; ki < 4; ++ki) thr[ki] = P.fraction * (double)(int)((mx >> (8 * ki)) & 255);  // :84-87
+      for (int ki = 0; ki < 4; ++ki) {
+        const double t = ceil(P.fraction * (double)(int)((mx >> (8 * ki)) & 255));
+        ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+      }
 #pragma unroll 4
       for (uint32_t sl = 0; sl < kTileSlots; ++sl) {
         const uint32_t tid = S.key[sl][lane];
@@ -701,9 +718,9 @@ __global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid
 #pragma unroll
         for (int ki = 0; ki < 4; ++ki)
           if (ki < (int)nk) {
-            const int cc = (int)((c >> (8 * ki)) & 255);
-            if ((double)cc < thr[ki]) ok = false;  // counts_vec[i] < thresholds[i], :95
-            score += (uint32_t)cc;
+            const uint32_t cc = (c >> (8 * ki)) & 255;
+            if (cc < ithr[ki]) ok = false;
+            score += cc;
           }
         if (ok) {  // nc <= sl: the slot written has already been consumed
           S.key[nc][lane] = tid;
