@@ -786,6 +786,259 @@ __global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------ 4 lanes per read (short reads)
+// Middle ground between one thread and one warp per read: a QUAD of 4 lanes owns a read, a warp 8 reads.
+// The read's hashes, the elements of each posting list and the table slots are dealt to the 4 lanes by
+// index (j % 4), so the loops of a warp run ceil(n/4) times with little spread, without the prefix sums and
+// owner searches of the tile kernel, and the per-warp shared memory is small enough (4.5 KB) for 48 resident
+// warps per SM.  Tables are [slot][quad]: lane g scanning slots g, g+4, ... is bank-conflict free.
+// Reads with several items, more than kQuadMaxHashes hashes for a k, more than kQuadMaxLists distinct lists
+// or more than kQuadMaxFill distinct transcripts go to the thread-per-read tier (mid_list).  nk <= 4.
+static constexpr int kQuadWarps = 4;
+static constexpr uint32_t kQuadSlots = 32;
+static constexpr uint32_t kQuadMaxFill = 24;
+static constexpr uint32_t kQuadMaxHashes = 16;
+static constexpr uint32_t kQuadMaxLists = 8;
+
+struct QuadSmem {
+  uint32_t key[kQuadSlots][8];
+  uint32_t cnt[kQuadSlots][8];
+  uint32_t ct[kQuadMaxFill][8];        // surviving candidates: transcript
+  uint32_t cs[kQuadMaxFill][8];        // surviving candidates: 0x7FFFFFFF - score
+  uint32_t ho[kQuadMaxHashes][8];      // posting offset per hash; rows < kQuadMaxLists reused for the distinct lists
+  uint32_t llw[kQuadMaxLists][8];      // list length (low 16 bits) | weight (high 16 bits)
+  uint16_t hh[kQuadMaxHashes][8];      // low 16 bits of each hash (duplicate pre-filter)
+};
+
+__global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid_constant__ VoteParams P) {
+  extern __shared__ __align__(16) unsigned char quad_smem_raw[];
+  QuadSmem& S = reinterpret_cast<QuadSmem*>(quad_smem_raw)[threadIdx.x >> 5];
+  const uint32_t lane = lane_id(), q = lane >> 2, g = lane & 3;
+  const uint32_t qmask = 0xFu << (q * 4);
+  const uint32_t nk = P.nk;
+  const uint32_t n_oct = (P.n_reads + 7) / 8;
+  uint32_t wq = 0, wh = 0, wp = 0;
+
+  for (uint32_t oct = blockIdx.x * kQuadWarps + (threadIdx.x >> 5); oct < n_oct; oct += gridDim.x * kQuadWarps) {
+    const uint32_t r = oct * 8 + q;
+    const bool valid = r < P.n_reads;
+#pragma unroll
+    for (uint32_t sl = g; sl < kQuadSlots; sl += 4) { S.key[sl][q] = SQ_EMPTY; S.cnt[sl][q] = 0; }
+    bool defer = false;
+    uint32_t item0 = 0, boff = 0, fill = 0, tq = 0, th = 0;
+    if (valid) {
+      item0 = P.item_start[r];
+      if (P.item_start[r + 1] - item0 != 1) defer = true;
+      boff = P.base_off[r] - P.bias;
+    }
+    __syncwarp();
+    for (uint32_t ki = 0; ki < nk; ++ki) {
+      const IndexTable& tb = P.tab[ki];
+      if (!tb.present) continue;
+      uint32_t n = 0;
+      if (valid && !defer) {
+        n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
+        if (n > kQuadMaxHashes) { defer = true; n = 0; }
+      }
+      const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
+      // ---- probe: lane g takes hashes g, g+4, ...
+      for (uint32_t j = g; j < n; j += 4) {
+        const uint32_t h = hs[j];
+        S.hh[j][q] = (uint16_t)h;
+        S.ho[j][q] = probe(tb, h);
+      }
+      __syncwarp();
+      // the sketch is a set: mark hashes that already occurred earlier in the read
+      for (uint32_t j = g; j < n; j += 4) {
+        const uint16_t h16 = S.hh[j][q];
+        bool dup = false;
+        for (uint32_t jj = 0; jj < j; ++jj)
+          if (S.hh[jj][q] == h16) dup |= hs[jj] == hs[j];
+        if (dup) S.ho[j][q] = 0xFFFFFFFEu;
+      }
+      __syncwarp();
+      // ---- lane 0 of the quad groups hits that share a posting list (rows [0, nd) of ho, nd <= j)
+      uint32_t nd = 0;
+      if (g == 0 && n) {
+        for (uint32_t j = 0; j < n; ++j) {
+          const uint32_t off = S.ho[j][q];
+          if (off == 0xFFFFFFFEu) continue;
+          ++tq;
+          if (off == SQ_EMPTY) continue;
+          ++th;
+          uint32_t i = 0;
+          for (; i < nd; ++i)
+            if (S.ho[i][q] == off) break;
+          if (i < nd) {
+            S.llw[i][q] += 1u << 16;
+          } else if (nd < kQuadMaxLists) {
+            S.ho[nd][q] = off;
+            S.llw[nd][q] = 1u << 16;
+            ++nd;
+          } else {
+            defer = true;
+            break;
+          }
+        }
+        if (defer) nd = 0;
+      }
+      nd = __shfl_sync(0xFFFFFFFFu, nd, q * 4);
+      defer = __shfl_sync(0xFFFFFFFFu, (int)defer, q * 4) != 0;
+      __syncwarp();
+      // ---- merge each distinct list into the read's table: lane g takes elements g, g+4, ... of the list.
+      //      Inside one list the transcripts are distinct, so only the slot claim needs an atomic.
+      for (uint32_t i = 0; i < nd; ++i) {
+        const uint32_t off = S.ho[i][q];
+        const uint32_t w = S.llw[i][q] >> 16;
+        const uint32_t len = __ldg(tb.postings + off);
+        const uint32_t add = w << (8 * ki);
+        for (uint32_t idx = g; idx < len; idx += 4) {
+          const uint32_t tid = __ldg(tb.postings + off + 1 + idx) & ~SQ_LAST;
+          uint32_t sl = (tid * kHashMul) >> 27;
+          uint32_t tries = 0;
+          for (; tries < kQuadSlots; ++tries) {
+            const uint32_t old = atomicCAS(&S.key[sl][q], SQ_EMPTY, tid);
+            if (old == SQ_EMPTY) ++fill;
+            if (old == SQ_EMPTY || old == tid) { S.cnt[sl][q] += add; break; }
+            sl = (sl + 1) & (kQuadSlots - 1);
+          }
+          if (tries == kQuadSlots) fill = 1000;  // table full
+          wp += w;
+        }
+        __syncwarp(qmask);
+      }
+      __syncwarp();
+    }
+    // distinct transcripts of the read = sum of the 4 lanes' claims
+    fill += __shfl_xor_sync(0xFFFFFFFFu, fill, 1);
+    fill += __shfl_xor_sync(0xFFFFFFFFu, fill, 2);
+    if (fill > kQuadMaxFill) defer = true;
+    // ---- per-k maximum over the table: lane g scans slots g, g+4, ...; combine inside the quad
+    uint32_t mx = 0;
+#pragma unroll
+    for (uint32_t sl = g; sl < kQuadSlots; sl += 4) {
+      const uint32_t c = S.cnt[sl][q];
+      uint32_t m2 = 0;
+#pragma unroll
+      for (int ki = 0; ki < 4; ++ki) {
+        const uint32_t a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
+        m2 |= (a > b ? a : b) << (8 * ki);
+      }
+      mx = m2;
+    }
+#pragma unroll
+    for (int d = 1; d <= 2; d <<= 1) {
+      const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
+      uint32_t m2 = 0;
+#pragma unroll
+      for (int ki = 0; ki < 4; ++ki) {
+        const uint32_t a = (o >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
+        m2 |= (a > b ? a : b) << (8 * ki);
+      }
+      mx = m2;
+    }
+    // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an integer
+    // count, count < x  <=>  count < ceil(x)
+    uint32_t ithr[4];
+#pragma unroll
+    for (int ki = 0; ki < 4; ++ki) {
+      const double t = ceil(P.fraction * (double)(int)((mx >> (8 * ki)) & 255));
+      ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+    }
+    // ---- survivors of my slots, compacted into the quad's candidate list (positions by a 4-lane prefix)
+    uint32_t mine = 0;  // bit m set: slot g+4m passes
+    uint32_t my_n = 0;
+    if (valid && !defer) {
+#pragma unroll
+      for (uint32_t m = 0; m < kQuadSlots / 4; ++m) {
+        const uint32_t sl = g + 4 * m;
+        const uint32_t c = S.cnt[sl][q];
+        bool ok = S.key[sl][q] != SQ_EMPTY;
+#pragma unroll
+        for (int ki = 0; ki < 4; ++ki)
+          if (ki < (int)nk && ((c >> (8 * ki)) & 255) < ithr[ki]) ok = false;
+        if (ok) { mine |= 1u << m; ++my_n; }
+      }
+    }
+    uint32_t pre = my_n;  // inclusive prefix inside the quad
+    {
+      const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, pre, 1);
+      if (g >= 1) pre += a;
+      const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, pre, 2);
+      if (g >= 2) pre += b;
+    }
+    const uint32_t nc = __shfl_sync(0xFFFFFFFFu, pre, q * 4 + 3);
+    {
+      uint32_t pos = pre - my_n;
+      for (uint32_t m = 0; m < kQuadSlots / 4; ++m)
+        if (mine & (1u << m)) {
+          const uint32_t sl = g + 4 * m;
+          const uint32_t c = S.cnt[sl][q];
+          uint32_t score = 0;
+#pragma unroll
+          for (int ki = 0; ki < 4; ++ki) score += (c >> (8 * ki)) & 255;
+          S.ct[pos][q] = S.key[sl][q];
+          S.cs[pos][q] = 0x7FFFFFFFu - score;
+          ++pos;
+        }
+    }
+    if (valid && !defer && g == 0) { wq += tq; wh += th; }
+    // hand reads that did not fit to the thread-per-read tier
+    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer && g == 0);
+    if (dmask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(P.mid_count, (uint32_t)__popc(dmask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (valid && defer && g == 0) P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+    }
+    // one staging allocation per warp (8 reads): exclusive prefix of nc over the quads
+    uint32_t qincl = g == 0 ? nc : 0;
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, qincl, d);
+      if ((int)lane >= d) qincl += t;
+    }
+    qincl = __shfl_sync(0xFFFFFFFFu, qincl, q * 4);      // inclusive prefix of my quad, on all its lanes
+    const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, qincl, 28);
+    unsigned long long wbase = 0;
+    if (lane == 0 && wtot) wbase = atomicAdd(P.stage_cursor, (unsigned long long)wtot);
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+    const bool fits = wbase + wtot <= P.stage_cap;
+    const unsigned long long rbase = wbase + (qincl - nc);
+    if (valid && g == 0) {
+      P.read_soff[r] = (uint32_t)rbase;
+      P.read_cnt[r] = (fits && !defer) ? nc : 0u;
+    }
+    __syncwarp();
+    // ---- order (score desc, transcript asc): lane g ranks candidates g, g+4, ... against the whole list
+    if (fits)
+      for (uint32_t c = g; c < nc; c += 4) {
+        const uint32_t inv = S.cs[c][q], tid = S.ct[c][q];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nc; ++j) {
+          const uint32_t pi = S.cs[j][q], pt = S.ct[j][q];
+          rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
+        }
+        P.stage_tid[rbase + rank] = tid;
+        P.stage_score[rbase + rank] = (int32_t)(0x7FFFFFFFu - inv);
+      }
+    __syncwarp();
+  }
+  if (P.work) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
+      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
+      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
+    }
+    if (lane == 0) {
+      if (wq) atomicAdd(P.work + 0, (unsigned long long)wq);
+      if (wh) atomicAdd(P.work + 1, (unsigned long long)wh);
+      if (wp) atomicAdd(P.work + 2, (unsigned long long)wp);
+    }
+  }
+}
+
 template <typename CT>
 static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
   constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
@@ -797,19 +1050,18 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
     attr = true;
   }
   if (p.nk <= 4) {
-    // warp-per-32-reads tile kernel first (persistent grid), what does not fit goes to the CAP=48 thread tier
+    // 4-lanes-per-read kernel first (persistent grid), what does not fit goes to the CAP=48 thread tier
     static int tile_grid = 0;
     if (!tile_grid) {
       int dev = 0, sms = 0, per_sm = 1;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(vote_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TileSmem) * kTileWarps));
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_tile_kernel, kTileWarps * 32, sizeof(TileSmem) * kTileWarps);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel, kQuadWarps * 32, sizeof(QuadSmem) * kQuadWarps);
       tile_grid = sms * (per_sm < 1 ? 1 : per_sm);
     }
-    const uint32_t need = ((p.n_reads + 31) / 32 + kTileWarps - 1) / kTileWarps;
-    vote_tile_kernel<<<need < (uint32_t)tile_grid ? need : (uint32_t)tile_grid, kTileWarps * 32,
-                       sizeof(TileSmem) * kTileWarps, s>>>(p);
+    const uint32_t need = ((p.n_reads + 7) / 8 + kQuadWarps - 1) / kQuadWarps;
+    vote_quad_kernel<<<need < (uint32_t)tile_grid ? need : (uint32_t)tile_grid, kQuadWarps * 32,
+                       sizeof(QuadSmem) * kQuadWarps, s>>>(p);
   } else {
     vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
   }
