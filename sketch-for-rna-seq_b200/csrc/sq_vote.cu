@@ -810,12 +810,13 @@ struct QuadSmem {
   uint16_t hh[kQuadMaxHashes][8];      // low 16 bits of each hash (duplicate pre-filter)
 };
 
+template <int NK>
 __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid_constant__ VoteParams P) {
   extern __shared__ __align__(16) unsigned char quad_smem_raw[];
   QuadSmem& S = reinterpret_cast<QuadSmem*>(quad_smem_raw)[threadIdx.x >> 5];
   const uint32_t lane = lane_id(), q = lane >> 2, g = lane & 3;
   const uint32_t qmask = 0xFu << (q * 4);
-  const uint32_t nk = P.nk;
+  constexpr uint32_t nk = NK;
   const uint32_t n_oct = (P.n_reads + 7) / 8;
   uint32_t wq = 0, wh = 0, wp = 0;
 
@@ -842,19 +843,36 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
       }
       const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
       // ---- probe: lane g takes hashes g, g+4, ...
+      unsigned long long m1 = 0, m2 = 0;  // which of 64 buckets (two independent 6-bit fields) my hashes fall in
+      bool maybe_dup = false;
       for (uint32_t j = g; j < n; j += 4) {
         const uint32_t h = hs[j];
         S.hh[j][q] = (uint16_t)h;
         S.ho[j][q] = probe(tb, h);
+        const unsigned long long b1 = 1ull << (h & 63), b2 = 1ull << ((h >> 6) & 63);
+        maybe_dup |= (m1 & b1) && (m2 & b2);
+        m1 |= b1;
+        m2 |= b2;
       }
+      // the sketch is a set: a hash that already occurred earlier in the read must not vote twice.  Equal
+      // hashes share both buckets, so the exact check runs only when some pair of hashes of the read does
+      // (about 1 % of the reads).
+#pragma unroll
+      for (int d = 1; d <= 2; d <<= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, d), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, d);
+        maybe_dup |= (m1 & o1) && (m2 & o2);
+        if (d == 1) { m1 |= o1; m2 |= o2; }  // pairs (0,1) and (2,3) merged, then compared across
+      }
+      maybe_dup = __ballot_sync(0xFFFFFFFFu, maybe_dup) & qmask;
       __syncwarp();
-      // the sketch is a set: mark hashes that already occurred earlier in the read
-      for (uint32_t j = g; j < n; j += 4) {
-        const uint16_t h16 = S.hh[j][q];
-        bool dup = false;
-        for (uint32_t jj = 0; jj < j; ++jj)
-          if (S.hh[jj][q] == h16) dup |= hs[jj] == hs[j];
-        if (dup) S.ho[j][q] = 0xFFFFFFFEu;
+      if (maybe_dup) {
+        for (uint32_t j = g; j < n; j += 4) {
+          const uint16_t h16 = S.hh[j][q];
+          bool dup = false;
+          for (uint32_t jj = 0; jj < j; ++jj)
+            if (S.hh[jj][q] == h16) dup |= hs[jj] == hs[j];
+          if (dup) S.ho[j][q] = 0xFFFFFFFEu;
+        }
       }
       __syncwarp();
       // ---- lane 0 of the quad groups hits that share a posting list (rows [0, nd) of ho, nd <= j)
@@ -920,7 +938,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
       const uint32_t c = S.cnt[sl][q];
       uint32_t m2 = 0;
 #pragma unroll
-      for (int ki = 0; ki < 4; ++ki) {
+      for (int ki = 0; ki < NK; ++ki) {
         const uint32_t a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
         m2 |= (a > b ? a : b) << (8 * ki);
       }
@@ -931,7 +949,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
       const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
       uint32_t m2 = 0;
 #pragma unroll
-      for (int ki = 0; ki < 4; ++ki) {
+      for (int ki = 0; ki < NK; ++ki) {
         const uint32_t a = (o >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
         m2 |= (a > b ? a : b) << (8 * ki);
       }
@@ -939,9 +957,9 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
     }
     // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an integer
     // count, count < x  <=>  count < ceil(x)
-    uint32_t ithr[4];
+    uint32_t ithr[NK];
 #pragma unroll
-    for (int ki = 0; ki < 4; ++ki) {
+    for (int ki = 0; ki < NK; ++ki) {
       const double t = ceil(P.fraction * (double)(int)((mx >> (8 * ki)) & 255));
       ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
     }
@@ -955,8 +973,8 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
         const uint32_t c = S.cnt[sl][q];
         bool ok = S.key[sl][q] != SQ_EMPTY;
 #pragma unroll
-        for (int ki = 0; ki < 4; ++ki)
-          if (ki < (int)nk && ((c >> (8 * ki)) & 255) < ithr[ki]) ok = false;
+        for (int ki = 0; ki < NK; ++ki)
+          if (((c >> (8 * ki)) & 255) < ithr[ki]) ok = false;
         if (ok) { mine |= 1u << m; ++my_n; }
       }
     }
@@ -976,7 +994,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
           const uint32_t c = S.cnt[sl][q];
           uint32_t score = 0;
 #pragma unroll
-          for (int ki = 0; ki < 4; ++ki) score += (c >> (8 * ki)) & 255;
+          for (int ki = 0; ki < NK; ++ki) score += (c >> (8 * ki)) & 255;
           S.ct[pos][q] = S.key[sl][q];
           S.cs[pos][q] = 0x7FFFFFFFu - score;
           ++pos;
@@ -1051,17 +1069,29 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
   }
   if (p.nk <= 4) {
     // 4-lanes-per-read kernel first (persistent grid), what does not fit goes to the CAP=48 thread tier
-    static int tile_grid = 0;
-    if (!tile_grid) {
+    static int quad_grid[5] = {0, 0, 0, 0, 0};
+    const int nkq = p.nk < 4 ? (int)p.nk : 4;
+    const size_t qsm = sizeof(QuadSmem) * kQuadWarps;
+    if (!quad_grid[nkq]) {
       int dev = 0, sms = 0, per_sm = 1;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel, kQuadWarps * 32, sizeof(QuadSmem) * kQuadWarps);
-      tile_grid = sms * (per_sm < 1 ? 1 : per_sm);
+      switch (nkq) {
+        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<1>, kQuadWarps * 32, qsm); break;
+        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<2>, kQuadWarps * 32, qsm); break;
+        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<3>, kQuadWarps * 32, qsm); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<4>, kQuadWarps * 32, qsm); break;
+      }
+      quad_grid[nkq] = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const uint32_t need = ((p.n_reads + 7) / 8 + kQuadWarps - 1) / kQuadWarps;
-    vote_quad_kernel<<<need < (uint32_t)tile_grid ? need : (uint32_t)tile_grid, kQuadWarps * 32,
-                       sizeof(QuadSmem) * kQuadWarps, s>>>(p);
+    const uint32_t qgrid = need < (uint32_t)quad_grid[nkq] ? need : (uint32_t)quad_grid[nkq];
+    switch (nkq) {
+      case 1: vote_quad_kernel<1><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      case 2: vote_quad_kernel<2><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      case 3: vote_quad_kernel<3><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      default: vote_quad_kernel<4><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+    }
   } else {
     vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
   }
