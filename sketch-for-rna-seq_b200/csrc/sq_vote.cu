@@ -524,276 +524,15 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
   }
 }
 
-// ------------------------------------------------------------------ warp-per-32-reads path (short reads)
-// Thread-per-read voting wastes most issue slots on divergence: reads differ in their number of hashes,
-// posting lists differ in length, candidate lists differ in size, and a warp always runs to the longest.
-// Here a warp owns a TILE of 32 consecutive reads and every data-dependent loop is FLATTENED over the tile:
-// the hashes of all 32 reads are dealt out to the lanes evenly for the table probes, then the posting
-// elements of all 32 reads (prefix sum of the list lengths, which the index stores in a header word) for the
-// vote into per-read shared-memory hash tables (atomics), then the surviving candidates for the ranking that
-// orders each read's list (score desc, transcript asc).  Only short bookkeeping stays "lane = read".
-// Tables are slot-major ([slot][read]), so lane=read accesses are bank-conflict free.
-// Reads with several items, more than kTileMaxHashes hashes for a k, more than kTileMaxLists distinct posting
-// lists or more than kTileMaxFill distinct transcripts go to the thread-per-read tier through mid_list.
-// Counts are packed 8 bits per k (nk <= 4).
-static constexpr int kTileWarps = 4;
-static constexpr uint32_t kTileSlots = 32;      // hash-table slots per read
-static constexpr uint32_t kTileMaxFill = 24;
-static constexpr uint32_t kTileMaxHashes = 16;  // selected hashes per (read, k)
-static constexpr uint32_t kTileMaxLists = 8;    // distinct posting lists per (read, k)
-
-struct TileSmem {
-  uint32_t key[kTileSlots][32];        // transcript id per slot, later the ordered candidate ids
-  uint32_t cnt[kTileSlots][32];        // packed votes, later 0x7FFFFFFF-score of the candidates
-  uint32_t ho[kTileMaxHashes][32];     // posting offset per hash; rows < kTileMaxLists are reused for the distinct lists
-  uint32_t llw[kTileMaxLists][32];     // list length (low 16 bits) | weight (high 16 bits)
-  uint16_t hh[kTileMaxHashes][32];     // low 16 bits of each hash (duplicate pre-filter)
-  uint32_t fill[32];
-};
-
-// owner of flattened element e: number of lanes whose inclusive prefix is <= e
-__device__ __forceinline__ uint32_t tile_owner(uint32_t incl, uint32_t e) {
-  uint32_t q = 0;
-#pragma unroll
-  for (int step = 16; step; step >>= 1) {
-    const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (q + step - 1) & 31);
-    if (t <= e) q += step;
-  }
-  return q;
-}
-
-__global__ void __launch_bounds__(kTileWarps * 32) vote_tile_kernel(const __grid_constant__ VoteParams P) {
-  extern __shared__ __align__(16) unsigned char tile_smem_raw[];
-  TileSmem& S = reinterpret_cast<TileSmem*>(tile_smem_raw)[threadIdx.x >> 5];
-  const uint32_t lane = lane_id();
-  const uint32_t nk = P.nk;
-  const uint32_t n_tiles = (P.n_reads + 31) / 32;
-  uint32_t wq = 0, wh = 0, wp = 0;
-
-  for (uint32_t tile = blockIdx.x * kTileWarps + (threadIdx.x >> 5); tile < n_tiles; tile += gridDim.x * kTileWarps) {
-    const uint32_t r = tile * 32 + lane;
-    const bool valid = r < P.n_reads;
-#pragma unroll
-    for (uint32_t sl = 0; sl < kTileSlots; ++sl) { S.key[sl][lane] = SQ_EMPTY; S.cnt[sl][lane] = 0; }
-    S.fill[lane] = 0;
-    bool defer = false;
-    uint32_t item0 = 0, boff = 0, tq = 0, th = 0;
-    if (valid) {
-      item0 = P.item_start[r];
-      if (P.item_start[r + 1] - item0 != 1) defer = true;
-      boff = P.base_off[r] - P.bias;
-    }
-    for (uint32_t ki = 0; ki < nk; ++ki) {
-      const IndexTable& tb = P.tab[ki];
-      if (!tb.present) continue;
-      uint32_t n = 0;
-      if (valid && !defer) {
-        n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
-        if (n > kTileMaxHashes) { defer = true; n = 0; }
-      }
-      // ---- flattened over the tile's hashes: probe the index table
-      {
-        const uint32_t incl = warp_incl_scan(n);
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        const uint32_t* sel = P.sel + (uint64_t)ki * P.slot_stride;
-        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-          const uint32_t e = e0 + lane;
-          const uint32_t q = tile_owner(incl, e);
-          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - n, q & 31);
-          const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, boff, q & 31);
-          if (e < total) {
-            const uint32_t j = e - base;
-            const uint32_t h = sel[qoff + j];
-            S.hh[j][q] = (uint16_t)h;
-            S.ho[j][q] = probe(tb, h);
-          }
-        }
-        __syncwarp();
-        // the sketch is a set: a hash that already occurred earlier in the same read is marked (bit 31 of the
-        // offset; posting offsets stay below 2^31).  16 bits in shared memory pre-filter, exact check on a match.
-        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-          const uint32_t e = e0 + lane;
-          const uint32_t q = tile_owner(incl, e);
-          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - n, q & 31);
-          const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, boff, q & 31);
-          if (e < total) {
-            const uint32_t j = e - base;
-            const uint16_t h16 = S.hh[j][q];
-            bool dup = false;
-            for (uint32_t jj = 0; jj < j; ++jj)
-              if (S.hh[jj][q] == h16) dup |= sel[qoff + jj] == sel[qoff + j];
-            if (dup) S.ho[j][q] = 0xFFFFFFFEu;
-          }
-        }
-      }
-      __syncwarp();
-      // ---- lane = read: drop duplicate hashes (the sketch is a set), group hits that share a posting list
-      uint32_t nd = 0, nel = 0;
-      if (n) {
-        for (uint32_t j = 0; j < n; ++j) {
-          const uint32_t off = S.ho[j][lane];
-          if (off == 0xFFFFFFFEu) continue;  // duplicate hash
-          ++tq;
-          if (off == SQ_EMPTY) continue;
-          ++th;
-          uint32_t i = 0;
-          for (; i < nd; ++i)
-            if (S.ho[i][lane] == off) break;  // rows [0, nd) of ho hold the distinct lists (nd <= j)
-          if (i < nd) {
-            S.llw[i][lane] += 1u << 16;
-          } else if (nd < kTileMaxLists) {
-            S.ho[nd][lane] = off;
-            S.llw[nd][lane] = 1u << 16;
-            ++nd;
-          } else {
-            defer = true;
-            break;
-          }
-        }
-        if (defer) nd = 0;
-        for (uint32_t i = 0; i < nd; ++i) {  // list lengths from the header words (independent loads)
-          const uint32_t len = __ldg(tb.postings + S.ho[i][lane]);
-          if (len > 0xFFFFu) { defer = true; break; }
-          S.llw[i][lane] |= len;
-          nel += len;
-        }
-        if (defer) { nd = 0; nel = 0; }
-      }
-      __syncwarp();
-      // ---- flattened over the tile's posting elements: vote into the owner's table
-      {
-        const uint32_t incl = warp_incl_scan(nel);
-        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-          const uint32_t e = e0 + lane;
-          const uint32_t q = tile_owner(incl, e);
-          const uint32_t base = __shfl_sync(0xFFFFFFFFu, incl - nel, q & 31);
-          if (e < total) {
-            uint32_t idx = e - base, i = 0, lw = S.llw[0][q];
-            while (idx >= (lw & 0xFFFFu)) { idx -= lw & 0xFFFFu; lw = S.llw[++i][q]; }
-            const uint32_t tid = __ldg(tb.postings + S.ho[i][q] + 1 + idx) & ~SQ_LAST;
-            const uint32_t add = (lw >> 16) << (8 * ki);
-            uint32_t sl = (tid * kHashMul) >> 27;
-            for (uint32_t tries = 0; tries < kTileSlots; ++tries) {
-              const uint32_t old = atomicCAS(&S.key[sl][q], SQ_EMPTY, tid);
-              if (old == SQ_EMPTY) atomicAdd(&S.fill[q], 1u);
-              if (old == SQ_EMPTY || old == tid) { atomicAdd(&S.cnt[sl][q], add); break; }
-              sl = (sl + 1) & (kTileSlots - 1);
-            }
-            wp += lw >> 16;
-          }
-        }
-      }
-      __syncwarp();
-      if (S.fill[lane] > kTileMaxFill) defer = true;
-    }
-    // ---- lane = read: per-k maximum, threshold filter, score; survivors compacted to slots [0, nc)
-    uint32_t nc = 0;
-    if (valid && !defer) {
-      uint32_t mx = 0;
-#pragma unroll 4
-      for (uint32_t sl = 0; sl < kTileSlots; ++sl) {
-        const uint32_t c = S.cnt[sl][lane];
-        uint32_t m2 = 0;
-        for (uint32_t ki = 0; ki < nk; ++ki) {
-          const uint32_t a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
-          m2 |= (a > b ? a : b) << (8 * ki);
-        }
-        mx = m2;
-      }
-      // thresholds[i] = fraction * max_counts[i] (:84-87) and the test (double)count < threshold (:95).  For an
-      // integer count, count < x  <=>  count < ceil(x): one double multiply per k, integer compares per slot.
-      uint32_t ithr[4];
-#pragma unroll
-      for (int ki = 0; ki < 4; ++ki) {
-        const double t = ceil(P.fraction * (double)(int)((mx >> (8 * ki)) & 255));
-        ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
-      }
-#pragma unroll 4
-      for (uint32_t sl = 0; sl < kTileSlots; ++sl) {
-        const uint32_t tid = S.key[sl][lane];
-        const uint32_t c = S.cnt[sl][lane];
-        bool ok = tid != SQ_EMPTY;
-        uint32_t score = 0;
-#pragma unroll
-        for (int ki = 0; ki < 4; ++ki)
-          if (ki < (int)nk) {
-            const uint32_t cc = (c >> (8 * ki)) & 255;
-            if (cc < ithr[ki]) ok = false;
-            score += cc;
-          }
-        if (ok) {  // nc <= sl: the slot written has already been consumed
-          S.key[nc][lane] = tid;
-          S.cnt[nc][lane] = 0x7FFFFFFFu - score;
-          ++nc;
-        }
-      }
-    }
-    if (valid && !defer) { wq += tq; wh += th; }  // deferred reads are recounted by the next tier
-    // hand reads that did not fit to the thread-per-read tier
-    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
-    if (dmask) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(P.mid_count, (uint32_t)__popc(dmask));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (valid && defer) P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
-    }
-    // one staging allocation per tile
-    const uint32_t cincl = warp_incl_scan(nc);
-    const uint32_t ctot = __shfl_sync(0xFFFFFFFFu, cincl, 31);
-    unsigned long long tbase = 0;
-    if (lane == 0 && ctot) tbase = atomicAdd(P.stage_cursor, (unsigned long long)ctot);
-    tbase = __shfl_sync(0xFFFFFFFFu, tbase, 0);
-    const bool fits = tbase + ctot <= P.stage_cap;
-    if (valid) {
-      P.read_soff[r] = (uint32_t)(tbase + (cincl - nc));
-      P.read_cnt[r] = (fits && !defer) ? nc : 0u;
-    }
-    __syncwarp();
-    // ---- flattened over the tile's candidates: rank inside the owner's list = position in the ordered output
-    if (fits)
-      for (uint32_t e0 = 0; e0 < ctot; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        const uint32_t q = tile_owner(cincl, e);
-        const uint32_t base = __shfl_sync(0xFFFFFFFFu, cincl - nc, q & 31);
-        const uint32_t qn = __shfl_sync(0xFFFFFFFFu, nc, q & 31);
-        if (e < ctot) {
-          const uint32_t idx = e - base;
-          const uint32_t inv = S.cnt[idx][q], tid = S.key[idx][q];
-          uint32_t rank = 0;
-          for (uint32_t j = 0; j < qn; ++j) {
-            const uint32_t pi = S.cnt[j][q], pt = S.key[j][q];
-            rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
-          }
-          P.stage_tid[tbase + base + rank] = tid;
-          P.stage_score[tbase + base + rank] = (int32_t)(0x7FFFFFFFu - inv);
-        }
-      }
-    __syncwarp();
-  }
-  if (P.work) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
-      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
-      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
-    }
-    if (lane == 0) {
-      if (wq) atomicAdd(P.work + 0, (unsigned long long)wq);
-      if (wh) atomicAdd(P.work + 1, (unsigned long long)wh);
-      if (wp) atomicAdd(P.work + 2, (unsigned long long)wp);
-    }
-  }
-}
-
 // ------------------------------------------------------------------ 4 lanes per read (short reads)
 // Middle ground between one thread and one warp per read: a QUAD of 4 lanes owns a read, a warp 8 reads.
 // The read's hashes, the elements of each posting list and the table slots are dealt to the 4 lanes by
-// index (j % 4), so the loops of a warp run ceil(n/4) times with little spread, without the prefix sums and
-// owner searches of the tile kernel, and the per-warp shared memory is small enough (4.5 KB) for 48 resident
-// warps per SM.  Tables are [slot][quad]: lane g scanning slots g, g+4, ... is bank-conflict free.
+// index (j % 4), so the loops of a warp run ceil(n/4) times with little spread, and the per-warp shared
+// memory is small enough (4.5 KB) for 48 resident warps per SM.  (A warp-per-32-reads variant with every loop
+// flattened over the tile by prefix sums was tried and was slower: 12 KB of tables per warp capped the
+// occupancy at 25 %, see profiles/r01_notes.md.)  Tables are [slot][quad]: lane g scanning slots g, g+4, ... is bank-conflict free.
 // Reads with several items, more than kQuadMaxHashes hashes for a k, more than kQuadMaxLists distinct lists
-// or more than kQuadMaxFill distinct transcripts go to the thread-per-read tier (mid_list).  nk <= 4.
+// or more than kQuadMaxFill distinct transcripts go to the warp-per-read kernel (slow_list).  nk <= 4.
 static constexpr int kQuadWarps = 4;
 static constexpr uint32_t kQuadSlots = 32;
 static constexpr uint32_t kQuadMaxFill = 24;
@@ -1001,13 +740,14 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
         }
     }
     if (valid && !defer && g == 0) { wq += tq; wh += th; }
-    // hand reads that did not fit to the thread-per-read tier
+    // hand reads that did not fit (long reads, many hashes, many lists, many transcripts) to the
+    // warp-per-read kernel: they are the heavy ones, a whole warp suits them better than one thread
     const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer && g == 0);
     if (dmask) {
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(P.mid_count, (uint32_t)__popc(dmask));
+      if (lane == 0) base = atomicAdd(P.slow_count, (uint32_t)__popc(dmask));
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (valid && defer && g == 0) P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+      if (valid && defer && g == 0) P.slow_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
     }
     // one staging allocation per warp (8 reads): exclusive prefix of nc over the quads
     uint32_t qincl = g == 0 ? nc : 0;
@@ -1093,9 +833,10 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
       default: vote_quad_kernel<4><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
     }
   } else {
+    // more than 4 k values: 64-bit packed counters, thread-per-read tiers (16 then 48 table entries)
     vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
+    vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
   }
-  vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
 }
 
 
