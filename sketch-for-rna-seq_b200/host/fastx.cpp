@@ -6,6 +6,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -95,7 +98,24 @@ FastqFile::~FastqFile() {
   if (data_) munmap(const_cast<char*>(data_), size_);
 }
 
+namespace {
+double wall() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+struct Trace {
+  bool on = getenv("SQ_TRACE") != nullptr;
+  double t = wall();
+  void lap(const char* what) {
+    if (!on) return;
+    const double n = wall();
+    fprintf(stderr, "[sq trace] %-28s %.3f s\n", what, n - t);
+    t = n;
+  }
+};
+}  // namespace
+
 std::vector<FastqFile::Rec> FastqFile::admitted_records(uint32_t max_k, int n_threads, uint64_t* n_seen) const {
+  Trace tr;
   // 1. line starts: newline positions are found in parallel, the record state machine (which depends on every
   //    earlier line) then runs over the line table only
   const char* d = data_;
@@ -114,6 +134,7 @@ std::vector<FastqFile::Rec> FastqFile::admitted_records(uint32_t max_k, int n_th
       p = q + 1;
     }
   });
+  tr.lap("fastq newline scan");
   std::vector<uint64_t> line_end;  // position of the terminating '\n' (or n for an unterminated last line)
   size_t total = 0;
   for (auto& v : nl) total += v.size();
@@ -122,6 +143,7 @@ std::vector<FastqFile::Rec> FastqFile::admitted_records(uint32_t max_k, int n_th
   if (n && (line_end.empty() || line_end.back() != n - 1)) line_end.push_back(n);
   const size_t n_lines = line_end.size();
   auto line_begin = [&](size_t i) { return i == 0 ? (uint64_t)0 : line_end[i - 1] + 1; };
+  tr.lap("fastq line table");
   // 2. records (sequential over lines, O(1) per line)
   std::vector<Rec> recs;
   recs.reserve(n_lines / 4 + 1);
@@ -143,30 +165,54 @@ std::vector<FastqFile::Rec> FastqFile::admitted_records(uint32_t max_k, int n_th
     recs.push_back(r);
   }
   if (n_seen) *n_seen = recs.size();
+  tr.lap("fastq record scan");
   // 3. admission (main.cpp:131-138), in parallel
   std::vector<uint8_t> ok(recs.size());
   parallel_for(recs.size(), nt, [&](size_t lo, size_t hi, int) {
     for (size_t i = lo; i < hi; ++i)
       ok[i] = recs[i].seq_len >= max_k && is_valid_sequence(d + recs[i].seq_off, recs[i].seq_len);
   });
-  // 4. duplicate ids: the LAST admitted record of an id survives (read_sketches[read.id] = ..., main.cpp:147)
-  std::unordered_map<std::string_view, uint32_t> last;
-  last.reserve(recs.size() * 2);
-  std::vector<Rec> out;
-  out.reserve(recs.size());
-  bool any_dup = false;
-  for (size_t i = 0; i < recs.size(); ++i) {
-    if (!ok[i]) continue;
-    std::string_view id(d + recs[i].id_off, recs[i].id_len);
-    auto ins = last.emplace(id, (uint32_t)out.size());
-    if (ins.second) {
-      out.push_back(recs[i]);
-    } else {
-      out[ins.first->second] = recs[i];
-      any_dup = true;
+  tr.lap("fastq admission");
+  // 4. duplicate ids: the LAST admitted record of an id survives (read_sketches[read.id] = ..., main.cpp:147),
+  //    at the position of the FIRST occurrence is irrelevant (unordered_map has no order): we keep file order of
+  //    the surviving records.  Sharded by a hash of the id: every thread owns the ids of one shard, walks the
+  //    records in file order and remembers the last record of each id, so no locks are needed.
+  const size_t nrec = recs.size();
+  std::vector<uint64_t> idh(nrec);
+  parallel_for(nrec, nt, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; ++i) {
+      uint64_t h = 0xcbf29ce484222325ull;
+      const unsigned char* p = reinterpret_cast<const unsigned char*>(d + recs[i].id_off);
+      for (uint32_t j = 0; j < recs[i].id_len; ++j) { h ^= p[j]; h *= 0x100000001b3ull; }
+      idh[i] = h ^ (h >> 29);
     }
+  });
+  std::vector<uint8_t> keep(nrec, 0);
+  const int shards = nt;
+  {
+    std::vector<std::thread> th;
+    for (int sh = 0; sh < shards; ++sh)
+      th.emplace_back([&, sh] {
+        std::unordered_map<std::string_view, uint32_t> last;  // id -> index of its last admitted record
+        last.reserve(nrec / shards * 2 + 16);
+        for (size_t i = 0; i < nrec; ++i) {
+          if (!ok[i] || (int)((idh[i] >> 40) % shards) != sh) continue;
+          std::string_view id(d + recs[i].id_off, recs[i].id_len);
+          auto ins = last.emplace(id, (uint32_t)i);
+          if (!ins.second) {
+            keep[ins.first->second] = 0;
+            ins.first->second = (uint32_t)i;
+          }
+          keep[i] = 1;
+        }
+      });
+    for (auto& t : th) t.join();
   }
-  (void)any_dup;
+  std::vector<Rec> out;
+  out.reserve(nrec);
+  for (size_t i = 0; i < nrec; ++i)
+    if (keep[i]) out.push_back(recs[i]);
+  tr.lap("fastq duplicate ids");
   return out;
 }
 

@@ -25,7 +25,8 @@ struct IndexData {
 };
 
 // false when the file cannot be opened (the reference prints an error and carries on, data_io.cpp:238-241)
-bool read_index(const std::string& path, IndexData* out, bool keep_sequences);
+// use_cache: read / write the optional sidecar <path>.sqidx (flat arrays, validated by size+mtime of <path>)
+bool read_index(const std::string& path, IndexData* out, bool keep_sequences, bool use_cache = false);
 bool write_index(const std::string& path, const std::vector<uint32_t>& ks, const std::vector<std::string>& names,
                  const std::vector<std::string>& sequences, const std::unordered_map<uint32_t, Postings>& maps);
 

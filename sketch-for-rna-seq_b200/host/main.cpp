@@ -9,7 +9,8 @@
 // Extras that default to the reference's behaviour: --gpus N (shard the reads over N GPUs of this box, one host
 // thread and one engine per GPU, NCCL all-reduce of the per-transcript vectors), --threads N (host parsing
 // threads), env SQ_SKETCH_SIZE / SQ_CHAIN_FRACTION / SQ_EM_ITERS / SQ_EM_TOL (the constants hard-coded at
-// src/main.cpp:43,185,188), --report FILE (JSON timing report).
+// src/main.cpp:43,185,188), --report FILE (JSON timing report), --index-cache / SQ_INDEX_CACHE=1 (keep a
+// parsed copy of the index next to it as <index>.sqidx, used only while the index file is unchanged).
 #include <getopt.h>
 
 #include <algorithm>
@@ -18,7 +19,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <condition_variable>
 #include <iostream>
+#include <memory>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -41,6 +45,7 @@ struct Options {
   double em_tol = 0.01;
   int gpus = 1;
   int threads = 0;
+  bool index_cache = false;
   std::string report;
 };
 
@@ -168,27 +173,27 @@ void quantification(const std::string& index_path, const std::string& reads_path
                     std::vector<unsigned>& kmer_lengths, const Options& opt) {
   const double t_start = now();
   IndexData idx;
-  const bool have_index = read_index(index_path, &idx, false);
+  const bool have_index = read_index(index_path, &idx, false, opt.index_cache);
   if (have_index) kmer_lengths.assign(idx.ks.begin(), idx.ks.end());  // load_index overwrites the -k list (main.cpp:174)
   std::cout << "Loading index completed" << std::endl;
   const double t_index = now();
   if (kmer_lengths.empty()) throw std::runtime_error("no k-mer length available");
   const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
 
-  FastqFile fq(reads_path);
+  if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] index file parsed            %.3f s\n", now() - t_start);
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  uint64_t n_seen = 0;
-  std::vector<FastqFile::Rec> recs = fq.admitted_records(kmax, threads, &n_seen);
-  const uint64_t R = recs.size();
   const size_t T = idx.names.size();
   std::vector<double> pi(T, 0.0), numreads(T, 0.0);
   std::vector<uint8_t> present(T, 0);
   double t_reads = 0, t_chain = 0, t_em = 0;
   sq_stats stats;
   memset(&stats, 0, sizeof(stats));
+  uint64_t n_seen = 0, R = 0;
 
   if (T == 0) {
     // unreadable/empty index: upstream carries on with empty maps and writes a header-only CSV
+    FastqFile fq(reads_path);
+    R = fq.admitted_records(kmax, threads, &n_seen).size();
     std::cout << "Loading read completed" << std::endl;
     std::cout << "Sparse chaining completed" << std::endl;
     std::cout << "EM estimation completed" << std::endl;
@@ -206,13 +211,19 @@ void quantification(const std::string& index_path, const std::string& reads_path
     std::vector<sq_engine*> eng(G, nullptr);
     uint8_t uid[SQ_NCCL_ID_BYTES];
     if (G > 1) SQ(nullptr, sq_nccl_unique_id(uid));
-    // one host thread per GPU: engine, index replica, its contiguous share of the records
+    // One host thread per GPU.  Each creates its engine and index replica right away (CUDA context, table
+    // build) while the main thread scans the FASTQ; then it packs and pushes its contiguous share of records.
     const size_t chunk_reads = 1u << 21;
     std::vector<std::thread> workers;
     std::vector<double> tr(G, 0), tc(G, 0), te(G, 0);
     std::vector<std::vector<double>> pis(G), nrs(G);
     std::vector<std::vector<uint8_t>> prs(G);
     std::vector<sq_stats> sts(G);
+    std::mutex mu;
+    std::condition_variable cv;
+    bool reads_ready = false, reads_failed = false;
+    const FastqFile* fqp = nullptr;
+    std::vector<FastqFile::Rec> recs;
     for (int g = 0; g < G; ++g) {
       workers.emplace_back([&, g] {
         sq_engine* e = nullptr;
@@ -228,6 +239,13 @@ void quantification(const std::string& index_path, const std::string& reads_path
           SQ(e, sq_load_index(e, (uint32_t)ki, P.keys.size(), P.keys.data(), P.off.data(), P.tid.data()));
         }
         if (G > 1) SQ(e, sq_comm_init(e, G, g, uid));
+        if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] gpu %d engine+index ready      %.3f s since start\n", g, now() - t_start);
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return reads_ready || reads_failed; });
+          if (reads_failed) return;
+        }
+        const FastqFile& fq = *fqp;
         const uint64_t per = (R + G - 1) / G, lo = std::min<uint64_t>(R, g * per), hi = std::min<uint64_t>(R, lo + per);
         PackedBatch pb[2];
         std::vector<const char*> ptr;
@@ -258,6 +276,21 @@ void quantification(const std::string& index_path, const std::string& reads_path
         sq_get_stats(e, &sts[g]);
       });
     }
+    // main thread: FASTQ scan (an unopenable file throws like upstream; release the workers first)
+    std::unique_ptr<FastqFile> fq;
+    try {
+      fq.reset(new FastqFile(reads_path));
+      recs = fq->admitted_records(kmax, threads, &n_seen);
+    } catch (...) {
+      { std::lock_guard<std::mutex> lk(mu); reads_failed = true; }
+      cv.notify_all();
+      for (auto& w : workers) w.join();
+      throw;
+    }
+    R = recs.size();
+    fqp = fq.get();
+    { std::lock_guard<std::mutex> lk(mu); reads_ready = true; }
+    cv.notify_all();
     for (auto& w : workers) w.join();
     std::cout << "Loading read completed" << std::endl;
     std::cout << "Sparse chaining completed" << std::endl;
@@ -303,6 +336,7 @@ int main(int argc, char* argv[]) {
   if (const char* v = getenv("SQ_CHAIN_FRACTION")) opt.chain_fraction = atof(v);
   if (const char* v = getenv("SQ_EM_ITERS")) opt.em_iters = atoi(v);
   if (const char* v = getenv("SQ_EM_TOL")) opt.em_tol = atof(v);
+  if (const char* v = getenv("SQ_INDEX_CACHE")) opt.index_cache = atoi(v) != 0;
 
   static struct option long_options[] = {{"help", no_argument, 0, 'h'},
                                          {"kmer-length", required_argument, 0, 'k'},
@@ -310,6 +344,7 @@ int main(int argc, char* argv[]) {
                                          {"gpus", required_argument, 0, 1000},
                                          {"threads", required_argument, 0, 1001},
                                          {"report", required_argument, 0, 1002},
+                                         {"index-cache", no_argument, 0, 1003},
                                          {0, 0, 0, 0}};
   int opt_c, option_index = 0;
   while ((opt_c = getopt_long(argc, argv, "hk:o:", long_options, &option_index)) != -1) {
@@ -332,6 +367,7 @@ int main(int argc, char* argv[]) {
       case 1000: opt.gpus = atoi(optarg); break;
       case 1001: opt.threads = atoi(optarg); break;
       case 1002: opt.report = optarg; break;
+      case 1003: opt.index_cache = true; break;
       default:
         print_help(argv[0]);
         return 1;

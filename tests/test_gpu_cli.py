@@ -80,3 +80,26 @@ def test_cli_report_and_default_mode(gpu_lib, tmp_path):
     import json
     j = json.load(open(rep))
     assert j["reads_admitted"] == 400 and j["kernel_launches"] > 0 and j["transcripts"] == len(d["names"])
+
+
+def test_index_sidecar_cache(gpu_lib, tmp_path):
+    d = dataset(n_genes=30, n_reads=500, seed=8)
+    fa, fq = write_inputs(tmp_path, d)
+    idx = str(tmp_path / "i.idx")
+    subprocess.run([OURS, "-k", "21,31", "-o", "index", fa, idx], check=True, capture_output=True)
+    out = {}
+    for tag, extra in (("plain", []), ("make", ["--index-cache"]), ("use", ["--index-cache"])):
+        csv = str(tmp_path / (tag + ".csv"))
+        r = subprocess.run([OURS] + extra + ["-o", "quant", idx, fq, csv], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Index loaded from " + idx in r.stdout
+        out[tag] = open(csv).read()
+    assert os.path.exists(idx + ".sqidx")
+    assert out["plain"] == out["make"] == out["use"]
+    # a changed index file invalidates the sidecar (size/mtime mismatch): rebuild the index with another k
+    subprocess.run([OURS, "-k", "25", "-o", "index", fa, idx], check=True, capture_output=True)
+    csv2 = str(tmp_path / "k25.csv")
+    ref2 = str(tmp_path / "k25_ref.csv")
+    subprocess.run([OURS, "--index-cache", "-o", "quant", idx, fq, csv2], check=True, capture_output=True)
+    subprocess.run([REF, "-o", "quant", idx, fq, ref2], check=True, capture_output=True)
+    assert_csv_equal(read_csv(csv2), read_csv(ref2))
