@@ -355,19 +355,26 @@ def run_ours(args):
     S = args.steps
     kern = {
         "sketch_kernel": {"ms": stage.get("ms_sketch", 0) / S, "bytes": b_sketch, "launches": stage.get("sketch_launches", 0) // S},
-        "vote_kernel": {"ms": stage.get("ms_vote", 0) / S, "bytes": b_vote, "launches": stage.get("vote_launches", 0) // S},
+        "vote_quad_kernel": {"ms": stage.get("ms_vote_main", 0) / S, "bytes": b_vote, "launches": stage.get("vote_launches", 0) // S},
         "em_iterations": {"ms": stage.get("ms_em", 0) / S, "bytes": b_em, "launches": iters},
     }
     for kname, kv in kern.items():
         kv["gbs"] = kv["bytes"] / (kv["ms"] / 1e3) / 1e9 if kv["ms"] > 0 else None
         kv["frac"] = kv["gbs"] / peak if kv["gbs"] else None
     dom = max(kern, key=lambda n: kern[n]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.workload == "short":
+        tj = json.load(open(tpath))
+        if dom in tj and kern[dom]["launches"]:
+            traffic = tj[dom] * (n_reads / kern[dom]["launches"]) / tj["reads_per_launch"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": kern[dom]["ms"] / max(kern[dom]["launches"], 1),
                 "algorithmic_bytes_per_launch": kern[dom]["bytes"] / max(kern[dom]["launches"], 1),
                 "kernels": {n: {"ms_per_step": round(v["ms"], 4), "GBps": v["gbs"] and round(v["gbs"], 1),
                                 "frac": v["frac"] and round(v["frac"], 4)} for n, v in kern.items()},
+                "traffic_source": "profiles/traffic.json (ncu --set full capture, scaled to this launch size)" if traffic else None,
                 "stage_ms_per_step": {k2: round(v / S, 4) for k2, v in stage.items() if k2.startswith("ms_")},
                 "sketch_gkmers_per_s": n_kmers / (kern["sketch_kernel"]["ms"] / 1e3) / 1e9
                 if kern["sketch_kernel"]["ms"] > 0 else None}

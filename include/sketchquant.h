@@ -61,6 +61,8 @@ typedef struct sq_stats {
   uint32_t sketch_launches, vote_launches; /* launches of the two named kernels while profiling was on */
   uint64_t slow_reads;     /* reads voted by the warp-per-read kernel instead of a thread-per-read kernel */
   uint64_t mid_reads;      /* reads voted by the 48-entry thread-per-read kernel (second tier) or later */
+  float ms_vote_main;      /* the short-read vote kernel alone (part of ms_vote) */
+  float reserved2;
   uint64_t em_classes;     /* equivalence classes (distinct candidate lists) the last sq_finish ran EM on */
   uint64_t em_class_pairs; /* (class, transcript) pairs of those classes */
 } sq_stats;

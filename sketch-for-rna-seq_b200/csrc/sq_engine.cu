@@ -298,7 +298,13 @@ int enqueue_vote(sq_engine* e, Slot& s) {
   SQ_CUDA(e, cudaMemsetAsync(ctr, 0, 32, e->stream));
   {
     StageScope st(e, 1);
-    launch_vote(s.vp, e->stream, &e->launches);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (e->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+    }
+    launch_vote(s.vp, e->stream, &e->launches, a, b);
+    if (a) e->events.push_back({a, b, 7});
   }
   SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 4 * s.id, ctr, 32, cudaMemcpyDeviceToHost, e->stream));
   SQ_CUDA(e, cudaGetLastError());
@@ -1037,6 +1043,7 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->launches = e->launches;
   out->queries = tot[1]; out->hits = tot[2]; out->postings = tot[3];
   out->ms_items = e->ms[6];
+  out->ms_vote_main = e->ms[7];
   out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
   out->slow_reads = e->slow_total;
   out->em_classes = e->n_classes_last;

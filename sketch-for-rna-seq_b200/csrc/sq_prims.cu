@@ -29,54 +29,74 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
   return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
-                                                               uint32_t* __restrict__ bsum) {
-  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i)
-    if (base + i < n) s += in[base + i];
-  uint32_t tot;
-  block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
+// Single-pass scan with decoupled look-back: tiles take a ticket (so a tile only ever waits for tiles that have
+// already started), publish their aggregate, and the first warp walks back over the predecessors' status words
+// 32 at a time until it meets an inclusive prefix.  status: one 64-bit word per tile, bit 63 = inclusive prefix
+// available, bit 62 = aggregate available, low 32 bits = value; zeroed (with the ticket) before every scan.
+static constexpr unsigned long long kScanIncl = 1ull << 63, kScanAgg = 1ull << 62;
 
-__global__ void __launch_bounds__(kScanThreads) scan_bsums(uint32_t* __restrict__ bsum, uint32_t nb) {
-  // single block: exclusive scan of bsum[0..nb) in place, bsum[nb] = total
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < nb; base += kScanThreads) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < nb ? bsum[i] : 0;
-    uint32_t tot;
-    const uint32_t ex = block_excl_scan(v, &tot);
-    if (i < nb) bsum[i] = carry + ex;
-    carry += tot;
-  }
-  if (threadIdx.x == 0) bsum[nb] = carry;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_apply(const uint32_t* __restrict__ in, uint32_t n,
-                                                           const uint32_t* __restrict__ bsum, uint32_t nb,
-                                                           uint32_t* __restrict__ out) {
-  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const uint32_t* __restrict__ in, uint32_t n,
+                                                                     uint32_t* __restrict__ out,
+                                                                     unsigned long long* status, uint32_t* ticket) {
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
-  uint32_t s = 0;
+  uint32_t sum = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     v[i] = base + i < n ? in[base + i] : 0;
-    s += v[i];
+    sum += v[i];
   }
   uint32_t tot;
-  uint32_t ex = block_excl_scan(s, &tot) + bsum[blockIdx.x];
+  uint32_t ex = block_excl_scan(sum, &tot);
+  if (threadIdx.x < 32) {
+    const uint32_t lane = threadIdx.x;
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) {
+        *(volatile unsigned long long*)&status[0] = kScanIncl | tot;
+      }
+    } else {
+      if (lane == 0) {
+        *(volatile unsigned long long*)&status[tile] = kScanAgg | tot;
+      }
+      __threadfence();
+      int64_t hi = (int64_t)tile - 1;  // nearest predecessor not yet accounted for
+      for (;;) {
+        const int64_t j = hi - lane;
+        unsigned long long w = kScanIncl;  // tiles before 0 act as an inclusive prefix of 0
+        if (j >= 0) {
+          do { w = *(volatile unsigned long long*)&status[j]; } while ((w & (kScanIncl | kScanAgg)) == 0);
+        }
+        const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (w & kScanIncl) != 0);
+        const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;  // closest inclusive prefix in the window
+        uint32_t contrib = (int)lane <= first ? (uint32_t)w : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, d);
+        prefix += contrib;
+        if (incl_mask) break;
+        hi -= 32;
+      }
+      if (lane == 0) {
+        *(volatile unsigned long long*)&status[tile] = kScanIncl | (unsigned long long)(prefix + tot);
+      }
+    }
+    if (lane == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  ex += s_prefix;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     if (base + i < n) out[base + i] = ex;
     ex += v[i];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bsum[nb];
+  if (base <= n - 1 && n - 1 < base + kScanItems) out[n] = ex;  // the thread holding the last element closes the scan
 }
 
-size_t scan_tmp_words(uint32_t n) { return (size_t)(n / kScanTile) + 4; }
+size_t scan_tmp_words(uint32_t n) { return 2 * ((size_t)(n / kScanTile) + 2) + 4; }
 
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t s,
                            uint64_t* launches) {
@@ -85,10 +105,10 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32
     return;
   }
   const uint32_t nb = (n + kScanTile - 1) / kScanTile;
-  scan_tile_sums<<<nb, kScanThreads, 0, s>>>(in, n, tmp);
-  scan_bsums<<<1, kScanThreads, 0, s>>>(tmp, nb);
-  scan_apply<<<nb, kScanThreads, 0, s>>>(in, n, tmp, nb, out);
-  if (launches) *launches += 3;
+  // tmp: [0] ticket (u32, padded to 8 bytes), then nb status words
+  cudaMemsetAsync(tmp, 0, 8 + (size_t)nb * 8, s);
+  scan_lookback_kernel<<<nb, kScanThreads, 0, s>>>(in, n, out, reinterpret_cast<unsigned long long*>(tmp + 2), tmp);
+  if (launches) *launches += 1;
 }
 
 // ------------------------------------------------------------------ radix sort
@@ -197,7 +217,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 size_t radix_tmp_words(uint64_t n) {
   const uint64_t ntiles = (n + kSortTile - 1) / kSortTile;
   // one pass's histogram + its scan (+1) + scan scratch
-  return (size_t)(256 * ntiles) + (size_t)(256 * ntiles + 1) + scan_tmp_words((uint32_t)(256 * ntiles)) + 16;
+  return (size_t)(256 * ntiles) + (size_t)(256 * ntiles + 2) + scan_tmp_words((uint32_t)(256 * ntiles)) + 16;
 }
 
 void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, uint64_t n, int nbits,
@@ -210,7 +230,7 @@ void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uin
   const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
   uint32_t* hist = tmp;
   uint32_t* offs = hist + (size_t)256 * ntiles;
-  uint32_t* scan_tmp = offs + (size_t)256 * ntiles + 1;
+  uint32_t* scan_tmp = offs + (size_t)256 * ntiles + 2;  // keeps the 8-byte alignment the scan's status words need
   uint64_t* kin = keys_a;
   uint64_t* kout = keys_b;
   uint32_t* vin = vals_a;

@@ -886,7 +886,7 @@ size_t vote_smem_bytes(uint32_t nk) {
   return (size_t)kVoteWarps * (tab + tab * nk + tab + set + 4) * sizeof(uint32_t);
 }
 
-void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches) {
+void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b) {
   if (p.n_reads == 0) return;
   static int sm_count = 0, configured_nk = -1;
   if (!sm_count) {
@@ -905,7 +905,9 @@ void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches) {
   uint32_t grid = (uint32_t)(sm_count * per_sm);
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
+  if (ev_a) cudaEventRecord(ev_a, s);
   if (p.nk <= 4) launch_fast_tiers<uint32_t>(p, s); else launch_fast_tiers<unsigned long long>(p, s);
+  if (ev_b) cudaEventRecord(ev_b, s);
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
   vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
   if (launches) *launches += 4;
