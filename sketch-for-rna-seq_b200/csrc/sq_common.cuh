@@ -26,10 +26,13 @@ __host__ __device__ inline uint64_t rol33(uint64_t s, uint32_t n) {
   return ((s << n) | (s >> (33 - n))) & 0x1FFFFFFFFULL;
 }
 
-// per-k lookup table in the two-word form: entries 0..15 = seed[in] ^ rol33^k(seed[out]) indexed by
-// in*4+out, entries 16..19 = seed[in] alone (used while the first window is being filled)
+// per-k lookup table in the two-word form (384 bytes, 128-byte aligned in shared memory):
+//   e[0..15]  = seed[in] ^ rol33^k(seed[out])       index in*4+out   (one rolling step)
+//   e[16..31] = rol33(seed[a]) ^ seed[b]            index a + 4*b    (two bases at once while the first
+//                                                                      window is being filled; a comes first)
+//   e[32..35] = seed[in]                                              (one base while filling)
 struct KLut {
-  uint2 e[20];
+  uint2 e[48];
 };
 
 struct SketchParams {

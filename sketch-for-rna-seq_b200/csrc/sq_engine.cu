@@ -215,13 +215,12 @@ uint32_t log2_ceil(uint64_t v) {
 }
 
 void make_lut(uint32_t k, KLut* out) {
+  memset(out, 0, sizeof(*out));
+  auto two = [](uint64_t v) { return make_uint2((uint32_t)v, (uint32_t)(v >> 1)); };
   for (uint32_t in = 0; in < 4; ++in) {
-    for (uint32_t o = 0; o < 4; ++o) {
-      const uint64_t s = seed33(in) ^ rol33(seed33(o), k);
-      out->e[in * 4 + o] = make_uint2((uint32_t)s, (uint32_t)(s >> 1));
-    }
-    const uint64_t s = seed33(in);
-    out->e[16 + in] = make_uint2((uint32_t)s, (uint32_t)(s >> 1));
+    for (uint32_t o = 0; o < 4; ++o) out->e[in * 4 + o] = two(seed33(in) ^ rol33(seed33(o), k));
+    for (uint32_t b = 0; b < 4; ++b) out->e[16 + in + 4 * b] = two(rol33(seed33(in), 1) ^ seed33(b));
+    out->e[32 + in] = two(seed33(in));
   }
 }
 

@@ -18,32 +18,23 @@ static constexpr int kStageWordsPerWarp = 32 * 24;  // 32 lanes x (256+~100 base
 
 __device__ __forceinline__ uint32_t items_of(uint32_t L) { return L == 0 ? 1u : (L + SQ_CHUNK - 1) / SQ_CHUNK; }
 
-// sequential reader of 2-bit codes starting at an arbitrary base position
-struct BaseReader {
-  const uint32_t* wp;
-  uint32_t w;
-  uint32_t pos;
-  __device__ __forceinline__ void init(const uint32_t* p, uint32_t start) {
-    wp = p;
-    pos = start;
-    w = wp[pos >> 4] >> ((pos & 15) * 2);
-  }
-  __device__ __forceinline__ uint32_t next() {
-    if ((pos & 15) == 0) w = wp[pos >> 4];
-    uint32_t c = w & 3;
-    w >>= 2;
-    ++pos;
-    return c;
-  }
-};
+static constexpr uint32_t kLutWords = 96;  // 48 uint2 per k
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t code_at(const uint32_t* wp, uint32_t pos) {
+  return (wp[pos >> 4] >> ((pos & 15) * 2)) & 3;
+}
 
 __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_constant__ SketchParams p) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  // layout: [nk][20] uint2 lookup tables, then one staging area per warp
+  extern __shared__ __align__(128) uint32_t smem[];
+  // layout: [nk] lookup tables of 384 bytes (128-byte aligned), then one staging area per warp
   uint2* lut = reinterpret_cast<uint2*>(smem);
-  const uint32_t lut_words = p.nk * 40;
-  for (uint32_t i = threadIdx.x; i < p.nk * 20; i += blockDim.x) lut[i] = p.lut[i / 20].e[i % 20];
-  uint32_t* stage = smem + ((lut_words + 3) & ~3u) + (threadIdx.x >> 5) * kStageWordsPerWarp;
+  for (uint32_t i = threadIdx.x; i < p.nk * 48; i += blockDim.x) lut[i] = p.lut[i / 48].e[i % 48];
+  uint32_t* stage = smem + p.nk * kLutWords + (threadIdx.x >> 5) * kStageWordsPerWarp;
   __syncthreads();
 
   const uint32_t n_items = p.item_start[p.n_reads];
@@ -90,39 +81,67 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   const uint32_t thr = p.threshold;
   for (uint32_t ki = 0; ki < p.nk; ++ki) {
     const uint32_t k = p.ks[ki];
-    const uint2* lk = lut + ki * 20;
-    uint32_t n_out = 0;
+    // shared-memory byte address of this k's tables; 128-byte aligned, so (index*8) can be OR-ed in
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(lut + ki * 48);
     uint32_t* out = p.sel + (uint64_t)ki * p.slot_stride + boff + c0;
+    uint32_t* const out0 = out;
     const uint32_t e_first = max(c0, k - 1);  // first window end that lies in this item
     if (L >= k && e_first < c1) {
-      // fill the first window: bases e_first-(k-1) .. e_first
-      BaseReader in;
-      in.init(wp, boff + e_first - (k - 1));
       uint32_t x = 0, y = 0;  // lane value s: x = s[31:0], y = s[32:1]
-      for (uint32_t j = 0; j < k; ++j) {
-        const uint2 d = lk[16 + in.next()];
+      // ---- fill the first window (k bases, no output): one base to reach an even position, then two bases
+      //      per table lookup (a nibble of the packed word), then a last single base if k is left odd
+      uint32_t pos = boff + e_first - (k - 1);
+      const uint32_t wend = pos + k;
+      if (pos & 1) {
+        const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
+        x = d.x;
+        y = d.y;
+        ++pos;
+      }
+      while (pos + 2 <= wend) {
+        uint32_t w = wp[pos >> 4] >> ((pos & 15) * 2);
+        uint32_t n2 = min((wend - pos) >> 1, (16 - (pos & 15)) >> 1);  // pairs left in this word
+        pos += 2 * n2;
+        for (; n2; --n2) {
+          const uint2 d = lds_v2(tb + 128 + (w & 15) * 8);
+          const uint32_t nx = __funnelshift_l(y, x, 2) ^ d.x;
+          y = __funnelshift_l(y, x, 1) ^ d.y;
+          x = nx;
+          w >>= 4;
+        }
+      }
+      if (pos < wend) {
+        const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
         const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
         y = x ^ d.y;
         x = nx;
+        ++pos;
       }
-      if (x <= thr) out[n_out++] = x;
-      uint32_t e = e_first + 1;
-      BaseReader ob;
-      ob.init(wp, boff + e - k);
-      // scalar steps until the incoming base is word aligned
-      while (e < c1 && ((boff + e) & 15) != 0) {
-        const uint2 d = lk[in.next() * 4 + ob.next()];
-        const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-        y = x ^ d.y;
-        x = nx;
-        if (x <= thr) out[n_out++] = x;
-        ++e;
-      }
-      // aligned blocks of 16 steps: one incoming word, the outgoing stream re-aligned by a funnel shift
+      if (x <= thr) *out++ = x;
+      // ---- roll: pos = absolute index of the incoming base, the outgoing one is k behind
+      const uint32_t end = boff + c1;
       const uint32_t q = k >> 4, dr = k & 15;
-      const char* lkb = reinterpret_cast<const char*>(lk);
-      while (e + 16 <= c1) {
-        const uint32_t iw = (boff + e) >> 4;
+      auto partial = [&](uint32_t stop) {  // steps pos .. stop-1, all inside one incoming word
+        const uint32_t iw = pos >> 4, j0 = pos & 15;
+        uint32_t win = wp[iw] >> (2 * j0);
+        uint32_t wout = wp[iw - q];
+        // the word before is only needed for steps j < dr; when j0 >= dr it may lie before the read
+        if (dr) wout = __funnelshift_r(dr > j0 ? wp[iw - q - 1] : 0u, wout, 32 - 2 * dr);
+        wout >>= 2 * j0;
+        for (; pos < stop; ++pos) {
+          const uint2 d = lds_v2(tb + ((win & 3) << 5) + ((wout & 3) << 3));
+          const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+          y = x ^ d.y;
+          x = nx;
+          if (x <= thr) *out++ = x;
+          win >>= 2;
+          wout >>= 2;
+        }
+      };
+      if ((pos & 15) && pos < end) partial(min(end, (pos + 15) & ~15u));
+      // aligned blocks of 16 steps: one incoming word, the outgoing stream re-aligned by a funnel shift
+      while (pos + 16 <= end) {
+        const uint32_t iw = pos >> 4;
         const uint32_t win = wp[iw];
         uint32_t wout = wp[iw - q];
         if (dr) wout = __funnelshift_r(wp[iw - q - 1], wout, 32 - 2 * dr);
@@ -131,45 +150,33 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           {
-            const uint32_t a = j == 0 ? (xe << 3) & 0x78u : (xe >> (4 * j - 3)) & 0x78u;
-            const uint2 d = *reinterpret_cast<const uint2*>(lkb + a);
+            const uint32_t a = (j == 0 ? (xe << 3) & 0x78u : (xe >> (4 * j - 3)) & 0x78u) | tb;
+            const uint2 d = lds_v2(a);
             const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
             y = x ^ d.y;
             x = nx;
-            if (x <= thr) out[n_out++] = x;
+            if (x <= thr) *out++ = x;
           }
           {
-            const uint32_t a = j == 0 ? (xo << 3) & 0x78u : (xo >> (4 * j - 3)) & 0x78u;
-            const uint2 d = *reinterpret_cast<const uint2*>(lkb + a);
+            const uint32_t a = (j == 0 ? (xo << 3) & 0x78u : (xo >> (4 * j - 3)) & 0x78u) | tb;
+            const uint2 d = lds_v2(a);
             const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
             y = x ^ d.y;
             x = nx;
-            if (x <= thr) out[n_out++] = x;
+            if (x <= thr) *out++ = x;
           }
         }
-        e += 16;
+        pos += 16;
       }
-      if (e < c1) {
-        in.init(wp, boff + e);
-        ob.init(wp, boff + e - k);
-        while (e < c1) {
-          const uint2 d = lk[in.next() * 4 + ob.next()];
-          const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-          y = x ^ d.y;
-          x = nx;
-          if (x <= thr) out[n_out++] = x;
-          ++e;
-        }
-      }
+      if (pos < end) partial(end);
     }
-    p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)n_out;
+    p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)(out - out0);
   }
 }
 
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches) {
   if (p.n_items_ub == 0) return;
-  const uint32_t lut_words = (p.nk * 40 + 3) & ~3u;
-  const size_t smem = (lut_words + (kSketchBlock / 32) * kStageWordsPerWarp) * sizeof(uint32_t);
+  const size_t smem = (p.nk * kLutWords + (kSketchBlock / 32) * kStageWordsPerWarp) * sizeof(uint32_t);
   const uint32_t grid = (p.n_items_ub + kSketchBlock - 1) / kSketchBlock;
   sketch_kernel<<<grid, kSketchBlock, smem, s>>>(p);
   if (launches) ++*launches;
