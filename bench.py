@@ -36,6 +36,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries write to the C-level stdout behind Python's back (NCCL prints "NCCL version ..." there).  The
+# contract is ONE JSON line on stdout, so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+# the saved original descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def apply_workload(args):
     """non-default configs of BASELINE.json (parity-test / sweep cases, not the headline line)"""
     global K_LIST, READ_LEN, SKETCH
@@ -417,7 +428,7 @@ def run_ours(args):
                                "sample": "first %d reads of the workload against the full index (T=%d), single thread; "
                                          "stages s: %s" % (n, T, {k2: round(float(v), 3) for k2, v in stages.items()})}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
     eng.close()
     if dist:
         dist.destroy_process_group()
@@ -459,7 +470,7 @@ def run_reference(args):
            "cpu_baseline": cb,
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "stages_s": {k2: round(float(v), 3) for k2, v in stages.items()}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 if __name__ == "__main__":
