@@ -103,7 +103,10 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
 
 /* Replaces process_fastq_single_pass()'s sketching (src/main.cpp:140-147) + sparse_chain()
  * (src/sparse_chaining.cpp:29-115) for a batch of admitted reads given in HOST memory.  Asynchronous:
- * returns once the batch is copied/enqueued. */
+ * returns once the batch is copied/enqueued.  base_off may be NULL when the reads are packed back to back,
+ * read 0 at base 0 and every read starting at the next multiple of 4 bases after the previous one: then only
+ * the lengths are copied to the GPU and the offsets are derived there (such a batch must fit option
+ * batch_bases). */
 int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, const uint32_t* base_off,
                   const uint32_t* len, uint32_t n_reads);
 /* Same with the batch already resident in DEVICE memory (the buffers must stay valid until sq_sync). */

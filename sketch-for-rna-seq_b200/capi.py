@@ -169,13 +169,16 @@ class Engine:
 
     # ---- reads
     def push_reads(self, packed, base_off, length):
-        packed, base_off, length = _u32(packed), _u32(base_off), _u32(length)
+        """base_off may be None: reads packed back to back on 4-base boundaries (offsets derived on the GPU)"""
+        packed, length = _u32(packed), _u32(length)
+        base_off = _u32(base_off) if base_off is not None else None
         self._check(self.lib.sq_push_reads(self._h, _ptr(packed), packed.shape[0], _ptr(base_off), _ptr(length),
-                                           base_off.shape[0]))
+                                           length.shape[0]))
 
     def push_reads_ptr(self, packed_ptr, n_words, base_off_ptr, len_ptr, n_reads):
         """host pointers (e.g. pinned torch tensors' data_ptr())"""
-        self._check(self.lib.sq_push_reads(self._h, C.c_void_p(packed_ptr), n_words, C.c_void_p(base_off_ptr),
+        self._check(self.lib.sq_push_reads(self._h, C.c_void_p(packed_ptr), n_words,
+                                           C.c_void_p(base_off_ptr) if base_off_ptr else None,
                                            C.c_void_p(len_ptr), n_reads))
 
     def push_reads_device(self, d_packed, n_words, d_base_off, d_len, n_reads, n_bases=0):

@@ -45,32 +45,66 @@ void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkey
   if (launches) ++*launches;
 }
 
+// ------------------------------------------------------------------ list fingerprint (EM classes, see below)
+// Two independent 64-bit hashes over (length, transcripts, scores) of a candidate list, folded step by step.
+struct ListHash {
+  uint64_t h, g;
+  __device__ __forceinline__ void init(uint32_t n) {
+    h = 0xcbf29ce484222325ull ^ n;
+    g = 0x9E3779B97F4A7C15ull + n;
+  }
+  __device__ __forceinline__ void add(uint32_t tid, int32_t score) {
+    const uint64_t x = ((uint64_t)tid << 32) | (uint32_t)score;
+    h ^= x;
+    h *= 0x100000001b3ull;
+    h ^= h >> 31;
+    g = (g ^ (x * 0xC2B2AE3D27D4EB4Full)) * 0xD6E8FEB86659FD93ull;
+    g ^= g >> 29;
+  }
+  // sort key in the high word (best candidate, then a few hash bits), read index in the low word
+  __device__ __forceinline__ uint64_t key(uint64_t top, uint32_t hash_bits, uint64_t r) const {
+    return (((top << hash_bits) | ((h ^ (h >> 32)) & ((1ull << hash_bits) - 1))) << 32) | r;
+  }
+};
+
 // ------------------------------------------------------------------ candidate compaction
-// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store
+// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store.  The read's
+// EM class key and list fingerprint are computed on the way (the list is in flight anyway).
 __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uint32_t* __restrict__ read_cnt,
                                const uint32_t* __restrict__ batch_off, uint32_t n_reads,
                                const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
                                uint64_t pbase, uint64_t read_base, uint32_t* __restrict__ cand_tid,
-                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off) {
+                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off, uint32_t T,
+                               uint32_t hash_bits, uint64_t* __restrict__ rkey, ulonglong2* __restrict__ rfp) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint64_t dst = pbase + batch_off[r];
   read_off[read_base + r] = (uint32_t)dst;
   if (r == n_reads - 1) read_off[read_base + n_reads] = (uint32_t)(pbase + batch_off[n_reads]);
   const uint32_t c = read_cnt[r], so = read_soff[r];
+  ListHash lh;
+  lh.init(c);
+  uint32_t top = T;  // reads without candidates go last (one empty class)
   for (uint32_t i = 0; i < c; ++i) {
-    cand_tid[dst + i] = stage_tid[so + i];
-    cand_score[dst + i] = stage_score[so + i];
+    const uint32_t t = stage_tid[so + i];
+    const int32_t sc = stage_score[so + i];
+    if (i == 0) top = t;
+    cand_tid[dst + i] = t;
+    cand_score[dst + i] = sc;
+    lh.add(t, sc);
   }
+  rkey[read_base + r] = lh.key(top, hash_bits, read_base + r);
+  rfp[read_base + r] = make_ulonglong2(lh.h, lh.g);
 }
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s,
-                    uint64_t* launches) {
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, uint32_t T, uint32_t hash_bits,
+                    uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
-                                                       stage_score, pbase, read_base, cand_tid, cand_score, read_off);
+                                                       stage_score, pbase, read_base, cand_tid, cand_score, read_off,
+                                                       T, hash_bits, rkey, static_cast<ulonglong2*>(rfp));
   if (launches) ++*launches;
 }
 
@@ -101,21 +135,12 @@ __global__ void class_key_kernel(const uint32_t* __restrict__ read_off, uint64_t
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = read_off[r], e = read_off[r + 1];
-  uint64_t h = 0xcbf29ce484222325ull ^ (e - b), g = 0x9E3779B97F4A7C15ull + (e - b);
-  for (uint32_t j = b; j < e; ++j) {
-    const uint64_t x = ((uint64_t)cand_tid[j] << 32) | (uint32_t)cand_score[j];
-    h ^= x;
-    h *= 0x100000001b3ull;
-    h ^= h >> 31;
-    g = (g ^ (x * 0xC2B2AE3D27D4EB4Full)) * 0xD6E8FEB86659FD93ull;
-    g ^= g >> 29;
-  }
-  fp[r] = make_ulonglong2(h, g);
+  ListHash lh;
+  lh.init(e - b);
+  for (uint32_t j = b; j < e; ++j) lh.add(cand_tid[j], cand_score[j]);
+  fp[r] = make_ulonglong2(lh.h, lh.g);
   const uint64_t top = b < e ? cand_tid[b] : T;  // reads without candidates go last (one empty class)
-  // few hash bits are enough: the hash only has to separate the handful of distinct lists that share a best
-  // candidate, and fewer key bits mean fewer radix passes
-  // (the sort key sits in the high word, the read index rides in the low word: a keys-only sort)
-  keys[r] = (((top << hash_bits) | ((h ^ (h >> 32)) & ((1ull << hash_bits) - 1))) << 32) | r;
+  keys[r] = lh.key(top, hash_bits, r);
 }
 
 __global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,

@@ -130,6 +130,10 @@ struct sq_engine {
   uint32_t* cand_tid = nullptr;
   int32_t* cand_score = nullptr;
   uint32_t* read_off = nullptr;
+  uint64_t* rkey = nullptr;   // per read: EM class sort key (computed by the compaction)
+  void* rfp = nullptr;        // per read: 128-bit list fingerprint
+  bool keys_valid = true;
+  uint32_t class_hash_bits = 14;
   uint64_t cand_cap = 0, read_cap = 0;
   uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
@@ -240,15 +244,25 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
   if (need_reads > e->read_cap) {
     uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
     uint32_t* p = nullptr;
+    uint64_t* pk = nullptr;
+    void* pf = nullptr;
     SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
+    SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
+    SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
     if (e->read_off) {
       SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, e->stream));
       SQ_CUDA(e, cudaStreamSynchronize(e->stream));
       SQ_CUDA(e, cudaFree(e->read_off));
+      SQ_CUDA(e, cudaFree(e->rkey));
+      SQ_CUDA(e, cudaFree(e->rfp));
     } else {
       SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), e->stream));
     }
     e->read_off = p;
+    e->rkey = pk;
+    e->rfp = pf;
     e->read_cap = cap;
   }
   const uint64_t need_pairs = e->P + pairs;
@@ -337,7 +351,8 @@ int finalize_slot(sq_engine* e, Slot& s) {
                           e->stream, &e->launches);
     launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
                    s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
-                   e->cand_score, e->read_off, e->stream, &e->launches);
+                   e->cand_score, e->read_off, (uint32_t)e->T, e->class_hash_bits, e->rkey, e->rfp, e->stream,
+                   &e->launches);
   }
   SQ_CUDA(e, cudaGetLastError());
   SQ_CUDA(e, cudaEventRecord(s.done, e->stream));
@@ -371,7 +386,8 @@ int acquire_slot(sq_engine* e, Slot** out) {
 
 // enqueue sketch + vote + compaction for one batch whose inputs are in device memory
 int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words, const uint32_t* d_boff, uint32_t bias,
-              const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases, cudaEvent_t inputs_ready) {
+              const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases, cudaEvent_t inputs_ready,
+              uint32_t* derive_boff = nullptr) {
   if (n_reads == 0) return SQ_OK;
   const uint64_t items_ub64 = (uint64_t)n_reads + n_bases / SQ_CHUNK + 1;
   if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
@@ -396,6 +412,11 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   // the batch before this one (other slot) can now be finalized: its vote overlaps our copies
   SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
   if (inputs_ready) SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
+  if (derive_boff) {  // offsets not supplied: reads are packed back to back on 4-base boundaries
+    StageScope st(e, 6);
+    launch_derive_offsets(d_len, n_reads, s.nit.as<uint32_t>(), derive_boff, s.scan_tmp.as<uint32_t>(), e->stream,
+                          &e->launches);
+  }
 
   {
     StageScope st(e, 6);
@@ -534,6 +555,11 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   e->threshold = threshold;
   e->fraction = chain_fraction;
   e->T = n_transcripts;
+  {
+    const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil(n_transcripts + 1));
+    if (top_bits > 24) { delete e; return fail(nullptr, SQ_ERR_CAPACITY, "more than 2^24 transcripts are not supported"); }
+    e->class_hash_bits = 32 - top_bits;  // class sort key = (best candidate, hash bits) in 32 bits: 4 radix passes
+  }
   auto bail = [&](cudaError_t ce, const char* what) {
     fail(nullptr, SQ_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
     delete e;
@@ -585,6 +611,8 @@ void sq_destroy(sq_engine* e) {
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
   if (e->read_off) cudaFree(e->read_off);
+  if (e->rkey) cudaFree(e->rkey);
+  if (e->rfp) cudaFree(e->rfp);
   if (e->d_totals) cudaFree(e->d_totals);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -734,8 +762,24 @@ int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, 
                   const uint32_t* len, uint32_t n_reads) {
   if (!e) return SQ_ERR_ARG;
   if (n_reads == 0) return SQ_OK;
-  if (!packed_words || !base_off || !len) return fail(e, SQ_ERR_ARG, "NULL host pointer");
+  if (!packed_words || !len) return fail(e, SQ_ERR_ARG, "NULL host pointer");
   SQ_CUDA(e, cudaSetDevice(e->device));
+  if (!base_off) {
+    // compact form: only the lengths travel; read r starts at the next multiple of 4 bases after read r-1
+    if (n_words * 16 > e->batch_bases + 64) return fail(e, SQ_ERR_ARG, "batch without base_off exceeds option batch_bases (%llu bases): push smaller batches", (unsigned long long)e->batch_bases);
+    Slot* s = nullptr;
+    SQ_TRY(acquire_slot(e, &s));
+    SQ_CUDA(e, s->packed.ensure(((n_words + 3) & ~3ull) * 4 + 64));
+    SQ_CUDA(e, s->base_off.ensure(((size_t)n_reads + 1) * 4));
+    SQ_CUDA(e, s->len.ensure((size_t)n_reads * 4));
+    SQ_CUDA(e, cudaMemcpyAsync(s->packed.p, packed_words, n_words * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaMemcpyAsync(s->len.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
+    SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (n_words + 3) & ~3ull, s->base_off.as<uint32_t>(), 0,
+                     s->len.as<uint32_t>(), n_reads, n_words * 16, s->copied, s->base_off.as<uint32_t>()));
+    SQ_CUDA(e, cudaEventSynchronize(s->copied));
+    return SQ_OK;
+  }
   uint32_t r0 = 0;
   while (r0 < n_reads) {
     // sub-batch [r0, r1): bases from word-aligned start of read r0, at most batch_bases
@@ -795,6 +839,7 @@ int sq_reset_reads(sq_engine* e) {
   e->ovf_total = 0;
   e->slow_total = 0;
   e->mid_total = 0;
+  e->keys_valid = true;
   e->n_reads = e->n_bases = e->n_batches = 0;
   for (int i = 0; i < 8; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
   return SQ_OK;
@@ -844,6 +889,7 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
   }
   e->P = P;
   e->n_reads = n_reads;
+  e->keys_valid = false;  // no compaction ran: sq_finish computes the class keys itself
   return SQ_OK;
 }
 
@@ -914,16 +960,22 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(std::max(P, R)) * 4));
       SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R + 1)) * 4));
       const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1));
-      const uint32_t hash_bits = top_bits <= 18 ? 32 - top_bits : 32 - top_bits >= 8 ? 32 - top_bits : 0;
-      if (hash_bits == 0) return fail(e, SQ_ERR_CAPACITY, "more than 2^24 transcripts are not supported");
-      SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
-      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
-                        e->cls_fp.p, st, &e->launches);
+      const uint32_t hash_bits = e->class_hash_bits;
+      const void* fp = e->rfp;
+      if (e->keys_valid) {
+        // keys and fingerprints were produced batch by batch by the compaction (the sort works on a copy)
+        SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));
+      } else {
+        SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
+        launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
+                          e->cls_fp.p, st, &e->launches);
+        fp = e->cls_fp.p;
+      }
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
                         (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
-      launch_class_heads(skeys, R, e->read_off, e->cls_fp.p, e->cls_head.as<uint32_t>(),
+      launch_class_heads(skeys, R, e->read_off, fp, e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));

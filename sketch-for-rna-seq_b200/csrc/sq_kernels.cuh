@@ -39,7 +39,8 @@ void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkey
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, cudaStream_t s, uint64_t* launches);
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, uint32_t T, uint32_t hash_bits,
+                    uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches);
 void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,

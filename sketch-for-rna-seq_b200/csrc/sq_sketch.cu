@@ -197,6 +197,20 @@ __global__ void items_expand_kernel(const uint32_t* __restrict__ item_start, uin
   for (uint32_t i = b; i < e; ++i) item_read[i] = r;
 }
 
+__global__ void padded_len_kernel(const uint32_t* __restrict__ len, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) out[r] = (len[r] + 3u) & ~3u;
+}
+
+// base_off[r] for reads packed back to back, each starting at the next multiple of 4 bases
+void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
+                           cudaStream_t s, uint64_t* launches) {
+  if (!n_reads) return;
+  padded_len_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(len, n_reads, tmp);
+  if (launches) ++*launches;
+  launch_exclusive_scan(tmp, base_off, n_reads, scan_tmp, s, launches);
+}
+
 void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t* item_start, uint32_t* item_read,
                   uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches) {
   if (n_reads == 0) return;

@@ -152,6 +152,27 @@ def test_overflow_path_many_transcripts(gpu_lib, sqb, port):
     np.testing.assert_allclose(pi, opi, rtol=RTOL)
 
 
+def test_offsets_derived_on_device(gpu_lib, sqb, port):
+    """sq_push_reads with base_off = NULL: reads packed back to back on 4-base boundaries"""
+    d = dataset()
+    ks = [21, 31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    reads = d["reads"][:150] + [d["tseqs"][0][:31], d["tseqs"][1][:1234]]  # ragged lengths
+    res = []
+    for explicit in (True, False):
+        with sqb.Engine(ks, len(d["names"])) as e:
+            for i, k in enumerate(ks):
+                e.load_index(i, *postings[k])
+            words, off, ln = sqb.packing.pack_reads(reads, align=4)
+            e.push_reads(words, off if explicit else None, ln)
+            res.append(e.candidates())
+    for a, b in zip(*res):
+        assert a.tolist() == b.tolist()
+    _, ooff, otid, oscore, _ = port.chain_batch(ks, thr, 0.9, postings, reads)
+    assert res[1][1].tolist() == otid.tolist() and res[1][2].tolist() == oscore.tolist()
+
+
 def test_unsorted_posting_lists(gpu_lib, sqb, port):
     """the reference's index file lists transcripts under a hash in arbitrary order"""
     d = dataset()
