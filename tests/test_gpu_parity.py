@@ -294,3 +294,83 @@ def test_against_reference_code_directly(gpu_lib, sqb, port):
     rc, rp = r.counts()
     assert present.tolist() == rp.tolist()
     np.testing.assert_allclose(nr, rc, rtol=RTOL, atol=1e-12)
+
+
+def test_more_edge_cases(gpu_lib, sqb, port):
+    """item boundaries (256/257/512/513 bases), a very long read, reads shorter than some k, eight k values,
+    chain fractions 0 / 1 / >1, threshold 0, a single transcript"""
+    rng = np.random.default_rng(23)
+    d = dataset()
+    T = len(d["names"])
+    base = d["tseqs"]
+    long_t = max(base, key=len)
+    reads = [long_t[:n] for n in (255, 256, 257, 511, 512, 513, 1024) if n <= len(long_t)]
+    reads += [(long_t * 40)[:100000]]                      # 100 kb of repeats: many items, heavy duplicate removal
+    reads += [base[3][:40], base[4][:31], base[5][:20]]    # the last one is shorter than k=21/31: no window at all
+    dd = dict(d, reads=reads)
+    for ks, frac, sk in (([21, 31], 0.9, SKETCH), ([31], 0.0, SKETCH), ([31], 1.0, SKETCH), ([31], 1.5, SKETCH),
+                         ([11, 13, 15, 17, 19, 21, 23, 25], 0.9, SKETCH), ([31], 0.9, 0.0), ([31], 0.9, 1.0)):
+        thr = port.threshold(sk)
+        kk = sorted(set(ks))
+        postings = port.postings_from_sequences(base, kk, thr)
+        rr = [r for r in reads if len(r) >= max(ks)]       # admission is the caller's job (main.cpp:136-138)
+        dd = dict(d, reads=rr)
+        off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, dd, ks, postings, fraction=frac, sketch=sk)
+        _, ooff, otid, oscore, R = port.chain_batch(ks, thr, frac, postings, rr)
+        assert off.tolist() == ooff.tolist(), (ks, frac, sk)
+        assert tid.tolist() == otid.tolist() and score.tolist() == oscore.tolist(), (ks, frac, sk)
+        opi, oit = port.em(ooff, otid, oscore, R, T)
+        onr, opres = port.assign(ooff, otid, oscore, T, opi)
+        assert it == oit
+        np.testing.assert_allclose(pi, opi, rtol=RTOL)
+        np.testing.assert_allclose(nr, onr, rtol=RTOL, atol=1e-12)
+        assert present.tolist() == opres.tolist()
+    # one transcript only
+    one = {"tseqs": [base[0]], "names": ["only"], "reads": [base[0][:150], base[0][10:200], base[1][:150]]}
+    thr = port.threshold(SKETCH)
+    p1 = port.postings_from_sequences(one["tseqs"], [31], thr)
+    off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, one, [31], p1)
+    _, ooff, otid, oscore, R = port.chain_batch([31], thr, 0.9, p1, one["reads"])
+    assert tid.tolist() == otid.tolist() and score.tolist() == oscore.tolist()
+    opi, _ = port.em(ooff, otid, oscore, R, 1)
+    np.testing.assert_allclose(pi, opi, rtol=RTOL)
+
+
+def test_engine_reuse_stream_and_errors(gpu_lib, sqb, port):
+    import torch
+    d = dataset()
+    ks = [31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    T = len(d["names"])
+    words, off, ln = sqb.packing.pack_reads(d["reads"])
+    with sqb.Engine(ks, T) as e:
+        e.load_index(0, *postings[31])
+        st = torch.cuda.Stream()
+        e.set_stream(st.cuda_stream)
+        e.set_profiling(True)
+        outs = []
+        for _ in range(3):  # same engine, reads forgotten in between: identical answers, bit for bit
+            e.reset_reads()
+            e.push_reads(words, off, ln)
+            outs.append(e.finish(0, 20, 0.01))
+        for o in outs[1:]:
+            assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        s = e.stats()
+        assert s["launches"] > 0 and s["ms_vote"] > 0 and s["em_classes"] > 0
+        # argument errors come back as codes with a message, never as a crash
+        with pytest.raises(sqb.SketchQuantError) as ei:
+            e.load_index(5, *postings[31])
+        assert ei.value.code == -2
+        bad = postings[31][2].copy()
+        bad[0] = T + 5
+        with pytest.raises(sqb.SketchQuantError):
+            e.load_index(0, postings[31][0], postings[31][1], bad)
+        with pytest.raises(sqb.SketchQuantError):
+            e.set_option("no_such_option", 1)
+    with pytest.raises(sqb.SketchQuantError):
+        sqb.Engine([], 10)
+    with pytest.raises(sqb.SketchQuantError):
+        sqb.Engine([31] * 9, 10)
+    with pytest.raises(sqb.SketchQuantError):
+        sqb.Engine([31], 0)
