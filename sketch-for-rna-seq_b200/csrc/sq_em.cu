@@ -162,6 +162,25 @@ __global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_
   if (valid) head[i] = (i == 0 || (k >> 32) != (pk >> 32) || mine.x != px || mine.y != py) ? 1u : 0u;
 }
 
+// exact variant (option exact_classes): equal key AND element-wise equal lists; ~10 random sectors per read
+__global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
+                                        const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ cand_tid,
+                                        const int32_t* __restrict__ cand_score, uint32_t* __restrict__ head) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  uint32_t h = 1;
+  if (i > 0 && (keys[i] >> 32) == (keys[i - 1] >> 32)) {
+    const uint32_t r = (uint32_t)keys[i], q = (uint32_t)keys[i - 1];
+    const uint32_t b = read_off[r], n = read_off[r + 1] - b, bq = read_off[q];
+    if (read_off[q + 1] - bq == n) {
+      h = 0;
+      for (uint32_t j = 0; j < n; ++j)
+        if (cand_tid[b + j] != cand_tid[bq + j] || cand_score[b + j] != cand_score[bq + j]) { h = 1; break; }
+    }
+  }
+  head[i] = h;
+}
+
 // class c = run of sorted positions starting at a head: its list is the head's, its weight the run length
 __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ cid,
                                   const uint64_t* __restrict__ keys, uint64_t n_reads,
@@ -204,12 +223,13 @@ void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_
 
 // heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + class table (read, position, count)
 void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
-                        uint32_t* head, uint32_t* cid,
+                        const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  class_head_kernel<<<grid, 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
+  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, read_off, cand_tid, cand_score, head);
+  else class_head_kernel<<<grid, 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
   launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
   class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, read_off, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;

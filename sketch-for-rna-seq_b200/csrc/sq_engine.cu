@@ -111,6 +111,7 @@ struct sq_engine {
   uint32_t n_workers = 64;
   uint32_t max_read_len = 1u << 20;
   uint32_t em_seg = 1024;
+  bool exact_classes = false;  // compare candidate lists element-wise instead of by 128-bit fingerprint
   // batch slots
   Slot slot[2];
   int next_slot = 0;
@@ -636,8 +637,9 @@ int sq_set_profiling(sq_engine* e, int enabled) {
 
 int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SQ_ERR_ARG;
-  if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   const std::string n(name);
+  if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
+  if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
   else if (n == "cand_per_read") e->cand_per_read = (uint32_t)value;
@@ -975,7 +977,8 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
                         (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
-      launch_class_heads(skeys, R, e->read_off, fp, e->cls_head.as<uint32_t>(),
+      launch_class_heads(skeys, R, e->read_off, fp, e->cand_tid, e->cand_score, e->exact_classes,
+                         e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));

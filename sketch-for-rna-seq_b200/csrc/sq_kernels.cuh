@@ -46,7 +46,7 @@ void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cu
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
                        uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);
 void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
-                        uint32_t* head, uint32_t* cid,
+                        const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches);
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,

@@ -768,17 +768,31 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
       P.read_cnt[r] = (fits && !defer) ? nc : 0u;
     }
     __syncwarp();
-    // ---- order (score desc, transcript asc): lane g ranks candidates g, g+4, ... against the whole list
+    // ---- order (score desc, transcript asc).  The candidates of the warp's 8 reads are dealt to the 32 lanes
+    //      evenly (lists differ a lot in size); each is ranked against its own read's list and written at its
+    //      rank, which is its position in the ordered output.
     if (fits)
-      for (uint32_t c = g; c < nc; c += 4) {
-        const uint32_t inv = S.cs[c][q], tid = S.ct[c][q];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < nc; ++j) {
-          const uint32_t pi = S.cs[j][q], pt = S.ct[j][q];
-          rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
+      for (uint32_t e0 = 0; e0 < wtot; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        uint32_t qq = 0;  // owner quad = number of quads whose inclusive prefix is <= e
+#pragma unroll
+        for (int step = 4; step; step >>= 1) {
+          const uint32_t t = __shfl_sync(0xFFFFFFFFu, qincl, ((qq + step - 1) & 7) * 4);
+          if (t <= e) qq += step;
         }
-        P.stage_tid[rbase + rank] = tid;
-        P.stage_score[rbase + rank] = (int32_t)(0x7FFFFFFFu - inv);
+        const uint32_t qn = __shfl_sync(0xFFFFFFFFu, nc, (qq & 7) * 4);
+        const uint32_t qex = __shfl_sync(0xFFFFFFFFu, qincl, (qq & 7) * 4) - qn;
+        if (e < wtot) {
+          const uint32_t idx = e - qex;
+          const uint32_t inv = S.cs[idx][qq], tid = S.ct[idx][qq];
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < qn; ++j) {
+            const uint32_t pi = S.cs[j][qq], pt = S.ct[j][qq];
+            rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
+          }
+          P.stage_tid[wbase + qex + rank] = tid;
+          P.stage_score[wbase + qex + rank] = (int32_t)(0x7FFFFFFFu - inv);
+        }
       }
     __syncwarp();
   }

@@ -87,6 +87,21 @@ def test_fullscale_properties_and_sampled_parity(big, sqb, port):
         assert score[a:b].tolist() == oscore[int(ooff[j]):int(ooff[j + 1])].tolist(), i
 
 
+def test_fingerprint_classes_equal_exact_classes(big, sqb):
+    """EM classes found by 128-bit list fingerprints are the classes found by comparing the lists"""
+    eng = big["eng"]
+    _push_all(eng, big["chunks"])
+    eng.set_option("exact_classes", 0)
+    pi0, nr0, pr0, _ = eng.finish(0, 20, 0.01)
+    c0 = eng.stats()["em_classes"]
+    eng.set_option("exact_classes", 1)
+    pi1, nr1, pr1, _ = eng.finish(0, 20, 0.01)
+    c1 = eng.stats()["em_classes"]
+    eng.set_option("exact_classes", 0)
+    assert c0 == c1 and c0 < 0.5 * 3_000_000
+    assert np.array_equal(pi0, pi1) and np.array_equal(nr0, nr1) and np.array_equal(pr0, pr1)
+
+
 def test_batching_is_invisible(big, sqb):
     eng = big["eng"]
     _push_all(eng, big["chunks"][:1])
