@@ -527,8 +527,9 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
 // ------------------------------------------------------------------ 4 lanes per read (short reads)
 // Middle ground between one thread and one warp per read: a QUAD of 4 lanes owns a read, a warp 8 reads.
 // The read's hashes, the elements of each posting list and the table slots are dealt to the 4 lanes by
-// index (j % 4), so the loops of a warp run ceil(n/4) times with little spread, and the per-warp shared
-// memory is small enough (4.5 KB) for 48 resident warps per SM.  (A warp-per-32-reads variant with every loop
+// index (j % 4), so those loops run ceil(n/4) times with little spread; the two phases whose work differs most
+// from read to read (voting the posting elements, ranking the candidates) are dealt across the whole warp by
+// a prefix sum over the 8 reads.  The per-warp shared memory is small enough (4.9 KB) for 44+ warps per SM.  (A warp-per-32-reads variant with every loop
 // flattened over the tile by prefix sums was tried and was slower: 12 KB of tables per warp capped the
 // occupancy at 25 %, see profiles/r01_notes.md.)  Tables are [slot][quad]: lane g scanning slots g, g+4, ... is bank-conflict free.
 // Reads with several items, more than kQuadMaxHashes hashes for a k, more than kQuadMaxLists distinct lists
@@ -544,8 +545,10 @@ struct QuadSmem {
   uint32_t cnt[kQuadSlots][8];
   uint32_t ct[kQuadMaxFill][8];        // surviving candidates: transcript
   uint32_t cs[kQuadMaxFill][8];        // surviving candidates: 0x7FFFFFFF - score
-  uint32_t ho[kQuadMaxHashes][8];      // posting offset per hash; rows < kQuadMaxLists reused for the distinct lists
-  uint32_t llw[kQuadMaxLists][8];      // list length (low 16 bits) | weight (high 16 bits)
+  uint32_t ho[kQuadMaxHashes][8];      // posting offset per hash (SQ_EMPTY: miss, 0xFFFFFFFE: duplicate hash)
+  uint32_t lo[kQuadMaxLists][8];       // distinct posting lists: offset
+  uint32_t llw[kQuadMaxLists][8];      // distinct posting lists: length (low 16 bits) | weight (high 16 bits)
+  uint32_t fill[8];                    // distinct transcripts in each read's table
   uint16_t hh[kQuadMaxHashes][8];      // low 16 bits of each hash (duplicate pre-filter)
 };
 
@@ -564,6 +567,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
     const bool valid = r < P.n_reads;
 #pragma unroll
     for (uint32_t sl = g; sl < kQuadSlots; sl += 4) { S.key[sl][q] = SQ_EMPTY; S.cnt[sl][q] = 0; }
+    if (g == 0) S.fill[q] = 0;
     bool defer = false;
     uint32_t item0 = 0, boff = 0, fill = 0, tq = 0, th = 0;
     if (valid) {
@@ -614,62 +618,103 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
         }
       }
       __syncwarp();
-      // ---- lane 0 of the quad groups hits that share a posting list (rows [0, nd) of ho, nd <= j)
-      uint32_t nd = 0;
-      if (g == 0 && n) {
-        for (uint32_t j = 0; j < n; ++j) {
+      // ---- group hits that share a posting list (equal offsets).  Lane g looks at hits g, g+4, ...: a hit is
+      //      the FIRST of its list when no earlier hit has the same offset, and then its weight is the number of
+      //      hits with that offset.  The firsts are compacted into (lo, llw) by a prefix inside the quad.
+      uint32_t first_off[kQuadMaxHashes / 4], first_w[kQuadMaxHashes / 4];
+      uint32_t my_first = 0;
+#pragma unroll
+      for (uint32_t m = 0; m < kQuadMaxHashes / 4; ++m) {
+        const uint32_t j = g + 4 * m;
+        first_w[m] = 0;
+        first_off[m] = 0;
+        if (j < n) {
           const uint32_t off = S.ho[j][q];
-          if (off == 0xFFFFFFFEu) continue;
-          ++tq;
-          if (off == SQ_EMPTY) continue;
-          ++th;
-          uint32_t i = 0;
-          for (; i < nd; ++i)
-            if (S.ho[i][q] == off) break;
-          if (i < nd) {
-            S.llw[i][q] += 1u << 16;
-          } else if (nd < kQuadMaxLists) {
-            S.ho[nd][q] = off;
-            S.llw[nd][q] = 1u << 16;
-            ++nd;
-          } else {
-            defer = true;
-            break;
+          if (off != 0xFFFFFFFEu) {  // not a duplicate hash
+            ++tq;
+            if (off != SQ_EMPTY) {
+              ++th;
+              bool seen = false;
+              for (uint32_t jj = 0; jj < j; ++jj) seen |= S.ho[jj][q] == off;
+              if (!seen) {
+                uint32_t w = 1;
+                for (uint32_t jj = j + 1; jj < n; ++jj) w += S.ho[jj][q] == off ? 1u : 0u;
+                first_off[m] = off;
+                first_w[m] = w;
+                ++my_first;
+              }
+            }
           }
         }
-        if (defer) nd = 0;
       }
-      nd = __shfl_sync(0xFFFFFFFFu, nd, q * 4);
-      defer = __shfl_sync(0xFFFFFFFFu, (int)defer, q * 4) != 0;
+      uint32_t fpre = my_first;  // inclusive prefix of the firsts inside the quad
+      {
+        const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, fpre, 1);
+        if (g >= 1) fpre += a1;
+        const uint32_t a2 = __shfl_up_sync(0xFFFFFFFFu, fpre, 2);
+        if (g >= 2) fpre += a2;
+      }
+      uint32_t nd = __shfl_sync(0xFFFFFFFFu, fpre, q * 4 + 3);
+      if (nd > kQuadMaxLists) { defer = true; nd = 0; }
+      uint32_t nel = 0;  // posting elements of my lists
+      if (nd) {
+        uint32_t pos = fpre - my_first;
+#pragma unroll
+        for (uint32_t m = 0; m < kQuadMaxHashes / 4; ++m)
+          if (first_w[m]) {
+            const uint32_t len = __ldg(tb.postings + first_off[m]);  // header word: list length
+            S.lo[pos][q] = first_off[m];
+            S.llw[pos][q] = (first_w[m] << 16) | (len & 0xFFFFu);
+            if (len > 0xFFFFu) nel = 0x40000000u;  // absurdly long list: leave the read to the warp kernel
+            nel += len;
+            ++pos;
+          }
+      }
+      nel += __shfl_xor_sync(0xFFFFFFFFu, nel, 1);
+      nel += __shfl_xor_sync(0xFFFFFFFFu, nel, 2);
+      if (nel >= 0x40000000u) { defer = true; nel = 0; }
+      // ---- vote: the posting elements of the warp's 8 reads are dealt to the 32 lanes evenly (prefix sum of the
+      //      per-read element counts); each goes into its read's hash table with shared-memory atomics
+      uint32_t eincl = g == 0 ? nel : 0;
+#pragma unroll
+      for (int d = 4; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, eincl, d);
+        if ((int)lane >= d) eincl += t;
+      }
+      eincl = __shfl_sync(0xFFFFFFFFu, eincl, q * 4);  // inclusive prefix of my quad, on all its lanes
+      const uint32_t etot = __shfl_sync(0xFFFFFFFFu, eincl, 28);
       __syncwarp();
-      // ---- merge each distinct list into the read's table: lane g takes elements g, g+4, ... of the list.
-      //      Inside one list the transcripts are distinct, so only the slot claim needs an atomic.
-      for (uint32_t i = 0; i < nd; ++i) {
-        const uint32_t off = S.ho[i][q];
-        const uint32_t w = S.llw[i][q] >> 16;
-        const uint32_t len = __ldg(tb.postings + off);
-        const uint32_t add = w << (8 * ki);
-        for (uint32_t idx = g; idx < len; idx += 4) {
-          const uint32_t tid = __ldg(tb.postings + off + 1 + idx) & ~SQ_LAST;
+      for (uint32_t e0 = 0; e0 < etot; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        uint32_t qq = 0;  // owner quad = number of quads whose inclusive prefix is <= e
+#pragma unroll
+        for (int step = 4; step; step >>= 1) {
+          const uint32_t t = __shfl_sync(0xFFFFFFFFu, eincl, ((qq + step - 1) & 7) * 4);
+          if (t <= e) qq += step;
+        }
+        const uint32_t qel = __shfl_sync(0xFFFFFFFFu, nel, (qq & 7) * 4);
+        const uint32_t qex = __shfl_sync(0xFFFFFFFFu, eincl, (qq & 7) * 4) - qel;
+        if (e < etot) {
+          uint32_t idx = e - qex, i = 0, lw = S.llw[0][qq];
+          while (idx >= (lw & 0xFFFFu)) { idx -= lw & 0xFFFFu; lw = S.llw[++i][qq]; }
+          const uint32_t tid = __ldg(tb.postings + S.lo[i][qq] + 1 + idx) & ~SQ_LAST;
+          const uint32_t add = (lw >> 16) << (8 * ki);
           uint32_t sl = (tid * kHashMul) >> 27;
           uint32_t tries = 0;
           for (; tries < kQuadSlots; ++tries) {
-            const uint32_t old = atomicCAS(&S.key[sl][q], SQ_EMPTY, tid);
-            if (old == SQ_EMPTY) ++fill;
-            if (old == SQ_EMPTY || old == tid) { S.cnt[sl][q] += add; break; }
+            const uint32_t old = atomicCAS(&S.key[sl][qq], SQ_EMPTY, tid);
+            if (old == SQ_EMPTY) atomicAdd(&S.fill[qq], 1u);
+            if (old == SQ_EMPTY || old == tid) { atomicAdd(&S.cnt[sl][qq], add); break; }
             sl = (sl + 1) & (kQuadSlots - 1);
           }
-          if (tries == kQuadSlots) fill = 1000;  // table full
-          wp += w;
+          if (tries == kQuadSlots) S.fill[qq] = 1000;  // table full
+          wp += lw >> 16;
         }
-        __syncwarp(qmask);
       }
       __syncwarp();
     }
-    // distinct transcripts of the read = sum of the 4 lanes' claims
-    fill += __shfl_xor_sync(0xFFFFFFFFu, fill, 1);
-    fill += __shfl_xor_sync(0xFFFFFFFFu, fill, 2);
-    if (fill > kQuadMaxFill) defer = true;
+    fill = S.fill[q];
+    if (fill > kQuadMaxFill) defer = true;  // too many distinct transcripts for the table
     // ---- per-k maximum over the table: lane g scans slots g, g+4, ...; combine inside the quad
     uint32_t mx = 0;
 #pragma unroll
@@ -739,7 +784,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
           ++pos;
         }
     }
-    if (valid && !defer && g == 0) { wq += tq; wh += th; }
+    if (valid && !defer) { wq += tq; wh += th; }  // every lane counted its own hashes
     // hand reads that did not fit (long reads, many hashes, many lists, many transcripts) to the
     // warp-per-read kernel: they are the heavy ones, a whole warp suits them better than one thread
     const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer && g == 0);
