@@ -100,8 +100,14 @@ struct VoteParams {
 };
 
 // ---------- launchers (definitions in the .cu files) ----------
+struct KList {
+  uint32_t nk;
+  uint32_t k[SQ_MAXK];
+};
+// stats (optional): [0] += k-mers of the batch, [1] += bases of the batch
 void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t* item_start, uint32_t* item_read,
-                  uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches);
+                  uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches, const KList& ks,
+                  unsigned long long* stats);
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches);
 void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
                            cudaStream_t s, uint64_t* launches);

@@ -116,7 +116,7 @@ struct sq_engine {
   Slot slot[2];
   int next_slot = 0;
   // device counters + pinned mirror
-  unsigned long long* d_totals = nullptr;        // [0] sketch hashes (stats)
+  unsigned long long* d_totals = nullptr;        // stats: [0] sketch hashes, [1..3] probes/hits/postings, [4] k-mers, [5] bases
   unsigned long long* d_slot_ctr = nullptr;      // per slot: [2*i] staging cursor, [2*i+1] = overflow reads (low u32) | slow-path reads (high u32)
   uint32_t* d_flags = nullptr;
   uint32_t* d_fail = nullptr;
@@ -136,7 +136,7 @@ struct sq_engine {
   bool keys_valid = true;
   uint32_t class_hash_bits = 14;
   uint64_t cand_cap = 0, read_cap = 0;
-  uint64_t n_reads = 0, n_bases = 0, n_kmers_known = 0, n_batches = 0;  // n_reads: all enqueued batches
+  uint64_t n_reads = 0, n_bases = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
       read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score,
@@ -421,8 +421,11 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
 
   {
     StageScope st(e, 6);
+    KList kl;
+    kl.nk = e->nk;
+    for (uint32_t i = 0; i < e->nk; ++i) kl.k[i] = e->ks[i];
     launch_items(d_len, n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(), s.item_read.as<uint32_t>(),
-                 items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches);
+                 items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches, kl, e->d_totals + 4);
     SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * e->nk * 2, e->stream));
   }
   {
@@ -505,11 +508,6 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   return SQ_OK;
 }
 
-int require_index(sq_engine* e) {
-  if (!e) return SQ_ERR_ARG;
-  return SQ_OK;
-}
-
 }  // namespace
 
 extern "C" {
@@ -572,12 +570,12 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   e->stream = e->own_stream;
   void* ctr = nullptr;
-  if ((ce = cudaMalloc(&ctr, 128)) != cudaSuccess) return bail(ce, "cudaMalloc");
-  if ((ce = cudaMemset(ctr, 0, 128)) != cudaSuccess) return bail(ce, "cudaMemset");
+  if ((ce = cudaMalloc(&ctr, 256)) != cudaSuccess) return bail(ce, "cudaMalloc");
+  if ((ce = cudaMemset(ctr, 0, 256)) != cudaSuccess) return bail(ce, "cudaMemset");
   e->d_totals = static_cast<unsigned long long*>(ctr);                 // byte 0
-  e->d_slot_ctr = e->d_totals + 4;                                     // bytes 32..95 (2 slots x 32 B)
-  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 12);          // byte 96
-  e->d_fail = e->d_flags + 1;                                          // byte 100
+  e->d_slot_ctr = e->d_totals + 8;                                     // bytes 64..127 (2 slots x 32 B)
+  e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 16);          // byte 128
+  e->d_fail = e->d_flags + 1;                                          // byte 132
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 64);
   *out = e;
@@ -833,7 +831,7 @@ int sq_sync(sq_engine* e) {
 int sq_reset_reads(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 128, e->stream));
+  SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 256, e->stream));
   if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   memset(e->h_mirror, 0, 64);
@@ -1081,12 +1079,12 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
 int sq_get_stats(sq_engine* e, sq_stats* out) {
   if (!e || !out) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
-  unsigned long long tot[4] = {0, 0, 0, 0};
+  unsigned long long tot[6] = {0, 0, 0, 0, 0, 0};
   SQ_CUDA(e, cudaMemcpy(tot, e->d_totals, sizeof(tot), cudaMemcpyDeviceToHost));
   memset(out, 0, sizeof(*out));
   out->reads = e->n_reads;
-  out->bases = e->n_bases;
-  out->kmers = e->n_kmers_known;
+  out->bases = tot[5];
+  out->kmers = tot[4];
   out->sketch_hashes = tot[0];
   out->pairs = e->P;
   out->overflow_reads = e->ovf_total;
@@ -1169,8 +1167,10 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
   SQ_CUDA(e, cudaMemcpyAsync(s.packed.p, packed_words + w0, nw * 4, cudaMemcpyHostToDevice, st));
   SQ_CUDA(e, cudaMemcpyAsync(s.base_off.p, base_off, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
   SQ_CUDA(e, cudaMemcpyAsync(s.len.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+  KList kl;
+  kl.nk = 0;
   launch_items(s.len.as<uint32_t>(), n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(),
-               s.item_read.as<uint32_t>(), items_ub, s.scan_tmp.as<uint32_t>(), st, &e->launches);
+               s.item_read.as<uint32_t>(), items_ub, s.scan_tmp.as<uint32_t>(), st, &e->launches, kl, nullptr);
   SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * nk * 2, st));
   SketchParams sp;
   memset(&sp, 0, sizeof(sp));

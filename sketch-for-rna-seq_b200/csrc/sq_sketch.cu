@@ -184,9 +184,28 @@ void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches) {
 
 // ---------- items: split reads into chunks of <= SQ_CHUNK window ends ----------
 
-__global__ void items_count_kernel(const uint32_t* __restrict__ len, uint32_t n, uint32_t* __restrict__ nit) {
+// items per read; also the batch's k-mer count sum_r sum_k max(len_r - k + 1, 0) and base count (stats)
+__global__ void items_count_kernel(const uint32_t* __restrict__ len, uint32_t n, uint32_t* __restrict__ nit,
+                                   KList ks, unsigned long long* __restrict__ stats) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n) nit[r] = items_of(len[r]);
+  unsigned long long km = 0, nb = 0;
+  if (r < n) {
+    const uint32_t L = len[r];
+    nit[r] = items_of(L);
+    nb = L;
+    for (uint32_t i = 0; i < ks.nk; ++i) km += L >= ks.k[i] ? L - ks.k[i] + 1 : 0;
+  }
+  if (stats) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      km += __shfl_xor_sync(0xFFFFFFFFu, km, d);
+      nb += __shfl_xor_sync(0xFFFFFFFFu, nb, d);
+    }
+    if (lane_id() == 0 && nb) {
+      atomicAdd(stats + 0, km);
+      atomicAdd(stats + 1, nb);
+    }
+  }
 }
 
 __global__ void items_expand_kernel(const uint32_t* __restrict__ item_start, uint32_t n, uint32_t n_items_ub,
@@ -212,10 +231,11 @@ void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp,
 }
 
 void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t* item_start, uint32_t* item_read,
-                  uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches) {
+                  uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches, const KList& ks,
+                  unsigned long long* stats) {
   if (n_reads == 0) return;
   const uint32_t grid = (n_reads + 255) / 256;
-  items_count_kernel<<<grid, 256, 0, s>>>(len, n_reads, nit);
+  items_count_kernel<<<grid, 256, 0, s>>>(len, n_reads, nit, ks, stats);
   if (launches) ++*launches;
   launch_exclusive_scan(nit, item_start, n_reads, scan_tmp, s, launches);
   items_expand_kernel<<<grid, 256, 0, s>>>(item_start, n_reads, n_items_ub, item_read);

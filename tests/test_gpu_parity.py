@@ -100,6 +100,8 @@ def test_quant_parity_short_reads(gpu_lib, sqb, port, ks, kw):
     off, tid, score, pi, nr, present, it, st = _gpu_quant(sqb, d, ks, postings, **kw)
     _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, d["reads"])
     assert st["reads"] == R == len(d["reads"])
+    assert st["bases"] == sum(len(s) for s in d["reads"])
+    assert st["kmers"] == sum(max(len(s) - k + 1, 0) for s in d["reads"] for k in ks)
     assert csr_to_lists(off, tid, score) == csr_to_lists(ooff, otid, oscore)
     # ordering contract of the tap: score descending, then transcript id
     assert tid.tolist() == otid.tolist() and score.tolist() == oscore.tolist()
