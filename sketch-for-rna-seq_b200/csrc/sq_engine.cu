@@ -694,15 +694,30 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
           hkey[slot] = h;
           hval[slot] = (uint32_t)dpost.size();
           off32[i] = hval[slot];
-          dpost.push_back((uint32_t)(b1 - b0));  // header: list length, then the ids (last one flagged)
+          // header: length, window base, 64-bit membership mask; then the ids (last one flagged), padded so
+          // that the next header is 16-byte aligned
+          const uint32_t tmin = post_tid[b0], tmax = post_tid[b1 - 1];
+          dpost.push_back((uint32_t)(b1 - b0));
+          if (tmax - tmin < 64) {
+            uint64_t mask = 0;
+            for (uint64_t j = b0; j < b1; ++j) mask |= 1ull << (post_tid[j] - tmin);
+            dpost.push_back(tmin);
+            dpost.push_back((uint32_t)mask);
+            dpost.push_back((uint32_t)(mask >> 32));
+          } else {
+            dpost.push_back(SQ_NOMASK);
+            dpost.push_back(0);
+            dpost.push_back(0);
+          }
           for (uint64_t j = b0; j < b1; ++j) dpost.push_back(post_tid[j] | (j + 1 == b1 ? SQ_LAST : 0u));
+          while (dpost.size() & 3) dpost.push_back(0);
           break;
         }
         if (hkey[slot] == h) {  // same hash: verify content
           const uint32_t o = hval[slot];
           bool same = true;
           uint64_t j = b0;
-          for (uint32_t q = o + 1;; ++q, ++j) {
+          for (uint32_t q = o + SQ_LIST_HDR;; ++q, ++j) {
             const uint32_t v = dpost[q];
             if (j >= b1 || (v & ~SQ_LAST) != post_tid[j]) { same = false; break; }
             if (v & SQ_LAST) { same = (j + 1 == b1); break; }

@@ -148,7 +148,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
           ++work[0];
           if (off != SQ_EMPTY) {
             ++work[1];
-            ++off;  // skip the length header
+            off += SQ_LIST_HDR;  // skip the list header
             uint32_t t;
             do {
               t = __ldg(tb.postings + off++);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant_
   // merge one posting list (ascending transcript ids) into the sorted table with weight `add`
   auto merge_list = [&](const IndexTable& tb, uint32_t off, CT add, uint32_t w, uint32_t room) {
     uint32_t p = 0, t;
-    ++off;  // skip the length header
+    off += SQ_LIST_HDR;  // skip the list header
     do {
       t = __ldg(tb.postings + off++);
       const uint32_t tid = t & ~SQ_LAST;
@@ -552,19 +552,20 @@ struct QuadSmem {
   uint16_t hh[kQuadMaxHashes][8];      // low 16 bits of each hash (duplicate pre-filter)
 };
 
-template <int NK>
+template <int NK, bool LISTED>  // LISTED: only the reads the bit-mask kernel left in mid_list
 __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid_constant__ VoteParams P) {
   extern __shared__ __align__(16) unsigned char quad_smem_raw[];
   QuadSmem& S = reinterpret_cast<QuadSmem*>(quad_smem_raw)[threadIdx.x >> 5];
   const uint32_t lane = lane_id(), q = lane >> 2, g = lane & 3;
   const uint32_t qmask = 0xFu << (q * 4);
   constexpr uint32_t nk = NK;
-  const uint32_t n_oct = (P.n_reads + 7) / 8;
+  const uint32_t n_in = LISTED ? *P.mid_count : P.n_reads;
+  const uint32_t n_oct = (n_in + 7) / 8;
   uint32_t wq = 0, wh = 0, wp = 0;
 
   for (uint32_t oct = blockIdx.x * kQuadWarps + (threadIdx.x >> 5); oct < n_oct; oct += gridDim.x * kQuadWarps) {
-    const uint32_t r = oct * 8 + q;
-    const bool valid = r < P.n_reads;
+    const bool valid = oct * 8 + q < n_in;
+    const uint32_t r = valid ? (LISTED ? P.mid_list[oct * 8 + q] : oct * 8 + q) : 0u;
 #pragma unroll
     for (uint32_t sl = g; sl < kQuadSlots; sl += 4) { S.key[sl][q] = SQ_EMPTY; S.cnt[sl][q] = 0; }
     if (g == 0) S.fill[q] = 0;
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
         if (e < etot) {
           uint32_t idx = e - qex, i = 0, lw = S.llw[0][qq];
           while (idx >= (lw & 0xFFFFu)) { idx -= lw & 0xFFFFu; lw = S.llw[++i][qq]; }
-          const uint32_t tid = __ldg(tb.postings + S.lo[i][qq] + 1 + idx) & ~SQ_LAST;
+          const uint32_t tid = __ldg(tb.postings + S.lo[i][qq] + SQ_LIST_HDR + idx) & ~SQ_LAST;
           const uint32_t add = (lw >> 16) << (8 * ki);
           uint32_t sl = (tid * kHashMul) >> 27;
           uint32_t tries = 0;
@@ -856,6 +857,182 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
   }
 }
 
+// ------------------------------------------------------------------ bit-mask path (short reads, one k)
+// The isoforms of a gene have neighbouring ids, so the posting lists a short read hits almost always fit a
+// window of 64 transcripts.  The index stores, per distinct list, the window base and a 64-bit membership
+// mask.  One THREAD votes for a read without any table: it probes the read's hashes, groups equal lists,
+// and adds each list's weight into a bit-sliced counter (5 planes of 64 bits = a count 0..31 for each of the
+// 64 window positions; adding a weight to all members of a list is a 5-step ripple-carry over whole words).
+// Per-position maximum, the `count < ceil(fraction*max)` filter and the (score desc, transcript asc) order
+// are word operations too, so there is no data-dependent inner loop left except the handful of probes.
+// Reads that do not fit (several items, > 16 hashes, > 8 distinct lists, a list or the union wider than 64
+// ids) are handed to the 4-lanes-per-read kernel through mid_list.
+static constexpr int kBitsBlock = 128;
+static constexpr uint32_t kBitsMaxHashes = 16;
+static constexpr uint32_t kBitsMaxLists = 8;
+
+__global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_constant__ VoteParams P) {
+  __shared__ uint32_t s_lo[kBitsMaxLists][kBitsBlock];
+  __shared__ uint32_t s_w[kBitsMaxLists][kBitsBlock];
+  __shared__ uint32_t s_work[3];
+  const uint32_t tx = threadIdx.x, lane = lane_id();
+  const uint32_t r = blockIdx.x * kBitsBlock + tx;
+  const bool valid = r < P.n_reads;
+  const IndexTable& tb = P.tab[0];
+  if (tx < 3) s_work[tx] = 0;
+  bool defer = false;
+  uint32_t wq = 0, wh = 0, wp = 0;
+  unsigned long long pl[5] = {0, 0, 0, 0, 0};  // bit-sliced vote count per window position
+  unsigned long long orm = 0, surv = 0;
+  uint32_t wbase = 0, mx = 0, ithr = 0, nc = 0;
+  if (valid && tb.present) {
+    const uint32_t item0 = P.item_start[r];
+    if (P.item_start[r + 1] - item0 != 1) defer = true;
+    const uint32_t n = defer ? 0u : (uint32_t)P.cnt[item0];
+    if (n > kBitsMaxHashes) defer = true;
+    const uint32_t* hs = P.sel + (P.base_off[r] - P.bias);
+    // ---- probe the distinct hashes, group hits that share a posting list
+    uint32_t nd = 0;
+    unsigned long long m1 = 0, m2 = 0;
+    for (uint32_t j = 0; j < n && !defer; ++j) {
+      const uint32_t h = hs[j];
+      const unsigned long long b1 = 1ull << (h & 63), b2 = 1ull << ((h >> 6) & 63);
+      if ((m1 & b1) && (m2 & b2)) {  // an equal hash would share both buckets: exact check (rare)
+        bool dup = false;
+        for (uint32_t jj = 0; jj < j; ++jj) dup |= hs[jj] == h;
+        if (dup) continue;
+      }
+      m1 |= b1;
+      m2 |= b2;
+      const uint32_t off = probe(tb, h);
+      ++wq;
+      if (off == SQ_EMPTY) continue;
+      ++wh;
+      uint32_t i = 0;
+      for (; i < nd; ++i)
+        if (s_lo[i][tx] == off) break;
+      if (i < nd) {
+        s_w[i][tx] += 1;
+      } else if (nd < kBitsMaxLists) {
+        s_lo[nd][tx] = off;
+        s_w[nd][tx] = 1;
+        ++nd;
+      } else {
+        defer = true;
+      }
+    }
+    // ---- add every distinct list's weight to its members
+    bool have = false;
+    for (uint32_t i = 0; i < nd && !defer; ++i) {
+      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(tb.postings + s_lo[i][tx]));
+      const uint32_t w = s_w[i][tx];
+      unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
+      if (hd.y == SQ_NOMASK) { defer = true; break; }
+      if (!have) {
+        wbase = hd.y;
+        have = true;
+      } else if (hd.y < wbase) {  // move the window down: shift what has been counted so far
+        const uint32_t d = wbase - hd.y;
+        if (d >= 64 || (orm >> (64 - d)) != 0) { defer = true; break; }
+#pragma unroll
+        for (int b = 0; b < 5; ++b) pl[b] <<= d;
+        orm <<= d;
+        wbase = hd.y;
+      }
+      const uint32_t d2 = hd.y - wbase;
+      if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) { defer = true; break; }
+      mask <<= d2;
+      orm |= mask;
+      unsigned long long carry = 0;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const unsigned long long a = ((w >> b) & 1u) ? mask : 0ull;
+        const unsigned long long sum = pl[b] ^ a ^ carry;
+        carry = (pl[b] & a) | (pl[b] & carry) | (a & carry);
+        pl[b] = sum;
+      }
+      wp += w * hd.x;
+    }
+    if (!defer && orm) {
+      // ---- maximum over the positions (sparse_chaining.cpp:76-82), MSB first
+      unsigned long long cand = orm;
+#pragma unroll
+      for (int b = 4; b >= 0; --b) {
+        const unsigned long long t = cand & pl[b];
+        if (t) { cand = t; mx |= 1u << b; }
+      }
+      // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an
+      // integer count, count < x  <=>  count < ceil(x)
+      const double t = ceil(P.fraction * (double)(int)mx);
+      ithr = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+      if (ithr <= 31) {
+        unsigned long long gt = 0, eq = orm;  // positions with count > / == the bits of ithr seen so far
+#pragma unroll
+        for (int b = 4; b >= 0; --b) {
+          const unsigned long long tbit = ((ithr >> b) & 1u) ? ~0ull : 0ull;
+          gt |= eq & pl[b] & ~tbit;
+          eq &= ~(pl[b] ^ tbit);
+        }
+        surv = gt | eq;
+      }
+      nc = (uint32_t)__popcll(surv);
+    }
+  }
+  // hand reads that did not fit to the 4-lanes-per-read kernel
+  {
+    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
+    if (dmask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(P.mid_count, (uint32_t)__popc(dmask));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (valid && defer) {
+        P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
+        wq = wh = wp = 0;
+        nc = 0;
+      }
+    }
+  }
+  // one staging allocation per warp
+  const uint32_t incl = warp_incl_scan(nc);
+  const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+  unsigned long long sbase = 0;
+  if (lane == 0 && wtot) sbase = atomicAdd(P.stage_cursor, (unsigned long long)wtot);
+  sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
+  const bool fits = sbase + wtot <= P.stage_cap;
+  sbase += incl - nc;
+  if (valid) {
+    P.read_soff[r] = (uint32_t)sbase;
+    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
+    if (fits && nc) {
+      // ---- order: score descending (:108-109), transcript ascending inside a score
+      const uint32_t lowest = ithr > 1 ? ithr : 1;
+      for (uint32_t c = mx; c >= lowest; --c) {
+        unsigned long long e = surv;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) e &= ((c >> b) & 1u) ? pl[b] : ~pl[b];
+        while (e) {
+          const uint32_t p = (uint32_t)__ffsll((long long)e) - 1;
+          e &= e - 1;
+          P.stage_tid[sbase] = wbase + p;
+          P.stage_score[sbase] = (int32_t)c;
+          ++sbase;
+        }
+      }
+    }
+  }
+  if (P.work) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
+      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
+      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
+    }
+    if (lane == 0) { atomicAdd(&s_work[0], wq); atomicAdd(&s_work[1], wh); atomicAdd(&s_work[2], wp); }
+    __syncthreads();
+    if (tx < 3 && s_work[tx]) atomicAdd(P.work + tx, (unsigned long long)s_work[tx]);
+  }
+}
+
 template <typename CT>
 static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
   constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
@@ -876,20 +1053,24 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       switch (nkq) {
-        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<1>, kQuadWarps * 32, qsm); break;
-        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<2>, kQuadWarps * 32, qsm); break;
-        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<3>, kQuadWarps * 32, qsm); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<4>, kQuadWarps * 32, qsm); break;
+        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<1, true>, kQuadWarps * 32, qsm); break;
+        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<2, false>, kQuadWarps * 32, qsm); break;
+        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<3, false>, kQuadWarps * 32, qsm); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<4, false>, kQuadWarps * 32, qsm); break;
       }
       quad_grid[nkq] = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const uint32_t need = ((p.n_reads + 7) / 8 + kQuadWarps - 1) / kQuadWarps;
     const uint32_t qgrid = need < (uint32_t)quad_grid[nkq] ? need : (uint32_t)quad_grid[nkq];
     switch (nkq) {
-      case 1: vote_quad_kernel<1><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
-      case 2: vote_quad_kernel<2><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
-      case 3: vote_quad_kernel<3><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
-      default: vote_quad_kernel<4><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      case 1:
+        // one k: the bit-mask kernel takes every read it can, the quad kernel the rest (mid_list)
+        vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
+        vote_quad_kernel<1, true><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
+        break;
+      case 2: vote_quad_kernel<2, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      case 3: vote_quad_kernel<3, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      default: vote_quad_kernel<4, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
     }
   } else {
     // more than 4 k values: 64-bit packed counters, thread-per-read tiers (16 then 48 table entries)
