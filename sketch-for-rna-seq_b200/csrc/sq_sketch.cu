@@ -185,14 +185,16 @@ void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches) {
 // ---------- items: split reads into chunks of <= SQ_CHUNK window ends ----------
 
 // items per read; also the batch's k-mer count sum_r sum_k max(len_r - k + 1, 0) and base count (stats)
-__global__ void items_count_kernel(const uint32_t* __restrict__ len, uint32_t n, uint32_t* __restrict__ nit,
-                                   KList ks, unsigned long long* __restrict__ stats) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) items_count_kernel(const uint32_t* __restrict__ len, uint32_t n,
+                                                          uint32_t* __restrict__ nit, KList ks,
+                                                          unsigned long long* __restrict__ stats) {
+  // grid-stride: a few hundred blocks, so the two counters see one atomic per block, not one per warp
+  __shared__ unsigned long long s_km[8], s_nb[8];
   unsigned long long km = 0, nb = 0;
-  if (r < n) {
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
     const uint32_t L = len[r];
     nit[r] = items_of(L);
-    nb = L;
+    nb += L;
     for (uint32_t i = 0; i < ks.nk; ++i) km += L >= ks.k[i] ? L - ks.k[i] + 1 : 0;
   }
   if (stats) {
@@ -201,9 +203,15 @@ __global__ void items_count_kernel(const uint32_t* __restrict__ len, uint32_t n,
       km += __shfl_xor_sync(0xFFFFFFFFu, km, d);
       nb += __shfl_xor_sync(0xFFFFFFFFu, nb, d);
     }
-    if (lane_id() == 0 && nb) {
-      atomicAdd(stats + 0, km);
-      atomicAdd(stats + 1, nb);
+    if (lane_id() == 0) { s_km[threadIdx.x >> 5] = km; s_nb[threadIdx.x >> 5] = nb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      km = nb = 0;
+      for (int w = 0; w < 8; ++w) { km += s_km[w]; nb += s_nb[w]; }
+      if (nb) {
+        atomicAdd(stats + 0, km);
+        atomicAdd(stats + 1, nb);
+      }
     }
   }
 }
@@ -235,7 +243,7 @@ void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t
                   unsigned long long* stats) {
   if (n_reads == 0) return;
   const uint32_t grid = (n_reads + 255) / 256;
-  items_count_kernel<<<grid, 256, 0, s>>>(len, n_reads, nit, ks, stats);
+  items_count_kernel<<<grid < 1184 ? grid : 1184, 256, 0, s>>>(len, n_reads, nit, ks, stats);
   if (launches) ++*launches;
   launch_exclusive_scan(nit, item_start, n_reads, scan_tmp, s, launches);
   items_expand_kernel<<<grid, 256, 0, s>>>(item_start, n_reads, n_items_ub, item_read);

@@ -865,83 +865,170 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
 // 64 window positions; adding a weight to all members of a list is a 5-step ripple-carry over whole words).
 // Per-position maximum, the `count < ceil(fraction*max)` filter and the (score desc, transcript asc) order
 // are word operations too, so there is no data-dependent inner loop left except the handful of probes.
-// Reads that do not fit (several items, > 16 hashes, > 8 distinct lists, a list or the union wider than 64
-// ids) are handed to the 4-lanes-per-read kernel through mid_list.
+//
+// 32-bit hashes below the 5 % threshold collide: about one list in 70 joins the k-mers of two unrelated genes
+// and one read in seven meets such a list.  Those lists (and any list that does not fit the window) are walked
+// element by element in a second pass: members inside the window go into the planes, the others into a few
+// (transcript, count) "outlier" slots that join the maximum, the filter and the ordering.
+// Reads that still do not fit (several items, > 16 hashes, > 8 distinct lists, a walked list longer than 48,
+// > 8 outliers) are handed to the 4-lanes-per-read kernel through mid_list.
 static constexpr int kBitsBlock = 128;
 static constexpr uint32_t kBitsMaxHashes = 16;
 static constexpr uint32_t kBitsMaxLists = 8;
+static constexpr uint32_t kBitsOutliers = 8;
+static constexpr uint32_t kBitsWalkMax = 48;
+static constexpr uint32_t kBitsFlat = 32 * kBitsMaxHashes;  // hashes of one warp's 32 reads
+
+// first bucket of the probe sequence already loaded: finish the lookup (see probe())
+__device__ __forceinline__ uint32_t probe_resolve(const IndexTable& tb, uint32_t h, uint32_t b, uint4 kk, uint4 oo) {
+  if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
+  if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
+  if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
+  if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
+  if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
+  for (uint32_t tries = 1; tries <= tb.mask; ++tries) {  // full bucket without the key: rare
+    b = (b + 1) & tb.mask;
+    kk = __ldg(tb.buckets + 2 * (size_t)b);
+    oo = __ldg(tb.buckets + 2 * (size_t)b + 1);
+    if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
+    if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
+    if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
+    if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
+    if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
+  }
+  return SQ_EMPTY;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_constant__ VoteParams P) {
-  __shared__ uint32_t s_lo[kBitsMaxLists][kBitsBlock];
-  __shared__ uint32_t s_w[kBitsMaxLists][kBitsBlock];
-  __shared__ uint32_t s_work[3];
-  const uint32_t tx = threadIdx.x, lane = lane_id();
+  // per warp: the hashes of its 32 reads back to back (read l owns [start_l, start_l + n_l)); the slots are
+  // rewritten in place: hash -> posting offset -> the read's distinct lists and their weights
+  __shared__ uint32_t s_o[kBitsBlock / 32][kBitsFlat];
+  __shared__ uint8_t s_w[kBitsBlock / 32][kBitsFlat];  // 1 = probe this slot / weight, bit 7: walk in pass 2
+  __shared__ uint32_t s_xt[kBitsOutliers][kBitsBlock];
+  __shared__ uint8_t s_xc[kBitsOutliers][kBitsBlock];  // outlier counts
+  __shared__ uint32_t s_work[4];
+  const uint32_t tx = threadIdx.x, lane = lane_id(), warp = tx >> 5;
   const uint32_t r = blockIdx.x * kBitsBlock + tx;
   const bool valid = r < P.n_reads;
   const IndexTable& tb = P.tab[0];
-  if (tx < 3) s_work[tx] = 0;
+  if (tx < 4) s_work[tx] = 0;
+  __syncthreads();
   bool defer = false;
   uint32_t wq = 0, wh = 0, wp = 0;
   unsigned long long pl[5] = {0, 0, 0, 0, 0};  // bit-sliced vote count per window position
   unsigned long long orm = 0, surv = 0;
-  uint32_t wbase = 0, mx = 0, ithr = 0, nc = 0;
+  uint32_t wbase = 0, mx = 0, ithr = 0, nc = 0, nx = 0, nxs = 0;
+  uint32_t n = 0;
+  const uint32_t* hs = nullptr;
   if (valid && tb.present) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
-    const uint32_t n = defer ? 0u : (uint32_t)P.cnt[item0];
-    if (n > kBitsMaxHashes) defer = true;
-    const uint32_t* hs = P.sel + (P.base_off[r] - P.bias);
-    // ---- probe the distinct hashes, group hits that share a posting list
-    uint32_t nd = 0;
+    n = defer ? 0u : (uint32_t)P.cnt[item0];
+    if (n > kBitsMaxHashes) { defer = true; n = 0; }
+    hs = P.sel + (P.base_off[r] - P.bias);
+  }
+  // ---- the warp's hashes, flattened: every lane probes, whatever the spread of n over the reads
+  const uint32_t incl_n = warp_incl_scan(n);
+  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl_n, 31);
+  uint32_t* so = s_o[warp] + (incl_n - n);
+  uint8_t* sw = s_w[warp] + (incl_n - n);
+  {
     unsigned long long m1 = 0, m2 = 0;
-    for (uint32_t j = 0; j < n && !defer; ++j) {
-      const uint32_t h = hs[j];
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint32_t h = __ldg(hs + j);
       const unsigned long long b1 = 1ull << (h & 63), b2 = 1ull << ((h >> 6) & 63);
-      if ((m1 & b1) && (m2 & b2)) {  // an equal hash would share both buckets: exact check (rare)
-        bool dup = false;
-        for (uint32_t jj = 0; jj < j; ++jj) dup |= hs[jj] == h;
-        if (dup) continue;
-      }
+      bool dup = false;
+      if ((m1 & b1) && (m2 & b2))  // an equal hash would share both buckets: exact check (rare)
+        for (uint32_t jj = 0; jj < j; ++jj) dup |= so[jj] == h;
       m1 |= b1;
       m2 |= b2;
-      const uint32_t off = probe(tb, h);
+      so[j] = h;
+      sw[j] = dup ? 0 : 1;
+    }
+  }
+  __syncwarp();
+  if (tb.present) {
+    uint32_t* fo = s_o[warp];
+    const uint8_t* fw = s_w[warp];
+    for (uint32_t f = lane; f < total; f += 64) {  // two independent probes in flight per lane
+      const uint32_t f2 = f + 32;
+      const bool v1 = fw[f] != 0, v2 = f2 < total && fw[f2] != 0;
+      const uint32_t h1 = fo[f], h2 = f2 < total ? fo[f2] : 0u;
+      const uint32_t b1 = (h1 * kHashMul) >> tb.shift, b2 = (h2 * kHashMul) >> tb.shift;
+      uint4 k1 = make_uint4(0, 0, 0, 0), o1 = k1, k2 = k1, o2 = k1;
+      if (v1) { k1 = __ldg(tb.buckets + 2 * (size_t)b1); o1 = __ldg(tb.buckets + 2 * (size_t)b1 + 1); }
+      if (v2) { k2 = __ldg(tb.buckets + 2 * (size_t)b2); o2 = __ldg(tb.buckets + 2 * (size_t)b2 + 1); }
+      if (v1) {
+        const uint32_t off = probe_resolve(tb, h1, b1, k1, o1);
+        if (off != SQ_EMPTY) prefetch_l2(tb.postings + off);
+        fo[f] = off;
+      }
+      if (v2) {
+        const uint32_t off = probe_resolve(tb, h2, b2, k2, o2);
+        if (off != SQ_EMPTY) prefetch_l2(tb.postings + off);
+        fo[f2] = off;
+      }
+    }
+  }
+  __syncwarp();
+  if (valid && tb.present) {
+    // ---- group the hits that share a posting list (in place: slot i <= j)
+    uint32_t nd = 0;
+    for (uint32_t j = 0; j < n && !defer; ++j) {
+      if (!sw[j]) continue;
       ++wq;
+      const uint32_t off = so[j];
       if (off == SQ_EMPTY) continue;
       ++wh;
       uint32_t i = 0;
       for (; i < nd; ++i)
-        if (s_lo[i][tx] == off) break;
+        if (so[i] == off) break;
       if (i < nd) {
-        s_w[i][tx] += 1;
+        sw[i] += 1;
       } else if (nd < kBitsMaxLists) {
-        s_lo[nd][tx] = off;
-        s_w[nd][tx] = 1;
+        so[nd] = off;
+        sw[nd] = 1;
         ++nd;
       } else {
         defer = true;
       }
     }
-    // ---- add every distinct list's weight to its members
-    bool have = false;
+    // ---- pass 1: add every list that fits the window, whole words at a time
+    bool have = false, walk = false;
     for (uint32_t i = 0; i < nd && !defer; ++i) {
-      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(tb.postings + s_lo[i][tx]));
-      const uint32_t w = s_w[i][tx];
+      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(tb.postings + so[i]));
+      const uint32_t w = sw[i];
       unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
-      if (hd.y == SQ_NOMASK) { defer = true; break; }
-      if (!have) {
-        wbase = hd.y;
-        have = true;
-      } else if (hd.y < wbase) {  // move the window down: shift what has been counted so far
-        const uint32_t d = wbase - hd.y;
-        if (d >= 64 || (orm >> (64 - d)) != 0) { defer = true; break; }
+      bool fit = hd.y != SQ_NOMASK;
+      if (fit) {
+        if (!have) {
+          wbase = hd.y;
+          have = true;
+        } else if (hd.y < wbase) {  // move the window down: shift what has been counted so far
+          const uint32_t d = wbase - hd.y;
+          if (d >= 64 || (orm >> (64 - d)) != 0) {
+            fit = false;
+          } else {
 #pragma unroll
-        for (int b = 0; b < 5; ++b) pl[b] <<= d;
-        orm <<= d;
-        wbase = hd.y;
+            for (int b = 0; b < 5; ++b) pl[b] <<= d;
+            orm <<= d;
+            wbase = hd.y;
+          }
+        }
       }
-      const uint32_t d2 = hd.y - wbase;
-      if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) { defer = true; break; }
-      mask <<= d2;
+      if (fit) {
+        const uint32_t d2 = hd.y - wbase;
+        if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) fit = false;
+        else mask <<= d2;
+      }
+      if (!fit) {
+        if (hd.x > kBitsWalkMax) defer = true;
+        sw[i] = (uint8_t)(w | 0x80u);
+        walk = true;
+        continue;
+      }
       orm |= mask;
       unsigned long long carry = 0;
 #pragma unroll
@@ -953,6 +1040,51 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
       }
       wp += w * hd.x;
     }
+    // ---- pass 2: lists that did not fit, element by element; the window no longer moves
+    if (walk && !defer) {
+      for (uint32_t i = 0; i < nd && !defer; ++i) {
+        const uint32_t wf = sw[i];
+        if (!(wf & 0x80u)) continue;
+        const uint32_t w = wf & 0x7Fu, o = so[i];
+        const uint32_t len = __ldg(tb.postings + o);
+        unsigned long long lm = 0;
+        for (uint32_t q = 0; q < len; ++q) {
+          const uint32_t t = __ldg(tb.postings + o + SQ_LIST_HDR + q) & 0x7FFFFFFFu;
+          if (!have) {
+            wbase = t;
+            have = true;
+          }
+          const uint32_t d = t - wbase;
+          if (d < 64u) {
+            lm |= 1ull << d;
+            continue;
+          }
+          uint32_t x = 0;
+          for (; x < nx; ++x)
+            if (s_xt[x][tx] == t) break;
+          if (x < nx) {
+            s_xc[x][tx] += (uint8_t)w;
+          } else if (nx < kBitsOutliers) {
+            s_xt[nx][tx] = t;
+            s_xc[nx][tx] = (uint8_t)w;
+            ++nx;
+          } else {
+            defer = true;
+            break;
+          }
+        }
+        orm |= lm;
+        unsigned long long carry = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          const unsigned long long a = ((w >> b) & 1u) ? lm : 0ull;
+          const unsigned long long sum = pl[b] ^ a ^ carry;
+          carry = (pl[b] & a) | (pl[b] & carry) | (a & carry);
+          pl[b] = sum;
+        }
+        wp += w * len;
+      }
+    }
     if (!defer && orm) {
       // ---- maximum over the positions (sparse_chaining.cpp:76-82), MSB first
       unsigned long long cand = orm;
@@ -961,6 +1093,7 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
         const unsigned long long t = cand & pl[b];
         if (t) { cand = t; mx |= 1u << b; }
       }
+      for (uint32_t x = 0; x < nx; ++x) mx = max(mx, (uint32_t)s_xc[x][tx]);
       // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an
       // integer count, count < x  <=>  count < ceil(x)
       const double t = ceil(P.fraction * (double)(int)mx);
@@ -975,7 +1108,8 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
         }
         surv = gt | eq;
       }
-      nc = (uint32_t)__popcll(surv);
+      for (uint32_t x = 0; x < nx; ++x) nxs += (uint32_t)s_xc[x][tx] >= ithr ? 1u : 0u;
+      nc = (uint32_t)__popcll(surv) + nxs;
     }
   }
   // hand reads that did not fit to the 4-lanes-per-read kernel
@@ -1010,12 +1144,35 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
         unsigned long long e = surv;
 #pragma unroll
         for (int b = 0; b < 5; ++b) e &= ((c >> b) & 1u) ? pl[b] : ~pl[b];
-        while (e) {
-          const uint32_t p = (uint32_t)__ffsll((long long)e) - 1;
-          e &= e - 1;
-          P.stage_tid[sbase] = wbase + p;
-          P.stage_score[sbase] = (int32_t)c;
-          ++sbase;
+        if (nxs == 0) {
+          while (e) {
+            const uint32_t p = (uint32_t)__ffsll((long long)e) - 1;
+            e &= e - 1;
+            P.stage_tid[sbase] = wbase + p;
+            P.stage_score[sbase] = (int32_t)c;
+            ++sbase;
+          }
+        } else {
+          for (;;) {  // merge the window with the outliers of this score, transcript ascending
+            uint32_t bt = 0xFFFFFFFFu, bi = 0;
+            for (uint32_t x = 0; x < nx; ++x) {
+              const uint32_t t = s_xt[x][tx];
+              if ((uint32_t)s_xc[x][tx] == c && t < bt) { bt = t; bi = x; }
+            }
+            const uint32_t tw = e ? wbase + (uint32_t)__ffsll((long long)e) - 1 : 0xFFFFFFFFu;
+            if (bt == 0xFFFFFFFFu && !e) break;
+            uint32_t out;
+            if (tw < bt) {
+              out = tw;
+              e &= e - 1;
+            } else {
+              out = bt;
+              s_xc[bi][tx] = 0;
+            }
+            P.stage_tid[sbase] = out;
+            P.stage_score[sbase] = (int32_t)c;
+            ++sbase;
+          }
         }
       }
     }
@@ -1027,14 +1184,24 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
       wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
       wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
     }
-    if (lane == 0) { atomicAdd(&s_work[0], wq); atomicAdd(&s_work[1], wh); atomicAdd(&s_work[2], wp); }
-    __syncthreads();
-    if (tx < 3 && s_work[tx]) atomicAdd(P.work + tx, (unsigned long long)s_work[tx]);
+    if (lane == 0) {  // the last warp to arrive flushes the block's sums: no barrier at the exit
+      atomicAdd(&s_work[0], wq);
+      atomicAdd(&s_work[1], wh);
+      atomicAdd(&s_work[2], wp);
+      __threadfence_block();
+      if (atomicAdd(&s_work[3], 1u) == kBitsBlock / 32 - 1) {
+        __threadfence_block();
+        for (int i = 0; i < 3; ++i) {
+          const uint32_t v = *(volatile uint32_t*)&s_work[i];
+          if (v) atomicAdd(P.work + i, (unsigned long long)v);
+        }
+      }
+    }
   }
 }
 
 template <typename CT>
-static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
+static void launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t ev_b) {
   constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
   constexpr size_t smA = (size_t)capA * blkA * (4 + sizeof(CT)), smB = (size_t)capB * blkB * (4 + sizeof(CT));
   static bool attr = false;
@@ -1064,17 +1231,26 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s) {
     const uint32_t qgrid = need < (uint32_t)quad_grid[nkq] ? need : (uint32_t)quad_grid[nkq];
     switch (nkq) {
       case 1:
-        // one k: the bit-mask kernel takes every read it can, the quad kernel the rest (mid_list)
-        vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
-        vote_quad_kernel<1, true><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
+        if ((uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4) {
+          // one k, mean read length up to ~320: the bit-mask kernel takes every read it can, the quad kernel
+          // the rest (mid_list); the profiling events bracket the first, dominant kernel of the chain
+          vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
+          if (ev_b) cudaEventRecord(ev_b, s);
+          vote_quad_kernel<1, true><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
+        } else {  // long reads span several items: straight to the quad kernel
+          vote_quad_kernel<1, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
+          if (ev_b) cudaEventRecord(ev_b, s);
+        }
         break;
       case 2: vote_quad_kernel<2, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
       case 3: vote_quad_kernel<3, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
       default: vote_quad_kernel<4, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
     }
+    if (ev_b && nkq != 1) cudaEventRecord(ev_b, s);
   } else {
     // more than 4 k values: 64-bit packed counters, thread-per-read tiers (16 then 48 table entries)
     vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
+    if (ev_b) cudaEventRecord(ev_b, s);
     vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
   }
 }
@@ -1146,8 +1322,7 @@ void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEv
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
   if (ev_a) cudaEventRecord(ev_a, s);
-  if (p.nk <= 4) launch_fast_tiers<uint32_t>(p, s); else launch_fast_tiers<unsigned long long>(p, s);
-  if (ev_b) cudaEventRecord(ev_b, s);
+  if (p.nk <= 4) launch_fast_tiers<uint32_t>(p, s, ev_b); else launch_fast_tiers<unsigned long long>(p, s, ev_b);
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
   vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
   if (launches) *launches += 4;
