@@ -7,8 +7,8 @@
 #define SQ_CHUNK 256          // window-end positions handled by one sketch thread
 #define SQ_EMPTY 0xFFFFFFFFu  // empty marker in hash tables / bucket offsets
 #define SQ_LAST 0x80000000u   // flag on the last transcript id of a posting list
-#define SQ_LIST_HDR 4          // header words of a posting list: length, window base, 64-bit membership mask
-#define SQ_NOMASK 0xFFFFFFFFu  // window base of a list whose transcripts span 64 ids or more
+#define SQ_LIST_HDR 8          // header words of a posting list: length, then one or two (base, 64-bit mask) id ranges
+#define SQ_NOMASK 0xFFFFFFFFu  // first base of a list whose transcripts need more than two 64-id ranges
 
 namespace sq {
 
@@ -60,9 +60,10 @@ struct SketchParams {
 // bucketed open-addressing table: bucket = 4 keys (uint4) + 4 posting offsets (uint4), 32 B, one sector
 struct IndexTable {
   const uint4* buckets;     // 2*nb uint4
-  const uint32_t* postings; // per list (16-byte aligned): header {length, base, mask_lo, mask_hi}, then the transcript
-                            // ids ascending, the last one flagged with SQ_LAST; bit i of the mask <=> transcript
-                            // base+i is in the list (base = SQ_NOMASK when the ids span 64 or more)
+  const uint32_t* postings; // per list (32-byte aligned): header {length, base1 | two<<31, mask1_lo, mask1_hi, base2,
+                            // mask2_lo, mask2_hi, 0}, then the transcript ids ascending, the last one flagged
+                            // with SQ_LAST; bit i of mask1 <=> transcript base1+i is in the list, same for the
+                            // optional second range (base1 = SQ_NOMASK when two 64-id ranges do not cover it)
   uint32_t shift;           // 32 - log2(nb)
   uint32_t mask;            // nb - 1
   uint32_t present;         // 0: k-index has no map (sparse_chaining.cpp:51-53)

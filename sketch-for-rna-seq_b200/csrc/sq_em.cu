@@ -292,7 +292,7 @@ __global__ void seg_expand_kernel(const uint32_t* __restrict__ toff, const uint3
 __global__ void em_init_kernel(double* pi, uint32_t T, uint32_t* state) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < T) pi[t] = 1.0 / (double)T;  // isoform_assignment.cpp:17-20
-  if (t == 0) { state[0] = 0; state[1] = 0; }  // [0]=converged flag, [1]=iterations executed
+  if (t == 0) { state[0] = 0; state[1] = 0; state[2] = 0; }  // [0]=converged flag, [1]=iterations executed, [2]=block ticket
 }
 
 // per read: den = sum_j pi[t_j]*s_j in candidate order; inv = 1/den when den > 1e-10 (:36-45), else 0
@@ -310,24 +310,28 @@ __global__ void em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_
   inv_den[r] = den > 1e-10 ? (1.0 / den) * weight[r] : 0.0;
 }
 
-// one warp per segment of <= seg pairs of one transcript: partial posterior sum (:46-49)
+// one group of G lanes per segment of <= seg pairs of one transcript: partial posterior sum (:46-49).  A
+// transcript has a few dozen pairs on average, so 8-lane groups keep the lanes busy; G = 32 for deep data.
+template <int G>
 __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
                                   const double* __restrict__ inv_den, const double* __restrict__ pi,
                                   double* __restrict__ partial, const uint32_t* __restrict__ state) {
   if (state[0]) return;
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n_seg) return;
-  const uint32_t t = seg_tid[w];
-  const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
-  const double p = pi[t];
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G, gl = threadIdx.x & (G - 1);
+  const bool valid = w < n_seg;
   double acc = 0.0;
-  for (uint32_t j = b + lane_id(); j < e; j += 32)
-    acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
+  if (valid) {
+    const uint32_t t = seg_tid[w];
+    const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
+    const double p = pi[t];
+    for (uint32_t j = b + gl; j < e; j += G)
+      acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
+  }
 #pragma unroll
-  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
-  if (lane_id() == 0) partial[w] = acc;
+  for (int d = G / 2; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d, G);
+  if (valid && gl == 0) partial[w] = acc;
 }
 
 __global__ void seg_sum_kernel(const uint32_t* __restrict__ seg_off, uint32_t T,
@@ -383,6 +387,58 @@ __global__ void __launch_bounds__(256) em_converge_kernel(const double* __restri
   }
 }
 
+// single GPU: segment sums, M-step and the convergence test in one launch.  The last block to finish (ticket
+// in state[2]) adds the per-block changes in the same fixed order as em_converge_kernel.
+__global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __restrict__ seg_off,
+                                                             const double* __restrict__ partial,
+                                                             double* __restrict__ ps, double* __restrict__ pi,
+                                                             uint32_t T, double add_a, double add_b,
+                                                             double* __restrict__ block_change, double tol,
+                                                             uint32_t* state, double* last_change) {
+  if (state[0]) return;
+  __shared__ double sh[256];
+  __shared__ uint32_t s_last;
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  double ch = 0.0;
+  if (t < T) {
+    double sum = 0.0;
+    for (uint32_t i = seg_off[t]; i < seg_off[t + 1]; ++i) sum += partial[i];
+    ps[t] = sum;
+    const double np = (sum + add_a) + add_b;
+    ch = fabs(np - pi[t]);
+    pi[t] = np;
+  }
+  sh[threadIdx.x] = ch;
+  __syncthreads();
+  for (int d = 128; d; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    block_change[blockIdx.x] = sh[0];
+    __threadfence();
+    s_last = atomicAdd(&state[2], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (uint32_t i = threadIdx.x; i < gridDim.x; i += 256) s += *(volatile double*)&block_change[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 128; d; d >>= 1) {
+    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    state[2] = 0;
+    *last_change = sh[0];
+    __threadfence();
+    state[1] += 1;
+    if (sh[0] < tol) state[0] = 1;  // :62-64
+  }
+}
+
 // ------------------------------------------------------------------ assignment (:70-97)
 __global__ void as_tot_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                               const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
@@ -395,33 +451,38 @@ __global__ void as_tot_kernel(const uint32_t* __restrict__ read_off, uint64_t n_
   tot[r] = s;
 }
 
+template <int G>
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
                                   const double* __restrict__ tot, const double* __restrict__ weight,
                                   const double* __restrict__ pi, double* __restrict__ partial,
                                   uint32_t* __restrict__ present_u32) {
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= n_seg) return;
-  const uint32_t t = seg_tid[w];
-  const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
-  const double p = pi[t];
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G, gl = threadIdx.x & (G - 1);
+  const bool valid = w < n_seg;
+  uint32_t t = 0;
   double acc = 0.0;
   bool any = false;
-  for (uint32_t j = b + lane_id(); j < e; j += 32) {
-    const uint32_t c = tm_read[j];
-    const double tt = tot[c];
-    if (tt > 0.0) {
-      acc += ((p * (double)(int32_t)tm_score[j]) / tt) * weight[c];  // :90 divides per term; w identical reads
-      any = true;
+  if (valid) {
+    t = seg_tid[w];
+    const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
+    const double p = pi[t];
+    for (uint32_t j = b + gl; j < e; j += G) {
+      const uint32_t c = tm_read[j];
+      const double tt = tot[c];
+      if (tt > 0.0) {
+        acc += ((p * (double)(int32_t)tm_score[j]) / tt) * weight[c];  // :90 divides per term; w identical reads
+        any = true;
+      }
     }
   }
 #pragma unroll
-  for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d);
+  for (int d = G / 2; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d, G);
   const uint32_t anyw = __ballot_sync(0xFFFFFFFFu, any);
-  if (lane_id() == 0) {
+  const uint32_t gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (lane_id() & ~(uint32_t)(G - 1));
+  if (valid && gl == 0) {
     partial[w] = acc;
-    if (anyw) present_u32[t] = 1;  // benign race: all writers store 1
+    if (anyw & gmask) present_u32[t] = 1;  // benign race: all writers store 1
   }
 }
 
@@ -453,19 +514,28 @@ void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uin
   if (launches) ++*launches;
 }
 
-void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches) {
+// lanes per segment: a transcript-major run averages n_pairs / n_seg pairs
+static inline bool narrow_groups(const EmView& v) { return v.n_seg && v.n_pairs / v.n_seg < 96; }
+
+void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum) {
   if (v.n_reads) {
     em_den_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
                                                                       v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
-    em_partial_kernel<<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+    if (narrow_groups(v))
+      em_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
+          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+    else
+      em_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
+          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
     if (launches) ++*launches;
   }
-  seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, v.ps, v.state);
-  if (launches) ++*launches;
+  if (with_sum) {
+    seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, v.ps, v.state);
+    if (launches) ++*launches;
+  }
 }
 
 void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches) {
@@ -473,6 +543,13 @@ void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cu
   em_update_kernel<<<nb, 256, 0, s>>>(v.ps, v.pi, v.T, add_a, add_b, v.block_change, v.state);
   em_converge_kernel<<<1, 256, 0, s>>>(v.block_change, nb, tol, v.state, v.last_change);
   if (launches) *launches += 2;
+}
+
+// segment sums + M-step + convergence test, no collective in between (one GPU)
+void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches) {
+  em_mstep_fused_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.partial, v.ps, v.pi, v.T, add_a, add_b,
+                                                         v.block_change, tol, v.state, v.last_change);
+  if (launches) ++*launches;
 }
 
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches) {
@@ -483,9 +560,14 @@ void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cud
     if (launches) ++*launches;
   }
   if (v.n_seg) {
-    as_partial_kernel<<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-        v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
-        present_u32);
+    if (narrow_groups(v))
+      as_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
+          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
+          present_u32);
+    else
+      as_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
+          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
+          present_u32);
     if (launches) ++*launches;
   }
   seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, numreads, nullptr);

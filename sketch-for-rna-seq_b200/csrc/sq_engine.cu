@@ -694,23 +694,28 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
           hkey[slot] = h;
           hval[slot] = (uint32_t)dpost.size();
           off32[i] = hval[slot];
-          // header: length, window base, 64-bit membership mask; then the ids (last one flagged), padded so
-          // that the next header is 16-byte aligned
-          const uint32_t tmin = post_tid[b0], tmax = post_tid[b1 - 1];
+          // header (8 words, one 32-byte sector): length; base and 64-bit membership mask of the first id
+          // range (bit 31 of the base: a second range follows); base and mask of the second range; then the ids
+          // (last one flagged), padded so that the next header is 32-byte aligned
+          const uint32_t tmin = post_tid[b0];
+          uint64_t mask1 = 0, mask2 = 0, j = b0;
+          for (; j < b1 && post_tid[j] - tmin < 64; ++j) mask1 |= 1ull << (post_tid[j] - tmin);
+          const uint32_t base2 = j < b1 ? post_tid[j] : 0;
+          for (; j < b1 && post_tid[j] - base2 < 64; ++j) mask2 |= 1ull << (post_tid[j] - base2);
           dpost.push_back((uint32_t)(b1 - b0));
-          if (tmax - tmin < 64) {
-            uint64_t mask = 0;
-            for (uint64_t j = b0; j < b1; ++j) mask |= 1ull << (post_tid[j] - tmin);
-            dpost.push_back(tmin);
-            dpost.push_back((uint32_t)mask);
-            dpost.push_back((uint32_t)(mask >> 32));
+          if (j < b1) {  // three or more ranges
+            dpost.insert(dpost.end(), {SQ_NOMASK, 0u, 0u, 0u, 0u, 0u, 0u});
           } else {
-            dpost.push_back(SQ_NOMASK);
-            dpost.push_back(0);
-            dpost.push_back(0);
+            dpost.push_back(tmin | (mask2 ? 0x80000000u : 0u));
+            dpost.push_back((uint32_t)mask1);
+            dpost.push_back((uint32_t)(mask1 >> 32));
+            dpost.push_back(base2);
+            dpost.push_back((uint32_t)mask2);
+            dpost.push_back((uint32_t)(mask2 >> 32));
+            dpost.push_back(0u);
           }
           for (uint64_t j = b0; j < b1; ++j) dpost.push_back(post_tid[j] | (j + 1 == b1 ? SQ_LAST : 0u));
-          while (dpost.size() & 3) dpost.push_back(0);
+          while (dpost.size() & 7) dpost.push_back(0);
           break;
         }
         if (hkey[slot] == h) {  // same hash: verify content
@@ -1048,6 +1053,7 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   v.seg_begin = e->seg_begin.as<uint32_t>();
   v.n_seg = n_seg;
   v.seg = e->em_seg;
+  v.n_pairs = n_cpairs;
   v.T = T;
   v.pi = e->pi.as<double>();
   v.ps = e->ps.as<double>();
@@ -1065,9 +1071,14 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     StageScope sc(e, 4);
     launch_em_init(v.pi, T, state, st, &e->launches);
     for (int it = 0; it < em_iters; ++it) {
-      launch_em_estep(v, st, &e->launches);
-      SQ_TRY(allreduce(e, v.ps, T, ncclDouble));
-      launch_em_mstep(v, add_a, add_b, em_tol, st, &e->launches);
+      if (e->comm) {
+        launch_em_estep(v, st, &e->launches, true);
+        SQ_TRY(allreduce(e, v.ps, T, ncclDouble));
+        launch_em_mstep(v, add_a, add_b, em_tol, st, &e->launches);
+      } else {
+        launch_em_estep(v, st, &e->launches, false);
+        launch_em_mstep_fused(v, add_a, add_b, em_tol, st, &e->launches);
+      }
     }
   }
   {

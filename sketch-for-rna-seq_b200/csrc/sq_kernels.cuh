@@ -20,6 +20,7 @@ struct EmView {
   const uint32_t* seg_begin;
   uint32_t n_seg;
   uint32_t seg;
+  uint64_t n_pairs;           // rows of the transcript-major copy
   uint32_t T;
   // state
   double* pi;
@@ -28,7 +29,7 @@ struct EmView {
   double* partial;       // per segment
   double* block_change;  // per 256-transcript block
   double* last_change;
-  uint32_t* state;       // [0] converged, [1] iterations executed
+  uint32_t* state;       // [0] converged, [1] iterations executed, [2] block ticket of the fused M-step
 };
 
 void launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
@@ -60,7 +61,8 @@ void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, u
 void launch_seg_expand(const uint32_t* toff, const uint32_t* seg_off, uint32_t T, uint32_t seg, uint32_t* seg_tid,
                        uint32_t* seg_begin, cudaStream_t s, uint64_t* launches);
 void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uint64_t* launches);
-void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches);
+void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum);
+void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches);
 void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches);
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches);
 

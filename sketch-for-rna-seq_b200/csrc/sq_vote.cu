@@ -867,16 +867,14 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
 // are word operations too, so there is no data-dependent inner loop left except the handful of probes.
 //
 // 32-bit hashes below the 5 % threshold collide: about one list in 70 joins the k-mers of two unrelated genes
-// and one read in seven meets such a list.  Those lists (and any list that does not fit the window) are walked
-// element by element in a second pass: members inside the window go into the planes, the others into a few
-// (transcript, count) "outlier" slots that join the maximum, the filter and the ordering.
-// Reads that still do not fit (several items, > 16 hashes, > 8 distinct lists, a walked list longer than 48,
-// > 8 outliers) are handed to the 4-lanes-per-read kernel through mid_list.
+// and one read in seven meets such a list (real annotations add paralogues).  The list header therefore holds
+// up to two (base, mask) ranges, and the thread keeps a second, 2-plane window (counts up to 3) for an id
+// range away from the first; the two windows never overlap, so maximum, filter and order stay word operations.
+// Reads that still do not fit (several items, > 16 hashes, > 8 distinct lists, a list that needs three ranges,
+// a third id range, a distant count above 3) are handed to the 4-lanes-per-read kernel through mid_list.
 static constexpr int kBitsBlock = 128;
 static constexpr uint32_t kBitsMaxHashes = 16;
 static constexpr uint32_t kBitsMaxLists = 8;
-static constexpr uint32_t kBitsOutliers = 8;
-static constexpr uint32_t kBitsWalkMax = 48;
 static constexpr uint32_t kBitsFlat = 32 * kBitsMaxHashes;  // hashes of one warp's 32 reads
 
 // first bucket of the probe sequence already loaded: finish the lookup (see probe())
@@ -901,13 +899,98 @@ __device__ __forceinline__ uint32_t probe_resolve(const IndexTable& tb, uint32_t
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_constant__ VoteParams P) {
+// bit-sliced counters: NP planes of 64 positions
+template <int NP>
+struct BitWin {
+  unsigned long long pl[NP];
+  unsigned long long orm;  // positions with a count
+  uint32_t base;
+  bool have;
+};
+
+// make room for a list part (window base `base`, membership `mask`) in W without touching the id range of the
+// other window O; on success `mask` is aligned to W.  Nothing is modified on failure.
+template <int NP, int NO>
+__device__ __forceinline__ bool win_place(BitWin<NP>& W, const BitWin<NO>& O, uint32_t base, unsigned long long& mask) {
+  if (!W.have || base < W.base) {
+    if (W.have) {
+      const uint32_t d = W.base - base;
+      if (d >= 64 || (W.orm >> (64 - d)) != 0) return false;
+    }
+    if (O.have && base < O.base + 64 && O.base < base + 64) return false;  // ranges would overlap
+    if (W.have) {
+      const uint32_t d = W.base - base;
+#pragma unroll
+      for (int b = 0; b < NP; ++b) W.pl[b] <<= d;
+      W.orm <<= d;
+    }
+    W.base = base;
+    W.have = true;
+    return true;
+  }
+  const uint32_t d2 = base - W.base;
+  if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) return false;
+  mask <<= d2;
+  return true;
+}
+
+// add weight w at the positions of mask; false if a counter would pass 2^NP - 1
+template <int NP>
+__device__ __forceinline__ bool win_add(BitWin<NP>& W, unsigned long long mask, uint32_t w) {
+  if (w >> NP) return false;
+  unsigned long long carry = 0, npl[NP];
+#pragma unroll
+  for (int b = 0; b < NP; ++b) {
+    const unsigned long long a = ((w >> b) & 1u) ? mask : 0ull;
+    npl[b] = W.pl[b] ^ a ^ carry;
+    carry = (W.pl[b] & a) | (W.pl[b] & carry) | (a & carry);
+  }
+  if (carry) return false;
+#pragma unroll
+  for (int b = 0; b < NP; ++b) W.pl[b] = npl[b];
+  W.orm |= mask;
+  return true;
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t win_max(const BitWin<NP>& W) {  // MSB first
+  uint32_t mx = 0;
+  unsigned long long cand = W.orm;
+#pragma unroll
+  for (int b = NP - 1; b >= 0; --b) {
+    const unsigned long long t = cand & W.pl[b];
+    if (t) { cand = t; mx |= 1u << b; }
+  }
+  return mx;
+}
+
+template <int NP>
+__device__ __forceinline__ unsigned long long win_at_least(const BitWin<NP>& W, uint32_t thr) {
+  if (thr >> NP) return 0ull;
+  unsigned long long gt = 0, eq = W.orm;  // positions with count > / == the bits of thr seen so far
+#pragma unroll
+  for (int b = NP - 1; b >= 0; --b) {
+    const unsigned long long tbit = ((thr >> b) & 1u) ? ~0ull : 0ull;
+    gt |= eq & W.pl[b] & ~tbit;
+    eq &= ~(W.pl[b] ^ tbit);
+  }
+  return gt | eq;
+}
+
+template <int NP>
+__device__ __forceinline__ unsigned long long win_equal(const BitWin<NP>& W, unsigned long long among, uint32_t c) {
+  if (c >> NP) return 0ull;
+  unsigned long long e = among;
+#pragma unroll
+  for (int b = 0; b < NP; ++b) e &= ((c >> b) & 1u) ? W.pl[b] : ~W.pl[b];
+  return e;
+}
+
+__global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_constant__ VoteParams P) {
   // per warp: the hashes of its 32 reads back to back (read l owns [start_l, start_l + n_l)); the slots are
   // rewritten in place: hash -> posting offset -> the read's distinct lists and their weights
   __shared__ uint32_t s_o[kBitsBlock / 32][kBitsFlat];
   __shared__ uint8_t s_w[kBitsBlock / 32][kBitsFlat];  // 1 = probe this slot / weight, bit 7: walk in pass 2
-  __shared__ uint32_t s_xt[kBitsOutliers][kBitsBlock];
-  __shared__ uint8_t s_xc[kBitsOutliers][kBitsBlock];  // outlier counts
   __shared__ uint32_t s_work[4];
   const uint32_t tx = threadIdx.x, lane = lane_id(), warp = tx >> 5;
   const uint32_t r = blockIdx.x * kBitsBlock + tx;
@@ -917,9 +1000,10 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
   __syncthreads();
   bool defer = false;
   uint32_t wq = 0, wh = 0, wp = 0;
-  unsigned long long pl[5] = {0, 0, 0, 0, 0};  // bit-sliced vote count per window position
-  unsigned long long orm = 0, surv = 0;
-  uint32_t wbase = 0, mx = 0, ithr = 0, nc = 0, nx = 0, nxs = 0;
+  BitWin<5> A = {{0, 0, 0, 0, 0}, 0, 0, false};  // the read's own gene: counts up to 31
+  BitWin<2> B = {{0, 0}, 0, 0, false};           // a second, distant id range (hash collisions, paralogs): up to 3
+  unsigned long long sa = 0, sb = 0;             // survivors
+  uint32_t mx = 0, ithr = 0, nc = 0;
   uint32_t n = 0;
   const uint32_t* hs = nullptr;
   if (valid && tb.present) {
@@ -995,121 +1079,41 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
         defer = true;
       }
     }
-    // ---- pass 1: add every list that fits the window, whole words at a time
-    bool have = false, walk = false;
-    for (uint32_t i = 0; i < nd && !defer; ++i) {
-      const uint4 hd = __ldg(reinterpret_cast<const uint4*>(tb.postings + so[i]));
-      const uint32_t w = sw[i];
-      unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
-      bool fit = hd.y != SQ_NOMASK;
-      if (fit) {
-        if (!have) {
-          wbase = hd.y;
-          have = true;
-        } else if (hd.y < wbase) {  // move the window down: shift what has been counted so far
-          const uint32_t d = wbase - hd.y;
-          if (d >= 64 || (orm >> (64 - d)) != 0) {
-            fit = false;
-          } else {
-#pragma unroll
-            for (int b = 0; b < 5; ++b) pl[b] <<= d;
-            orm <<= d;
-            wbase = hd.y;
-          }
-        }
-      }
-      if (fit) {
-        const uint32_t d2 = hd.y - wbase;
-        if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) fit = false;
-        else mask <<= d2;
-      }
-      if (!fit) {
-        if (hd.x > kBitsWalkMax) defer = true;
-        sw[i] = (uint8_t)(w | 0x80u);
-        walk = true;
-        continue;
-      }
-      orm |= mask;
-      unsigned long long carry = 0;
-#pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        const unsigned long long a = ((w >> b) & 1u) ? mask : 0ull;
-        const unsigned long long sum = pl[b] ^ a ^ carry;
-        carry = (pl[b] & a) | (pl[b] & carry) | (a & carry);
-        pl[b] = sum;
-      }
-      wp += w * hd.x;
-    }
-    // ---- pass 2: lists that did not fit, element by element; the window no longer moves
-    if (walk && !defer) {
+    // ---- add every distinct list's weight to its members: single-range lists first (they fix window A)
+    bool any_two = false;
+    for (uint32_t phase = 0; phase < 2 && !defer; ++phase) {
+      if (phase && !any_two) break;
       for (uint32_t i = 0; i < nd && !defer; ++i) {
-        const uint32_t wf = sw[i];
-        if (!(wf & 0x80u)) continue;
-        const uint32_t w = wf & 0x7Fu, o = so[i];
-        const uint32_t len = __ldg(tb.postings + o);
-        unsigned long long lm = 0;
-        for (uint32_t q = 0; q < len; ++q) {
-          const uint32_t t = __ldg(tb.postings + o + SQ_LIST_HDR + q) & 0x7FFFFFFFu;
-          if (!have) {
-            wbase = t;
-            have = true;
-          }
-          const uint32_t d = t - wbase;
-          if (d < 64u) {
-            lm |= 1ull << d;
-            continue;
-          }
-          uint32_t x = 0;
-          for (; x < nx; ++x)
-            if (s_xt[x][tx] == t) break;
-          if (x < nx) {
-            s_xc[x][tx] += (uint8_t)w;
-          } else if (nx < kBitsOutliers) {
-            s_xt[nx][tx] = t;
-            s_xc[nx][tx] = (uint8_t)w;
-            ++nx;
-          } else {
-            defer = true;
-            break;
-          }
+        const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + so[i]);
+        const uint4 hd = __ldg(hp);
+        if (hd.y == SQ_NOMASK) { defer = true; break; }
+        const uint32_t two = hd.y >> 31;
+        any_two |= two != 0;
+        if (two != phase) continue;
+        const uint32_t w = sw[i];
+        unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
+        const uint32_t base = hd.y & 0x7FFFFFFFu;
+        if (win_place(A, B, base, mask)) win_add(A, mask, w);
+        else if (!(win_place(B, A, base, mask) && win_add(B, mask, w))) { defer = true; break; }
+        if (two) {
+          const uint4 h2 = __ldg(hp + 1);
+          unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
+          if (win_place(A, B, h2.x, mask2)) win_add(A, mask2, w);
+          else if (!(win_place(B, A, h2.x, mask2) && win_add(B, mask2, w))) { defer = true; break; }
         }
-        orm |= lm;
-        unsigned long long carry = 0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) {
-          const unsigned long long a = ((w >> b) & 1u) ? lm : 0ull;
-          const unsigned long long sum = pl[b] ^ a ^ carry;
-          carry = (pl[b] & a) | (pl[b] & carry) | (a & carry);
-          pl[b] = sum;
-        }
-        wp += w * len;
+        wp += w * hd.x;
       }
     }
-    if (!defer && orm) {
-      // ---- maximum over the positions (sparse_chaining.cpp:76-82), MSB first
-      unsigned long long cand = orm;
-#pragma unroll
-      for (int b = 4; b >= 0; --b) {
-        const unsigned long long t = cand & pl[b];
-        if (t) { cand = t; mx |= 1u << b; }
-      }
-      for (uint32_t x = 0; x < nx; ++x) mx = max(mx, (uint32_t)s_xc[x][tx]);
+    if (!defer && (A.orm | B.orm)) {
+      // ---- maximum over the positions (sparse_chaining.cpp:76-82)
+      mx = max(win_max(A), win_max(B));
       // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an
       // integer count, count < x  <=>  count < ceil(x)
       const double t = ceil(P.fraction * (double)(int)mx);
       ithr = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
-      if (ithr <= 31) {
-        unsigned long long gt = 0, eq = orm;  // positions with count > / == the bits of ithr seen so far
-#pragma unroll
-        for (int b = 4; b >= 0; --b) {
-          const unsigned long long tbit = ((ithr >> b) & 1u) ? ~0ull : 0ull;
-          gt |= eq & pl[b] & ~tbit;
-          eq &= ~(pl[b] ^ tbit);
-        }
-        surv = gt | eq;
-      }
-      for (uint32_t x = 0; x < nx; ++x) nxs += (uint32_t)s_xc[x][tx] >= ithr ? 1u : 0u;
-      nc = (uint32_t)__popcll(surv) + nxs;
+      sa = win_at_least(A, ithr);
+      sb = win_at_least(B, ithr);
+      nc = (uint32_t)(__popcll(sa) + __popcll(sb));
     }
   }
   // hand reads that did not fit to the 4-lanes-per-read kernel
@@ -1138,41 +1142,30 @@ __global__ void __launch_bounds__(kBitsBlock) vote_bits_kernel(const __grid_cons
     P.read_soff[r] = (uint32_t)sbase;
     P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
     if (fits && nc) {
-      // ---- order: score descending (:108-109), transcript ascending inside a score
+      // ---- order: score descending (:108-109), transcript ascending inside a score; the two windows
+      // cover disjoint id ranges, so inside a score the lower window goes first
       const uint32_t lowest = ithr > 1 ? ithr : 1;
+      const bool b_first = B.have && B.base < A.base;
       for (uint32_t c = mx; c >= lowest; --c) {
-        unsigned long long e = surv;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) e &= ((c >> b) & 1u) ? pl[b] : ~pl[b];
-        if (nxs == 0) {
-          while (e) {
-            const uint32_t p = (uint32_t)__ffsll((long long)e) - 1;
-            e &= e - 1;
-            P.stage_tid[sbase] = wbase + p;
-            P.stage_score[sbase] = (int32_t)c;
-            ++sbase;
-          }
-        } else {
-          for (;;) {  // merge the window with the outliers of this score, transcript ascending
-            uint32_t bt = 0xFFFFFFFFu, bi = 0;
-            for (uint32_t x = 0; x < nx; ++x) {
-              const uint32_t t = s_xt[x][tx];
-              if ((uint32_t)s_xc[x][tx] == c && t < bt) { bt = t; bi = x; }
-            }
-            const uint32_t tw = e ? wbase + (uint32_t)__ffsll((long long)e) - 1 : 0xFFFFFFFFu;
-            if (bt == 0xFFFFFFFFu && !e) break;
-            uint32_t out;
-            if (tw < bt) {
-              out = tw;
-              e &= e - 1;
-            } else {
-              out = bt;
-              s_xc[bi][tx] = 0;
-            }
-            P.stage_tid[sbase] = out;
-            P.stage_score[sbase] = (int32_t)c;
-            ++sbase;
-          }
+        unsigned long long e1 = win_equal(A, sa, c), e2 = win_equal(B, sb, c);
+        uint32_t base1 = A.base, base2 = B.base;
+        if (b_first) {
+          const unsigned long long te = e1; e1 = e2; e2 = te;
+          base1 = B.base; base2 = A.base;
+        }
+        while (e1) {
+          const uint32_t p = (uint32_t)__ffsll((long long)e1) - 1;
+          e1 &= e1 - 1;
+          P.stage_tid[sbase] = base1 + p;
+          P.stage_score[sbase] = (int32_t)c;
+          ++sbase;
+        }
+        while (e2) {
+          const uint32_t p = (uint32_t)__ffsll((long long)e2) - 1;
+          e2 &= e2 - 1;
+          P.stage_tid[sbase] = base2 + p;
+          P.stage_score[sbase] = (int32_t)c;
+          ++sbase;
         }
       }
     }
