@@ -278,11 +278,17 @@ def run_ours(args):
                                   c["len"].data_ptr(), c["n"], c["bases"] + 4 * c["n"])
         return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), 0, 20, 0.01)
 
+    # equal-length reads (the short-read workloads): sq_push_reads_fixed, only the packed words travel;
+    # otherwise the lengths travel too (base_off = NULL, offsets derived on the GPU)
+    fixed_len = READ_LEN if READ_LEN and all(int(c["h_len"].min()) == READ_LEN == int(c["h_len"].max()) for c in chunks) else 0
+
     def step_host():
         eng.reset_reads()
         for c in chunks:
-            # reads are packed back to back on 4-base boundaries: only the lengths travel (base_off = NULL)
-            eng.push_reads_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), 0, c["h_len"].data_ptr(), c["n"])
+            if fixed_len:
+                eng.push_reads_fixed_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), fixed_len, c["n"])
+            else:
+                eng.push_reads_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), 0, c["h_len"].data_ptr(), c["n"])
         return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), 0, 20, 0.01)
 
     def timed(fn, steps, warmup, profile=False):
@@ -416,9 +422,10 @@ def run_ours(args):
                                 % (n_bases / 4 / 1e6, sum(32 * (1 << int(np.ceil(np.log2(max(postings[k][0].shape[0] / 2, 2))))) for k in K_LIST) / 1e6),
                    "parallelism": "reads sharded across %d GPU(s), index replicated, NCCL all-reduce of T-vectors" % world},
         "gkmers_per_s": n_kmers * world * args.steps / (ms / 1e3) / 1e9,
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(sum(c["h_words"].numel() * 4 + 4 * c["n"] for c in chunks)),
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(sum(c["h_words"].numel() * 4 + (0 if fixed_len else 4 * c["n"]) for c in chunks)),
                 "d2h_bytes_per_step": int(T * 17), "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
-                "input": "2-bit packed reads + lengths in pinned host memory (sq_push_reads, offsets derived on the GPU)"},
+                "input": "2-bit packed reads of one length in pinned host memory (sq_push_reads_fixed: lengths and offsets written on the GPU)"
+                if fixed_len else "2-bit packed reads + lengths in pinned host memory (sq_push_reads, offsets derived on the GPU)"},
         "gpu_launches": int(launches), "wall_ms_per_step": wall / args.steps,
         "clocks": clk, "roofline": roofline, "em_iterations": iters,
         "work": {k2: int(st[k2]) for k2 in ("reads", "sketch_hashes", "queries", "hits", "postings", "pairs",

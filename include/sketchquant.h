@@ -111,6 +111,10 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
  * batch_bases). */
 int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, const uint32_t* base_off,
                   const uint32_t* len, uint32_t n_reads);
+/* Same for reads of one length (untrimmed short-read runs), packed back to back with every read starting at the
+ * next multiple of 4 bases: only the packed words travel, lengths and offsets are written on the GPU. */
+int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, uint32_t read_len,
+                        uint32_t n_reads);
 /* Same with the batch already resident in DEVICE memory (the buffers must stay valid until sq_sync). */
 int sq_push_reads_device(sq_engine* e, const uint32_t* d_packed_words, uint64_t n_words,
                          const uint32_t* d_base_off, const uint32_t* d_len, uint32_t n_reads,

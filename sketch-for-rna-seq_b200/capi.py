@@ -14,7 +14,7 @@ SQ_MAX_K_COUNT = 8
 
 EXPORTS = [
     "sq_version", "sq_device_count", "sq_last_error", "sq_threshold_from_fraction", "sq_create", "sq_destroy",
-    "sq_set_stream", "sq_set_profiling", "sq_set_option", "sq_load_index", "sq_push_reads", "sq_push_reads_device",
+    "sq_set_stream", "sq_set_profiling", "sq_set_option", "sq_load_index", "sq_push_reads", "sq_push_reads_fixed", "sq_push_reads_device",
     "sq_sync", "sq_reset_reads", "sq_finish", "sq_sketch", "sq_num_pairs", "sq_get_candidates", "sq_build_postings",
     "sq_nccl_unique_id", "sq_comm_init", "sq_get_stats", "sq_set_candidates",
 ]
@@ -68,6 +68,7 @@ def load_library():
     lib.sq_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.sq_load_index.argtypes = [vp, C.c_uint32, C.c_uint64, vp, vp, vp]
     lib.sq_push_reads.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32]
+    lib.sq_push_reads_fixed.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
     lib.sq_push_reads_device.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_uint32, C.c_uint64]
     lib.sq_sync.argtypes = [vp]
     lib.sq_reset_reads.argtypes = [vp]
@@ -180,6 +181,14 @@ class Engine:
         self._check(self.lib.sq_push_reads(self._h, C.c_void_p(packed_ptr), n_words,
                                            C.c_void_p(base_off_ptr) if base_off_ptr else None,
                                            C.c_void_p(len_ptr), n_reads))
+
+    def push_reads_fixed(self, packed, read_len, n_reads):
+        """n_reads reads of read_len bases each, packed back to back on 4-base boundaries: only the words are copied"""
+        packed = _u32(packed)
+        self._check(self.lib.sq_push_reads_fixed(self._h, _ptr(packed), packed.shape[0], read_len, n_reads))
+
+    def push_reads_fixed_ptr(self, packed_ptr, n_words, read_len, n_reads):
+        self._check(self.lib.sq_push_reads_fixed(self._h, C.c_void_p(packed_ptr), n_words, read_len, n_reads))
 
     def push_reads_device(self, d_packed, n_words, d_base_off, d_len, n_reads, n_bases=0):
         self._check(self.lib.sq_push_reads_device(self._h, C.c_void_p(d_packed), n_words, C.c_void_p(d_base_off),

@@ -114,6 +114,8 @@ void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t
                   uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches, const KList& ks,
                   unsigned long long* stats);
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches);
+void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, cudaStream_t s,
+                         uint64_t* launches);
 void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
                            cudaStream_t s, uint64_t* launches);
 // ev_a/ev_b (optional): recorded right before/after the main short-read kernel only

@@ -388,7 +388,7 @@ int acquire_slot(sq_engine* e, Slot** out) {
 // enqueue sketch + vote + compaction for one batch whose inputs are in device memory
 int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words, const uint32_t* d_boff, uint32_t bias,
               const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases, cudaEvent_t inputs_ready,
-              uint32_t* derive_boff = nullptr) {
+              uint32_t* derive_boff = nullptr, uint32_t fixed_len = 0) {
   if (n_reads == 0) return SQ_OK;
   const uint64_t items_ub64 = (uint64_t)n_reads + n_bases / SQ_CHUNK + 1;
   if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
@@ -413,7 +413,10 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   // the batch before this one (other slot) can now be finalized: its vote overlaps our copies
   SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
   if (inputs_ready) SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
-  if (derive_boff) {  // offsets not supplied: reads are packed back to back on 4-base boundaries
+  if (derive_boff && fixed_len) {  // equal lengths: offsets and lengths are written on the GPU, nothing was copied
+    StageScope st(e, 6);
+    launch_fixed_layout(const_cast<uint32_t*>(d_len), derive_boff, n_reads, fixed_len, e->stream, &e->launches);
+  } else if (derive_boff) {  // offsets not supplied: reads are packed back to back on 4-base boundaries
     StageScope st(e, 6);
     launch_derive_offsets(d_len, n_reads, s.nit.as<uint32_t>(), derive_boff, s.scan_tmp.as<uint32_t>(), e->stream,
                           &e->launches);
@@ -832,6 +835,32 @@ int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, 
     SQ_CUDA(e, cudaEventSynchronize(s->copied));
     r0 = r1;
   }
+  return SQ_OK;
+}
+
+int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, uint32_t read_len,
+                        uint32_t n_reads) {
+  if (!e) return SQ_ERR_ARG;
+  if (n_reads == 0) return SQ_OK;
+  if (!packed_words) return fail(e, SQ_ERR_ARG, "NULL host pointer");
+  const uint64_t stride = ((uint64_t)read_len + 3) & ~3ull;
+  const uint64_t bases = stride * n_reads;
+  if (stride == 0 || bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
+  if ((bases + 15) / 16 > n_words) return fail(e, SQ_ERR_ARG, "%u reads of %u bases need %llu words, got %llu", n_reads, read_len,
+                                                (unsigned long long)((bases + 15) / 16), (unsigned long long)n_words);
+  if (bases > e->batch_bases + 64) return fail(e, SQ_ERR_ARG, "batch exceeds option batch_bases (%llu bases): push smaller batches", (unsigned long long)e->batch_bases);
+  SQ_CUDA(e, cudaSetDevice(e->device));
+  const uint64_t nw = (bases + 15) / 16;
+  Slot* s = nullptr;
+  SQ_TRY(acquire_slot(e, &s));
+  SQ_CUDA(e, s->packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
+  SQ_CUDA(e, s->base_off.ensure(((size_t)n_reads + 1) * 4));
+  SQ_CUDA(e, s->len.ensure((size_t)n_reads * 4));
+  SQ_CUDA(e, cudaMemcpyAsync(s->packed.p, packed_words, nw * 4, cudaMemcpyHostToDevice, e->copy_stream));
+  SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
+  SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (nw + 3) & ~3ull, s->base_off.as<uint32_t>(), 0,
+                   s->len.as<uint32_t>(), n_reads, bases, s->copied, s->base_off.as<uint32_t>(), read_len));
+  SQ_CUDA(e, cudaEventSynchronize(s->copied));
   return SQ_OK;
 }
 

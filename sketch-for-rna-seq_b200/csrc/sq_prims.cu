@@ -35,6 +35,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
 // available, bit 62 = aggregate available, low 32 bits = value; zeroed (with the ticket) before every scan.
 static constexpr unsigned long long kScanIncl = 1ull << 63, kScanAgg = 1ull << 62;
 
+template <bool VEC>  // VEC: in and out are 16-byte aligned, whole tiles move as uint4
 __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const uint32_t* __restrict__ in, uint32_t n,
                                                                      uint32_t* __restrict__ out,
                                                                      unsigned long long* status, uint32_t* ticket) {
@@ -45,10 +46,21 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const uint3
   const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
+  const bool whole = VEC && base + kScanItems <= n;
+  if (whole) {
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    v[i] = base + i < n ? in[base + i] : 0;
-    sum += v[i];
+    for (int i = 0; i < kScanItems; i += 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(in + base + i);
+      v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) sum += v[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      v[i] = base + i < n ? in[base + i] : 0;
+      sum += v[i];
+    }
   }
   uint32_t tot;
   uint32_t ex = block_excl_scan(sum, &tot);
@@ -88,10 +100,22 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const uint3
   }
   __syncthreads();
   ex += s_prefix;
+  if (whole) {
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < n) out[base + i] = ex;
-    ex += v[i];
+    for (int i = 0; i < kScanItems; i += 4) {
+      uint4 q;
+      q.x = ex; ex += v[i];
+      q.y = ex; ex += v[i + 1];
+      q.z = ex; ex += v[i + 2];
+      q.w = ex; ex += v[i + 3];
+      *reinterpret_cast<uint4*>(out + base + i) = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      if (base + i < n) out[base + i] = ex;
+      ex += v[i];
+    }
   }
   if (base <= n - 1 && n - 1 < base + kScanItems) out[n] = ex;  // the thread holding the last element closes the scan
 }
@@ -107,7 +131,10 @@ void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32
   const uint32_t nb = (n + kScanTile - 1) / kScanTile;
   // tmp: [0] ticket (u32, padded to 8 bytes), then nb status words
   cudaMemsetAsync(tmp, 0, 8 + (size_t)nb * 8, s);
-  scan_lookback_kernel<<<nb, kScanThreads, 0, s>>>(in, n, out, reinterpret_cast<unsigned long long*>(tmp + 2), tmp);
+  if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    scan_lookback_kernel<true><<<nb, kScanThreads, 0, s>>>(in, n, out, reinterpret_cast<unsigned long long*>(tmp + 2), tmp);
+  else
+    scan_lookback_kernel<false><<<nb, kScanThreads, 0, s>>>(in, n, out, reinterpret_cast<unsigned long long*>(tmp + 2), tmp);
   if (launches) *launches += 1;
 }
 

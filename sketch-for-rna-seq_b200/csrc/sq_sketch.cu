@@ -238,6 +238,20 @@ void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp,
   launch_exclusive_scan(tmp, base_off, n_reads, scan_tmp, s, launches);
 }
 
+__global__ void fixed_layout_kernel(uint32_t* __restrict__ len, uint32_t* __restrict__ base_off, uint32_t n,
+                                    uint32_t L, uint32_t stride) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) len[r] = L;
+  if (r <= n) base_off[r] = r * stride;
+}
+
+// equal-length reads packed back to back, each starting at the next multiple of 4 bases: nothing to scan
+void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, cudaStream_t s,
+                         uint64_t* launches) {
+  fixed_layout_kernel<<<n_reads / 256 + 1, 256, 0, s>>>(len, base_off, n_reads, read_len, (read_len + 3u) & ~3u);
+  if (launches) ++*launches;
+}
+
 void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t* item_start, uint32_t* item_read,
                   uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches, const KList& ks,
                   unsigned long long* stats) {

@@ -175,6 +175,28 @@ def test_offsets_derived_on_device(gpu_lib, sqb, port):
     assert res[1][1].tolist() == otid.tolist() and res[1][2].tolist() == oscore.tolist()
 
 
+def test_fixed_length_push(gpu_lib, sqb, port):
+    """sq_push_reads_fixed: equal-length reads, only the packed words are copied"""
+    d = dataset()
+    ks = [21, 31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    for L in (150, 33):  # 33: not a multiple of 4, the stride is padded
+        reads = [r[:L] for r in d["reads"] if len(r) >= L][:180]
+        assert len(reads) > 50
+        with sqb.Engine(ks, len(d["names"])) as e:
+            for i, k in enumerate(ks):
+                e.load_index(i, *postings[k])
+            words, off, ln = sqb.packing.pack_reads(reads, align=4)
+            e.push_reads_fixed(words, L, len(reads))
+            off_g, tid_g, score_g = e.candidates()
+            with pytest.raises(sqb.SketchQuantError):
+                e.push_reads_fixed(words[:4], L, len(reads))  # too few words for that many reads
+        _, ooff, otid, oscore, _ = port.chain_batch(ks, thr, 0.9, postings, reads)
+        assert off_g.tolist() == ooff.tolist()
+        assert tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
+
+
 def test_unsorted_posting_lists(gpu_lib, sqb, port):
     """the reference's index file lists transcripts under a hash in arbitrary order"""
     d = dataset()
