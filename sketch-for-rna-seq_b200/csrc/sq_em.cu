@@ -295,19 +295,39 @@ __global__ void em_init_kernel(double* pi, uint32_t T, uint32_t* state) {
   if (t == 0) { state[0] = 0; state[1] = 0; state[2] = 0; }  // [0]=converged flag, [1]=iterations executed, [2]=block ticket
 }
 
-// per read: den = sum_j pi[t_j]*s_j in candidate order; inv = 1/den when den > 1e-10 (:36-45), else 0
-__global__ void em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
-                              const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                              const double* __restrict__ pi, const double* __restrict__ weight,
-                              double* __restrict__ inv_den, const uint32_t* __restrict__ state) {
-  if (state[0]) return;
-  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
+// per read (class): den = sum_j pi[t_j]*s_j in candidate order; E-step: inv = 1/den when den > 1e-10 (:36-45),
+// else 0; assignment: tot = den (:80-85).  A block owns 256 consecutive rows: their pairs are one contiguous
+// range, so the products are formed with coalesced loads into shared memory and each thread then adds up its
+// own row in order (same sums as a plain per-thread loop, without the strided global reads).
+static constexpr uint32_t kDenCap = 3072;
+
+template <bool ASSIGN>
+__global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
+                                                     const uint32_t* __restrict__ cand_tid,
+                                                     const int32_t* __restrict__ cand_score,
+                                                     const double* __restrict__ pi, const double* __restrict__ weight,
+                                                     double* __restrict__ out, const uint32_t* __restrict__ state) {
+  __shared__ double s_term[kDenCap];
+  if (!ASSIGN && state[0]) return;
+  const uint64_t c0 = (uint64_t)blockIdx.x * 256;
+  const uint32_t nc = (uint32_t)min((uint64_t)256, n_reads - c0);
+  const uint32_t b0 = read_off[c0], np = read_off[c0 + nc] - b0;
+  const bool staged = np <= kDenCap;
+  if (staged) {
+    for (uint32_t j = threadIdx.x; j < np; j += 256) s_term[j] = pi[cand_tid[b0 + j]] * (double)cand_score[b0 + j];
+    __syncthreads();
+  }
+  if (threadIdx.x >= nc) return;
+  const uint64_t r = c0 + threadIdx.x;
   const uint32_t b = read_off[r], e = read_off[r + 1];
   double den = 0.0;
-  for (uint32_t j = b; j < e; ++j) den += pi[cand_tid[j]] * (double)cand_score[j];
+  if (staged) {
+    for (uint32_t j = b; j < e; ++j) den += s_term[j - b0];
+  } else {
+    for (uint32_t j = b; j < e; ++j) den += pi[cand_tid[j]] * (double)cand_score[j];
+  }
   // a class of w identical reads adds w identical posteriors: fold w into the reciprocal (exact for w = 1)
-  inv_den[r] = den > 1e-10 ? (1.0 / den) * weight[r] : 0.0;
+  out[r] = ASSIGN ? den : (den > 1e-10 ? (1.0 / den) * weight[r] : 0.0);
 }
 
 // one group of G lanes per segment of <= seg pairs of one transcript: partial posterior sum (:46-49).  A
@@ -440,17 +460,6 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------ assignment (:70-97)
-__global__ void as_tot_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
-                              const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                              const double* __restrict__ pi, double* __restrict__ tot) {
-  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const uint32_t b = read_off[r], e = read_off[r + 1];
-  double s = 0.0;
-  for (uint32_t j = b; j < e; ++j) s += pi[cand_tid[j]] * (double)cand_score[j];
-  tot[r] = s;
-}
-
 template <int G>
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
@@ -519,8 +528,8 @@ static inline bool narrow_groups(const EmView& v) { return v.n_seg && v.n_pairs 
 
 void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum) {
   if (v.n_reads) {
-    em_den_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
-                                                                      v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
+    em_den_kernel<false><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+        v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
@@ -555,8 +564,8 @@ void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double t
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches) {
   cudaMemsetAsync(present_u32, 0, sizeof(uint32_t) * v.T, s);
   if (v.n_reads) {
-    as_tot_kernel<<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(v.read_off, v.n_reads, v.cand_tid,
-                                                                      v.cand_score, v.pi, v.read_tmp);
+    em_den_kernel<true><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+        v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, nullptr, v.read_tmp, nullptr);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
