@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sketchquant.h"
@@ -664,77 +665,117 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   KTab& t = e->tab[kidx];
   // Posting lists with identical content are stored once (all k-mers of an exon shared by the same isoforms
   // have the same list), so the postings array shrinks to the distinct isoform sets and a read whose hits
-  // share a list can walk it once with a weight.  Open-addressing table on a 64-bit content hash, verified
-  // by comparing the content.
+  // share a list can merge it once with a weight.  Host threads: (1) sort the lists that are not ascending (the
+  // reference's file order is arbitrary) and hash every list's content; (2) each thread owns the lists whose
+  // hash falls in its partition: open-addressing table on the 64-bit hash, verified by comparing the content;
+  // (3) the partitions' arrays are concatenated.
   std::vector<uint32_t> off32(nkeys + 1, SQ_EMPTY);
   std::vector<uint32_t> dpost;
-  dpost.reserve(npost / 4 + 16);
   {
-    uint64_t cap = 16;
-    while (cap < nkeys * 2 + 2) cap <<= 1;
-    std::vector<uint64_t> hkey(cap, 0);
-    std::vector<uint32_t> hval(cap, SQ_EMPTY);
-    std::vector<uint32_t> sorted_list;
-    for (uint64_t i = 0; i < nkeys; ++i) {
-      uint64_t b0 = post_off[i], b1 = post_off[i + 1];
-      if (b1 <= b0) continue;
-      // the kernels merge lists assuming ascending transcript ids; the reference's file order is arbitrary
-      const uint32_t* post_tid_i = post_tid;
-      if (!std::is_sorted(post_tid + b0, post_tid + b1)) {
-        sorted_list.assign(post_tid + b0, post_tid + b1);
-        std::sort(sorted_list.begin(), sorted_list.end());
-        post_tid_i = sorted_list.data();
-        b1 -= b0;
-        b0 = 0;
-      }
-      const uint32_t* post_tid = post_tid_i;  // shadow: this key's (sorted) list lives at [b0, b1) of this array
-      uint64_t h = 0xcbf29ce484222325ull ^ (b1 - b0);
-      for (uint64_t j = b0; j < b1; ++j) { h ^= post_tid[j]; h *= 0x100000001b3ull; h ^= h >> 29; }
-      if (h == 0) h = 1;
-      uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
-      for (;;) {
-        if (hval[slot] == SQ_EMPTY) {
-          hkey[slot] = h;
-          hval[slot] = (uint32_t)dpost.size();
-          off32[i] = hval[slot];
-          // header (8 words, one 32-byte sector): length; base and 64-bit membership mask of the first id
-          // range (bit 31 of the base: a second range follows); base and mask of the second range; then the ids
-          // (last one flagged), padded so that the next header is 32-byte aligned
-          const uint32_t tmin = post_tid[b0];
-          uint64_t mask1 = 0, mask2 = 0, j = b0;
-          for (; j < b1 && post_tid[j] - tmin < 64; ++j) mask1 |= 1ull << (post_tid[j] - tmin);
-          const uint32_t base2 = j < b1 ? post_tid[j] : 0;
-          for (; j < b1 && post_tid[j] - base2 < 64; ++j) mask2 |= 1ull << (post_tid[j] - base2);
-          dpost.push_back((uint32_t)(b1 - b0));
-          if (j < b1) {  // three or more ranges
-            dpost.insert(dpost.end(), {SQ_NOMASK, 0u, 0u, 0u, 0u, 0u, 0u});
-          } else {
-            dpost.push_back(tmin | (mask2 ? 0x80000000u : 0u));
-            dpost.push_back((uint32_t)mask1);
-            dpost.push_back((uint32_t)(mask1 >> 32));
-            dpost.push_back(base2);
-            dpost.push_back((uint32_t)mask2);
-            dpost.push_back((uint32_t)(mask2 >> 32));
-            dpost.push_back(0u);
-          }
-          for (uint64_t j = b0; j < b1; ++j) dpost.push_back(post_tid[j] | (j + 1 == b1 ? SQ_LAST : 0u));
-          while (dpost.size() & 7) dpost.push_back(0);
-          break;
-        }
-        if (hkey[slot] == h) {  // same hash: verify content
-          const uint32_t o = hval[slot];
-          bool same = true;
-          uint64_t j = b0;
-          for (uint32_t q = o + SQ_LIST_HDR;; ++q, ++j) {
-            const uint32_t v = dpost[q];
-            if (j >= b1 || (v & ~SQ_LAST) != post_tid[j]) { same = false; break; }
-            if (v & SQ_LAST) { same = (j + 1 == b1); break; }
-          }
-          if (same) { off32[i] = o; break; }
-        }
-        slot = (slot + 1) & (cap - 1);
-      }
+    unsigned nth = std::thread::hardware_concurrency();
+    if (const char* ev = getenv("SQ_HOST_THREADS")) nth = (unsigned)atoi(ev);
+    nth = std::max(1u, std::min(nth, 32u));
+    if (nkeys < 200000) nth = 1;
+    auto run = [&](auto&& fn) {
+      if (nth == 1) { fn(0u); return; }
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < nth; ++t) th.emplace_back(fn, t);
+      for (auto& x : th) x.join();
+    };
+    // (1) ascending copies where needed, content hashes
+    std::vector<uint64_t> lh(nkeys);
+    std::vector<uint32_t> sorted_tid;
+    std::vector<uint8_t> unsorted_any(nth, 0);
+    run([&](unsigned t) {
+      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
+      for (uint64_t i = i0; i < i1 && !unsorted_any[t]; ++i)
+        if (!std::is_sorted(post_tid + post_off[i], post_tid + post_off[i + 1])) unsorted_any[t] = 1;
+    });
+    const uint32_t* pt = post_tid;
+    if (std::any_of(unsorted_any.begin(), unsorted_any.end(), [](uint8_t v) { return v != 0; })) {
+      sorted_tid.assign(post_tid, post_tid + npost);
+      run([&](unsigned t) {
+        const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
+        for (uint64_t i = i0; i < i1; ++i) std::sort(sorted_tid.begin() + post_off[i], sorted_tid.begin() + post_off[i + 1]);
+      });
+      pt = sorted_tid.data();
     }
+    run([&](unsigned t) {
+      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
+      for (uint64_t i = i0; i < i1; ++i) {
+        const uint64_t b0 = post_off[i], b1 = post_off[i + 1];
+        uint64_t h = 0xcbf29ce484222325ull ^ (b1 - b0);
+        for (uint64_t j = b0; j < b1; ++j) { h ^= pt[j]; h *= 0x100000001b3ull; h ^= h >> 29; }
+        lh[i] = h ? h : 1;
+      }
+    });
+    // (2) per-partition de-duplication
+    std::vector<std::vector<uint32_t>> part(nth);
+    std::vector<uint32_t> loc(nkeys, SQ_EMPTY);  // offset inside the partition's array
+    auto part_of = [&](uint64_t h) { return (unsigned)(((h >> 40) * nth) >> 24); };
+    run([&](unsigned t) {
+      uint64_t mine = 0;
+      for (uint64_t i = 0; i < nkeys; ++i) mine += post_off[i + 1] > post_off[i] && part_of(lh[i]) == t;
+      uint64_t cap = 16;
+      while (cap < mine * 2 + 2) cap <<= 1;
+      std::vector<uint64_t> hkey(cap, 0);
+      std::vector<uint32_t> hval(cap, SQ_EMPTY);
+      std::vector<uint32_t>& dp = part[t];
+      dp.reserve(mine * 6 + 16);
+      for (uint64_t i = 0; i < nkeys; ++i) {
+        const uint64_t b0 = post_off[i], b1 = post_off[i + 1], h = lh[i];
+        if (b1 <= b0 || part_of(h) != t) continue;
+        uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
+        for (;;) {
+          if (hval[slot] == SQ_EMPTY) {
+            hkey[slot] = h;
+            hval[slot] = (uint32_t)dp.size();
+            loc[i] = hval[slot];
+            // header (8 words, one 32-byte sector): length; base and 64-bit membership mask of the first id
+            // range (bit 31 of the base: a second range follows); base and mask of the second range; then the ids
+            // (last one flagged), padded so that the next header is 32-byte aligned
+            const uint32_t tmin = pt[b0];
+            uint64_t mask1 = 0, mask2 = 0, j = b0;
+            for (; j < b1 && pt[j] - tmin < 64; ++j) mask1 |= 1ull << (pt[j] - tmin);
+            const uint32_t base2 = j < b1 ? pt[j] : 0;
+            for (; j < b1 && pt[j] - base2 < 64; ++j) mask2 |= 1ull << (pt[j] - base2);
+            dp.push_back((uint32_t)(b1 - b0));
+            if (j < b1) {  // three or more ranges
+              dp.insert(dp.end(), {SQ_NOMASK, 0u, 0u, 0u, 0u, 0u, 0u});
+            } else {
+              dp.push_back(tmin | (mask2 ? 0x80000000u : 0u));
+              dp.push_back((uint32_t)mask1);
+              dp.push_back((uint32_t)(mask1 >> 32));
+              dp.push_back(base2);
+              dp.push_back((uint32_t)mask2);
+              dp.push_back((uint32_t)(mask2 >> 32));
+              dp.push_back(0u);
+            }
+            for (uint64_t q = b0; q < b1; ++q) dp.push_back(pt[q] | (q + 1 == b1 ? SQ_LAST : 0u));
+            while (dp.size() & 7) dp.push_back(0);
+            break;
+          }
+          if (hkey[slot] == h) {  // same hash: verify content
+            const uint32_t o = hval[slot];
+            bool same = dp[o] == (uint32_t)(b1 - b0);
+            for (uint64_t q = b0; same && q < b1; ++q) same = (dp[o + SQ_LIST_HDR + (q - b0)] & ~SQ_LAST) == pt[q];
+            if (same) { loc[i] = o; break; }
+          }
+          slot = (slot + 1) & (cap - 1);
+        }
+      }
+    });
+    // (3) concatenate
+    std::vector<uint64_t> pbase(nth + 1, 0);
+    for (unsigned t = 0; t < nth; ++t) pbase[t + 1] = pbase[t] + part[t].size();
+    if (pbase[nth] >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "posting store exceeds 2^32 words for one k");
+    dpost.resize(pbase[nth]);
+    run([&](unsigned t) {
+      if (!part[t].empty()) memcpy(dpost.data() + pbase[t], part[t].data(), part[t].size() * 4);
+      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
+      for (uint64_t i = i0; i < i1; ++i)
+        if (loc[i] != SQ_EMPTY) off32[i] = (uint32_t)(pbase[part_of(lh[i])] + loc[i]);
+    });
   }
   const uint64_t ndp = dpost.size();
   const uint32_t nb_log2 = std::max<uint32_t>(1, log2_ceil((nkeys + 1) / 2 + 1));

@@ -231,6 +231,7 @@ void quantification(const std::string& index_path, const std::string& reads_path
                            opt.chain_fraction, T);
         if (rc != SQ_OK) die(nullptr, rc, "sq_create");
         eng[g] = e;
+        if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] gpu %d engine created           %.3f s since start\n", g, now() - t_start);
         if (opt.report.size()) sq_set_profiling(e, 1);
         for (size_t ki = 0; ki < k32.size(); ++ki) {
           auto it = idx.maps.find(k32[ki]);
