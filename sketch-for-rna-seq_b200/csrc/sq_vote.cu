@@ -992,12 +992,13 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
   __shared__ uint32_t s_o[kBitsBlock / 32][kBitsFlat];
   __shared__ uint8_t s_w[kBitsBlock / 32][kBitsFlat];  // 1 = probe this slot / weight, bit 7: walk in pass 2
   __shared__ uint32_t s_work[4];
+  __shared__ uint32_t s_hist[kBitsMaxHashes + 2];
+  __shared__ uint32_t s_perm[kBitsBlock];
   const uint32_t tx = threadIdx.x, lane = lane_id(), warp = tx >> 5;
-  const uint32_t r = blockIdx.x * kBitsBlock + tx;
-  const bool valid = r < P.n_reads;
+  uint32_t r = blockIdx.x * kBitsBlock + tx;
+  bool valid = r < P.n_reads;
   const IndexTable& tb = P.tab[0];
   if (tx < 4) s_work[tx] = 0;
-  __syncthreads();
   bool defer = false;
   uint32_t wq = 0, wh = 0, wp = 0;
   BitWin<5> A = {{0, 0, 0, 0, 0}, 0, 0, false};  // the read's own gene: counts up to 31
@@ -1006,6 +1007,29 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
   uint32_t mx = 0, ithr = 0, nc = 0;
   uint32_t n = 0;
   const uint32_t* hs = nullptr;
+  // Every per-thread loop below runs for the longest lane of its warp, and the hash count of a read varies
+  // 2..14: deal the block's reads to the threads in order of hash count (counting sort in shared memory), so
+  // that a warp holds reads of similar size.  `r` is the read this thread works for from here on.
+  if (tx < kBitsMaxHashes + 2) s_hist[tx] = 0;
+  __syncthreads();
+  {
+    uint32_t key = kBitsMaxHashes + 1;  // beyond the batch, several items or too many hashes: no work, go last
+    if (valid && tb.present) {
+      const uint32_t item0 = P.item_start[r];
+      if (P.item_start[r + 1] - item0 == 1) key = min((uint32_t)P.cnt[item0], kBitsMaxHashes + 1);
+    }
+    const uint32_t rank = atomicAdd(&s_hist[key], 1u);
+    __syncthreads();
+    if (tx == 0) {
+      uint32_t acc = 0;
+      for (uint32_t i = 0; i < kBitsMaxHashes + 2; ++i) { const uint32_t c = s_hist[i]; s_hist[i] = acc; acc += c; }
+    }
+    __syncthreads();
+    s_perm[s_hist[key] + rank] = tx;
+    __syncthreads();
+    r = blockIdx.x * kBitsBlock + s_perm[tx];
+    valid = r < P.n_reads;
+  }
   if (valid && tb.present) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
