@@ -8,6 +8,7 @@
 #define SQ_EMPTY 0xFFFFFFFFu  // empty marker in hash tables / bucket offsets
 #define SQ_LAST 0x80000000u   // flag on the last transcript id of a posting list
 #define SQ_LIST_HDR 8          // header words of a posting list: length, then one or two (base, 64-bit mask) id ranges
+#define SQ_DIRECT_EMPTY 0xFFFFFFFEu
 #define SQ_NOMASK 0xFFFFFFFFu  // first base of a list whose transcripts need more than two 64-id ranges
 
 namespace sq {
@@ -67,6 +68,13 @@ struct IndexTable {
   uint32_t shift;           // 32 - log2(nb)
   uint32_t mask;            // nb - 1
   uint32_t present;         // 0: k-index has no map (sparse_chaining.cpp:51-53)
+  // "direct" table of the bit-mask vote kernel (one k only, else NULL): buckets of 32 B = 2 entries
+  // {key, base1 | two<<31, mask1_lo, mask1_hi} -- the list header travels with the key, so a probe needs no
+  // second access.  Two-range and SQ_NOMASK lists keep {key, base word, posting offset, 0}; an entry whose
+  // second word is SQ_DIRECT_EMPTY is free.
+  const uint4* direct;
+  uint32_t dshift;
+  uint32_t dmask;
 };
 
 struct VoteParams {

@@ -45,6 +45,43 @@ void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkey
   if (launches) ++*launches;
 }
 
+// direct table (see IndexTable): the entry carries the list header
+__global__ void direct_insert_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ off,
+                                     uint64_t nkeys, const uint32_t* __restrict__ postings, uint4* direct,
+                                     uint32_t shift, uint32_t mask, uint32_t* fail) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= nkeys) return;
+  const uint32_t o = off[i];
+  if (o == SQ_EMPTY) return;
+  const uint32_t key = keys[i];
+  const uint4 hd = *reinterpret_cast<const uint4*>(postings + o);
+  const bool indirect = hd.y == SQ_NOMASK || (hd.y >> 31);
+  const uint4 ent = indirect ? make_uint4(key, hd.y, o, 0u) : make_uint4(key, hd.y, hd.z, hd.w);
+  uint32_t b = (key * kHashMul) >> shift;
+  for (uint32_t tries = 0; tries <= mask; ++tries) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(direct + 2 * (size_t)b);
+    for (int s = 0; s < 2; ++s)
+      if (atomicCAS(&w[4 * s + 1], SQ_DIRECT_EMPTY, ent.y) == SQ_DIRECT_EMPTY) {
+        w[4 * s] = ent.x;
+        w[4 * s + 2] = ent.z;
+        w[4 * s + 3] = ent.w;
+        return;
+      }
+    b = (b + 1) & mask;
+  }
+  atomicExch(fail, 1u);
+}
+
+void launch_direct_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, const uint32_t* postings,
+                         uint4* direct, uint32_t shift, uint32_t mask, uint32_t* fail, cudaStream_t s,
+                         uint64_t* launches) {
+  launch_fill_u32(reinterpret_cast<uint32_t*>(direct), (size_t)(mask + 1) * 8, SQ_DIRECT_EMPTY, s);
+  if (launches) ++*launches;
+  if (nkeys == 0) return;
+  direct_insert_kernel<<<(uint32_t)((nkeys + 255) / 256), 256, 0, s>>>(keys, off, nkeys, postings, direct, shift, mask, fail);
+  if (launches) ++*launches;
+}
+
 // ------------------------------------------------------------------ list fingerprint (EM classes, see below)
 // Two independent 64-bit hashes over (length, transcripts, scores) of a candidate list, folded step by step.
 struct ListHash {

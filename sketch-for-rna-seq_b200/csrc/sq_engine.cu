@@ -59,8 +59,9 @@ struct Slot {
 };
 
 struct KTab {
-  DevBuf buckets, postings;
-  uint32_t shift = 0, mask = 0;
+  DevBuf buckets, postings, direct;
+  uint32_t shift = 0, mask = 0, dshift = 0, dmask = 0;
+  bool has_direct = false;
   bool present = false;
   uint64_t nkeys = 0, npost = 0, npost_stored = 0;
 };
@@ -478,6 +479,9 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
       vp.tab[i].shift = e->tab[i].shift;
       vp.tab[i].mask = e->tab[i].mask;
       vp.tab[i].present = e->tab[i].present ? 1u : 0u;
+      vp.tab[i].direct = e->tab[i].has_direct ? e->tab[i].direct.as<uint4>() : nullptr;
+      vp.tab[i].dshift = e->tab[i].dshift;
+      vp.tab[i].dmask = e->tab[i].dmask;
     }
     vp.stage_tid = s.stage_tid.as<uint32_t>();
     vp.stage_score = s.stage_score.as<int32_t>();
@@ -598,7 +602,7 @@ void sq_destroy(sq_engine* e) {
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.voted) cudaEventDestroy(s.voted);
   }
-  for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); }
+  for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); t.direct.release(); }
   e->tap.release();
   {
     DevBuf* tb[] = {&e->tap_counts, &e->tap_offs, &e->tap_out, &e->tap_tid, &e->bp_newpair, &e->bp_newkey,
@@ -798,6 +802,16 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   SQ_CUDA(e, cudaMemsetAsync(e->d_fail, 0, 4, e->stream));
   launch_table_build(dkeys.as<uint32_t>(), doff.as<uint32_t>(), nkeys, t.buckets.as<uint4>(), t.shift, t.mask,
                      e->d_fail, e->stream, &e->launches);
+  t.has_direct = false;
+  if (e->nk == 1) {  // the bit-mask vote kernel runs for one k only: its table carries the list headers
+    const uint32_t db_log2 = std::max<uint32_t>(1, log2_ceil(nkeys + 1));
+    SQ_CUDA(e, t.direct.ensure((1ull << db_log2) * 32));
+    t.dshift = 32 - db_log2;
+    t.dmask = (uint32_t)((1ull << db_log2) - 1);
+    launch_direct_build(dkeys.as<uint32_t>(), doff.as<uint32_t>(), nkeys, t.postings.as<uint32_t>(), t.direct.as<uint4>(),
+                        t.dshift, t.dmask, e->d_fail, e->stream, &e->launches);
+    t.has_direct = true;
+  }
   uint32_t failed = 0;
   SQ_CUDA(e, cudaMemcpyAsync(&failed, e->d_fail, 4, cudaMemcpyDeviceToHost, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));

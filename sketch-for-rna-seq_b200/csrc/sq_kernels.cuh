@@ -35,6 +35,9 @@ struct EmView {
 void launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 size_t vote_smem_bytes(uint32_t nk);
 
+void launch_direct_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, const uint32_t* postings,
+                         uint4* direct, uint32_t shift, uint32_t mask, uint32_t* fail, cudaStream_t s,
+                         uint64_t* launches);
 void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
                         uint32_t mask, uint32_t* fail, cudaStream_t s, uint64_t* launches);
 

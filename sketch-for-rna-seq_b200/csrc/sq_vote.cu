@@ -859,45 +859,23 @@ __global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid
 
 // ------------------------------------------------------------------ bit-mask path (short reads, one k)
 // The isoforms of a gene have neighbouring ids, so the posting lists a short read hits almost always fit a
-// window of 64 transcripts.  The index stores, per distinct list, the window base and a 64-bit membership
-// mask.  One THREAD votes for a read without any table: it probes the read's hashes, groups equal lists,
-// and adds each list's weight into a bit-sliced counter (5 planes of 64 bits = a count 0..31 for each of the
-// 64 window positions; adding a weight to all members of a list is a 5-step ripple-carry over whole words).
-// Per-position maximum, the `count < ceil(fraction*max)` filter and the (score desc, transcript asc) order
-// are word operations too, so there is no data-dependent inner loop left except the handful of probes.
+// window of 64 transcripts.  The index keeps, per distinct list, the window base and a 64-bit membership mask,
+// and for one-k indexes a second, "direct" hash table whose entries carry that header next to the key: a probe
+// is one 32-byte bucket and nothing else.  One THREAD votes for a read without any table of its own: every hit
+// adds 1 at the list's positions of a bit-sliced counter (5 planes of 64 bits = a count 0..31 per window
+// position, a ripple-carry over whole words).  Per-position maximum, the `count < ceil(fraction*max)` filter
+// and the (score desc, transcript asc) order are word operations too.  The block first deals its reads to the
+// threads in order of hash count, so that the probe loop of a warp diverges little.
 //
 // 32-bit hashes below the 5 % threshold collide: about one list in 70 joins the k-mers of two unrelated genes
-// and one read in seven meets such a list (real annotations add paralogues).  The list header therefore holds
+// and one read in seven meets such a list (real annotations add paralogues).  A list header therefore holds
 // up to two (base, mask) ranges, and the thread keeps a second, 2-plane window (counts up to 3) for an id
 // range away from the first; the two windows never overlap, so maximum, filter and order stay word operations.
-// Reads that still do not fit (several items, > 16 hashes, > 8 distinct lists, a list that needs three ranges,
-// a third id range, a distant count above 3) are handed to the 4-lanes-per-read kernel through mid_list.
+// Reads that still do not fit (several items, > 16 hashes, > 4 two-range lists, a list that needs three
+// ranges, a third id range, a distant count above 3) are handed to the 4-lanes-per-read kernel through mid_list.
 static constexpr int kBitsBlock = 128;
 static constexpr uint32_t kBitsMaxHashes = 16;
-static constexpr uint32_t kBitsMaxLists = 8;
-static constexpr uint32_t kBitsFlat = 32 * kBitsMaxHashes;  // hashes of one warp's 32 reads
-
-// first bucket of the probe sequence already loaded: finish the lookup (see probe())
-__device__ __forceinline__ uint32_t probe_resolve(const IndexTable& tb, uint32_t h, uint32_t b, uint4 kk, uint4 oo) {
-  if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
-  if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
-  if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
-  if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
-  if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
-  for (uint32_t tries = 1; tries <= tb.mask; ++tries) {  // full bucket without the key: rare
-    b = (b + 1) & tb.mask;
-    kk = __ldg(tb.buckets + 2 * (size_t)b);
-    oo = __ldg(tb.buckets + 2 * (size_t)b + 1);
-    if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
-    if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
-    if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
-    if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
-    if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
-  }
-  return SQ_EMPTY;
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+static constexpr uint32_t kBitsMaxInd = 4;  // two-range lists per read
 
 // bit-sliced counters: NP planes of 64 positions
 template <int NP>
@@ -986,11 +964,22 @@ __device__ __forceinline__ unsigned long long win_equal(const BitWin<NP>& W, uns
   return e;
 }
 
+// first bucket of the direct table already loaded: the entry of h, or .y == SQ_DIRECT_EMPTY when h is not a key
+__device__ __forceinline__ uint4 direct_resolve(const IndexTable& tb, uint32_t h, uint32_t b, uint4 a, uint4 c) {
+  for (uint32_t tries = 0;; ++tries) {
+    if (a.x == h && a.y != SQ_DIRECT_EMPTY) return a;
+    if (c.x == h && c.y != SQ_DIRECT_EMPTY) return c;
+    if (a.y == SQ_DIRECT_EMPTY || c.y == SQ_DIRECT_EMPTY || tries >= tb.dmask) break;
+    b = (b + 1) & tb.dmask;  // full bucket without the key: next one (rare)
+    a = __ldg(tb.direct + 2 * (size_t)b);
+    c = __ldg(tb.direct + 2 * (size_t)b + 1);
+  }
+  return make_uint4(h, SQ_DIRECT_EMPTY, 0u, 0u);
+}
+
 __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_constant__ VoteParams P) {
-  // per warp: the hashes of its 32 reads back to back (read l owns [start_l, start_l + n_l)); the slots are
-  // rewritten in place: hash -> posting offset -> the read's distinct lists and their weights
-  __shared__ uint32_t s_o[kBitsBlock / 32][kBitsFlat];
-  __shared__ uint8_t s_w[kBitsBlock / 32][kBitsFlat];  // 1 = probe this slot / weight, bit 7: walk in pass 2
+  __shared__ uint32_t s_h[kBitsMaxHashes][kBitsBlock];  // the read's hashes so far (exact duplicate check)
+  __shared__ uint32_t s_ind[kBitsMaxInd][kBitsBlock];   // posting offsets of the two-range lists it met
   __shared__ uint32_t s_work[4];
   __shared__ uint32_t s_hist[kBitsMaxHashes + 2];
   __shared__ uint32_t s_perm[kBitsBlock];
@@ -1037,96 +1026,57 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     if (n > kBitsMaxHashes) { defer = true; n = 0; }
     hs = P.sel + (P.base_off[r] - P.bias);
   }
-  // ---- the warp's hashes, flattened: every lane probes, whatever the spread of n over the reads
-  const uint32_t incl_n = warp_incl_scan(n);
-  const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl_n, 31);
-  uint32_t* so = s_o[warp] + (incl_n - n);
-  uint8_t* sw = s_w[warp] + (incl_n - n);
-  {
-    unsigned long long m1 = 0, m2 = 0;
-    for (uint32_t j = 0; j < n; ++j) {
-      const uint32_t h = __ldg(hs + j);
-      const unsigned long long b1 = 1ull << (h & 63), b2 = 1ull << ((h >> 6) & 63);
+  if (valid && tb.present) {
+    // ---- probe the read's hashes two at a time (independent loads in flight) and vote hit by hit.  After
+    // the deal above the lanes of a warp have about the same number of hashes, so this loop diverges little.
+    uint32_t m1 = 0, m2 = 0, nind = 0;
+    auto seen = [&](uint32_t h, uint32_t upto) {  // is h one of the read's first `upto` hashes?
+      const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
       bool dup = false;
-      if ((m1 & b1) && (m2 & b2))  // an equal hash would share both buckets: exact check (rare)
-        for (uint32_t jj = 0; jj < j; ++jj) dup |= so[jj] == h;
+      if ((m1 & b1) && (m2 & b2))  // an equal hash would share both filter bits: exact check (rare)
+        for (uint32_t jj = 0; jj < upto; ++jj) dup |= s_h[jj][tx] == h;
       m1 |= b1;
       m2 |= b2;
-      so[j] = h;
-      sw[j] = dup ? 0 : 1;
-    }
-  }
-  __syncwarp();
-  if (tb.present) {
-    uint32_t* fo = s_o[warp];
-    const uint8_t* fw = s_w[warp];
-    for (uint32_t f = lane; f < total; f += 64) {  // two independent probes in flight per lane
-      const uint32_t f2 = f + 32;
-      const bool v1 = fw[f] != 0, v2 = f2 < total && fw[f2] != 0;
-      const uint32_t h1 = fo[f], h2 = f2 < total ? fo[f2] : 0u;
-      const uint32_t b1 = (h1 * kHashMul) >> tb.shift, b2 = (h2 * kHashMul) >> tb.shift;
-      uint4 k1 = make_uint4(0, 0, 0, 0), o1 = k1, k2 = k1, o2 = k1;
-      if (v1) { k1 = __ldg(tb.buckets + 2 * (size_t)b1); o1 = __ldg(tb.buckets + 2 * (size_t)b1 + 1); }
-      if (v2) { k2 = __ldg(tb.buckets + 2 * (size_t)b2); o2 = __ldg(tb.buckets + 2 * (size_t)b2 + 1); }
-      if (v1) {
-        const uint32_t off = probe_resolve(tb, h1, b1, k1, o1);
-        if (off != SQ_EMPTY) prefetch_l2(tb.postings + off);
-        fo[f] = off;
-      }
-      if (v2) {
-        const uint32_t off = probe_resolve(tb, h2, b2, k2, o2);
-        if (off != SQ_EMPTY) prefetch_l2(tb.postings + off);
-        fo[f2] = off;
-      }
-    }
-  }
-  __syncwarp();
-  if (valid && tb.present) {
-    // ---- group the hits that share a posting list (in place: slot i <= j)
-    uint32_t nd = 0;
-    for (uint32_t j = 0; j < n && !defer; ++j) {
-      if (!sw[j]) continue;
+      return dup;
+    };
+    auto vote = [&](const uint4& e) {
       ++wq;
-      const uint32_t off = so[j];
-      if (off == SQ_EMPTY) continue;
+      if (e.y == SQ_DIRECT_EMPTY) return;
       ++wh;
-      uint32_t i = 0;
-      for (; i < nd; ++i)
-        if (so[i] == off) break;
-      if (i < nd) {
-        sw[i] += 1;
-      } else if (nd < kBitsMaxLists) {
-        so[nd] = off;
-        sw[nd] = 1;
-        ++nd;
-      } else {
-        defer = true;
+      if (e.y == SQ_NOMASK) { defer = true; return; }
+      if (e.y >> 31) {  // two-range list: after the single-range ones (they fix window A)
+        if (nind < kBitsMaxInd) s_ind[nind++][tx] = e.z; else defer = true;
+        return;
       }
+      unsigned long long mask = ((unsigned long long)e.w << 32) | e.z;
+      wp += (uint32_t)__popcll(mask);
+      if (win_place(A, B, e.y, mask)) win_add(A, mask, 1u);
+      else if (!(win_place(B, A, e.y, mask) && win_add(B, mask, 1u))) defer = true;
+    };
+    for (uint32_t j = 0; j < n && !defer; j += 2) {
+      const bool two = j + 1 < n;
+      const uint32_t h1 = __ldg(hs + j), h2 = two ? __ldg(hs + j + 1) : 0u;
+      const bool v1 = !seen(h1, j);
+      s_h[j][tx] = h1;
+      const bool v2 = two && !seen(h2, j + 1);
+      if (two) s_h[j + 1][tx] = h2;
+      const uint32_t b1 = (h1 * kHashMul) >> tb.dshift, b2 = (h2 * kHashMul) >> tb.dshift;
+      uint4 a1 = make_uint4(0, 0, 0, 0), c1 = a1, a2 = a1, c2 = a1;
+      if (v1) { a1 = __ldg(tb.direct + 2 * (size_t)b1); c1 = __ldg(tb.direct + 2 * (size_t)b1 + 1); }
+      if (v2) { a2 = __ldg(tb.direct + 2 * (size_t)b2); c2 = __ldg(tb.direct + 2 * (size_t)b2 + 1); }
+      if (v1) vote(direct_resolve(tb, h1, b1, a1, c1));
+      if (v2 && !defer) vote(direct_resolve(tb, h2, b2, a2, c2));
     }
-    // ---- add every distinct list's weight to its members: single-range lists first (they fix window A)
-    bool any_two = false;
-    for (uint32_t phase = 0; phase < 2 && !defer; ++phase) {
-      if (phase && !any_two) break;
-      for (uint32_t i = 0; i < nd && !defer; ++i) {
-        const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + so[i]);
-        const uint4 hd = __ldg(hp);
-        if (hd.y == SQ_NOMASK) { defer = true; break; }
-        const uint32_t two = hd.y >> 31;
-        any_two |= two != 0;
-        if (two != phase) continue;
-        const uint32_t w = sw[i];
-        unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
-        const uint32_t base = hd.y & 0x7FFFFFFFu;
-        if (win_place(A, B, base, mask)) win_add(A, mask, w);
-        else if (!(win_place(B, A, base, mask) && win_add(B, mask, w))) { defer = true; break; }
-        if (two) {
-          const uint4 h2 = __ldg(hp + 1);
-          unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
-          if (win_place(A, B, h2.x, mask2)) win_add(A, mask2, w);
-          else if (!(win_place(B, A, h2.x, mask2) && win_add(B, mask2, w))) { defer = true; break; }
-        }
-        wp += w * hd.x;
-      }
+    for (uint32_t i = 0; i < nind && !defer; ++i) {  // two-range lists: both ranges from the list header
+      const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + s_ind[i][tx]);
+      const uint4 hd = __ldg(hp), h2 = __ldg(hp + 1);
+      unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
+      unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
+      wp += hd.x;
+      if (win_place(A, B, hd.y & 0x7FFFFFFFu, mask)) win_add(A, mask, 1u);
+      else if (!(win_place(B, A, hd.y & 0x7FFFFFFFu, mask) && win_add(B, mask, 1u))) { defer = true; break; }
+      if (win_place(A, B, h2.x, mask2)) win_add(A, mask2, 1u);
+      else if (!(win_place(B, A, h2.x, mask2) && win_add(B, mask2, 1u))) { defer = true; break; }
     }
     if (!defer && (A.orm | B.orm)) {
       // ---- maximum over the positions (sparse_chaining.cpp:76-82)
@@ -1248,7 +1198,7 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t e
     const uint32_t qgrid = need < (uint32_t)quad_grid[nkq] ? need : (uint32_t)quad_grid[nkq];
     switch (nkq) {
       case 1:
-        if ((uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4) {
+        if (p.tab[0].direct && (uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4) {
           // one k, mean read length up to ~320: the bit-mask kernel takes every read it can, the quad kernel
           // the rest (mid_list); the profiling events bracket the first, dominant kernel of the chain
           vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
