@@ -234,6 +234,24 @@ def write_sample_fastq(chunk, n_sample, path):
     return n
 
 
+def pin_to_gpu_node(local):
+    """Bind this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers (first
+    touch) and the copy engine's reads stay on that socket.  Returns a short description for the log."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d" % (len(cpus), local)
+    except Exception as ex:  # no NVML / not permitted: run unpinned
+        return "unpinned (%s)" % type(ex).__name__
+    return "unpinned"
+
+
 # ----------------------------------------------------------------------------- arms
 def run_ours(args):
     import torch
@@ -245,11 +263,13 @@ def run_ours(args):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
     torch.cuda.set_device(local)
     dev = "cuda:%d" % local
+    numa = pin_to_gpu_node(local)  # before any pinned allocation: host buffers land on the GPU's NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
     sqb.load_library()  # fails loudly when the CUDA extension is missing
+    log("[bench] rank %d: host affinity %s" % (rank, numa))
 
     tx, T, tlen, chunks = make_workload(args, dev, rank)
     eng = sqb.Engine(K_LIST, T, sketch_fraction=SKETCH, chain_fraction=0.9, device=local)

@@ -90,7 +90,8 @@ void sq_destroy(sq_engine* e);
 int sq_set_stream(sq_engine* e, void* cuda_stream);
 int sq_set_profiling(sq_engine* e, int enabled);
 /* Tunables: "batch_bases" (max bases per internal batch), "cand_per_read" (initial staging slots per read),
- * "overflow_workers", "max_read_len", "em_segment": set before the first push.  "exact_classes" (any time):
+ * "overflow_workers", "max_read_len", "em_segment", "sub_batch_reads" (reads per internal batch of
+ * sq_push_reads_fixed, default 2^20): set before the first push.  "exact_classes" (any time):
  * 1 = reads are merged into one EM term only after comparing their candidate lists element by element,
  * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads). */
 int sq_set_option(sq_engine* e, const char* name, int64_t value);

@@ -113,6 +113,7 @@ struct sq_engine {
   uint32_t n_workers = 64;
   uint32_t max_read_len = 1u << 20;
   uint32_t em_seg = 1024;
+  uint32_t sub_batch_reads = 1u << 20;  // sq_push_reads_fixed: reads per internal batch
   bool exact_classes = false;  // compare candidate lists element-wise instead of by 128-bit fingerprint
   // batch slots
   Slot slot[2];
@@ -652,6 +653,7 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   else if (n == "overflow_workers") { e->n_workers = (uint32_t)value; e->big_ready = false; }
   else if (n == "max_read_len") { e->max_read_len = (uint32_t)value; e->big_ready = false; }
   else if (n == "em_segment") e->em_seg = (uint32_t)value;
+  else if (n == "sub_batch_reads") e->sub_batch_reads = (uint32_t)std::min<uint64_t>((uint64_t)value, 1u << 30);
   else return fail(e, SQ_ERR_ARG, "unknown option %s", name);
   return SQ_OK;
 }
@@ -905,17 +907,27 @@ int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_w
                                                 (unsigned long long)((bases + 15) / 16), (unsigned long long)n_words);
   if (bases > e->batch_bases + 64) return fail(e, SQ_ERR_ARG, "batch exceeds option batch_bases (%llu bases): push smaller batches", (unsigned long long)e->batch_bases);
   SQ_CUDA(e, cudaSetDevice(e->device));
-  const uint64_t nw = (bases + 15) / 16;
-  Slot* s = nullptr;
-  SQ_TRY(acquire_slot(e, &s));
-  SQ_CUDA(e, s->packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
-  SQ_CUDA(e, s->base_off.ensure(((size_t)n_reads + 1) * 4));
-  SQ_CUDA(e, s->len.ensure((size_t)n_reads * 4));
-  SQ_CUDA(e, cudaMemcpyAsync(s->packed.p, packed_words, nw * 4, cudaMemcpyHostToDevice, e->copy_stream));
-  SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
-  SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (nw + 3) & ~3ull, s->base_off.as<uint32_t>(), 0,
-                   s->len.as<uint32_t>(), n_reads, bases, s->copied, s->base_off.as<uint32_t>(), read_len));
-  SQ_CUDA(e, cudaEventSynchronize(s->copied));
+  // Sub-batches of about sub_batch_reads reads (a multiple of 4 reads is a whole number of packed words): the
+  // kernels of one overlap the copy of the next, so less work is left when the last copy lands.
+  const uint32_t sub = std::max<uint32_t>(4, e->sub_batch_reads & ~3u);
+  const uint32_t parts = n_reads <= sub + sub / 2 ? 1u : (n_reads + sub - 1) / sub;
+  const uint32_t per = ((n_reads + parts - 1) / parts + 3) & ~3u;
+  for (uint32_t r0 = 0; r0 < n_reads; r0 += per) {
+    const uint32_t nr = std::min(per, n_reads - r0);
+    const uint64_t w0 = stride * r0 / 16, nb = stride * nr, nw = (nb + 15) / 16;
+    Slot* s = nullptr;
+    SQ_TRY(acquire_slot(e, &s));
+    SQ_CUDA(e, s->packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
+    SQ_CUDA(e, s->base_off.ensure(((size_t)nr + 1) * 4));
+    SQ_CUDA(e, s->len.ensure((size_t)nr * 4));
+    SQ_CUDA(e, cudaMemcpyAsync(s->packed.p, packed_words + w0, nw * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    SQ_CUDA(e, cudaEventRecord(s->copied, e->copy_stream));
+    SQ_TRY(run_batch(e, *s, s->packed.as<uint32_t>(), (nw + 3) & ~3ull, s->base_off.as<uint32_t>(), 0,
+                     s->len.as<uint32_t>(), nr, nb, s->copied, s->base_off.as<uint32_t>(), read_len));
+    // the caller may reuse its buffer when we return: wait for the last copy (not for the kernels); the copies
+    // in between are queued back to back
+    if (r0 + per >= n_reads) SQ_CUDA(e, cudaEventSynchronize(s->copied));
+  }
   return SQ_OK;
 }
 
