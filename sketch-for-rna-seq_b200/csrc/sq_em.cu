@@ -351,7 +351,23 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
   const uint32_t b0 = read_off[c0], np = read_off[c0 + nc] - b0;
   const bool staged = np <= kDenCap;
   if (staged) {
-    for (uint32_t j = threadIdx.x; j < np; j += 256) s_term[j] = pi[cand_tid[b0 + j]] * (double)cand_score[b0 + j];
+    // four independent (id, score, pi) load chains per thread: the kernel waits on DRAM latency, not bandwidth
+    for (uint32_t j = threadIdx.x; j < np; j += 1024) {
+      uint32_t t[4];
+      int32_t sc[4];
+      double p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t q = j + 256 * u;
+        t[u] = q < np ? cand_tid[b0 + q] : 0u;
+        sc[u] = q < np ? cand_score[b0 + q] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = j + 256 * u < np ? pi[t[u]] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + 256 * u < np) s_term[j + 256 * u] = p[u] * (double)sc[u];
+    }
     __syncthreads();
   }
   if (threadIdx.x >= nc) return;
@@ -383,8 +399,18 @@ __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
     const uint32_t t = seg_tid[w];
     const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
     const double p = pi[t];
-    for (uint32_t j = b + gl; j < e; j += G)
-      acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
+    uint32_t j = b + gl;
+    for (; j + 3 * G < e; j += 4 * G) {  // four gathers in flight, added in the same order as the plain loop
+      uint32_t sc[4], c[4];
+      double iv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { sc[u] = tm_score[j + u * G]; c[u] = tm_read[j + u * G]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) iv[u] = inv_den[c[u]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += (p * (double)(int32_t)sc[u]) * iv[u];
+    }
+    for (; j < e; j += G) acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
   }
 #pragma unroll
   for (int d = G / 2; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d, G);
@@ -444,8 +470,20 @@ __global__ void __launch_bounds__(256) em_converge_kernel(const double* __restri
   }
 }
 
+// fixed-order sum of one double per thread over a 256-thread block (warp shuffles, then the 8 warp sums)
+__device__ __forceinline__ double block_sum_256(double v, double* sh8) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+  if ((threadIdx.x & 31) == 0) sh8[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < 8; ++w) s += sh8[w];
+  return s;  // valid in thread 0
+}
+
 // single GPU: segment sums, M-step and the convergence test in one launch.  The last block to finish (ticket
-// in state[2]) adds the per-block changes in the same fixed order as em_converge_kernel.
+// in state[2]) adds the per-block changes in a fixed order.
 __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __restrict__ seg_off,
                                                              const double* __restrict__ partial,
                                                              double* __restrict__ ps, double* __restrict__ pi,
@@ -453,7 +491,7 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
                                                              double* __restrict__ block_change, double tol,
                                                              uint32_t* state, double* last_change) {
   if (state[0]) return;
-  __shared__ double sh[256];
+  __shared__ double sh[8], sh2[8];
   __shared__ uint32_t s_last;
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   double ch = 0.0;
@@ -465,14 +503,9 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
     ch = fabs(np - pi[t]);
     pi[t] = np;
   }
-  sh[threadIdx.x] = ch;
-  __syncthreads();
-  for (int d = 128; d; d >>= 1) {
-    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
-    __syncthreads();
-  }
+  const double bsum = block_sum_256(ch, sh);
   if (threadIdx.x == 0) {
-    block_change[blockIdx.x] = sh[0];
+    block_change[blockIdx.x] = bsum;
     __threadfence();
     s_last = atomicAdd(&state[2], 1u) == gridDim.x - 1;
   }
@@ -481,18 +514,13 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
   __threadfence();
   double s = 0.0;
   for (uint32_t i = threadIdx.x; i < gridDim.x; i += 256) s += *(volatile double*)&block_change[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int d = 128; d; d >>= 1) {
-    if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
-    __syncthreads();
-  }
+  const double tot = block_sum_256(s, sh2);
   if (threadIdx.x == 0) {
     state[2] = 0;
-    *last_change = sh[0];
+    *last_change = tot;
     __threadfence();
     state[1] += 1;
-    if (sh[0] < tol) state[0] = 1;  // :62-64
+    if (tot < tol) state[0] = 1;  // :62-64
   }
 }
 
