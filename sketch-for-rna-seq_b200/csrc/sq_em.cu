@@ -122,13 +122,23 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
   ListHash lh;
   lh.init(c);
   uint32_t top = T;  // reads without candidates go last (one empty class)
-  for (uint32_t i = 0; i < c; ++i) {
-    const uint32_t t = stage_tid[so + i];
-    const int32_t sc = stage_score[so + i];
-    if (i == 0) top = t;
-    cand_tid[dst + i] = t;
-    cand_score[dst + i] = sc;
-    lh.add(t, sc);
+  // blocks of 4 candidates: the eight loads go out together (the kernel waits on latency, the fold is serial)
+  for (uint32_t i0 = 0; i0 < c; i0 += 4) {
+    uint32_t t[4];
+    int32_t sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      t[u] = i0 + u < c ? stage_tid[so + i0 + u] : 0u;
+      sc[u] = i0 + u < c ? stage_score[so + i0 + u] : 0;
+    }
+    if (i0 == 0) top = t[0];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u < c) {
+        cand_tid[dst + i0 + u] = t[u];
+        cand_score[dst + i0 + u] = sc[u];
+        lh.add(t[u], sc[u]);
+      }
   }
   rkey[read_base + r] = lh.key(top, hash_bits, read_base + r);
   rfp[read_base + r] = make_ulonglong2(lh.h, lh.g);
@@ -541,7 +551,22 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
     t = seg_tid[w];
     const uint32_t b = seg_begin[w], e = min(b + seg, toff[t + 1]);
     const double p = pi[t];
-    for (uint32_t j = b + gl; j < e; j += G) {
+    uint32_t j = b + gl;
+    for (; j + 3 * G < e; j += 4 * G) {  // four gather chains in flight, terms added in the plain loop's order
+      uint32_t c[4], sc[4];
+      double tt[4], wt[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { c[u] = tm_read[j + u * G]; sc[u] = tm_score[j + u * G]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { tt[u] = tot[c[u]]; wt[u] = weight[c[u]]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (tt[u] > 0.0) {
+          acc += ((p * (double)(int32_t)sc[u]) / tt[u]) * wt[u];
+          any = true;
+        }
+    }
+    for (; j < e; j += G) {
       const uint32_t c = tm_read[j];
       const double tt = tot[c];
       if (tt > 0.0) {
