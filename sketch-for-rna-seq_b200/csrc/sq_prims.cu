@@ -6,7 +6,7 @@ namespace sq {
 
 // ------------------------------------------------------------------ scan
 static constexpr int kScanThreads = 256;
-static constexpr int kScanItems = 8;
+static constexpr int kScanItems = 16;
 static constexpr int kScanTile = kScanThreads * kScanItems;  // 2048
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
   hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ kin,
+template <bool VALS>  // keys-only sorts carry no payload registers or staging
+__global__ void __launch_bounds__(kSortThreads, VALS ? 4 : 5) radix_scatter_kernel(const uint64_t* __restrict__ kin,
                                                                      const uint32_t* __restrict__ vin,
                                                                      uint64_t* __restrict__ kout,
                                                                      uint32_t* __restrict__ vout, uint64_t n,
@@ -176,14 +177,14 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
   __shared__ uint32_t dstart[256];            // tile-local start of each digit
   __shared__ uint32_t gbase[256];             // global start of this tile's run of each digit
   __shared__ uint64_t skey[kSortTile];
-  __shared__ uint32_t sval[kSortTile];
+  __shared__ uint32_t sval[VALS ? kSortTile : 1];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
   __syncthreads();
   const uint64_t tbase = (uint64_t)blockIdx.x * kSortTile;
   // element order inside the tile: warp-major, then round, then lane (this defines stability)
   uint64_t key[kSortItems];
-  uint32_t val[kSortItems];
+  uint32_t val[VALS ? kSortItems : 1];
   uint32_t rank[kSortItems];
   const uint64_t wbase = tbase + (uint64_t)warp * (kSortItems * 32);
 #pragma unroll
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
     const uint64_t idx = wbase + i * 32 + lane;
     const bool ok = idx < n;
     key[i] = ok ? kin[idx] : ~0ull;
-    val[i] = ok && vin ? vin[idx] : 0u;
+    if (VALS) val[i] = ok ? vin[idx] : 0u;
     const uint32_t d = ok ? (uint32_t)(key[i] >> shift) & 255u : 256u;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
     const uint32_t before = __popc(peers & ((1u << lane) - 1));
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
       const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
       const uint32_t pos = dstart[d] + wcnt[warp][d] + rank[i];
       skey[pos] = key[i];
-      sval[pos] = val[i];
+      if (VALS) sval[pos] = val[i];
     }
   }
   __syncthreads();
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
     const uint32_t d = (uint32_t)(k >> shift) & 255u;
     const uint64_t dst = (uint64_t)gbase[d] + (i - dstart[d]);
     kout[dst] = k;
-    if (vout) vout[dst] = sval[i];
+    if (VALS) vout[dst] = sval[i];
   }
 }
 
@@ -266,7 +267,10 @@ void launch_radix_sort(uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uin
     radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, n, bit_lo + 8 * p, ntiles, hist);
     if (launches) ++*launches;
     launch_exclusive_scan(hist, offs, 256 * ntiles, scan_tmp, s, launches);
-    radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, bit_lo + 8 * p, ntiles, offs);
+    if (vin && vout)
+      radix_scatter_kernel<true><<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, bit_lo + 8 * p, ntiles, offs);
+    else
+      radix_scatter_kernel<false><<<ntiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, bit_lo + 8 * p, ntiles, offs);
     if (launches) ++*launches;
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
