@@ -55,6 +55,7 @@ struct SketchParams {
   uint32_t* sel;               // [nk][slot_stride] selected hashes; item slots start at base_off+chunk start
   uint64_t slot_stride;
   uint16_t* cnt;               // [nk][n_items_ub] selected count per item
+  unsigned long long* stats;   // optional: += selected hashes of the launch (one atomic per block)
   KLut lut[SQ_MAXK];
 };
 

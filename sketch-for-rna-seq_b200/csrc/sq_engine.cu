@@ -453,12 +453,12 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     sp.sel = s.sel.as<uint32_t>();
     sp.slot_stride = slot_stride;
     sp.cnt = s.cnt.as<uint16_t>();
+    sp.stats = e->d_totals;  // [0] += sketch hashes
     {
       StageScope st(e, 0);  // the sketch kernel alone
       launch_sketch(sp, e->stream, &e->launches);
     }
     StageScope st2(e, 6);
-    launch_sum_u16(s.cnt.as<uint16_t>(), (uint64_t)items_ub * e->nk, e->d_totals, e->stream, &e->launches);
   }
   {
     VoteParams& vp = s.vp;
@@ -1316,6 +1316,7 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
   sp.sel = s.sel.as<uint32_t>();
   sp.slot_stride = stride;
   sp.cnt = s.cnt.as<uint16_t>();
+  sp.stats = nullptr;
   launch_sketch(sp, st, &e->launches);
   launch_tap_count(s.item_start.as<uint32_t>(), n_reads, nk, s.cnt.as<uint16_t>(), items_ub,
                    e->tap_counts.as<uint32_t>(), st, &e->launches);

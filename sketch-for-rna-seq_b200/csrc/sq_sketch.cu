@@ -35,12 +35,28 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   uint2* lut = reinterpret_cast<uint2*>(smem);
   for (uint32_t i = threadIdx.x; i < p.nk * 48; i += blockDim.x) lut[i] = p.lut[i / 48].e[i % 48];
   uint32_t* stage = smem + p.nk * kLutWords + (threadIdx.x >> 5) * kStageWordsPerWarp;
+  // statistics: warps add their selected-hash counts here, the last one to arrive flushes (no exit barrier)
+  __shared__ uint32_t s_sel, s_arrived;
+  if (threadIdx.x == 0) { s_sel = 0; s_arrived = 0; }
   __syncthreads();
+  auto arrive = [&](uint32_t v) {  // called by one lane per warp
+    if (!p.stats) return;
+    if (v) atomicAdd(&s_sel, v);
+    __threadfence_block();
+    if (atomicAdd(&s_arrived, 1u) == kSketchBlock / 32 - 1) {
+      __threadfence_block();
+      const uint32_t t = *(volatile uint32_t*)&s_sel;
+      if (t) atomicAdd(p.stats, (unsigned long long)t);
+    }
+  };
 
   const uint32_t n_items = p.item_start[p.n_reads];
   const uint32_t item = blockIdx.x * kSketchBlock + threadIdx.x;
   const bool valid = item < n_items;
-  if (__all_sync(0xFFFFFFFFu, !valid)) return;
+  if (__all_sync(0xFFFFFFFFu, !valid)) {
+    if (lane_id() == 0) arrive(0);
+    return;
+  }
 
   uint32_t L = 0, boff = 0, c0 = 0, c1 = 0;
   if (valid) {
@@ -79,6 +95,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   if (!valid) return;
 
   const uint32_t thr = p.threshold;
+  uint32_t n_sel = 0;
   for (uint32_t ki = 0; ki < p.nk; ++ki) {
     const uint32_t k = p.ks[ki];
     // shared-memory byte address of this k's tables; 128-byte aligned, so (index*8) can be OR-ed in
@@ -171,6 +188,12 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
       if (pos < end) partial(end);
     }
     p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)(out - out0);
+    n_sel += (uint32_t)(out - out0);
+  }
+  {
+    const uint32_t act = __activemask();
+    const uint32_t tot = __reduce_add_sync(act, n_sel);
+    if (lane_id() == (uint32_t)__ffs(act) - 1) arrive(tot);
   }
 }
 
