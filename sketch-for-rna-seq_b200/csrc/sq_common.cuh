@@ -127,9 +127,11 @@ void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, ui
                          uint64_t* launches);
 void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
                            cudaStream_t s, uint64_t* launches);
-// ev_a/ev_b (optional): recorded right before/after the main short-read kernel only
-void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a = nullptr,
-                 cudaEvent_t ev_b = nullptr);
+// ev_a/ev_b (optional): recorded right before/after the main short-read kernel only.  tail/fork (optional): the
+// small follow-up kernels (reads the first kernel handed on) run on `tail` after `fork`, so that they overlap
+// whatever the caller enqueues next on `s`.  Returns the stream the last kernel went to.
+cudaStream_t launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a = nullptr,
+                         cudaEvent_t ev_b = nullptr, cudaStream_t tail = nullptr, cudaEvent_t fork = nullptr);
 
 // exclusive scan of n u32 values; out[n] receives the total (out has n+1 entries); tmp holds >= n/2048+2 u32
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t s,

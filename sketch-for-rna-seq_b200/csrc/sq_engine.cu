@@ -43,7 +43,7 @@ struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
   DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, slow_list, mid_list,
       stage_tid, stage_score, scan_tmp;
-  cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr;
+  cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr, fork = nullptr;
   bool in_flight = false;   // compaction enqueued, `done` recorded
   bool pending = false;     // vote enqueued, compaction not yet (needs the exact candidate count)
   uint64_t stage_cap = 0;
@@ -103,7 +103,7 @@ struct sq_engine {
   double fraction = 0.9;
   uint64_t T = 0;
   KLut lut[SQ_MAXK];
-  cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   bool profiling = false;
   std::string err;
   KTab tab[SQ_MAXK];
@@ -313,6 +313,9 @@ int ensure_big_scratch(sq_engine* e) {
 int enqueue_vote(sq_engine* e, Slot& s) {
   unsigned long long* ctr = e->d_slot_ctr + 4 * s.id;
   SQ_CUDA(e, cudaMemsetAsync(ctr, 0, 32, e->stream));
+  // The vote's follow-up kernels (the few reads its first kernel hands on) go to the tail stream: nothing on
+  // the engine stream needs them until the host has seen `voted`, and the next batch's sketch overlaps them.
+  cudaStream_t last = e->stream;
   {
     StageScope st(e, 1);
     cudaEvent_t a = nullptr, b = nullptr;
@@ -320,12 +323,12 @@ int enqueue_vote(sq_engine* e, Slot& s) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
     }
-    launch_vote(s.vp, e->stream, &e->launches, a, b);
+    last = launch_vote(s.vp, e->stream, &e->launches, a, b, e->tail_stream, s.fork);
     if (a) e->events.push_back({a, b, 7});
   }
-  SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 4 * s.id, ctr, 32, cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 4 * s.id, ctr, 32, cudaMemcpyDeviceToHost, last));
   SQ_CUDA(e, cudaGetLastError());
-  SQ_CUDA(e, cudaEventRecord(s.voted, e->stream));
+  SQ_CUDA(e, cudaEventRecord(s.voted, last));
   return SQ_OK;
 }
 
@@ -378,6 +381,7 @@ int acquire_slot(sq_engine* e, Slot** out) {
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.voted, cudaEventDisableTiming));
+    SQ_CUDA(e, cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
   }
   SQ_TRY(finalize_slot(e, s));
   if (s.in_flight) {
@@ -413,9 +417,14 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
   SQ_TRY(ensure_big_scratch(e));
-  // the batch before this one (other slot) can now be finalized: its vote overlaps our copies
-  SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
-  if (inputs_ready) SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
+  // The batch before this one (other slot) must be finalized (host waits for its vote, then enqueues its
+  // compaction).  Host batches: now, before the engine stream starts waiting for our copy, so the compaction
+  // is not held up behind that wait (its vote has been overlapping our copies).  Device batches: after our
+  // sketch is enqueued (below), so the sketch runs while the previous vote's tail kernels finish.
+  if (inputs_ready) {
+    SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
+    SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
+  }
   if (derive_boff && fixed_len) {  // equal lengths: offsets and lengths are written on the GPU, nothing was copied
     StageScope st(e, 6);
     launch_fixed_layout(const_cast<uint32_t*>(d_len), derive_boff, n_reads, fixed_len, e->stream, &e->launches);
@@ -460,6 +469,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     }
     StageScope st2(e, 6);
   }
+  if (!inputs_ready) SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
   {
     VoteParams& vp = s.vp;
     memset(&vp, 0, sizeof(vp));
@@ -577,6 +587,7 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
   if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
+  if ((ce = cudaStreamCreateWithFlags(&e->tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   e->stream = e->own_stream;
   void* ctr = nullptr;
   if ((ce = cudaMalloc(&ctr, 256)) != cudaSuccess) return bail(ce, "cudaMalloc");
@@ -602,6 +613,7 @@ void sq_destroy(sq_engine* e) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.voted) cudaEventDestroy(s.voted);
+    if (s.fork) cudaEventDestroy(s.fork);
   }
   for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); t.direct.release(); }
   e->tap.release();
@@ -625,6 +637,7 @@ void sq_destroy(sq_engine* e) {
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->tail_stream) cudaStreamDestroy(e->tail_stream);
   delete e;
 }
 

@@ -1168,7 +1168,8 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
 }
 
 template <typename CT>
-static void launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t ev_b) {
+static cudaStream_t launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t ev_b, cudaStream_t tail,
+                                      cudaEvent_t fork) {
   constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
   constexpr size_t smA = (size_t)capA * blkA * (4 + sizeof(CT)), smB = (size_t)capB * blkB * (4 + sizeof(CT));
   static bool attr = false;
@@ -1203,6 +1204,11 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t e
           // the rest (mid_list); the profiling events bracket the first, dominant kernel of the chain
           vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
           if (ev_b) cudaEventRecord(ev_b, s);
+          if (tail && fork) {  // the rest is a few latency-bound launches for ~2 % of the reads: off the main stream
+            cudaEventRecord(fork, s);
+            cudaStreamWaitEvent(tail, fork, 0);
+            s = tail;
+          }
           vote_quad_kernel<1, true><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
         } else {  // long reads span several items: straight to the quad kernel
           vote_quad_kernel<1, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
@@ -1220,6 +1226,7 @@ static void launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t e
     if (ev_b) cudaEventRecord(ev_b, s);
     vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
   }
+  return s;
 }
 
 
@@ -1269,8 +1276,9 @@ size_t vote_smem_bytes(uint32_t nk) {
   return (size_t)kVoteWarps * (tab + tab * nk + tab + set + 4) * sizeof(uint32_t);
 }
 
-void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b) {
-  if (p.n_reads == 0) return;
+cudaStream_t launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
+                         cudaStream_t tail, cudaEvent_t fork) {
+  if (p.n_reads == 0) return s;
   static int sm_count = 0, configured_nk = -1;
   if (!sm_count) {
     int dev = 0;
@@ -1289,10 +1297,12 @@ void launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEv
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
   if (ev_a) cudaEventRecord(ev_a, s);
-  if (p.nk <= 4) launch_fast_tiers<uint32_t>(p, s, ev_b); else launch_fast_tiers<unsigned long long>(p, s, ev_b);
+  s = p.nk <= 4 ? launch_fast_tiers<uint32_t>(p, s, ev_b, tail, fork)
+                : launch_fast_tiers<unsigned long long>(p, s, ev_b, tail, fork);
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
   vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
   if (launches) *launches += 4;
+  return s;
 }
 
 }  // namespace sq
