@@ -191,16 +191,17 @@ struct StageScope {
   sq_engine* e;
   int stage;
   cudaEvent_t a = nullptr, b = nullptr;
-  StageScope(sq_engine* e_, int s) : e(e_), stage(s) {
+  cudaStream_t st;
+  StageScope(sq_engine* e_, int s, cudaStream_t on = nullptr) : e(e_), stage(s), st(on ? on : e_->stream) {
     if (e->profiling) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
-      cudaEventRecord(a, e->stream);
+      cudaEventRecord(a, st);
     }
   }
   ~StageScope() {
     if (e->profiling) {
-      cudaEventRecord(b, e->stream);
+      cudaEventRecord(b, st);
       e->events.push_back({a, b, stage});
     }
   }
@@ -244,6 +245,8 @@ int check_flags(sq_engine* e) {
 // make sure the CSR store can take `reads` more reads (beyond read_base) and `pairs` more pairs (beyond P);
 // contents are preserved
 int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pairs) {
+  // the store is written by the compactions, which run on the tail stream
+  cudaStream_t cs = e->tail_stream;
   const uint64_t need_reads = read_base + reads + 1;
   if (need_reads > e->read_cap) {
     uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
@@ -254,15 +257,15 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
     SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
     SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
     if (e->read_off) {
-      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaStreamSynchronize(cs));
       SQ_CUDA(e, cudaFree(e->read_off));
       SQ_CUDA(e, cudaFree(e->rkey));
       SQ_CUDA(e, cudaFree(e->rfp));
     } else {
-      SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), e->stream));
+      SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), cs));
     }
     e->read_off = p;
     e->rkey = pk;
@@ -279,9 +282,9 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
     SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint32_t)));
     SQ_CUDA(e, cudaMalloc(&sc, cap * sizeof(int32_t)));
     if (e->cand_tid) {
-      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, e->P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaMemcpyAsync(sc, e->cand_score, e->P * sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
-      SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, e->P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(sc, e->cand_score, e->P * sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaStreamSynchronize(cs));
       SQ_CUDA(e, cudaFree(e->cand_tid));
       SQ_CUDA(e, cudaFree(e->cand_score));
     }
@@ -353,16 +356,19 @@ int finalize_slot(sq_engine* e, Slot& s) {
   const uint64_t ovf = e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull;
   SQ_TRY(ensure_store(e, s.read_base, s.n_reads, needed));
   {
-    StageScope st(e, 2);
+    // on the tail stream, behind this batch's vote follow-ups (the host has seen `voted`): the compaction is
+    // latency-bound and overlaps the next batch's sketch and vote on the engine stream
+    cudaStream_t cs = e->tail_stream;
+    StageScope st(e, 2, cs);
     launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads, s.scan_tmp.as<uint32_t>(),
-                          e->stream, &e->launches);
+                          cs, &e->launches);
     launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
                    s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
-                   e->cand_score, e->read_off, (uint32_t)e->T, e->class_hash_bits, e->rkey, e->rfp, e->stream,
+                   e->cand_score, e->read_off, (uint32_t)e->T, e->class_hash_bits, e->rkey, e->rfp, cs,
                    &e->launches);
+    SQ_CUDA(e, cudaGetLastError());
+    SQ_CUDA(e, cudaEventRecord(s.done, cs));
   }
-  SQ_CUDA(e, cudaGetLastError());
-  SQ_CUDA(e, cudaEventRecord(s.done, e->stream));
   s.in_flight = true;
   s.pending = false;
   e->P += needed;
@@ -952,6 +958,7 @@ int sq_sync(sq_engine* e) {
   SQ_TRY(finalize_slot(e, e->slot[e->next_slot]));
   SQ_TRY(finalize_slot(e, e->slot[e->next_slot ^ 1]));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->tail_stream));
   for (auto& s : e->slot) s.in_flight = false;
   resolve_events(e);
   return check_flags(e);
