@@ -386,16 +386,16 @@ def run_ours(args):
     nk = len(K_LIST)
     n_kmers = sum(n_bases - n_reads * (k - 1) for k in K_LIST)
     b_sketch = n_bases / 4 + 12 * n_reads + 4 * st["sketch_hashes"] + 4 * n_reads * nk
+    # vote kernels (whatever their internal encoding): per read item_start/cnt/base_off in and soff/cnt out, 4 B per
+    # sketch hash, 12 B per probe (hash + table slot: key, offset), 4 B per posting of a hit list (SURVEY 8d:
+    # 4 B x deg; the bit-mask kernel gets them as 64-bit masks, the information is the same), 8 B per candidate
     if nk == 1 and args.workload == "short":
-        # bit-mask kernel: per read item_start+cnt+base_off (10 B) and soff/cnt out (8 B), its hashes, one 16-byte
-        # direct-table entry {key, base, mask} per probe (no list is walked), 8 B per candidate pair
         vote_name = "vote_bits_kernel"
-        b_vote = 18 * n_reads + 4 * st["sketch_hashes"] + 16 * st["queries"] + 8 * st["pairs"]
     else:
         # long reads span several items: the warp-per-read kernel does the work (timed with the whole vote stage)
         vote_name = "vote_kernel" if args.workload == "long" else ("vote_quad_kernel" if nk <= 4 else "vote_fast_kernel")
-        b_vote = (12 + 2 * nk) * n_reads + 4 * st["sketch_hashes"] + (4 + 8) * st["queries"] + 4 * st["postings"] \
-            + 8 * st["pairs"] + 8 * n_reads
+    b_vote = (12 + 2 * nk) * n_reads + 4 * st["sketch_hashes"] + (4 + 8) * st["queries"] + 4 * st["postings"] \
+        + 8 * st["pairs"] + 8 * n_reads
     b_em = iters * (24 * st["pairs"] + 16 * T)
     S = args.steps
     kern = {
