@@ -447,7 +447,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     for (uint32_t i = 0; i < e->nk; ++i) kl.k[i] = e->ks[i];
     launch_items(d_len, n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(), s.item_read.as<uint32_t>(),
                  items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches, kl, e->d_totals + 4);
-    SQ_CUDA(e, cudaMemsetAsync(s.cnt.p, 0, (size_t)items_ub * e->nk * 2, e->stream));
+    // cnt needs no clearing: the sketch kernel writes the count of every item that exists, for every k
   }
   {
     SketchParams sp;
