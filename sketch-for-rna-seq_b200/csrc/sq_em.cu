@@ -155,16 +155,6 @@ void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const u
   if (launches) ++*launches;
 }
 
-// number of selected hashes in a batch (stats): sum of the u16 counters
-__global__ void sum_u16_kernel(const uint16_t* __restrict__ cnt, uint64_t n, unsigned long long* out) {
-  unsigned long long s = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    s += cnt[i];
-#pragma unroll
-  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-  if (lane_id() == 0 && s) atomicAdd(out, s);
-}
-
 // ------------------------------------------------------------------ EM equivalence classes
 // EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
 // contribute identical terms, so they are collapsed into one class with a weight.  Reads are
@@ -673,11 +663,5 @@ void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cud
   if (launches) ++*launches;
 }
 
-void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches) {
-  if (!n) return;
-  const uint32_t grid = (uint32_t)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-  sum_u16_kernel<<<grid, 256, 0, s>>>(cnt, n, out);
-  if (launches) ++*launches;
-}
 
 }  // namespace sq

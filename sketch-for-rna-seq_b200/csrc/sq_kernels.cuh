@@ -45,7 +45,6 @@ void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const u
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
                     uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, uint32_t T, uint32_t hash_bits,
                     uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches);
-void launch_sum_u16(const uint16_t* cnt, uint64_t n, unsigned long long* out, cudaStream_t s, uint64_t* launches);
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
                        uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);
