@@ -64,12 +64,20 @@ __device__ __forceinline__ void table_vote(const Scratch& S, uint32_t t, uint32_
   S.ctr[1] = 1;
 }
 
+// one 32-byte table bucket in a single 256-bit load (sm_100), not allocated in L1: a probe has no reuse, and L1 is
+// better spent on the reads' hash sectors (3.97 ms against 4.27 with allocation, 4.15 with two 128-bit loads)
+__device__ __forceinline__ void ld_bucket(const uint4* p, uint4& a, uint4& c) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+               : "l"(p));
+}
+
 // look h up in the bucketed table; returns the posting offset or SQ_EMPTY
 __device__ __forceinline__ uint32_t probe(const IndexTable& tb, uint32_t h) {
   uint32_t b = (h * kHashMul) >> tb.shift;
   for (uint32_t tries = 0; tries <= tb.mask; ++tries) {
-    const uint4 kk = __ldg(tb.buckets + 2 * (size_t)b);
-    const uint4 oo = __ldg(tb.buckets + 2 * (size_t)b + 1);
+    uint4 kk, oo;
+    ld_bucket(tb.buckets + 2 * (size_t)b, kk, oo);
     if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
     if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
     if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
@@ -971,8 +979,7 @@ __device__ __forceinline__ uint4 direct_resolve(const IndexTable& tb, uint32_t h
     if (c.x == h && c.y != SQ_DIRECT_EMPTY) return c;
     if (a.y == SQ_DIRECT_EMPTY || c.y == SQ_DIRECT_EMPTY || tries >= tb.dmask) break;
     b = (b + 1) & tb.dmask;  // full bucket without the key: next one (rare)
-    a = __ldg(tb.direct + 2 * (size_t)b);
-    c = __ldg(tb.direct + 2 * (size_t)b + 1);
+    ld_bucket(tb.direct + 2 * (size_t)b, a, c);
   }
   return make_uint4(h, SQ_DIRECT_EMPTY, 0u, 0u);
 }
@@ -1062,8 +1069,8 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
       if (two) s_h[j + 1][tx] = h2;
       const uint32_t b1 = (h1 * kHashMul) >> tb.dshift, b2 = (h2 * kHashMul) >> tb.dshift;
       uint4 a1 = make_uint4(0, 0, 0, 0), c1 = a1, a2 = a1, c2 = a1;
-      if (v1) { a1 = __ldg(tb.direct + 2 * (size_t)b1); c1 = __ldg(tb.direct + 2 * (size_t)b1 + 1); }
-      if (v2) { a2 = __ldg(tb.direct + 2 * (size_t)b2); c2 = __ldg(tb.direct + 2 * (size_t)b2 + 1); }
+      if (v1) ld_bucket(tb.direct + 2 * (size_t)b1, a1, c1);
+      if (v2) ld_bucket(tb.direct + 2 * (size_t)b2, a2, c2);
       if (v1) vote(direct_resolve(tb, h1, b1, a1, c1));
       if (v2 && !defer) vote(direct_resolve(tb, h2, b2, a2, c2));
     }
