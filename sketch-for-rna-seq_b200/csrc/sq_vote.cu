@@ -1002,7 +1002,6 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
   unsigned long long sa = 0, sb = 0;             // survivors
   uint32_t mx = 0, ithr = 0, nc = 0;
   uint32_t n = 0;
-  const uint32_t* hs = nullptr;
   // Every per-thread loop below runs for the longest lane of its warp, and the hash count of a read varies
   // 2..14: deal the block's reads to the threads in order of hash count (counting sort in shared memory), so
   // that a warp holds reads of similar size.  `r` is the read this thread works for from here on.
@@ -1014,6 +1013,25 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
       const uint32_t item0 = P.item_start[r];
       if (P.item_start[r + 1] - item0 == 1) key = min((uint32_t)P.cnt[item0], kBitsMaxHashes + 1);
     }
+    // The read's hashes go into this thread's shared-memory column now (one or two 256-bit loads when the slot
+    // is 32-byte aligned, as it is for reads packed at a fixed stride): their DRAM latency passes behind the
+    // deal's barriers, and the vote loop below never waits on global memory for a hash.
+    if (key <= kBitsMaxHashes && key) {
+      const uint32_t* hp = P.sel + (P.base_off[r] - P.bias);
+      if ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) {
+        for (uint32_t j0 = 0; j0 < key; j0 += 8) {
+          uint4 a, c;
+          asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                       : "l"(hp + j0));
+          // (the slot is as long as the read, >= 8 words past any selected hash's group for reads >= k bases)
+          s_h[j0 + 0][tx] = a.x; s_h[j0 + 1][tx] = a.y; s_h[j0 + 2][tx] = a.z; s_h[j0 + 3][tx] = a.w;
+          s_h[j0 + 4][tx] = c.x; s_h[j0 + 5][tx] = c.y; s_h[j0 + 6][tx] = c.z; s_h[j0 + 7][tx] = c.w;
+        }
+      } else {
+        for (uint32_t j = 0; j < key; ++j) s_h[j][tx] = __ldg(hp + j);
+      }
+    }
     const uint32_t rank = atomicAdd(&s_hist[key], 1u);
     __syncthreads();
     if (tx == 0) {
@@ -1023,15 +1041,15 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     __syncthreads();
     s_perm[s_hist[key] + rank] = tx;
     __syncthreads();
-    r = blockIdx.x * kBitsBlock + s_perm[tx];
-    valid = r < P.n_reads;
   }
+  const uint32_t col = s_perm[tx];  // the thread that loaded the hashes of the read this thread votes for
+  r = blockIdx.x * kBitsBlock + col;
+  valid = r < P.n_reads;
   if (valid && tb.present) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
     n = defer ? 0u : (uint32_t)P.cnt[item0];
     if (n > kBitsMaxHashes) { defer = true; n = 0; }
-    hs = P.sel + (P.base_off[r] - P.bias);
   }
   if (valid && tb.present) {
     // ---- probe the read's hashes two at a time (independent loads in flight) and vote hit by hit.  After
@@ -1041,7 +1059,7 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
       const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
       bool dup = false;
       if ((m1 & b1) && (m2 & b2))  // an equal hash would share both filter bits: exact check (rare)
-        for (uint32_t jj = 0; jj < upto; ++jj) dup |= s_h[jj][tx] == h;
+        for (uint32_t jj = 0; jj < upto; ++jj) dup |= s_h[jj][col] == h;
       m1 |= b1;
       m2 |= b2;
       return dup;
@@ -1062,11 +1080,9 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     };
     for (uint32_t j = 0; j < n && !defer; j += 2) {
       const bool two = j + 1 < n;
-      const uint32_t h1 = __ldg(hs + j), h2 = two ? __ldg(hs + j + 1) : 0u;
+      const uint32_t h1 = s_h[j][col], h2 = two ? s_h[j + 1][col] : 0u;
       const bool v1 = !seen(h1, j);
-      s_h[j][tx] = h1;
       const bool v2 = two && !seen(h2, j + 1);
-      if (two) s_h[j + 1][tx] = h2;
       const uint32_t b1 = (h1 * kHashMul) >> tb.dshift, b2 = (h2 * kHashMul) >> tb.dshift;
       uint4 a1 = make_uint4(0, 0, 0, 0), c1 = a1, a2 = a1, c2 = a1;
       if (v1) ld_bucket(tb.direct + 2 * (size_t)b1, a1, c1);
