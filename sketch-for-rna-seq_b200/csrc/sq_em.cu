@@ -332,6 +332,16 @@ __global__ void em_init_kernel(double* pi, uint32_t T, uint32_t* state) {
   if (t == 0) { state[0] = 0; state[1] = 0; state[2] = 0; }  // [0]=converged flag, [1]=iterations executed, [2]=block ticket
 }
 
+// streaming read of data that is used once per pass: do not let it displace the gathered vectors (pi, 1/den) in L1
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_stream(const int32_t* p) {
+  return (int32_t)ld_stream(reinterpret_cast<const uint32_t*>(p));
+}
+
 // per read (class): den = sum_j pi[t_j]*s_j in candidate order; E-step: inv = 1/den when den > 1e-10 (:36-45),
 // else 0; assignment: tot = den (:80-85).  A block owns 256 consecutive rows: their pairs are one contiguous
 // range, so the products are formed with coalesced loads into shared memory and each thread then adds up its
@@ -359,8 +369,8 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t q = j + 256 * u;
-        t[u] = q < np ? cand_tid[b0 + q] : 0u;
-        sc[u] = q < np ? cand_score[b0 + q] : 0;
+        t[u] = q < np ? ld_stream(cand_tid + b0 + q) : 0u;
+        sc[u] = q < np ? ld_stream(cand_score + b0 + q) : 0;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) p[u] = j + 256 * u < np ? pi[t[u]] : 0.0;
@@ -404,13 +414,13 @@ __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
       uint32_t sc[4], c[4];
       double iv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { sc[u] = tm_score[j + u * G]; c[u] = tm_read[j + u * G]; }
+      for (int u = 0; u < 4; ++u) { sc[u] = ld_stream(tm_score + j + u * G); c[u] = ld_stream(tm_read + j + u * G); }
 #pragma unroll
       for (int u = 0; u < 4; ++u) iv[u] = inv_den[c[u]];
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc += (p * (double)(int32_t)sc[u]) * iv[u];
     }
-    for (; j < e; j += G) acc += (p * (double)(int32_t)tm_score[j]) * inv_den[tm_read[j]];
+    for (; j < e; j += G) acc += (p * (double)(int32_t)ld_stream(tm_score + j)) * inv_den[ld_stream(tm_read + j)];
   }
 #pragma unroll
   for (int d = G / 2; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d, G);
@@ -546,7 +556,7 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
       uint32_t c[4], sc[4];
       double tt[4], wt[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { c[u] = tm_read[j + u * G]; sc[u] = tm_score[j + u * G]; }
+      for (int u = 0; u < 4; ++u) { c[u] = ld_stream(tm_read + j + u * G); sc[u] = ld_stream(tm_score + j + u * G); }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { tt[u] = tot[c[u]]; wt[u] = weight[c[u]]; }
 #pragma unroll
