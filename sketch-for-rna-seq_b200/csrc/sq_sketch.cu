@@ -25,6 +25,11 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
+// out0[n++] = x with the address formed at the store (see sketch_kernel)
+__device__ __forceinline__ void emit(uint32_t* out0, uint32_t& n, uint32_t x) {
+  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.u32 [a], %2;\n\t}" ::"l"(out0), "r"(n), "r"(x) : "memory");
+  ++n;
+}
 __device__ __forceinline__ uint32_t code_at(const uint32_t* wp, uint32_t pos) {
   return (wp[pos >> 4] >> ((pos & 15) * 2)) & 3;
 }
@@ -100,8 +105,11 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
     const uint32_t k = p.ks[ki];
     // shared-memory byte address of this k's tables; 128-byte aligned, so (index*8) can be OR-ed in
     const uint32_t tb = (uint32_t)__cvta_generic_to_shared(lut + ki * 48);
-    uint32_t* out = p.sel + (uint64_t)ki * p.slot_stride + boff + c0;
-    uint32_t* const out0 = out;
+    // selected hashes go to out0[nout++]: a fixed base and a 32-bit count, so that the (mostly predicated-off)
+    // append is the address (base + 4*count), the store and an increment -- a 64-bit pointer carried through the
+    // unrolled loop cost seven issue slots per k-mer instead of four
+    uint32_t* const out0 = p.sel + (uint64_t)ki * p.slot_stride + boff + c0;
+    uint32_t nout = 0;
     const uint32_t e_first = max(c0, k - 1);  // first window end that lies in this item
     if (L >= k && e_first < c1) {
       uint32_t x = 0, y = 0;  // lane value s: x = s[31:0], y = s[32:1]
@@ -134,7 +142,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
         x = nx;
         ++pos;
       }
-      if (x <= thr) *out++ = x;
+      if (x <= thr) emit(out0, nout, x);
       // ---- roll: pos = absolute index of the incoming base, the outgoing one is k behind
       const uint32_t end = boff + c1;
       const uint32_t q = k >> 4, dr = k & 15;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
           const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
           y = x ^ d.y;
           x = nx;
-          if (x <= thr) *out++ = x;
+          if (x <= thr) emit(out0, nout, x);
           win >>= 2;
           wout >>= 2;
         }
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
             const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
             y = x ^ d.y;
             x = nx;
-            if (x <= thr) *out++ = x;
+            if (x <= thr) emit(out0, nout, x);
           }
           {
             const uint32_t a = (j == 0 ? (xo << 3) & 0x78u : (xo >> (4 * j - 3)) & 0x78u) | tb;
@@ -180,15 +188,15 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
             const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
             y = x ^ d.y;
             x = nx;
-            if (x <= thr) *out++ = x;
+            if (x <= thr) emit(out0, nout, x);
           }
         }
         pos += 16;
       }
       if (pos < end) partial(end);
     }
-    p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)(out - out0);
-    n_sel += (uint32_t)(out - out0);
+    p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)nout;
+    n_sel += nout;
   }
   {
     const uint32_t act = __activemask();
