@@ -1018,13 +1018,12 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     // deal's barriers, and the vote loop below never waits on global memory for a hash.
     if (key <= kBitsMaxHashes && key) {
       const uint32_t* hp = P.sel + (P.base_off[r] - P.bias);
-      if ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) {
+      if ((reinterpret_cast<uintptr_t>(hp) & 31) == 0 && P.len[r] >= kBitsMaxHashes) {  // the slot is len words long
         for (uint32_t j0 = 0; j0 < key; j0 += 8) {
           uint4 a, c;
           asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
                        : "l"(hp + j0));
-          // (the slot is as long as the read, >= 8 words past any selected hash's group for reads >= k bases)
           s_h[j0 + 0][tx] = a.x; s_h[j0 + 1][tx] = a.y; s_h[j0 + 2][tx] = a.z; s_h[j0 + 3][tx] = a.w;
           s_h[j0 + 4][tx] = c.x; s_h[j0 + 5][tx] = c.y; s_h[j0 + 6][tx] = c.z; s_h[j0 + 7][tx] = c.w;
         }
