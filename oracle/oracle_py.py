@@ -216,6 +216,9 @@ class RefOracle:
         L.refq_read_candidates.restype = C.c_int64
         L.refq_read_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.refq_get_pi.argtypes = [C.c_void_p, C.c_void_p]
+        L.refq_candidates_csr.restype = C.c_uint64
+        L.refq_candidates_csr.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_uint64]
         L.refq_get_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.refq_write_csv.argtypes = [C.c_void_p, C.c_char_p]
         karr = np.asarray(ks, dtype=np.uint32)
@@ -308,6 +311,18 @@ class RefOracle:
         sc = np.zeros(cap, dtype=np.int32)
         n = self.lib.refq_read_candidates(self.h, rid, _p(tid), _p(sc), cap)
         return None if n < 0 else (tid[:n], sc[:n])
+
+    def candidates_csr(self, prefix, n):
+        """sparse_chain() output of the reads named prefix+str(i), i < n, as CSR ordered (score desc, index asc)"""
+        off = np.zeros(n + 1, dtype=np.uint64)
+        cap = max(1024, 8 * n)
+        while True:
+            tid = np.zeros(cap, dtype=np.uint32)
+            score = np.zeros(cap, dtype=np.int32)
+            tot = int(self.lib.refq_candidates_csr(self.h, prefix.encode(), n, _p(off), _p(tid), _p(score), cap))
+            if tot <= cap:
+                return off, tid[:tot], score[:tot]
+            cap = tot
 
     def pi(self):
         out = np.zeros(self.T, dtype=np.float64)

@@ -228,6 +228,30 @@ int64_t refq_read_candidates(void* h, const char* id, uint32_t* tid, int32_t* sc
   return static_cast<int64_t>(v.size());
 }
 
+// candidate lists of the reads named <prefix><i>, i = 0..n-1, as one CSR (each list ordered like
+// refq_read_candidates); a read without an entry gets an empty list.  Returns the total number of
+// pairs; tid/score receive at most cap of them.
+uint64_t refq_candidates_csr(void* h, const char* prefix, uint64_t n, uint64_t* off, uint32_t* tid, int32_t* score,
+                             uint64_t cap) {
+  auto* q = static_cast<RefQuant*>(h);
+  uint64_t tot = 0;
+  std::vector<std::pair<int32_t, uint32_t>> v;
+  for (uint64_t i = 0; i < n; ++i) {
+    off[i] = tot;
+    auto it = q->segments.find(std::string(prefix) + std::to_string(i));
+    if (it == q->segments.end()) continue;
+    v.clear();
+    for (const auto& pr : it->second) v.emplace_back(-pr.second, q->tindex.at(pr.first));
+    std::sort(v.begin(), v.end());
+    for (const auto& e : v) {
+      if (tot < cap) { tid[tot] = e.second; score[tot] = -e.first; }
+      ++tot;
+    }
+  }
+  off[n] = tot;
+  return tot;
+}
+
 void refq_get_pi(void* h, double* out) {
   auto* q = static_cast<RefQuant*>(h);
   for (size_t i = 0; i < q->tnames.size(); ++i) {

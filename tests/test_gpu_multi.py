@@ -25,3 +25,28 @@ def test_two_gpus_equal_one(gpu_lib, tmp_path):
         assert r.returncode == 0, r.stderr
         out[g] = read_csv(csv)
     assert_csv_equal(out[2], out[1])
+
+
+@pytest.mark.parametrize("world,klist", [(2, "31"), (2, "21,31"), (4, "31"), (8, "31")])
+def test_ranks_equal_one_engine(gpu_lib, tmp_path, world, klist):
+    """C-ABI level: N per-rank engines with sq_comm_init (torchrun, NCCL) against one engine fed all reads"""
+    import json
+    import sys
+    if gpu_lib.sq_device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    out = str(tmp_path / "res.json")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multirank_worker.py")
+    port = 29500 + (os.getpid() % 500)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), worker, out, klist, "20000"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    keep = os.environ.get("SQ_TEST_ARTIFACTS")
+    if keep:
+        os.makedirs(keep, exist_ok=True)
+        json.dump(res, open(os.path.join(keep, "ranks_equal_one_engine_n%d_k%s.json" % (world, klist.replace(",", "_"))), "w"))
+    assert res["candidates_equal"], res
+    assert res["present_equal"] and res["ranks_bitwise_identical"], res
+    assert res["pi_max_rel"] <= 1e-9 and res["numreads_max_rel"] <= 1e-9, res
+    assert res["iterations"] == [res["iterations_one"]] * world, res
