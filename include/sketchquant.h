@@ -54,15 +54,15 @@ typedef struct sq_stats {
   float ms_sketch, ms_vote, ms_compact, ms_sort, ms_em, ms_assign;
   uint64_t launches;       /* kernels launched by this engine so far */
   /* vote-kernel work counters (for the roofline's algorithmic bytes) */
-  uint64_t queries;        /* distinct (read, k, hash) looked up in the index table */
+  uint64_t queries;        /* (item, k, hash) looked up in the index table */
   uint64_t hits;           /* of which found */
   uint64_t postings;       /* posting-list entries walked */
   float ms_items;          /* item split + counters (everything of the sketch stage except the sketch kernel) */
   uint32_t sketch_launches, vote_launches; /* launches of the two named kernels while profiling was on */
-  uint64_t slow_reads;     /* reads voted by the warp-per-read kernel instead of a thread-per-read kernel */
-  uint64_t mid_reads;      /* reads voted by the 48-entry thread-per-read kernel (second tier) or later */
-  float ms_vote_main;      /* the short-read vote kernel alone (part of ms_vote) */
-  float reserved2;
+  uint64_t slow_reads;     /* reads voted by the general warp-per-read kernel (third tier) */
+  uint64_t mid_reads;      /* short reads the bit-sliced kernel handed to the warp-per-read window kernel (second tier) */
+  float ms_vote_main;      /* the first, dominant vote kernel alone (part of ms_vote) */
+  float ms_lookup;         /* seed lookup kernels (one per k-index and batch) */
   uint64_t em_classes;     /* equivalence classes (distinct candidate lists) the last sq_finish ran EM on */
   uint64_t em_class_pairs; /* (class, transcript) pairs of those classes */
 } sq_stats;

@@ -34,7 +34,7 @@ class Stats(C.Structure):
                 ("ms_em", C.c_float), ("ms_assign", C.c_float), ("launches", C.c_uint64),
                 ("queries", C.c_uint64), ("hits", C.c_uint64), ("postings", C.c_uint64), ("ms_items", C.c_float),
                 ("sketch_launches", C.c_uint32), ("vote_launches", C.c_uint32), ("slow_reads", C.c_uint64),
-                ("mid_reads", C.c_uint64), ("ms_vote_main", C.c_float), ("reserved2", C.c_float), ("em_classes", C.c_uint64), ("em_class_pairs", C.c_uint64)]
+                ("mid_reads", C.c_uint64), ("ms_vote_main", C.c_float), ("ms_lookup", C.c_float), ("em_classes", C.c_uint64), ("em_class_pairs", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("reserved")}

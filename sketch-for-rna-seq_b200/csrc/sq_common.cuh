@@ -8,7 +8,6 @@
 #define SQ_EMPTY 0xFFFFFFFFu  // empty marker in hash tables / bucket offsets
 #define SQ_LAST 0x80000000u   // flag on the last transcript id of a posting list
 #define SQ_LIST_HDR 8          // header words of a posting list: length, then one or two (base, 64-bit mask) id ranges
-#define SQ_DIRECT_EMPTY 0xFFFFFFFEu
 #define SQ_NOMASK 0xFFFFFFFFu  // first base of a list whose transcripts need more than two 64-id ranges
 
 namespace sq {
@@ -52,30 +51,51 @@ struct SketchParams {
   uint32_t threshold;
   uint32_t ks[SQ_MAXK];
   uint32_t kmax;
-  uint32_t* sel;               // [nk][slot_stride] selected hashes; item slots start at base_off+chunk start
-  uint64_t slot_stride;
-  uint16_t* cnt;               // [nk][n_items_ub] selected count per item
-  unsigned long long* stats;   // optional: += selected hashes of the launch (one atomic per block)
+  // output: the selected hashes of the batch, DENSE per k-index: an item's hashes are hsel[k*hstride + hoff .. + cnt);
+  // the regions of a warp's 32 items are contiguous and in item order, warps reserve theirs with one atomic
+  uint32_t* hsel;
+  uint64_t hstride;            // words per k-index (capacity: every k-mer of the batch)
+  uint32_t* hoff;              // [nk][n_items_ub]
+  uint16_t* cnt;               // [nk][n_items_ub] hashes of the item; SQ_CNT_RAW set: not de-duplicated
+  uint32_t* cursor;            // [nk] words used so far (zeroed by the caller)
+  uint32_t cap;                // staging entries per lane in shared memory (a lane that selects more re-rolls)
+  uint32_t dedup;              // 1: an item's equal hashes are stored once (the sketch is a set, include/sketch.h:15)
+  unsigned long long* stats;   // optional: += selected hashes of the launch before de-duplication (one atomic per block)
   KLut lut[SQ_MAXK];
 };
+#define SQ_CNT_RAW 0x8000u     // flag in cnt: the item overflowed its staging area, duplicates were not removed
+#define SQ_CNT_MASK 0x7FFFu
 
-// bucketed open-addressing table: bucket = 4 keys (uint4) + 4 posting offsets (uint4), 32 B, one sector
+// Index of one k in HBM (replicated per GPU), sized to stay in L2 at human scale (random 32-byte gathers run at
+// 230 G/s from <= 64 MB and fall to 45-60 G/s from DRAM, profiles/micro/gather_bench.cu):
+//   bmap     the key set as a bitmap over [0, max key] with interleaved ranks: sectors of 32 B = {number of keys
+//            in all earlier sectors, 224 bits}.  One sector answers "is h a key" exactly (no chains, no
+//            divergence, whatever the load) and gives the key's rank.  Keys are FracMinHash values <= threshold:
+//            31 MB at scale 0.05.
+//   desc     32-bit list descriptor of every key, in key order (the rank indexes it): 6.2 M keys -> 25 MB
+//            bit 31 = 0  the list itself: transcript `base` (low tbits bits) and, above it, a mask of the following
+//                        31 - tbits ids (bit i <=> base+1+i is in the list) -- the isoforms of a gene have neighbouring
+//                        ids, nine lists in ten fit and need no further access
+//            bit 31 = 1  id of the list in lhdr
+//            (SQ_EMPTY is what the lookup reports for a hash that is not a key)
+//   lhdr     one 16-byte header per DISTINCT posting list (lists with equal content are stored once, so equal
+//            descriptors <=> equal lists): {base1 | two<<31, mask1_lo, mask1_hi, posting offset}: bit i of mask1 <=>
+//            transcript base1+i is in the list; SQ_NOMASK in the first word when two 64-id ranges do not cover
+//            the list.  1.2 M lists -> 20 MB, touched by one hit in ten
+//   postings per list (32-byte aligned): 8 header words {length, base1 | two<<31, mask1_lo, mask1_hi, base2,
+//            mask2_lo, mask2_hi, 0}, then the transcript ids ascending, the last one flagged with SQ_LAST
+// Transcript ids in here are the engine's INTERNAL ids (see sq_load_index: transcripts that share posting
+// lists are renumbered next to each other, so that a list is a window base + bit mask whatever order the
+// caller's ids came in).
+#define SQ_BMAP_BITS 224u   // key values per bitmap sector
 struct IndexTable {
-  const uint4* buckets;     // 2*nb uint4
-  const uint32_t* postings; // per list (32-byte aligned): header {length, base1 | two<<31, mask1_lo, mask1_hi, base2,
-                            // mask2_lo, mask2_hi, 0}, then the transcript ids ascending, the last one flagged
-                            // with SQ_LAST; bit i of mask1 <=> transcript base1+i is in the list, same for the
-                            // optional second range (base1 = SQ_NOMASK when two 64-id ranges do not cover it)
-  uint32_t shift;           // 32 - log2(nb)
-  uint32_t mask;            // nb - 1
+  const uint4* bmap;        // 2*n_sectors uint4
+  const uint32_t* desc;     // one per key, ascending key order
+  const uint4* lhdr;        // n_lists
+  const uint32_t* postings;
+  uint32_t n_sectors;       // covers keys < n_sectors * SQ_BMAP_BITS
   uint32_t present;         // 0: k-index has no map (sparse_chaining.cpp:51-53)
-  // "direct" table of the bit-mask vote kernel (one k only, else NULL): buckets of 32 B = 2 entries
-  // {key, base1 | two<<31, mask1_lo, mask1_hi} -- the list header travels with the key, so a probe needs no
-  // second access.  Two-range and SQ_NOMASK lists keep {key, base word, posting offset, 0}; an entry whose
-  // second word is SQ_DIRECT_EMPTY is free.
-  const uint4* direct;
-  uint32_t dshift;
-  uint32_t dmask;
+  uint32_t tbits;           // bits of a transcript id inside an inline descriptor
 };
 
 struct VoteParams {
@@ -87,9 +107,13 @@ struct VoteParams {
   uint32_t n_items_ub;
   uint32_t nk;
   double fraction;
-  const uint32_t* sel;
-  uint64_t slot_stride;
+  const uint32_t* hsel;              // the sketch kernel's output (see SketchParams)
+  uint32_t* pay;                     // list descriptor of every selected hash (lookup kernel), same layout as hsel
+  uint64_t hstride;
+  const uint32_t* hoff;
   const uint16_t* cnt;
+  const uint32_t* hcursor;           // [nk] selected hashes of the batch per k-index
+  uint32_t count_bits;               // planes of the bit-sliced counters (5: up to 31 hashes per read and k, 7: 127)
   IndexTable tab[SQ_MAXK];
   // staging output (batch local)
   uint32_t* stage_tid;
@@ -98,14 +122,14 @@ struct VoteParams {
   unsigned long long* stage_cursor;  // device counter
   uint32_t* read_soff;               // per read: staging offset
   uint32_t* read_cnt;                // per read: candidates
-  uint32_t* mid_list;                // reads the 16-entry thread kernel hands to the 48-entry thread kernel
+  uint32_t* mid_list;                // reads the bit-sliced kernel hands to the warp-per-read window kernel
   uint32_t* mid_count;
-  uint32_t* slow_list;               // reads the thread-per-read kernels hand to the warp-per-read kernel
+  uint32_t* slow_list;               // reads the window kernel hands to the general warp-per-read kernel
   uint32_t* slow_count;
   uint32_t* ovf_list;                // reads that overflowed the shared-memory tables
   uint32_t* ovf_count;
   uint32_t* flags;                   // bit1: large-table overflow
-  unsigned long long* work;          // [0] queries, [1] hits, [2] postings walked (stats)
+  unsigned long long* work;          // [0] queries, [1] hits (lookup kernel), [2] postings voted (vote kernels)
   // large-table scratch (one region per worker block of the overflow kernel)
   uint32_t* big_keys; uint32_t* big_cnt; uint32_t* big_list; uint32_t* big_set; unsigned long long* big_cand;
   uint32_t big_cap_log2;     // table slots per worker
@@ -123,6 +147,10 @@ void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t
                   uint32_t n_items_ub, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches, const KList& ks,
                   unsigned long long* stats);
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches);
+cudaError_t sketch_configure();  // per device
+// list descriptor (see IndexTable) of every selected hash of the batch, one k-index at a time
+struct VoteDeviceCfg;
+void launch_lookup(const VoteParams& p, const VoteDeviceCfg& cfg, uint32_t ki, cudaStream_t s, uint64_t* launches);
 void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, cudaStream_t s,
                          uint64_t* launches);
 void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
@@ -130,8 +158,17 @@ void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp,
 // ev_a/ev_b (optional): recorded right before/after the main short-read kernel only.  tail/fork (optional): the
 // small follow-up kernels (reads the first kernel handed on) run on `tail` after `fork`, so that they overlap
 // whatever the caller enqueues next on `s`.  Returns the stream the last kernel went to.
-cudaStream_t launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a = nullptr,
-                         cudaEvent_t ev_b = nullptr, cudaStream_t tail = nullptr, cudaEvent_t fork = nullptr);
+struct VoteDeviceCfg {  // per engine, i.e. per device: filled by vote_configure() with the engine's device current
+  int sm_count = 0;
+  int vote_grid = 0;  // persistent grid of the warp-per-read kernel
+  int long_grid = 0;  // persistent grid of the warp-per-read window kernel
+  int lookup_grid = 0;
+  uint32_t nk = 0;
+};
+cudaError_t vote_configure(uint32_t nk, VoteDeviceCfg* cfg);
+cudaStream_t launch_vote(const VoteParams& p, const VoteDeviceCfg& cfg, cudaStream_t s, uint64_t* launches,
+                         cudaEvent_t ev_a = nullptr, cudaEvent_t ev_b = nullptr, cudaStream_t tail = nullptr,
+                         cudaEvent_t fork = nullptr);
 
 // exclusive scan of n u32 values; out[n] receives the total (out has n+1 entries); tmp holds >= n/2048+2 u32
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t s,

@@ -13,72 +13,58 @@ namespace sq {
 static constexpr uint32_t kHashMul = 0x9E3779B1u;
 
 // ------------------------------------------------------------------ index table
-__global__ void table_insert_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ off,
-                                    uint64_t nkeys, uint4* buckets, uint32_t shift, uint32_t mask, uint32_t* fail) {
+// key bitmap with interleaved ranks (see IndexTable): sector s = {keys below s*224, bits of keys s*224 .. s*224+223}
+__global__ void bmap_set_kernel(const uint32_t* __restrict__ keys, uint64_t nkeys, uint32_t* __restrict__ words) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= nkeys) return;
-  const uint32_t o = off[i];
-  if (o == SQ_EMPTY) return;  // a key without postings cannot vote
-  const uint32_t key = keys[i];
-  uint32_t b = (key * kHashMul) >> shift;
-  for (uint32_t tries = 0; tries <= mask; ++tries) {
-    uint32_t* bk = reinterpret_cast<uint32_t*>(buckets + 2 * (size_t)b);
-    uint32_t* bo = bk + 4;
-    for (int s = 0; s < 4; ++s)
-      if (atomicCAS(&bo[s], SQ_EMPTY, o) == SQ_EMPTY) {
-        bk[s] = key;
-        return;
-      }
-    b = (b + 1) & mask;
+  const uint32_t key = keys[i], sec = key / SQ_BMAP_BITS, r = key - sec * SQ_BMAP_BITS;
+  atomicOr(words + (size_t)sec * 8 + 1 + (r >> 5), 1u << (r & 31));
+}
+__global__ void bmap_count_kernel(const uint32_t* __restrict__ words, uint32_t n_sectors, uint32_t* __restrict__ cnt) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sectors) return;
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) c += __popc(words[(size_t)s * 8 + j]);
+  cnt[s] = c;
+}
+__global__ void bmap_rank_kernel(uint32_t* __restrict__ words, uint32_t n_sectors, const uint32_t* __restrict__ excl) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_sectors) words[(size_t)s * 8] = excl[s];
+}
+
+// distinct keys (device) -> bitmap + ranks; cnt/excl/scan_tmp are scratch of n_sectors+1 / scan_tmp_words(n_sectors)
+void launch_bmap_build(const uint32_t* keys, uint64_t nkeys, uint4* bmap, uint32_t n_sectors, uint32_t* cnt,
+                       uint32_t* excl, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches) {
+  cudaMemsetAsync(bmap, 0, (size_t)n_sectors * 32, s);
+  uint32_t* words = reinterpret_cast<uint32_t*>(bmap);
+  if (nkeys) {
+    bmap_set_kernel<<<(uint32_t)((nkeys + 255) / 256), 256, 0, s>>>(keys, nkeys, words);
+    if (launches) ++*launches;
   }
-  atomicExch(fail, 1u);
+  bmap_count_kernel<<<(n_sectors + 255) / 256, 256, 0, s>>>(words, n_sectors, cnt);
+  launch_exclusive_scan(cnt, excl, n_sectors, scan_tmp, s, launches);
+  bmap_rank_kernel<<<(n_sectors + 255) / 256, 256, 0, s>>>(words, n_sectors, excl);
+  if (launches) *launches += 2;
 }
 
-// keys[i] -> posting offset off[i] (SQ_EMPTY: no list); lists are already flagged with SQ_LAST
-void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
-                        uint32_t mask, uint32_t* fail, cudaStream_t s, uint64_t* launches) {
-  launch_fill_u32(reinterpret_cast<uint32_t*>(buckets), (size_t)(mask + 1) * 8, SQ_EMPTY, s);
-  if (launches) ++*launches;
-  if (nkeys == 0) return;
-  const uint32_t grid = (uint32_t)((nkeys + 255) / 256);
-  table_insert_kernel<<<grid, 256, 0, s>>>(keys, off, nkeys, buckets, shift, mask, fail);
-  if (launches) ++*launches;
+// results leave the engine in the caller's transcript numbering: out[ext_of[i]] = in[i]
+__global__ void permute_out_kernel(const double* __restrict__ pi, const double* __restrict__ numreads,
+                                   const uint32_t* __restrict__ present, const uint32_t* __restrict__ ext_of,
+                                   uint32_t T, double* __restrict__ pi_out, double* __restrict__ nr_out,
+                                   uint8_t* __restrict__ present_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const uint32_t x = ext_of ? ext_of[i] : i;
+  pi_out[x] = pi[i];
+  nr_out[x] = numreads[i];
+  present_out[x] = present[i] ? 1 : 0;
 }
 
-// direct table (see IndexTable): the entry carries the list header
-__global__ void direct_insert_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ off,
-                                     uint64_t nkeys, const uint32_t* __restrict__ postings, uint4* direct,
-                                     uint32_t shift, uint32_t mask, uint32_t* fail) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  if (i >= nkeys) return;
-  const uint32_t o = off[i];
-  if (o == SQ_EMPTY) return;
-  const uint32_t key = keys[i];
-  const uint4 hd = *reinterpret_cast<const uint4*>(postings + o);
-  const bool indirect = hd.y == SQ_NOMASK || (hd.y >> 31);
-  const uint4 ent = indirect ? make_uint4(key, hd.y, o, 0u) : make_uint4(key, hd.y, hd.z, hd.w);
-  uint32_t b = (key * kHashMul) >> shift;
-  for (uint32_t tries = 0; tries <= mask; ++tries) {
-    uint32_t* w = reinterpret_cast<uint32_t*>(direct + 2 * (size_t)b);
-    for (int s = 0; s < 2; ++s)
-      if (atomicCAS(&w[4 * s + 1], SQ_DIRECT_EMPTY, ent.y) == SQ_DIRECT_EMPTY) {
-        w[4 * s] = ent.x;
-        w[4 * s + 2] = ent.z;
-        w[4 * s + 3] = ent.w;
-        return;
-      }
-    b = (b + 1) & mask;
-  }
-  atomicExch(fail, 1u);
-}
-
-void launch_direct_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, const uint32_t* postings,
-                         uint4* direct, uint32_t shift, uint32_t mask, uint32_t* fail, cudaStream_t s,
-                         uint64_t* launches) {
-  launch_fill_u32(reinterpret_cast<uint32_t*>(direct), (size_t)(mask + 1) * 8, SQ_DIRECT_EMPTY, s);
-  if (launches) ++*launches;
-  if (nkeys == 0) return;
-  direct_insert_kernel<<<(uint32_t)((nkeys + 255) / 256), 256, 0, s>>>(keys, off, nkeys, postings, direct, shift, mask, fail);
+void launch_permute_out(const double* pi, const double* numreads, const uint32_t* present, const uint32_t* ext_of,
+                        uint32_t T, double* pi_out, double* nr_out, uint8_t* present_out, cudaStream_t s,
+                        uint64_t* launches) {
+  permute_out_kernel<<<(T + 255) / 256, 256, 0, s>>>(pi, numreads, present, ext_of, T, pi_out, nr_out, present_out);
   if (launches) ++*launches;
 }
 

@@ -41,7 +41,7 @@ struct DevBuf {
 
 struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
-  DevBuf nit, item_start, item_read, cnt, sel, read_soff, read_cnt, batch_off, ovf_list, slow_list, mid_list,
+  DevBuf nit, item_start, item_read, cnt, hsel, pay, hoff, read_soff, read_cnt, batch_off, ovf_list, slow_list, mid_list,
       stage_tid, stage_score, scan_tmp;
   cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr, fork = nullptr;
   bool in_flight = false;   // compaction enqueued, `done` recorded
@@ -52,18 +52,17 @@ struct Slot {
   VoteParams vp;
   int id = 0;
   void release() {
-    DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &sel, &read_soff, &read_cnt,
+    DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &hsel, &pay, &hoff, &read_soff, &read_cnt,
                      &batch_off, &ovf_list, &slow_list, &mid_list, &stage_tid, &stage_score, &scan_tmp};
     for (DevBuf* b : all) b->release();
   }
 };
 
 struct KTab {
-  DevBuf buckets, postings, direct;
-  uint32_t shift = 0, mask = 0, dshift = 0, dmask = 0;
-  bool has_direct = false;
+  DevBuf bmap, desc, lhdr, postings;
+  uint32_t n_sectors = 0;
   bool present = false;
-  uint64_t nkeys = 0, npost = 0, npost_stored = 0;
+  uint64_t nkeys = 0, npost = 0, npost_stored = 0, nlists = 0;
 };
 
 struct StageEvent { cudaEvent_t a, b; int stage; };
@@ -103,10 +102,15 @@ struct sq_engine {
   double fraction = 0.9;
   uint64_t T = 0;
   KLut lut[SQ_MAXK];
+  VoteDeviceCfg vote_cfg;  // kernel attributes and grids of THIS engine's device
   cudaStream_t stream = nullptr, own_stream = nullptr, copy_stream = nullptr, tail_stream = nullptr;
   bool profiling = false;
   std::string err;
   KTab tab[SQ_MAXK];
+  // internal transcript numbering (decided by the first sq_load_index): ext_of[internal] = caller's id
+  std::vector<uint32_t> ext_of, int_of;
+  bool perm_ready = false, perm_identity = true;
+  DevBuf d_ext_of;
   // options
   uint64_t batch_bases = 1ull << 28;
   uint32_t cand_per_read = 16;
@@ -123,6 +127,7 @@ struct sq_engine {
   unsigned long long* d_slot_ctr = nullptr;      // per slot: [2*i] staging cursor, [2*i+1] = overflow reads (low u32) | slow-path reads (high u32)
   uint32_t* d_flags = nullptr;
   uint32_t* d_fail = nullptr;
+  uint32_t* d_hcur = nullptr;                    // selected-hash cursors: [8*slot + k], slot 2 = tap
   unsigned long long* h_mirror = nullptr;        // pinned copy of d_slot_ctr after each vote
   uint64_t P = 0;                                 // candidate pairs of all finalized batches (exact)
   uint64_t ovf_total = 0, slow_total = 0, mid_total = 0;
@@ -143,7 +148,7 @@ struct sq_engine {
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
       read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score,
-      cls_head, cls_id, cls_read, cls_pos, cls_weight, cls_fp;
+      cls_head, cls_id, cls_read, cls_pos, cls_weight, cls_fp, out_pi, out_nr, out_present;
   uint64_t n_classes_last = 0, n_cpairs_last = 0;
   int em_iterations = 0;
   // sq_sketch / sq_build_postings scratch
@@ -154,8 +159,8 @@ struct sq_engine {
   const void* bp_sig = nullptr;
   // profiling
   std::vector<StageEvent> events;
-  float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // sketch, vote, compact, sort, em, assign, items
-  uint32_t n_stage[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // sketch, vote, compact, sort, em, assign, items, vote main kernel, lookup
+  uint32_t n_stage[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   // NCCL
   ncclComm_t comm = nullptr;
@@ -232,6 +237,16 @@ void make_lut(uint32_t k, KLut* out) {
     out->e[32 + in] = two(seed33(in));
   }
 }
+
+// expected upper end of the selected hashes of one item (SQ_CHUNK window ends at most): twice the mean + 8
+uint32_t item_hash_bound(const sq_engine* e, uint64_t n_bases, uint32_t n_reads) {
+  const double scale = ((double)e->threshold + 1.0) / 4294967296.0;
+  const uint64_t mean_len = n_reads ? n_bases / n_reads : 0;
+  const double windows = mean_len <= 200 ? (double)mean_len + 32.0 : (double)SQ_CHUNK;
+  const double b = windows * scale * 2.0 + 8.0;
+  return (uint32_t)std::min<double>(b, (double)SQ_CHUNK);
+}
+uint32_t sketch_cap(uint32_t bound) { return std::min<uint32_t>(SQ_CHUNK, std::max<uint32_t>(8, (bound + 7) & ~7u)); }
 
 int check_flags(sq_engine* e) {
   uint32_t flags = 0;
@@ -326,7 +341,7 @@ int enqueue_vote(sq_engine* e, Slot& s) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
     }
-    last = launch_vote(s.vp, e->stream, &e->launches, a, b, e->tail_stream, s.fork);
+    last = launch_vote(s.vp, e->vote_cfg, e->stream, &e->launches, a, b, e->tail_stream, s.fork);
     if (a) e->events.push_back({a, b, 7});
   }
   SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 4 * s.id, ctr, 32, cudaMemcpyDeviceToHost, last));
@@ -342,13 +357,32 @@ int finalize_slot(sq_engine* e, Slot& s) {
   if (!s.pending) return SQ_OK;
   SQ_CUDA(e, cudaEventSynchronize(s.voted));
   uint64_t needed = e->h_mirror[4 * s.id];
-  while (needed > s.stage_cap) {
-    s.stage_cap = needed + needed / 8;
-    SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
-    SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
-    s.vp.stage_tid = s.stage_tid.as<uint32_t>();
-    s.vp.stage_score = s.stage_score.as<int32_t>();
-    s.vp.stage_cap = s.stage_cap;
+  // Re-run the vote chain (the batch's descriptors are still in the slot) when the staging area was too small, or
+  // when a read needs the large-table scratch for the first time.  The work counters were complete after the
+  // first pass (every read was voted, only not stored), so the re-runs do not count.
+  for (;;) {
+    const bool need_big = (e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull) != 0 && s.vp.n_workers == 0;
+    if (needed <= s.stage_cap && !need_big) break;
+    if (needed > s.stage_cap) {
+      s.stage_cap = needed + needed / 8;
+      SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
+      SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
+      s.vp.stage_tid = s.stage_tid.as<uint32_t>();
+      s.vp.stage_score = s.stage_score.as<int32_t>();
+      s.vp.stage_cap = s.stage_cap;
+    }
+    if (need_big) {
+      SQ_TRY(ensure_big_scratch(e));
+      s.vp.big_keys = e->big_keys.as<uint32_t>();
+      s.vp.big_cnt = e->big_cnt.as<uint32_t>();
+      s.vp.big_list = e->big_list.as<uint32_t>();
+      s.vp.big_set = e->big_set.as<uint32_t>();
+      s.vp.big_cand = e->big_cand.as<unsigned long long>();
+      s.vp.big_cap_log2 = e->big_cap_log2;
+      s.vp.big_set_log2 = e->big_set_log2;
+      s.vp.n_workers = e->n_workers;
+    }
+    s.vp.work = nullptr;
     SQ_TRY(enqueue_vote(e, s));
     SQ_CUDA(e, cudaEventSynchronize(s.voted));
     needed = e->h_mirror[4 * s.id];
@@ -406,13 +440,15 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   const uint64_t items_ub64 = (uint64_t)n_reads + n_bases / SQ_CHUNK + 1;
   if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
   const uint32_t items_ub = (uint32_t)items_ub64;
-  const uint64_t slot_stride = (n_bases + 3) & ~3ull;
+  const uint64_t hstride = ((n_bases + 3) & ~3ull) + 4;  // capacity per k: every k-mer of the batch (+ lookup padding)
   s.stage_cap = std::max<uint64_t>((uint64_t)e->cand_per_read * n_reads, 4096);
   SQ_CUDA(e, s.nit.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.item_start.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.item_read.ensure((size_t)items_ub * 4));
   SQ_CUDA(e, s.cnt.ensure((size_t)items_ub * e->nk * 2));
-  SQ_CUDA(e, s.sel.ensure((size_t)slot_stride * e->nk * 4));
+  SQ_CUDA(e, s.hsel.ensure((size_t)hstride * e->nk * 4));
+  SQ_CUDA(e, s.pay.ensure((size_t)hstride * e->nk * 4));
+  SQ_CUDA(e, s.hoff.ensure((size_t)items_ub * e->nk * 4));
   SQ_CUDA(e, s.read_soff.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.read_cnt.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.batch_off.ensure(((size_t)n_reads + 1) * 4));
@@ -422,7 +458,6 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
-  SQ_TRY(ensure_big_scratch(e));
   // The batch before this one (other slot) must be finalized (host waits for its vote, then enqueues its
   // compaction).  Host batches: now, before the engine stream starts waiting for our copy, so the compaction
   // is not held up behind that wait (its vote has been overlapping our copies).  Device batches: after our
@@ -465,15 +500,19 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     sp.threshold = e->threshold;
     for (uint32_t i = 0; i < e->nk; ++i) { sp.ks[i] = e->ks[i]; sp.lut[i] = e->lut[i]; }
     sp.kmax = e->kmax;
-    sp.sel = s.sel.as<uint32_t>();
-    sp.slot_stride = slot_stride;
+    sp.hsel = s.hsel.as<uint32_t>();
+    sp.hstride = hstride;
+    sp.hoff = s.hoff.as<uint32_t>();
     sp.cnt = s.cnt.as<uint16_t>();
+    sp.cursor = e->d_hcur + 8 * s.id;
+    sp.cap = sketch_cap(item_hash_bound(e, n_bases, n_reads));
+    sp.dedup = 1;
     sp.stats = e->d_totals;  // [0] += sketch hashes
+    SQ_CUDA(e, cudaMemsetAsync(sp.cursor, 0, 32, e->stream));
     {
       StageScope st(e, 0);  // the sketch kernel alone
       launch_sketch(sp, e->stream, &e->launches);
     }
-    StageScope st2(e, 6);
   }
   if (!inputs_ready) SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
   {
@@ -487,18 +526,22 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.n_items_ub = items_ub;
     vp.nk = e->nk;
     vp.fraction = e->fraction;
-    vp.sel = s.sel.as<uint32_t>();
-    vp.slot_stride = slot_stride;
+    vp.hsel = s.hsel.as<uint32_t>();
+    vp.pay = s.pay.as<uint32_t>();
+    vp.hstride = hstride;
+    vp.hoff = s.hoff.as<uint32_t>();
     vp.cnt = s.cnt.as<uint16_t>();
+    vp.hcursor = e->d_hcur + 8 * s.id;
+    vp.count_bits = item_hash_bound(e, n_bases, n_reads) <= 31 ? 5 : 7;
+    const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(e->T));
     for (uint32_t i = 0; i < e->nk; ++i) {
-      vp.tab[i].buckets = e->tab[i].buckets.as<uint4>();
+      vp.tab[i].bmap = e->tab[i].bmap.as<uint4>();
+      vp.tab[i].desc = e->tab[i].desc.as<uint32_t>();
+      vp.tab[i].lhdr = e->tab[i].lhdr.as<uint4>();
       vp.tab[i].postings = e->tab[i].postings.as<uint32_t>();
-      vp.tab[i].shift = e->tab[i].shift;
-      vp.tab[i].mask = e->tab[i].mask;
+      vp.tab[i].n_sectors = e->tab[i].n_sectors;
       vp.tab[i].present = e->tab[i].present ? 1u : 0u;
-      vp.tab[i].direct = e->tab[i].has_direct ? e->tab[i].direct.as<uint4>() : nullptr;
-      vp.tab[i].dshift = e->tab[i].dshift;
-      vp.tab[i].dmask = e->tab[i].dmask;
+      vp.tab[i].tbits = tbits;
     }
     vp.stage_tid = s.stage_tid.as<uint32_t>();
     vp.stage_score = s.stage_score.as<int32_t>();
@@ -513,7 +556,6 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.mid_list = s.mid_list.as<uint32_t>();
     vp.mid_count = vp.ovf_count + 2;
     vp.flags = e->d_flags;
-    vp.work = e->d_totals + 1;
     vp.big_keys = e->big_keys.as<uint32_t>();
     vp.big_cnt = e->big_cnt.as<uint32_t>();
     vp.big_list = e->big_list.as<uint32_t>();
@@ -521,9 +563,14 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.big_cand = e->big_cand.as<unsigned long long>();
     vp.big_cap_log2 = e->big_cap_log2;
     vp.big_set_log2 = e->big_set_log2;
-    vp.n_workers = e->n_workers;
+    vp.n_workers = e->big_ready ? e->n_workers : 0;  // the large-table scratch is made when a read first needs it
+    vp.work = e->d_totals + 1;
     s.n_reads = n_reads;
     s.read_base = e->n_reads;
+    {
+      StageScope st(e, 8);  // seed lookup, one k-index at a time (each table L2-resident during its pass)
+      for (uint32_t i = 0; i < e->nk; ++i) launch_lookup(vp, e->vote_cfg, i, e->stream, &e->launches);
+    }
     SQ_TRY(enqueue_vote(e, s));
     s.pending = true;
   }
@@ -591,6 +638,8 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   };
   cudaError_t ce;
   if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail(ce, "cudaSetDevice");
+  if ((ce = vote_configure(nk, &e->vote_cfg)) != cudaSuccess) return bail(ce, "vote_configure");
+  if ((ce = sketch_configure()) != cudaSuccess) return bail(ce, "sketch_configure");
   if ((ce = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   if ((ce = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
   if ((ce = cudaStreamCreateWithFlags(&e->tail_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(ce, "cudaStreamCreate");
@@ -602,6 +651,7 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   e->d_slot_ctr = e->d_totals + 8;                                     // bytes 64..127 (2 slots x 32 B)
   e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 16);          // byte 128
   e->d_fail = e->d_flags + 1;                                          // byte 132
+  e->d_hcur = reinterpret_cast<uint32_t*>(e->d_totals + 20);           // bytes 160..255 (3 x 8 counters)
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 64);
   *out = e;
@@ -621,7 +671,8 @@ void sq_destroy(sq_engine* e) {
     if (s.voted) cudaEventDestroy(s.voted);
     if (s.fork) cudaEventDestroy(s.fork);
   }
-  for (auto& t : e->tab) { t.buckets.release(); t.postings.release(); t.direct.release(); }
+  for (auto& t : e->tab) { t.bmap.release(); t.desc.release(); t.lhdr.release(); t.postings.release(); }
+  e->d_ext_of.release();
   e->tap.release();
   {
     DevBuf* tb[] = {&e->tap_counts, &e->tap_offs, &e->tap_out, &e->tap_tid, &e->bp_newpair, &e->bp_newkey,
@@ -632,7 +683,8 @@ void sq_destroy(sq_engine* e) {
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
                    &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score,
-                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->cls_fp};
+                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->cls_fp, &e->out_pi,
+                   &e->out_nr, &e->out_present};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
@@ -685,161 +737,254 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   SQ_CUDA(e, cudaSetDevice(e->device));
   const uint64_t npost = nkeys ? post_off[nkeys] : 0;
   if (npost >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "more than 2^32 postings for one k");
+  if (nkeys >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "more than 2^32 keys for one k");
   for (uint64_t i = 0; i < npost; ++i)
     if (post_tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "posting %llu names transcript %u >= T", (unsigned long long)i, post_tid[i]);
   KTab& t = e->tab[kidx];
+  const uint32_t T = (uint32_t)e->T;
   // Posting lists with identical content are stored once (all k-mers of an exon shared by the same isoforms
-  // have the same list), so the postings array shrinks to the distinct isoform sets and a read whose hits
-  // share a list can merge it once with a weight.  Host threads: (1) sort the lists that are not ascending (the
-  // reference's file order is arbitrary) and hash every list's content; (2) each thread owns the lists whose
-  // hash falls in its partition: open-addressing table on the 64-bit hash, verified by comparing the content;
-  // (3) the partitions' arrays are concatenated.
-  std::vector<uint32_t> off32(nkeys + 1, SQ_EMPTY);
-  std::vector<uint32_t> dpost;
-  {
-    unsigned nth = std::thread::hardware_concurrency();
-    if (const char* ev = getenv("SQ_HOST_THREADS")) nth = (unsigned)atoi(ev);
-    nth = std::max(1u, std::min(nth, 32u));
-    if (nkeys < 200000) nth = 1;
-    auto run = [&](auto&& fn) {
-      if (nth == 1) { fn(0u); return; }
-      std::vector<std::thread> th;
-      for (unsigned t = 0; t < nth; ++t) th.emplace_back(fn, t);
-      for (auto& x : th) x.join();
-    };
-    // (1) ascending copies where needed, content hashes
-    std::vector<uint64_t> lh(nkeys);
-    std::vector<uint32_t> sorted_tid;
-    std::vector<uint8_t> unsorted_any(nth, 0);
-    run([&](unsigned t) {
-      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
-      for (uint64_t i = i0; i < i1 && !unsorted_any[t]; ++i)
-        if (!std::is_sorted(post_tid + post_off[i], post_tid + post_off[i + 1])) unsorted_any[t] = 1;
+  // have the same list): the table maps a key to the id of its DISTINCT list, so equal ids mean equal lists and
+  // a read whose hits share a list merges it once with a weight.  Host threads: (1) sort the lists that are not
+  // ascending (the reference's file order is arbitrary) and hash every list's content; (2) each thread owns the
+  // lists whose hash falls in its partition: open-addressing table on the 64-bit hash, verified by comparing the
+  // content; (3) transcripts are renumbered (first index loaded into this engine only); (4) headers and id lists
+  // are laid out in the internal numbering.
+  unsigned nth = std::thread::hardware_concurrency();
+  if (const char* ev = getenv("SQ_HOST_THREADS")) nth = (unsigned)atoi(ev);
+  nth = std::max(1u, std::min(nth, 32u));
+  if (nkeys < 200000) nth = 1;
+  auto run = [&](auto&& fn) {
+    if (nth == 1) { fn(0u); return; }
+    std::vector<std::thread> th;
+    for (unsigned x = 0; x < nth; ++x) th.emplace_back(fn, x);
+    for (auto& x : th) x.join();
+  };
+  // (1) ascending copies where needed, content hashes
+  std::vector<uint64_t> lh(nkeys);
+  std::vector<uint32_t> sorted_tid;
+  std::vector<uint8_t> unsorted_any(nth, 0);
+  run([&](unsigned x) {
+    const uint64_t i0 = nkeys * x / nth, i1 = nkeys * (x + 1) / nth;
+    for (uint64_t i = i0; i < i1 && !unsorted_any[x]; ++i)
+      if (!std::is_sorted(post_tid + post_off[i], post_tid + post_off[i + 1])) unsorted_any[x] = 1;
+  });
+  const uint32_t* pt = post_tid;
+  if (std::any_of(unsorted_any.begin(), unsorted_any.end(), [](uint8_t v) { return v != 0; })) {
+    sorted_tid.assign(post_tid, post_tid + npost);
+    run([&](unsigned x) {
+      const uint64_t i0 = nkeys * x / nth, i1 = nkeys * (x + 1) / nth;
+      for (uint64_t i = i0; i < i1; ++i) std::sort(sorted_tid.begin() + post_off[i], sorted_tid.begin() + post_off[i + 1]);
     });
-    const uint32_t* pt = post_tid;
-    if (std::any_of(unsorted_any.begin(), unsorted_any.end(), [](uint8_t v) { return v != 0; })) {
-      sorted_tid.assign(post_tid, post_tid + npost);
-      run([&](unsigned t) {
-        const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
-        for (uint64_t i = i0; i < i1; ++i) std::sort(sorted_tid.begin() + post_off[i], sorted_tid.begin() + post_off[i + 1]);
-      });
-      pt = sorted_tid.data();
+    pt = sorted_tid.data();
+  }
+  run([&](unsigned x) {
+    const uint64_t i0 = nkeys * x / nth, i1 = nkeys * (x + 1) / nth;
+    for (uint64_t i = i0; i < i1; ++i) {
+      const uint64_t b0 = post_off[i], b1 = post_off[i + 1];
+      uint64_t h = 0xcbf29ce484222325ull ^ (b1 - b0);
+      for (uint64_t j = b0; j < b1; ++j) { h ^= pt[j]; h *= 0x100000001b3ull; h ^= h >> 29; }
+      lh[i] = h ? h : 1;
     }
-    run([&](unsigned t) {
-      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
-      for (uint64_t i = i0; i < i1; ++i) {
-        const uint64_t b0 = post_off[i], b1 = post_off[i + 1];
-        uint64_t h = 0xcbf29ce484222325ull ^ (b1 - b0);
-        for (uint64_t j = b0; j < b1; ++j) { h ^= pt[j]; h *= 0x100000001b3ull; h ^= h >> 29; }
-        lh[i] = h ? h : 1;
-      }
-    });
-    // (2) per-partition de-duplication
-    std::vector<std::vector<uint32_t>> part(nth);
-    std::vector<uint32_t> loc(nkeys, SQ_EMPTY);  // offset inside the partition's array
-    auto part_of = [&](uint64_t h) { return (unsigned)(((h >> 40) * nth) >> 24); };
-    run([&](unsigned t) {
-      uint64_t mine = 0;
-      for (uint64_t i = 0; i < nkeys; ++i) mine += post_off[i + 1] > post_off[i] && part_of(lh[i]) == t;
-      uint64_t cap = 16;
-      while (cap < mine * 2 + 2) cap <<= 1;
-      std::vector<uint64_t> hkey(cap, 0);
-      std::vector<uint32_t> hval(cap, SQ_EMPTY);
-      std::vector<uint32_t>& dp = part[t];
-      dp.reserve(mine * 6 + 16);
-      for (uint64_t i = 0; i < nkeys; ++i) {
-        const uint64_t b0 = post_off[i], b1 = post_off[i + 1], h = lh[i];
-        if (b1 <= b0 || part_of(h) != t) continue;
-        uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
-        for (;;) {
-          if (hval[slot] == SQ_EMPTY) {
-            hkey[slot] = h;
-            hval[slot] = (uint32_t)dp.size();
+  });
+  // (2) per-partition de-duplication: rep = first key of each distinct list, support = keys that share it
+  std::vector<std::vector<uint32_t>> rep(nth), support(nth);
+  std::vector<uint32_t> loc(nkeys, SQ_EMPTY);  // distinct-list number inside the partition
+  auto part_of = [&](uint64_t h) { return (unsigned)(((h >> 40) * nth) >> 24); };
+  run([&](unsigned x) {
+    uint64_t mine = 0;
+    for (uint64_t i = 0; i < nkeys; ++i) mine += post_off[i + 1] > post_off[i] && part_of(lh[i]) == x;
+    uint64_t cap = 16;
+    while (cap < mine * 2 + 2) cap <<= 1;
+    std::vector<uint64_t> hkey(cap, 0);
+    std::vector<uint32_t> hval(cap, SQ_EMPTY);
+    for (uint64_t i = 0; i < nkeys; ++i) {
+      const uint64_t b0 = post_off[i], b1 = post_off[i + 1], h = lh[i];
+      if (b1 <= b0 || part_of(h) != x) continue;
+      uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
+      for (;;) {
+        if (hval[slot] == SQ_EMPTY) {
+          hkey[slot] = h;
+          hval[slot] = (uint32_t)rep[x].size();
+          loc[i] = hval[slot];
+          rep[x].push_back((uint32_t)i);
+          support[x].push_back(1);
+          break;
+        }
+        if (hkey[slot] == h) {  // same hash: verify content
+          const uint64_t q = rep[x][hval[slot]];
+          const uint64_t q0 = post_off[q], q1 = post_off[q + 1];
+          if (q1 - q0 == b1 - b0 && std::equal(pt + b0, pt + b1, pt + q0)) {
             loc[i] = hval[slot];
-            // header (8 words, one 32-byte sector): length; base and 64-bit membership mask of the first id
-            // range (bit 31 of the base: a second range follows); base and mask of the second range; then the ids
-            // (last one flagged), padded so that the next header is 32-byte aligned
-            const uint32_t tmin = pt[b0];
-            uint64_t mask1 = 0, mask2 = 0, j = b0;
-            for (; j < b1 && pt[j] - tmin < 64; ++j) mask1 |= 1ull << (pt[j] - tmin);
-            const uint32_t base2 = j < b1 ? pt[j] : 0;
-            for (; j < b1 && pt[j] - base2 < 64; ++j) mask2 |= 1ull << (pt[j] - base2);
-            dp.push_back((uint32_t)(b1 - b0));
-            if (j < b1) {  // three or more ranges
-              dp.insert(dp.end(), {SQ_NOMASK, 0u, 0u, 0u, 0u, 0u, 0u});
-            } else {
-              dp.push_back(tmin | (mask2 ? 0x80000000u : 0u));
-              dp.push_back((uint32_t)mask1);
-              dp.push_back((uint32_t)(mask1 >> 32));
-              dp.push_back(base2);
-              dp.push_back((uint32_t)mask2);
-              dp.push_back((uint32_t)(mask2 >> 32));
-              dp.push_back(0u);
-            }
-            for (uint64_t q = b0; q < b1; ++q) dp.push_back(pt[q] | (q + 1 == b1 ? SQ_LAST : 0u));
-            while (dp.size() & 7) dp.push_back(0);
+            ++support[x][hval[slot]];
             break;
           }
-          if (hkey[slot] == h) {  // same hash: verify content
-            const uint32_t o = hval[slot];
-            bool same = dp[o] == (uint32_t)(b1 - b0);
-            for (uint64_t q = b0; same && q < b1; ++q) same = (dp[o + SQ_LIST_HDR + (q - b0)] & ~SQ_LAST) == pt[q];
-            if (same) { loc[i] = o; break; }
-          }
-          slot = (slot + 1) & (cap - 1);
         }
+        slot = (slot + 1) & (cap - 1);
       }
-    });
-    // (3) concatenate
-    std::vector<uint64_t> pbase(nth + 1, 0);
-    for (unsigned t = 0; t < nth; ++t) pbase[t + 1] = pbase[t] + part[t].size();
-    if (pbase[nth] >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "posting store exceeds 2^32 words for one k");
-    dpost.resize(pbase[nth]);
-    run([&](unsigned t) {
-      if (!part[t].empty()) memcpy(dpost.data() + pbase[t], part[t].data(), part[t].size() * 4);
-      const uint64_t i0 = nkeys * t / nth, i1 = nkeys * (t + 1) / nth;
-      for (uint64_t i = i0; i < i1; ++i)
-        if (loc[i] != SQ_EMPTY) off32[i] = (uint32_t)(pbase[part_of(lh[i])] + loc[i]);
-    });
+    }
+  });
+  std::vector<uint64_t> lbase(nth + 1, 0);
+  for (unsigned x = 0; x < nth; ++x) lbase[x + 1] = lbase[x] + rep[x].size();
+  const uint64_t n_lists = lbase[nth];
+  std::vector<uint32_t> lid(nkeys, SQ_EMPTY), lrep(n_lists), lsup(n_lists);
+  run([&](unsigned x) {
+    std::copy(rep[x].begin(), rep[x].end(), lrep.begin() + lbase[x]);
+    std::copy(support[x].begin(), support[x].end(), lsup.begin() + lbase[x]);
+    const uint64_t i0 = nkeys * x / nth, i1 = nkeys * (x + 1) / nth;
+    for (uint64_t i = i0; i < i1; ++i)
+      if (loc[i] != SQ_EMPTY) lid[i] = (uint32_t)(lbase[part_of(lh[i])] + loc[i]);
+  });
+  // (3) Internal transcript numbering.  The vote kernels want the transcripts that share posting lists (the
+  // isoforms of a gene) to have neighbouring ids, whatever order the caller's ids came in: a reference-written
+  // index stores its transcripts in unordered_map order (src/data_io.cpp:185-196).  Union-find over the lists
+  // that at least two keys share (a list with a single key may be a 32-bit hash collision joining two unrelated
+  // genes), components ordered by their smallest external id, members ascending.  Decided once per engine.
+  if (!e->perm_ready) {
+    std::vector<uint32_t> parent(T);
+    for (uint32_t i = 0; i < T; ++i) parent[i] = i;
+    auto find = [&](uint32_t v) {
+      while (parent[v] != v) { parent[v] = parent[parent[v]]; v = parent[v]; }
+      return v;
+    };
+    for (uint64_t l = 0; l < n_lists; ++l) {
+      if (lsup[l] < 2) continue;
+      const uint64_t b0 = post_off[lrep[l]], b1 = post_off[lrep[l] + 1];
+      uint32_t r0 = find(pt[b0]);
+      for (uint64_t j = b0 + 1; j < b1; ++j) {
+        const uint32_t r1 = find(pt[j]);
+        if (r1 != r0) { if (r1 < r0) { parent[r0] = r1; r0 = r1; } else parent[r1] = r0; }  // root = smallest id
+      }
+    }
+    std::vector<uint64_t> order(T);
+    for (uint32_t i = 0; i < T; ++i) order[i] = ((uint64_t)find(i) << 32) | i;
+    std::sort(order.begin(), order.end());
+    e->ext_of.resize(T);
+    e->int_of.resize(T);
+    e->perm_identity = true;
+    for (uint32_t i = 0; i < T; ++i) {
+      e->ext_of[i] = (uint32_t)order[i];
+      e->int_of[(uint32_t)order[i]] = i;
+      if (e->ext_of[i] != i) e->perm_identity = false;
+    }
+    SQ_CUDA(e, e->d_ext_of.ensure((size_t)T * 4));
+    SQ_CUDA(e, cudaMemcpy(e->d_ext_of.p, e->ext_of.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+    e->perm_ready = true;
   }
-  const uint64_t ndp = dpost.size();
-  const uint32_t nb_log2 = std::max<uint32_t>(1, log2_ceil((nkeys + 1) / 2 + 1));
-  const uint64_t nb = 1ull << nb_log2;
-  SQ_CUDA(e, t.buckets.ensure(nb * 32));
-  SQ_CUDA(e, t.postings.ensure((ndp + 1) * 4));
-  t.shift = 32 - nb_log2;
-  t.mask = (uint32_t)(nb - 1);
-  t.nkeys = nkeys;
+  // (4) per distinct list: 8 header words + the internal ids ascending (last one flagged), 32-byte aligned; and
+  // the 16-byte entry of the header table
+  std::vector<uint32_t> loff(n_lists + 1, 0);
+  {
+    uint64_t acc = 0;
+    for (uint64_t l = 0; l < n_lists; ++l) {
+      loff[l] = (uint32_t)acc;
+      const uint64_t len = post_off[lrep[l] + 1] - post_off[lrep[l]];
+      acc += SQ_LIST_HDR + ((len + 7) & ~7ull);
+      if (acc >= 0xFFFFFFF0ull) return fail(e, SQ_ERR_CAPACITY, "posting store exceeds 2^32 words for one k");
+    }
+    loff[n_lists] = (uint32_t)acc;
+  }
+  const uint64_t ndp = loff[n_lists];
+  std::vector<uint32_t> dpost(ndp, 0);
+  std::vector<uint4> hdr(n_lists);
+  // descriptor of each list (see IndexTable): the list itself when it is a base and up to 31 - tbits following ids
+  std::vector<uint32_t> ldesc(n_lists);
+  const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(T));
+  const uint32_t wbits = 31 - tbits;
+  run([&](unsigned x) {
+    const uint64_t l0 = n_lists * x / nth, l1 = n_lists * (x + 1) / nth;
+    std::vector<uint32_t> ids;
+    for (uint64_t l = l0; l < l1; ++l) {
+      const uint64_t b0 = post_off[lrep[l]], b1 = post_off[lrep[l] + 1];
+      ids.resize(b1 - b0);
+      for (uint64_t j = b0; j < b1; ++j) ids[j - b0] = e->int_of[pt[j]];
+      std::sort(ids.begin(), ids.end());
+      // a list that names a transcript twice votes twice for it (the reference increments per posting,
+      // src/sparse_chaining.cpp:64-69): masks cannot say that, every kernel walks such a list
+      const bool dup = std::adjacent_find(ids.begin(), ids.end()) != ids.end();
+      const uint32_t tmin = ids[0];
+      uint64_t mask1 = 0, mask2 = 0;
+      size_t j = 0;
+      for (; j < ids.size() && ids[j] - tmin < 64; ++j) mask1 |= 1ull << (ids[j] - tmin);
+      const uint32_t base2 = j < ids.size() ? ids[j] : 0;
+      for (; j < ids.size() && ids[j] - base2 < 64; ++j) mask2 |= 1ull << (ids[j] - base2);
+      uint32_t* d = dpost.data() + loff[l];
+      d[0] = (uint32_t)ids.size();
+      if (j < ids.size() || dup) {  // three or more ranges (or a repeated id): walked by the general kernels
+        d[1] = SQ_NOMASK;
+      } else {
+        d[1] = tmin | (mask2 ? 0x80000000u : 0u);
+        d[2] = (uint32_t)mask1;
+        d[3] = (uint32_t)(mask1 >> 32);
+        d[4] = base2;
+        d[5] = (uint32_t)mask2;
+        d[6] = (uint32_t)(mask2 >> 32);
+      }
+      for (size_t q = 0; q < ids.size(); ++q) d[SQ_LIST_HDR + q] = ids[q] | (q + 1 == ids.size() ? SQ_LAST : 0u);
+      hdr[l] = make_uint4(d[1], d[2], d[3], loff[l]);
+      const bool fits = d[1] != SQ_NOMASK && !mask2 && (mask1 >> 1) < (1ull << wbits);
+      ldesc[l] = fits ? (uint32_t)((mask1 >> 1) << tbits) | tmin : 0x80000000u | (uint32_t)l;
+    }
+  });
+  if (n_lists >= 0x7FFFFFFFull) return fail(e, SQ_ERR_CAPACITY, "more than 2^31 distinct posting lists for one k");
+  // keys with a list, in ascending order, each once: the reference's loader does mapping[kmer] = vec
+  // (src/data_io.cpp:297), so of a key that a hand-made index repeats the LAST occurrence counts
+  std::vector<uint32_t> k2, d2;
+  k2.reserve(nkeys);
+  d2.reserve(nkeys);
+  {
+    bool ascending = true;
+    for (uint64_t i = 0; i < nkeys; ++i) {
+      if (lid[i] == SQ_EMPTY) continue;
+      if (!k2.empty() && keys[i] <= k2.back()) ascending = false;
+      k2.push_back(keys[i]);
+      d2.push_back(ldesc[lid[i]]);
+    }
+    if (!ascending) {
+      std::vector<uint64_t> ord(k2.size());
+      for (uint64_t i = 0; i < ord.size(); ++i) ord[i] = ((uint64_t)k2[i] << 32) | i;
+      std::sort(ord.begin(), ord.end());
+      std::vector<uint32_t> ks, ds;
+      ks.reserve(ord.size());
+      ds.reserve(ord.size());
+      for (uint64_t i = 0; i < ord.size(); ++i) {
+        if (i + 1 < ord.size() && (ord[i + 1] >> 32) == (ord[i] >> 32)) continue;  // a later occurrence follows
+        ks.push_back((uint32_t)(ord[i] >> 32));
+        ds.push_back(d2[(uint32_t)ord[i]]);
+      }
+      k2.swap(ks);
+      d2.swap(ds);
+    }
+  }
+  const uint64_t n2 = k2.size();
+  const uint32_t n_sectors = n2 ? k2.back() / SQ_BMAP_BITS + 1 : 1;
+  SQ_CUDA(e, t.bmap.ensure((size_t)n_sectors * 32));
+  SQ_CUDA(e, t.desc.ensure((n2 + 1) * 4));
+  SQ_CUDA(e, t.lhdr.ensure((n_lists + 1) * 16));
+  SQ_CUDA(e, t.postings.ensure((ndp + 8) * 4));
+  t.n_sectors = n_sectors;
+  t.nkeys = n2;
   t.npost = npost;
   t.npost_stored = ndp;
-  DevBuf dkeys, doff;
-  SQ_CUDA(e, dkeys.ensure((nkeys + 1) * 4));
-  SQ_CUDA(e, doff.ensure((nkeys + 1) * 4));
-  if (nkeys) {
-    SQ_CUDA(e, cudaMemcpyAsync(dkeys.p, keys, nkeys * 4, cudaMemcpyHostToDevice, e->stream));
-    SQ_CUDA(e, cudaMemcpyAsync(doff.p, off32.data(), nkeys * 4, cudaMemcpyHostToDevice, e->stream));
+  t.nlists = n_lists;
+  DevBuf dkeys, dcnt, dexcl, dtmp;
+  SQ_CUDA(e, dkeys.ensure((n2 + 1) * 4));
+  SQ_CUDA(e, dcnt.ensure(((size_t)n_sectors + 1) * 4));
+  SQ_CUDA(e, dexcl.ensure(((size_t)n_sectors + 2) * 4));
+  SQ_CUDA(e, dtmp.ensure(scan_tmp_words(n_sectors) * 4));
+  if (n2) {
+    SQ_CUDA(e, cudaMemcpyAsync(dkeys.p, k2.data(), n2 * 4, cudaMemcpyHostToDevice, e->stream));
+    SQ_CUDA(e, cudaMemcpyAsync(t.desc.p, d2.data(), n2 * 4, cudaMemcpyHostToDevice, e->stream));
     if (ndp) SQ_CUDA(e, cudaMemcpyAsync(t.postings.p, dpost.data(), ndp * 4, cudaMemcpyHostToDevice, e->stream));
+    if (n_lists) SQ_CUDA(e, cudaMemcpyAsync(t.lhdr.p, hdr.data(), n_lists * 16, cudaMemcpyHostToDevice, e->stream));
   }
-  SQ_CUDA(e, cudaMemsetAsync(e->d_fail, 0, 4, e->stream));
-  launch_table_build(dkeys.as<uint32_t>(), doff.as<uint32_t>(), nkeys, t.buckets.as<uint4>(), t.shift, t.mask,
-                     e->d_fail, e->stream, &e->launches);
-  t.has_direct = false;
-  if (e->nk == 1) {  // the bit-mask vote kernel runs for one k only: its table carries the list headers
-    const uint32_t db_log2 = std::max<uint32_t>(1, log2_ceil(nkeys + 1));
-    SQ_CUDA(e, t.direct.ensure((1ull << db_log2) * 32));
-    t.dshift = 32 - db_log2;
-    t.dmask = (uint32_t)((1ull << db_log2) - 1);
-    launch_direct_build(dkeys.as<uint32_t>(), doff.as<uint32_t>(), nkeys, t.postings.as<uint32_t>(), t.direct.as<uint4>(),
-                        t.dshift, t.dmask, e->d_fail, e->stream, &e->launches);
-    t.has_direct = true;
-  }
-  uint32_t failed = 0;
-  SQ_CUDA(e, cudaMemcpyAsync(&failed, e->d_fail, 4, cudaMemcpyDeviceToHost, e->stream));
+  launch_bmap_build(dkeys.as<uint32_t>(), n2, t.bmap.as<uint4>(), n_sectors, dcnt.as<uint32_t>(), dexcl.as<uint32_t>(),
+                    dtmp.as<uint32_t>(), e->stream, &e->launches);
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   SQ_CUDA(e, cudaGetLastError());
   dkeys.release();
-  doff.release();
-  if (failed) return fail(e, SQ_ERR_CAPACITY, "index table build failed (table full)");
+  dcnt.release();
+  dexcl.release();
+  dtmp.release();
   t.present = true;
   return SQ_OK;
 }
@@ -977,7 +1122,7 @@ int sq_reset_reads(sq_engine* e) {
   e->mid_total = 0;
   e->keys_valid = true;
   e->n_reads = e->n_bases = e->n_batches = 0;
-  for (int i = 0; i < 8; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
+  for (int i = 0; i < 10; ++i) { e->ms[i] = 0; e->n_stage[i] = 0; }
   return SQ_OK;
 }
 
@@ -993,13 +1138,31 @@ int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* 
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
   const uint64_t R = e->n_reads, P = e->P;
-  if (read_off) {
-    std::vector<uint32_t> tmp(R + 1, 0);
-    if (R) SQ_CUDA(e, cudaMemcpy(tmp.data(), e->read_off, (R + 1) * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> tmp(R + 1, 0);
+  if (R) SQ_CUDA(e, cudaMemcpy(tmp.data(), e->read_off, (R + 1) * 4, cudaMemcpyDeviceToHost));
+  if (read_off)
     for (uint64_t i = 0; i <= R; ++i) read_off[i] = tmp[i];
-  }
   if (P && tid) SQ_CUDA(e, cudaMemcpy(tid, e->cand_tid, P * 4, cudaMemcpyDeviceToHost));
   if (P && score) SQ_CUDA(e, cudaMemcpy(score, e->cand_score, P * 4, cudaMemcpyDeviceToHost));
+  if (P && tid && e->perm_ready && !e->perm_identity) {
+    // the store holds internal ids, ordered (score desc, internal id asc): hand out the caller's ids, equal
+    // scores in ascending order of those
+    std::vector<int32_t> sc_own;
+    const int32_t* sc = score;
+    if (!sc) {
+      sc_own.resize(P);
+      SQ_CUDA(e, cudaMemcpy(sc_own.data(), e->cand_score, P * 4, cudaMemcpyDeviceToHost));
+      sc = sc_own.data();
+    }
+    for (uint64_t i = 0; i < P; ++i) tid[i] = e->ext_of[tid[i]];
+    for (uint64_t r = 0; r < R; ++r)
+      for (uint32_t a = tmp[r]; a < tmp[r + 1];) {
+        uint32_t b = a + 1;
+        while (b < tmp[r + 1] && sc[b] == sc[a]) ++b;
+        if (b - a > 1) std::sort(tid + a, tid + b);
+        a = b;
+      }
+  }
   return SQ_OK;
 }
 
@@ -1012,6 +1175,16 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
   if (P && (!tid || !score)) return fail(e, SQ_ERR_ARG, "NULL candidate array");
   for (uint64_t i = 0; i < P; ++i)
     if (tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "candidate %llu names transcript %u >= T", (unsigned long long)i, tid[i]);
+  if (!e->perm_ready) {  // no index yet: the numbering is the caller's from here on
+    const uint32_t T = (uint32_t)e->T;
+    e->ext_of.resize(T);
+    e->int_of.resize(T);
+    for (uint32_t i = 0; i < T; ++i) e->ext_of[i] = e->int_of[i] = i;
+    SQ_CUDA(e, e->d_ext_of.ensure((size_t)T * 4));
+    SQ_CUDA(e, cudaMemcpy(e->d_ext_of.p, e->ext_of.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
+    e->perm_identity = true;
+    e->perm_ready = true;
+  }
   SQ_TRY(ensure_store(e, 0, n_reads, P));
   std::vector<uint32_t> off32(n_reads + 1, 0);
   for (uint64_t i = 0; i <= n_reads && n_reads; ++i) {
@@ -1020,7 +1193,13 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
   }
   SQ_CUDA(e, cudaMemcpy(e->read_off, off32.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice));
   if (P) {
-    SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
+    if (e->perm_identity) {
+      SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<uint32_t> itid(P);
+      for (uint64_t i = 0; i < P; ++i) itid[i] = e->int_of[tid[i]];
+      SQ_CUDA(e, cudaMemcpy(e->cand_tid, itid.data(), P * 4, cudaMemcpyHostToDevice));
+    }
     SQ_CUDA(e, cudaMemcpy(e->cand_score, score, P * 4, cudaMemcpyHostToDevice));
   }
   e->P = P;
@@ -1203,15 +1382,20 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_TRY(allreduce(e, e->numreads.p, T, ncclDouble));
     SQ_TRY(allreduce(e, e->present.p, T, ncclUint32));
   }
-  std::vector<uint32_t> pres(T);
+  // results leave in the caller's transcript numbering
+  SQ_CUDA(e, e->out_pi.ensure((size_t)T * 8));
+  SQ_CUDA(e, e->out_nr.ensure((size_t)T * 8));
+  SQ_CUDA(e, e->out_present.ensure((size_t)T));
+  launch_permute_out(v.pi, e->numreads.as<double>(), e->present.as<uint32_t>(),
+                     e->perm_ready && !e->perm_identity ? e->d_ext_of.as<uint32_t>() : nullptr, T, e->out_pi.as<double>(),
+                     e->out_nr.as<double>(), e->out_present.as<uint8_t>(), st, &e->launches);
   uint32_t st_host[2] = {0, 0};
-  SQ_CUDA(e, cudaMemcpyAsync(pi, v.pi, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
-  SQ_CUDA(e, cudaMemcpyAsync(numreads, e->numreads.p, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
-  SQ_CUDA(e, cudaMemcpyAsync(pres.data(), e->present.p, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(pi, e->out_pi.p, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(numreads, e->out_nr.p, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
+  SQ_CUDA(e, cudaMemcpyAsync(present, e->out_present.p, (size_t)T, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaMemcpyAsync(st_host, state, 8, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaStreamSynchronize(st));
   SQ_CUDA(e, cudaGetLastError());
-  for (uint32_t t = 0; t < T; ++t) present[t] = pres[t] ? 1 : 0;
   e->em_iterations = (int)st_host[1];
   if (iters_done) *iters_done = e->em_iterations;
   resolve_events(e);
@@ -1238,6 +1422,7 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->queries = tot[1]; out->hits = tot[2]; out->postings = tot[3];
   out->ms_items = e->ms[6];
   out->ms_vote_main = e->ms[7];
+  out->ms_lookup = e->ms[8];
   out->sketch_launches = e->n_stage[0]; out->vote_launches = e->n_stage[1];
   out->slow_reads = e->slow_total;
   out->em_classes = e->n_classes_last;
@@ -1294,7 +1479,7 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
   const uint64_t items_ub64 = (uint64_t)n_reads + nb / SQ_CHUNK + 1;
   if (items_ub64 >= 0xFFFFFFFFull || nb >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
   const uint32_t items_ub = (uint32_t)items_ub64;
-  const uint64_t stride = (nb + 3) & ~3ull;
+  const uint64_t stride = ((nb + 3) & ~3ull) + 4;
   SQ_CUDA(e, s.packed.ensure(((nw + 3) & ~3ull) * 4 + 64));
   SQ_CUDA(e, s.base_off.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.len.ensure((size_t)n_reads * 4));
@@ -1302,7 +1487,8 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
   SQ_CUDA(e, s.item_start.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.item_read.ensure((size_t)items_ub * 4));
   SQ_CUDA(e, s.cnt.ensure((size_t)items_ub * nk * 2));
-  SQ_CUDA(e, s.sel.ensure((size_t)stride * nk * 4));
+  SQ_CUDA(e, s.hsel.ensure((size_t)stride * nk * 4));
+  SQ_CUDA(e, s.hoff.ensure((size_t)items_ub * nk * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max<uint32_t>(items_ub, n_reads * nk)) * 4));
   SQ_CUDA(e, e->tap_counts.ensure((size_t)n_reads * nk * 4));
   SQ_CUDA(e, e->tap_offs.ensure(((size_t)n_reads * nk + 1) * 4));
@@ -1333,10 +1519,15 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
     sp.lut[i] = e->lut[k0 + i];
     sp.kmax = std::max(sp.kmax, sp.ks[i]);
   }
-  sp.sel = s.sel.as<uint32_t>();
-  sp.slot_stride = stride;
+  sp.hsel = s.hsel.as<uint32_t>();
+  sp.hstride = stride;
+  sp.hoff = s.hoff.as<uint32_t>();
   sp.cnt = s.cnt.as<uint16_t>();
+  sp.cursor = e->d_hcur + 16;
+  sp.cap = sketch_cap(item_hash_bound(e, nb, n_reads));
+  sp.dedup = 0;  // the tap hands out the multiset, the postings build removes repeats after its sort
   sp.stats = nullptr;
+  SQ_CUDA(e, cudaMemsetAsync(sp.cursor, 0, 32, st));
   launch_sketch(sp, st, &e->launches);
   launch_tap_count(s.item_start.as<uint32_t>(), n_reads, nk, s.cnt.as<uint16_t>(), items_ub,
                    e->tap_counts.as<uint32_t>(), st, &e->launches);
@@ -1372,9 +1563,9 @@ int sq_sketch(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, cons
   cudaStream_t st = e->stream;
   const uint64_t ncopy = std::min<uint64_t>(tot, cap);
   SQ_CUDA(e, e->tap_out.ensure((ncopy + 1) * 4));
-  launch_tap_gather(s.item_start.as<uint32_t>(), s.base_off.as<uint32_t>(), bias, s.len.as<uint32_t>(), n_reads, e->nk,
-                    s.cnt.as<uint16_t>(), items_ub, s.sel.as<uint32_t>(), stride, e->tap_offs.as<uint32_t>(), ncopy,
-                    e->tap_out.as<uint32_t>(), nullptr, nullptr, 0, st, &e->launches);
+  launch_tap_gather(s.item_start.as<uint32_t>(), n_reads, e->nk, s.cnt.as<uint16_t>(), items_ub, s.hsel.as<uint32_t>(),
+                    stride, s.hoff.as<uint32_t>(), e->tap_offs.as<uint32_t>(), ncopy, e->tap_out.as<uint32_t>(), nullptr,
+                    nullptr, 0, st, &e->launches);
   SQ_CUDA(e, cudaMemcpyAsync(counts, e->tap_counts.p, (size_t)n_reads * e->nk * 4, cudaMemcpyDeviceToHost, st));
   if (ncopy && hashes) SQ_CUDA(e, cudaMemcpyAsync(hashes, e->tap_out.p, ncopy * 4, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaStreamSynchronize(st));
@@ -1408,9 +1599,9 @@ int sq_build_postings(sq_engine* e, uint32_t kidx, const uint32_t* packed_words,
       SQ_CUDA(e, e->keys_a.ensure((tot + 1) * 8));
       SQ_CUDA(e, e->keys_b.ensure((tot + 1) * 8));
       SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(tot) * 4));
-      launch_tap_gather(s.item_start.as<uint32_t>(), s.base_off.as<uint32_t>(), bias, s.len.as<uint32_t>(), n_seqs, 1,
-                        s.cnt.as<uint16_t>(), items_ub, s.sel.as<uint32_t>(), stride, e->tap_offs.as<uint32_t>(), tot,
-                        nullptr, e->keys_a.as<uint64_t>(), e->tap_tid.as<uint32_t>(), tbits, st, &e->launches);
+      launch_tap_gather(s.item_start.as<uint32_t>(), n_seqs, 1, s.cnt.as<uint16_t>(), items_ub, s.hsel.as<uint32_t>(),
+                        stride, s.hoff.as<uint32_t>(), e->tap_offs.as<uint32_t>(), tot, nullptr, e->keys_a.as<uint64_t>(),
+                        e->tap_tid.as<uint32_t>(), tbits, st, &e->launches);
       uint64_t* sorted = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, tot, 32 + (int)tbits,

@@ -35,11 +35,11 @@ struct EmView {
 void launch_fill_u32(uint32_t* p, size_t n, uint32_t v, cudaStream_t s);
 size_t vote_smem_bytes(uint32_t nk);
 
-void launch_direct_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, const uint32_t* postings,
-                         uint4* direct, uint32_t shift, uint32_t mask, uint32_t* fail, cudaStream_t s,
-                         uint64_t* launches);
-void launch_table_build(const uint32_t* keys, const uint32_t* off, uint64_t nkeys, uint4* buckets, uint32_t shift,
-                        uint32_t mask, uint32_t* fail, cudaStream_t s, uint64_t* launches);
+void launch_bmap_build(const uint32_t* keys, uint64_t nkeys, uint4* bmap, uint32_t n_sectors, uint32_t* cnt,
+                       uint32_t* excl, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches);
+void launch_permute_out(const double* pi, const double* numreads, const uint32_t* present, const uint32_t* ext_of,
+                        uint32_t T, double* pi_out, double* nr_out, uint8_t* present_out, cudaStream_t s,
+                        uint64_t* launches);
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,

@@ -8,7 +8,11 @@
 // stream, so the warp stages its whole span in shared memory with coalesced 128-bit loads and every lane
 // then rolls through its own bases from shared memory.  Per step the lane does one 8-byte table lookup
 // (seed[in] ^ rot_k(seed[out]), 16 entries, conflict-free in shared memory), one funnel shift (33-bit
-// rotate in two-word form) and two XORs; hashes <= threshold are appended to the item's output slot.
+// rotate in two-word form) and two XORs.  Hashes <= threshold go to the lane's column of a shared-memory
+// staging area; when the warp is through with a k, each lane removes the duplicates of its item (the sketch is
+// a set), the warp reserves one contiguous region of the batch's dense output with a single atomic and
+// writes its 32 items there back to back, coalesced.  Downstream kernels (lookup, vote) thus stream 4 bytes
+// per selected hash instead of touching one sparse sector per read.
 #include "sq_common.cuh"
 
 namespace sq {
@@ -25,21 +29,152 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
-// out0[n++] = x with the address formed at the store (see sketch_kernel)
-__device__ __forceinline__ void emit(uint32_t* out0, uint32_t& n, uint32_t x) {
-  asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.u32 [a], %2;\n\t}" ::"l"(out0), "r"(n), "r"(x) : "memory");
-  ++n;
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ uint32_t code_at(const uint32_t* wp, uint32_t pos) {
   return (wp[pos >> 4] >> ((pos & 15) * 2)) & 3;
 }
 
+// where a lane's selected hashes go: its column of the shared-memory staging area (entry e at sp0 + 128*e; `sp`
+// walks it, `n` counts the selected hashes that did not fit any more), or -- for the rare lane that selected
+// more than the area holds and rolls a second time -- straight to its reserved place in global memory (`n`
+// counts them all)
+struct Emitter {
+  uint32_t sp, sp_end, n;
+  uint32_t* gout;
+};
+template <bool GLOBAL>
+__device__ __forceinline__ void emit_checked(Emitter& E, uint32_t x) {
+  if (GLOBAL) {
+    E.gout[E.n++] = x;
+  } else if (E.sp < E.sp_end) {
+    sts_u32(E.sp, x);
+    E.sp += 128;
+  } else {
+    ++E.n;
+  }
+}
+// staging variant without the capacity test: the caller made sure 16 more entries fit
+template <bool GLOBAL>
+__device__ __forceinline__ void emit_room(Emitter& E, uint32_t x) {
+  if (GLOBAL) {
+    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %0;\n\tst.global.u32 [a], %2;\n\t}" ::"l"(E.gout), "r"(E.n), "r"(x) : "memory");
+    ++E.n;
+  } else {
+    sts_u32(E.sp, x);
+    E.sp += 128;
+  }
+}
+
+// every window end in [c0, c1) of the read at bases [boff, boff+L): hashes <= thr are emitted in window order
+template <bool GLOBAL>
+__device__ __forceinline__ void roll_item(const uint32_t* wp, uint32_t tb, uint32_t k, uint32_t L, uint32_t boff,
+                                          uint32_t c0, uint32_t c1, uint32_t thr, Emitter& E) {
+  const uint32_t e_first = max(c0, k - 1);  // first window end that lies in this item
+  if (L < k || e_first >= c1) return;
+  uint32_t x = 0, y = 0;  // lane value s: x = s[31:0], y = s[32:1]
+  // ---- fill the first window (k bases, no output): one base to reach an even position, then two bases
+  //      per table lookup (a nibble of the packed word), then a last single base if k is left odd
+  uint32_t pos = boff + e_first - (k - 1);
+  const uint32_t wend = pos + k;
+  if (pos & 1) {
+    const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
+    x = d.x;
+    y = d.y;
+    ++pos;
+  }
+  while (pos + 2 <= wend) {
+    uint32_t w = wp[pos >> 4] >> ((pos & 15) * 2);
+    uint32_t n2 = min((wend - pos) >> 1, (16 - (pos & 15)) >> 1);  // pairs left in this word
+    pos += 2 * n2;
+    for (; n2; --n2) {
+      const uint2 d = lds_v2(tb + 128 + (w & 15) * 8);
+      const uint32_t nx = __funnelshift_l(y, x, 2) ^ d.x;
+      y = __funnelshift_l(y, x, 1) ^ d.y;
+      x = nx;
+      w >>= 4;
+    }
+  }
+  if (pos < wend) {
+    const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
+    const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+    y = x ^ d.y;
+    x = nx;
+    ++pos;
+  }
+  if (x <= thr) emit_checked<GLOBAL>(E, x);
+  // ---- roll: pos = absolute index of the incoming base, the outgoing one is k behind
+  const uint32_t end = boff + c1;
+  const uint32_t q = k >> 4, dr = k & 15;
+  auto partial = [&](uint32_t stop) {  // steps pos .. stop-1, all inside one incoming word
+    const uint32_t iw = pos >> 4, j0 = pos & 15;
+    uint32_t win = wp[iw] >> (2 * j0);
+    uint32_t wout = wp[iw - q];
+    // the word before is only needed for steps j < dr; when j0 >= dr it may lie before the read
+    if (dr) wout = __funnelshift_r(dr > j0 ? wp[iw - q - 1] : 0u, wout, 32 - 2 * dr);
+    wout >>= 2 * j0;
+    for (; pos < stop; ++pos) {
+      const uint2 d = lds_v2(tb + ((win & 3) << 5) + ((wout & 3) << 3));
+      const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+      y = x ^ d.y;
+      x = nx;
+      if (x <= thr) emit_checked<GLOBAL>(E, x);
+      win >>= 2;
+      wout >>= 2;
+    }
+  };
+  if ((pos & 15) && pos < end) partial(min(end, (pos + 15) & ~15u));
+  // aligned blocks of 16 steps: one incoming word, the outgoing stream re-aligned by a funnel shift
+  while (pos + 16 <= end) {
+    if (!GLOBAL && E.sp + 16 * 128 > E.sp_end) {  // the staging column may fill up inside this block: careful steps
+      partial(pos + 16);
+      continue;
+    }
+    const uint32_t iw = pos >> 4;
+    const uint32_t win = wp[iw];
+    uint32_t wout = wp[iw - q];
+    if (dr) wout = __funnelshift_r(wp[iw - q - 1], wout, 32 - 2 * dr);
+    const uint32_t xe = ((win & 0x33333333u) << 2) | (wout & 0x33333333u);
+    const uint32_t xo = (win & 0xCCCCCCCCu) | ((wout >> 2) & 0x33333333u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      {
+        const uint32_t a = (j == 0 ? (xe << 3) & 0x78u : (xe >> (4 * j - 3)) & 0x78u) | tb;
+        const uint2 d = lds_v2(a);
+        const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+        y = x ^ d.y;
+        x = nx;
+        if (x <= thr) emit_room<GLOBAL>(E, x);
+      }
+      {
+        const uint32_t a = (j == 0 ? (xo << 3) & 0x78u : (xo >> (4 * j - 3)) & 0x78u) | tb;
+        const uint2 d = lds_v2(a);
+        const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+        y = x ^ d.y;
+        x = nx;
+        if (x <= thr) emit_room<GLOBAL>(E, x);
+      }
+    }
+    pos += 16;
+  }
+  if (pos < end) partial(end);
+}
+
 __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_constant__ SketchParams p) {
   extern __shared__ __align__(128) uint32_t smem[];
-  // layout: [nk] lookup tables of 384 bytes (128-byte aligned), then one staging area per warp
+  // layout: [nk] lookup tables of 384 bytes (128-byte aligned), one read staging area per warp, one output
+  // staging area per warp ([entry][lane])
   uint2* lut = reinterpret_cast<uint2*>(smem);
   for (uint32_t i = threadIdx.x; i < p.nk * 48; i += blockDim.x) lut[i] = p.lut[i / 48].e[i % 48];
-  uint32_t* stage = smem + p.nk * kLutWords + (threadIdx.x >> 5) * kStageWordsPerWarp;
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  uint32_t* stage = smem + p.nk * kLutWords + warp * kStageWordsPerWarp;
+  uint32_t* ostage = smem + p.nk * kLutWords + (kSketchBlock / 32) * kStageWordsPerWarp + warp * (p.cap * 32);
   // statistics: warps add their selected-hash counts here, the last one to arrive flushes (no exit barrier)
   __shared__ uint32_t s_sel, s_arrived;
   if (threadIdx.x == 0) { s_sel = 0; s_arrived = 0; }
@@ -59,7 +194,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   const uint32_t item = blockIdx.x * kSketchBlock + threadIdx.x;
   const bool valid = item < n_items;
   if (__all_sync(0xFFFFFFFFu, !valid)) {
-    if (lane_id() == 0) arrive(0);
+    if (lane == 0) arrive(0);
     return;
   }
 
@@ -92,124 +227,91 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
       const uint32_t n4 = (nw + 3) >> 2;
       const uint4* src = reinterpret_cast<const uint4*>(p.packed + base4);
       uint4* dst = reinterpret_cast<uint4*>(stage);
-      for (uint32_t i = lane_id(); i < n4; i += 32) dst[i] = __ldg(src + i);
+      for (uint32_t i = lane; i < n4; i += 32) dst[i] = __ldg(src + i);
       __syncwarp();
       wp = stage - base4;  // generic pointer: word index w lives at stage[w - base4]
     }
   }
-  if (!valid) return;
 
   const uint32_t thr = p.threshold;
+  const uint32_t col = (uint32_t)__cvta_generic_to_shared(ostage) + lane * 4;  // entry e of this lane: col + 128*e
   uint32_t n_sel = 0;
   for (uint32_t ki = 0; ki < p.nk; ++ki) {
     const uint32_t k = p.ks[ki];
     // shared-memory byte address of this k's tables; 128-byte aligned, so (index*8) can be OR-ed in
     const uint32_t tb = (uint32_t)__cvta_generic_to_shared(lut + ki * 48);
-    // selected hashes go to out0[nout++]: a fixed base and a 32-bit count, so that the (mostly predicated-off)
-    // append is the address (base + 4*count), the store and an increment -- a 64-bit pointer carried through the
-    // unrolled loop cost seven issue slots per k-mer instead of four
-    uint32_t* const out0 = p.sel + (uint64_t)ki * p.slot_stride + boff + c0;
-    uint32_t nout = 0;
-    const uint32_t e_first = max(c0, k - 1);  // first window end that lies in this item
-    if (L >= k && e_first < c1) {
-      uint32_t x = 0, y = 0;  // lane value s: x = s[31:0], y = s[32:1]
-      // ---- fill the first window (k bases, no output): one base to reach an even position, then two bases
-      //      per table lookup (a nibble of the packed word), then a last single base if k is left odd
-      uint32_t pos = boff + e_first - (k - 1);
-      const uint32_t wend = pos + k;
-      if (pos & 1) {
-        const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
-        x = d.x;
-        y = d.y;
-        ++pos;
-      }
-      while (pos + 2 <= wend) {
-        uint32_t w = wp[pos >> 4] >> ((pos & 15) * 2);
-        uint32_t n2 = min((wend - pos) >> 1, (16 - (pos & 15)) >> 1);  // pairs left in this word
-        pos += 2 * n2;
-        for (; n2; --n2) {
-          const uint2 d = lds_v2(tb + 128 + (w & 15) * 8);
-          const uint32_t nx = __funnelshift_l(y, x, 2) ^ d.x;
-          y = __funnelshift_l(y, x, 1) ^ d.y;
-          x = nx;
-          w >>= 4;
-        }
-      }
-      if (pos < wend) {
-        const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
-        const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-        y = x ^ d.y;
-        x = nx;
-        ++pos;
-      }
-      if (x <= thr) emit(out0, nout, x);
-      // ---- roll: pos = absolute index of the incoming base, the outgoing one is k behind
-      const uint32_t end = boff + c1;
-      const uint32_t q = k >> 4, dr = k & 15;
-      auto partial = [&](uint32_t stop) {  // steps pos .. stop-1, all inside one incoming word
-        const uint32_t iw = pos >> 4, j0 = pos & 15;
-        uint32_t win = wp[iw] >> (2 * j0);
-        uint32_t wout = wp[iw - q];
-        // the word before is only needed for steps j < dr; when j0 >= dr it may lie before the read
-        if (dr) wout = __funnelshift_r(dr > j0 ? wp[iw - q - 1] : 0u, wout, 32 - 2 * dr);
-        wout >>= 2 * j0;
-        for (; pos < stop; ++pos) {
-          const uint2 d = lds_v2(tb + ((win & 3) << 5) + ((wout & 3) << 3));
-          const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-          y = x ^ d.y;
-          x = nx;
-          if (x <= thr) emit(out0, nout, x);
-          win >>= 2;
-          wout >>= 2;
-        }
-      };
-      if ((pos & 15) && pos < end) partial(min(end, (pos + 15) & ~15u));
-      // aligned blocks of 16 steps: one incoming word, the outgoing stream re-aligned by a funnel shift
-      while (pos + 16 <= end) {
-        const uint32_t iw = pos >> 4;
-        const uint32_t win = wp[iw];
-        uint32_t wout = wp[iw - q];
-        if (dr) wout = __funnelshift_r(wp[iw - q - 1], wout, 32 - 2 * dr);
-        const uint32_t xe = ((win & 0x33333333u) << 2) | (wout & 0x33333333u);
-        const uint32_t xo = (win & 0xCCCCCCCCu) | ((wout >> 2) & 0x33333333u);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          {
-            const uint32_t a = (j == 0 ? (xe << 3) & 0x78u : (xe >> (4 * j - 3)) & 0x78u) | tb;
-            const uint2 d = lds_v2(a);
-            const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-            y = x ^ d.y;
-            x = nx;
-            if (x <= thr) emit(out0, nout, x);
-          }
-          {
-            const uint32_t a = (j == 0 ? (xo << 3) & 0x78u : (xo >> (4 * j - 3)) & 0x78u) | tb;
-            const uint2 d = lds_v2(a);
-            const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-            y = x ^ d.y;
-            x = nx;
-            if (x <= thr) emit(out0, nout, x);
+    Emitter E;
+    E.sp = col;
+    E.sp_end = col + p.cap * 128;
+    E.n = 0;
+    E.gout = nullptr;
+    if (valid) roll_item<false>(wp, tb, k, L, boff, c0, c1, thr, E);
+    uint32_t c = (E.sp - col) / 128 + E.n;  // staged + those that did not fit
+    n_sel += c;
+    const bool raw = c > p.cap;  // did not fit: this lane rolls again, straight to global memory
+    __syncwarp();
+    // ---- the sketch is a set: drop the repeats inside the item (a two-word filter says when to look at all)
+    if (p.dedup && !raw && c > 1) {
+      uint32_t m1 = 0, m2 = 0;
+      for (uint32_t i = 0; i < c; ++i) {
+        const uint32_t h = lds_u32(col + 128 * i);
+        const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
+        if ((m1 & b1) && (m2 & b2)) {
+          bool dup = false;
+          for (uint32_t j = 0; j < i; ++j) dup |= lds_u32(col + 128 * j) == h;
+          if (dup) {  // the last entry takes its place (order inside a set does not matter)
+            --c;
+            if (i < c) sts_u32(col + 128 * i, lds_u32(col + 128 * c));
+            --i;
+            continue;
           }
         }
-        pos += 16;
+        m1 |= b1;
+        m2 |= b2;
       }
-      if (pos < end) partial(end);
     }
-    p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)nout;
-    n_sel += nout;
+    // ---- one region of the dense output per warp, the 32 items back to back
+    const uint32_t incl = warp_incl_scan(c);
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0 && tot) base = atomicAdd(p.cursor + ki, tot);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const uint32_t mine = base + incl - c;
+    if (valid) {
+      p.hoff[(uint64_t)ki * p.n_items_ub + item] = mine;
+      p.cnt[(uint64_t)ki * p.n_items_ub + item] = (uint16_t)(c | (raw && p.dedup ? SQ_CNT_RAW : 0u));
+    }
+    // each lane copies its own entries: the warp's stores of one round land in one ~1 KB stretch of the region
+    // (far fewer instructions than dealing the outputs to the lanes, and this kernel is issue-bound)
+    uint32_t* out = p.hsel + (uint64_t)ki * p.hstride;
+    if (!raw)
+      for (uint32_t i = 0; i < c; ++i) out[mine + i] = lds_u32(col + 128 * i);
+    if (raw) {
+      E.n = 0;
+      E.gout = out + mine;
+      roll_item<true>(wp, tb, k, L, boff, c0, c1, thr, E);
+    }
+    __syncwarp();
   }
   {
-    const uint32_t act = __activemask();
-    const uint32_t tot = __reduce_add_sync(act, n_sel);
-    if (lane_id() == (uint32_t)__ffs(act) - 1) arrive(tot);
+    const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, n_sel);
+    if (lane == 0) arrive(tot);
   }
+}
+
+size_t sketch_smem_bytes(uint32_t nk, uint32_t cap) {
+  return (nk * kLutWords + (kSketchBlock / 32) * (kStageWordsPerWarp + cap * 32)) * sizeof(uint32_t);
+}
+
+cudaError_t sketch_configure() {  // per device (sq_create): the staging area may pass the default 48 KB
+  return cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sketch_smem_bytes(SQ_MAXK, SQ_CHUNK));
 }
 
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches) {
   if (p.n_items_ub == 0) return;
-  const size_t smem = (p.nk * kLutWords + (kSketchBlock / 32) * kStageWordsPerWarp) * sizeof(uint32_t);
   const uint32_t grid = (p.n_items_ub + kSketchBlock - 1) / kSketchBlock;
-  sketch_kernel<<<grid, kSketchBlock, smem, s>>>(p);
+  sketch_kernel<<<grid, kSketchBlock, sketch_smem_bytes(p.nk, p.cap), s>>>(p);
   if (launches) ++*launches;
 }
 

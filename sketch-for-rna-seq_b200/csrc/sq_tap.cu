@@ -15,28 +15,25 @@ __global__ void tap_count_kernel(const uint32_t* __restrict__ item_start, uint32
   if (i >= (uint64_t)n_reads * nk) return;
   const uint32_t r = (uint32_t)(i / nk), ki = (uint32_t)(i % nk);
   uint32_t s = 0;
-  for (uint32_t it = item_start[r]; it < item_start[r + 1]; ++it) s += cnt[(uint64_t)ki * n_items_ub + it];
+  for (uint32_t it = item_start[r]; it < item_start[r + 1]; ++it) s += cnt[(uint64_t)ki * n_items_ub + it] & SQ_CNT_MASK;
   counts[i] = s;
 }
 
 // copy the selected hashes of (r, ki) to out[offs[r*nk+ki] ..]; when keys64 != NULL write
 // (hash << tbits | seq_tid[r]) instead (input of the postings sort)
-__global__ void tap_gather_kernel(const uint32_t* __restrict__ item_start, const uint32_t* __restrict__ base_off,
-                                  uint32_t bias, const uint32_t* __restrict__ len, uint32_t n_reads, uint32_t nk,
+__global__ void tap_gather_kernel(const uint32_t* __restrict__ item_start, uint32_t n_reads, uint32_t nk,
                                   const uint16_t* __restrict__ cnt, uint32_t n_items_ub,
-                                  const uint32_t* __restrict__ sel, uint64_t slot_stride,
+                                  const uint32_t* __restrict__ hsel, uint64_t hstride, const uint32_t* __restrict__ hoff,
                                   const uint32_t* __restrict__ offs, uint64_t cap, uint32_t* __restrict__ out,
                                   uint64_t* __restrict__ keys64, const uint32_t* __restrict__ seq_tid, uint32_t tbits) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= (uint64_t)n_reads * nk) return;
   const uint32_t r = (uint32_t)(i / nk), ki = (uint32_t)(i % nk);
   const uint32_t item0 = item_start[r], n_it = item_start[r + 1] - item0;
-  const uint32_t L = len[r], boff = base_off[r] - bias;
-  const uint32_t clen = (L + n_it - 1) / (n_it ? n_it : 1);
   uint64_t o = offs[i];
   for (uint32_t it = 0; it < n_it; ++it) {
-    const uint32_t c = cnt[(uint64_t)ki * n_items_ub + item0 + it];
-    const uint32_t* src = sel + (uint64_t)ki * slot_stride + boff + (uint64_t)it * clen;
+    const uint32_t c = cnt[(uint64_t)ki * n_items_ub + item0 + it] & SQ_CNT_MASK;
+    const uint32_t* src = hsel + (uint64_t)ki * hstride + hoff[(uint64_t)ki * n_items_ub + item0 + it];
     for (uint32_t j = 0; j < c; ++j, ++o) {
       if (o >= cap) continue;
       if (keys64) keys64[o] = ((uint64_t)src[j] << tbits) | seq_tid[r];
@@ -53,15 +50,14 @@ void launch_tap_count(const uint32_t* item_start, uint32_t n_reads, uint32_t nk,
   if (launches) ++*launches;
 }
 
-void launch_tap_gather(const uint32_t* item_start, const uint32_t* base_off, uint32_t bias, const uint32_t* len,
-                       uint32_t n_reads, uint32_t nk, const uint16_t* cnt, uint32_t n_items_ub, const uint32_t* sel,
-                       uint64_t slot_stride, const uint32_t* offs, uint64_t cap, uint32_t* out, uint64_t* keys64,
-                       const uint32_t* seq_tid, uint32_t tbits, cudaStream_t s, uint64_t* launches) {
+void launch_tap_gather(const uint32_t* item_start, uint32_t n_reads, uint32_t nk, const uint16_t* cnt,
+                       uint32_t n_items_ub, const uint32_t* hsel, uint64_t hstride, const uint32_t* hoff,
+                       const uint32_t* offs, uint64_t cap, uint32_t* out, uint64_t* keys64, const uint32_t* seq_tid,
+                       uint32_t tbits, cudaStream_t s, uint64_t* launches) {
   const uint64_t n = (uint64_t)n_reads * nk;
   if (!n) return;
-  tap_gather_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(item_start, base_off, bias, len, n_reads, nk, cnt,
-                                                                n_items_ub, sel, slot_stride, offs, cap, out, keys64,
-                                                                seq_tid, tbits);
+  tap_gather_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(item_start, n_reads, nk, cnt, n_items_ub, hsel, hstride,
+                                                                hoff, offs, cap, out, keys64, seq_tid, tbits);
   if (launches) ++*launches;
 }
 

@@ -1,23 +1,33 @@
 // Seed lookup + per-read transcript vote (the reference's "sparse chaining", src/sparse_chaining.cpp:29-115).
 //
-// One warp per read.  For every k-index the warp walks the read's selected hashes (written by the sketch
-// kernel), removes duplicates (the sketch is a SET, include/sketch.h:15), probes the GPU-resident bucketed
-// hash table (one 32-byte sector per probe), walks the posting list of every hit and counts
-// (transcript, k-index) votes in a per-warp shared-memory table.  Then: per-k maximum over the transcripts
-// seen (shuffle reduction), the double-precision `count < fraction*max` filter for every k, integer score =
-// sum of counts, candidates ordered by (score desc, transcript asc) and appended to the batch staging area.
-// Reads whose tables do not fit in shared memory are queued for the large-table kernel, which runs the same
-// code on a per-worker global-memory scratch sized for the worst case (every transcript of the index).
+// The sketch kernel leaves the selected hashes of a batch as one dense array per k-index.  From there:
+//   lookup_kernel      thread per hash: the hash's list descriptor (see IndexTable): one 32-byte bitmap sector says
+//                      whether it is a key and which, one word of the descriptor array follows for a hit.  It runs
+//                      one k-index at a time over the whole batch, so that k's 31 + 25 MB are the only randomly
+//                      accessed data in flight and stay in L2.
+//   vote_bits_kernel   short reads, thread per read: bit-sliced counters over a 64-transcript window.
+//   vote_long_kernel   warp per read on 64 shared-memory counters per k-index: long (multi-item) reads, and the
+//                      short reads the bit-sliced kernel hands on.
+//   vote_kernel        warp per read with a general transcript hash table in shared memory: whatever is left
+//                      (lists outside the window that matter, three-range lists, more than 4 k values).
+//   vote_overflow_kernel  the same on a per-worker global-memory scratch sized for every transcript of the index.
+// Every tier produces, per read: per-k maximum over the transcripts seen, the double-precision
+// `count < fraction*max` filter for every k, integer score = sum of counts, candidates ordered by (score desc,
+// transcript asc), appended to the batch staging area.
+#include <algorithm>
+
 #include "sq_common.cuh"
 
 namespace sq {
+
+size_t vote_smem_bytes(uint32_t nk);
 
 static constexpr int kVoteWarps = 8;
 static constexpr uint32_t kTabLog2 = 8;      // 256 transcript slots per warp
 static constexpr uint32_t kTabMaxFill = 192;
 static constexpr uint32_t kSetLog2 = 10;     // 1024 dedup-set slots per warp (aliased with the candidate buffer)
 static constexpr uint32_t kSetMaxFill = 768;
-static constexpr uint32_t kHashMul = 0x9E3779B1u;
+static constexpr uint32_t kHashMul = 0x9E3779B1u;  // slot hashing of the per-read tables
 
 struct Scratch {
   uint32_t* tkeys;  // transcript id per slot, SQ_EMPTY when free
@@ -64,28 +74,77 @@ __device__ __forceinline__ void table_vote(const Scratch& S, uint32_t t, uint32_
   S.ctr[1] = 1;
 }
 
-// one 32-byte table bucket in a single 256-bit load (sm_100), not allocated in L1: a probe has no reuse, and L1 is
-// better spent on the reads' hash sectors (3.97 ms against 4.27 with allocation, 4.15 with two 128-bit loads)
-__device__ __forceinline__ void ld_bucket(const uint4* p, uint4& a, uint4& c) {
+// one 32-byte sector in a single 256-bit load (sm_100), not allocated in L1: a probe has no reuse there
+__device__ __forceinline__ void ld_sector(const uint4* p, uint32_t (&w)[8]) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                : "l"(p));
 }
 
-// look h up in the bucketed table; returns the posting offset or SQ_EMPTY
-__device__ __forceinline__ uint32_t probe(const IndexTable& tb, uint32_t h) {
-  uint32_t b = (h * kHashMul) >> tb.shift;
-  for (uint32_t tries = 0; tries <= tb.mask; ++tries) {
-    uint4 kk, oo;
-    ld_bucket(tb.buckets + 2 * (size_t)b, kk, oo);
-    if (kk.x == h && oo.x != SQ_EMPTY) return oo.x;
-    if (kk.y == h && oo.y != SQ_EMPTY) return oo.y;
-    if (kk.z == h && oo.z != SQ_EMPTY) return oo.z;
-    if (kk.w == h && oo.w != SQ_EMPTY) return oo.w;
-    if (oo.x == SQ_EMPTY || oo.y == SQ_EMPTY || oo.z == SQ_EMPTY || oo.w == SQ_EMPTY) return SQ_EMPTY;
-    b = (b + 1) & tb.mask;
+// ------------------------------------------------------------------ seed lookup (sparse_chaining.cpp:61-63)
+// pay[i] = descriptor of hsel[i] for the n selected hashes of k-index ki: the hash's bitmap sector says whether it
+// is a key and which one (rank), the rank indexes the descriptor array.  Four independent probes per thread, no
+// loops, no divergence beyond hit / miss.
+static constexpr int kLookupBlock = 256;
+
+__global__ void __launch_bounds__(kLookupBlock) lookup_kernel(const uint32_t* __restrict__ hsel, uint32_t* __restrict__ pay,
+                                                              const uint32_t* __restrict__ n_ptr, const IndexTable tb,
+                                                              unsigned long long* __restrict__ work) {
+  const uint32_t n = *n_ptr;
+  uint32_t hits = 0;
+  for (uint32_t i0 = (blockIdx.x * kLookupBlock + threadIdx.x) * 4; i0 < n; i0 += gridDim.x * kLookupBlock * 4) {
+    const uint4 h4 = __ldg(reinterpret_cast<const uint4*>(hsel + i0));  // the arrays are padded to a multiple of 4
+    const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w};
+    uint32_t w[4][8], rem[4];
+    bool in[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t sec = hh[u] / SQ_BMAP_BITS;
+      rem[u] = hh[u] - sec * SQ_BMAP_BITS;
+      in[u] = sec < tb.n_sectors && i0 + u < n;
+      if (in[u]) ld_sector(tb.bmap + 2 * (size_t)sec, w[u]);
+    }
+    uint32_t d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      d[u] = SQ_EMPTY;
+      if (in[u]) {
+        const uint32_t wi = (rem[u] >> 5) + 1, bit = rem[u] & 31;
+        uint32_t rank = w[u][0], cur = 0;
+#pragma unroll
+        for (uint32_t j = 1; j < 8; ++j) {
+          rank += j < wi ? (uint32_t)__popc(w[u][j]) : 0u;
+          cur = j == wi ? w[u][j] : cur;
+        }
+        if ((cur >> bit) & 1u) d[u] = __ldg(tb.desc + rank + __popc(cur & ((1u << bit) - 1u)));
+      }
+      hits += d[u] != SQ_EMPTY ? 1u : 0u;
+    }
+    *reinterpret_cast<uint4*>(pay + i0) = make_uint4(d[0], d[1], d[2], d[3]);
   }
-  return SQ_EMPTY;
+  if (work) {
+    __shared__ uint32_t s_hits;
+    if (threadIdx.x == 0) s_hits = 0;
+    __syncthreads();
+    hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+    if (lane_id() == 0 && hits) atomicAdd(&s_hits, hits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_hits) atomicAdd(work + 1, (unsigned long long)s_hits);
+      if (blockIdx.x == 0) atomicAdd(work + 0, (unsigned long long)n);
+    }
+  }
+}
+
+// ---- list descriptors
+__device__ __forceinline__ bool desc_inline(uint32_t d) { return (d >> 31) == 0; }
+__device__ __forceinline__ uint32_t desc_base(const IndexTable& tb, uint32_t d) { return d & ((1u << tb.tbits) - 1u); }
+// 64-bit membership mask of an inline list relative to its base (bit 0 = the base itself)
+__device__ __forceinline__ unsigned long long desc_mask(const IndexTable& tb, uint32_t d) {
+  return ((unsigned long long)(d >> tb.tbits) << 1) | 1ull;
+}
+__device__ __forceinline__ uint4 ld_hdr(const uint4* p) {  // one 16-byte list header, read-only path
+  return __ldg(p);
 }
 
 __device__ __forceinline__ uint32_t items_of(uint32_t L) { return L == 0 ? 1u : (L + SQ_CHUNK - 1) / SQ_CHUNK; }
@@ -113,25 +172,27 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
   const uint32_t nk = P.nk;
   const uint32_t item0 = P.item_start[r];
   const uint32_t n_it = P.item_start[r + 1] - item0;
-  const uint32_t L = P.len[r], boff = P.base_off[r] - P.bias;
-  const uint32_t clen = (L + n_it - 1) / (n_it ? n_it : 1);
   if (lane == 0) { S.ctr[0] = 0; S.ctr[1] = 0; }
   __syncwarp();
 
   for (uint32_t ki = 0; ki < nk; ++ki) {
     const IndexTable& tb = P.tab[ki];
     if (!tb.present) continue;
+    // the sketch kernel removed the repeats inside an item: a hash can only come twice in a read of several
+    // items (or in an item flagged SQ_CNT_RAW); then the hits go through a per-read set
     bool use_set = n_it > 1;
     if (lane == 0) { S.ctr[2] = 0; S.ctr[3] = 0; }
     __syncwarp();
     bool set_used = false;
     for (uint32_t g = 0; g < n_it; g += 32) {
       const uint32_t it = g + lane;
-      const uint32_t c = it < n_it ? P.cnt[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+      const uint32_t craw = it < n_it ? P.cnt[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+      const uint32_t c = craw & SQ_CNT_MASK;
+      const uint32_t my_off = it < n_it ? P.hoff[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+      if (__any_sync(0xFFFFFFFFu, (craw & SQ_CNT_RAW) != 0)) use_set = true;
       const uint32_t incl = warp_incl_scan(c);
       const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
       const uint32_t excl = incl - c;
-      if (tot > 32) use_set = true;
       for (uint32_t f = 0; f < tot; f += 32) {
         const uint32_t idx = f + lane;
         const bool v = idx < tot;
@@ -142,21 +203,33 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
           if (t <= idx) j += step;
         }
         const uint32_t exj = __shfl_sync(0xFFFFFFFFu, excl, j & 31);
-        uint32_t h = 0;
-        if (v) h = P.sel[(uint64_t)ki * P.slot_stride + boff + (uint64_t)(g + j) * clen + (idx - exj)];
-        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, v);
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h) & vm;
-        bool first = v && (peers & ((1u << lane) - 1)) == 0;
+        const uint32_t ofj = __shfl_sync(0xFFFFFFFFu, my_off, j & 31);
+        const uint64_t at = (uint64_t)ki * P.hstride + ofj + (idx - exj);
+        uint32_t d = SQ_EMPTY, h = 0;
+        if (v) d = P.pay[at];
+        bool first = d != SQ_EMPTY;
         if (use_set) {
+          if (first) h = P.hsel[at];
+          const uint32_t vm = __ballot_sync(0xFFFFFFFFu, first);
+          const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h) & vm;
+          first = first && (peers & ((1u << lane) - 1)) == 0;
           set_used = true;
           if (first) first = set_insert(S, h);
         }
         if (first) {
-          uint32_t off = probe(tb, h);
-          ++work[0];
-          if (off != SQ_EMPTY) {
-            ++work[1];
-            off += SQ_LIST_HDR;  // skip the list header
+          if (desc_inline(d)) {
+            const uint32_t base = desc_base(tb, d);
+            uint32_t rest = d >> tb.tbits;
+            table_vote(S, base, ki, nk);
+            ++work[2];
+            while (rest) {
+              const uint32_t q = (uint32_t)__ffs((int)rest);
+              rest &= rest - 1;
+              table_vote(S, base + q, ki, nk);
+              ++work[2];
+            }
+          } else {
+            uint32_t off = __ldg(reinterpret_cast<const uint32_t*>(tb.lhdr + (d & 0x7FFFFFFFu)) + 3) + SQ_LIST_HDR;
             uint32_t t;
             do {
               t = __ldg(tb.postings + off++);
@@ -330,789 +403,230 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
 }
 
 
-// ------------------------------------------------------------------ thread-per-read path (short reads)
-// A short read has one item and a handful of selected hashes, so one THREAD votes for it: duplicates are
-// removed by comparing with the earlier hashes of the same (read, k), every distinct hash is probed, and the
-// posting lists of the hits are merged into a table (transcript -> per-k counts packed 8 bits each) that is
-// kept sorted by transcript id.  Identical posting lists are stored once in the index, so hits with the same
-// offset are walked once with a weight.  The table lives in shared memory, entry-major ([entry][thread]):
-// a warp's accesses are bank-conflict free whatever entry each lane touches, and nothing spills to local
-// memory.  Two instantiations run back to back: CAP=16 entries for every read, then CAP=48 for the reads
-// that did not fit; what still does not fit (or has several items / more than kFastMaxHashes hashes for a
-// k) goes to the warp-per-read kernel through slow_list.
-static constexpr uint32_t kFastMaxHashes = 32;
-
-template <typename CT, int CAP, int BLOCK, bool LISTED>  // CT: uint32_t for nk <= 4, unsigned long long for nk <= 8
-__global__ void __launch_bounds__(BLOCK) vote_fast_kernel(const __grid_constant__ VoteParams P) {
-  extern __shared__ __align__(16) unsigned char fast_smem[];
-  CT* tc = reinterpret_cast<CT*>(fast_smem);                       // [CAP][BLOCK]
-  uint32_t* tt = reinterpret_cast<uint32_t*>(tc + CAP * BLOCK);    // [CAP][BLOCK]
-  __shared__ uint32_t s_warp[BLOCK / 32];
-  __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_work[3];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tx = threadIdx.x;
-  const uint32_t gi = blockIdx.x * BLOCK + tx;
-  const uint32_t n_in = LISTED ? *P.mid_count : P.n_reads;
-  if (blockIdx.x * BLOCK >= n_in) return;
-  const bool valid = gi < n_in;
-  const uint32_t r = valid ? (LISTED ? P.mid_list[gi] : gi) : 0u;
-  const uint32_t nk = P.nk;
-  if (tx < 3) s_work[tx] = 0;
-
-  uint32_t ntab = 0;
-  bool defer = false;
-  uint32_t wq = 0, wh = 0, wp = 0;
-  // merge one posting list (ascending transcript ids) into the sorted table with weight `add`
-  auto merge_list = [&](const IndexTable& tb, uint32_t off, CT add, uint32_t w, uint32_t room) {
-    uint32_t p = 0, t;
-    off += SQ_LIST_HDR;  // skip the list header
-    do {
-      t = __ldg(tb.postings + off++);
-      const uint32_t tid = t & ~SQ_LAST;
-      while (p < ntab && tt[p * BLOCK + tx] < tid) ++p;
-      if (p < ntab && tt[p * BLOCK + tx] == tid) {
-        tc[p * BLOCK + tx] += add;
-      } else {
-        if (ntab >= room) { defer = true; return; }
-        for (uint32_t q = ntab; q > p; --q) {
-          tt[q * BLOCK + tx] = tt[(q - 1) * BLOCK + tx];
-          tc[q * BLOCK + tx] = tc[(q - 1) * BLOCK + tx];
-        }
-        tt[p * BLOCK + tx] = tid;
-        tc[p * BLOCK + tx] = add;
-        ++ntab;
-      }
-      wp += w;
-    } while (!(t & SQ_LAST));
-  };
-  if (valid) {
-    const uint32_t item0 = P.item_start[r];
-    if (P.item_start[r + 1] - item0 != 1) defer = true;
-    const uint32_t boff = P.base_off[r] - P.bias;
-    for (uint32_t ki = 0; ki < nk && !defer; ++ki) {
-      const IndexTable& tb = P.tab[ki];
-      if (!tb.present) continue;
-      const uint32_t n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
-      if (n > kFastMaxHashes) { defer = true; break; }
-      const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
-      // (1) probe every distinct hash; park the posting offsets of the hits in this thread's column of the
-      //     still unused top rows of the table (row CAP-1 downwards).  Without room the list is merged at once.
-      uint32_t nh = 0;
-      uint32_t* hit = tt + (CAP - 1) * BLOCK + tx;
-      // the probes of one read are independent: pull every bucket towards L2/L1 before the dependent loop, so
-      // the DRAM latencies overlap instead of adding up
-      for (uint32_t j = 0; j < n; ++j) {
-        const uint32_t b = (hs[j] * kHashMul) >> tb.shift;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.buckets + 2 * (size_t)b));
-      }
-      for (uint32_t j = 0; j < n && !defer; ++j) {
-        const uint32_t h = hs[j];
-        bool dup = false;
-        for (uint32_t jj = 0; jj < j; ++jj) dup |= hs[jj] == h;
-        if (dup) continue;
-        const uint32_t off = probe(tb, h);
-        ++wq;
-        if (off == SQ_EMPTY) continue;
-        ++wh;
-        if (nh + ntab + 1 < (uint32_t)CAP) {
-          hit[-(int)(nh * BLOCK)] = off;
-          ++nh;
-        } else {
-          merge_list(tb, off, (CT)1 << (8 * ki), 1, (uint32_t)CAP - nh);
-        }
-      }
-      // (2) group the parked offsets: equal offsets are the same list (weight = how many hits share it);
-      //     the distinct ones are compacted to the first rows, their weights kept in the same rows of tc
-      uint32_t nd = 0;
-      CT* wgt = tc + (CAP - 1) * BLOCK + tx;
-      for (uint32_t a = 0; a < nh; ++a) {
-        const uint32_t off = hit[-(int)(a * BLOCK)];
-        if (off == SQ_EMPTY) continue;
-        uint32_t w = 1;
-        for (uint32_t b = a + 1; b < nh; ++b)
-          if (hit[-(int)(b * BLOCK)] == off) { ++w; hit[-(int)(b * BLOCK)] = SQ_EMPTY; }
-        hit[-(int)(nd * BLOCK)] = off;
-        wgt[-(int)(nd * BLOCK)] = (CT)w;
-        ++nd;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(tb.postings + off));
-      }
-      // (3) merge each distinct list once, last parked first, so the rows they occupy free up as the table grows
-      for (uint32_t a = nd; a-- > 0 && !defer;) {
-        const uint32_t w = (uint32_t)wgt[-(int)(a * BLOCK)];
-        merge_list(tb, hit[-(int)(a * BLOCK)], (CT)w << (8 * ki), w, (uint32_t)CAP - a);
-      }
-    }
-  }
-  // hand reads that did not fit to the next tier (their work counters are recounted there)
-  {
-    uint32_t* list = LISTED ? P.slow_list : P.mid_list;
-    uint32_t* count = LISTED ? P.slow_count : P.mid_count;
-    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
-    if (dmask) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(dmask));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (valid && defer) {
-        list[base + __popc(dmask & ((1u << lane) - 1))] = r;
-        wq = wh = wp = 0;
-      }
-    }
-  }
-  // per-k maximum (bytes of the packed word), threshold, filter, score; the surviving entries are sorted in
-  // place (entry i is consumed before any slot <= i is overwritten): tc := 0x7FFFFFFF-score, tt := transcript
-  uint32_t nc = 0;
-  if (valid && !defer && ntab) {
-    CT mx = 0;
-    for (uint32_t i = 0; i < ntab; ++i) {
-      const CT c = tc[i * BLOCK + tx];
-      CT m2 = 0;
-      for (uint32_t ki = 0; ki < nk; ++ki) {
-        const CT a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
-        m2 |= (a > b ? a : b) << (8 * ki);
-      }
-      mx = m2;
-    }
-    for (uint32_t i = 0; i < ntab; ++i) {
-      const CT c = tc[i * BLOCK + tx];
-      const uint32_t tid = tt[i * BLOCK + tx];
-      bool ok = true;
-      uint32_t score = 0;
-      for (uint32_t ki = 0; ki < nk; ++ki) {
-        const int cc = (int)((c >> (8 * ki)) & 255), mm = (int)((mx >> (8 * ki)) & 255);
-        if ((double)cc < P.fraction * (double)mm) ok = false;  // sparse_chaining.cpp:84-98
-        score += (uint32_t)cc;
-      }
-      if (ok) {
-        // insertion sort: score descending, transcript ascending
-        const uint32_t inv = 0x7FFFFFFFu - score;
-        uint32_t pos = nc++;
-        while (pos > 0) {
-          const uint32_t pi = (uint32_t)tc[(pos - 1) * BLOCK + tx], pt = tt[(pos - 1) * BLOCK + tx];
-          if (pi < inv || (pi == inv && pt < tid)) break;
-          tc[pos * BLOCK + tx] = (CT)pi;
-          tt[pos * BLOCK + tx] = pt;
-          --pos;
-        }
-        tc[pos * BLOCK + tx] = (CT)inv;
-        tt[pos * BLOCK + tx] = tid;
-      }
-    }
-  }
-  // one staging allocation per block
-  const uint32_t incl = warp_incl_scan(nc);
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (tx == 0) {
-    uint32_t tot = 0;
-    for (int w = 0; w < BLOCK / 32; ++w) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
-    s_base = tot ? atomicAdd(P.stage_cursor, (unsigned long long)tot) : 0ull;
-  }
-  __syncthreads();
-  if (valid) {
-    const unsigned long long sbase = s_base + s_warp[warp] + (incl - nc);
-    const bool fits = sbase + nc <= P.stage_cap;
-    P.read_soff[r] = (uint32_t)sbase;
-    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next tier
-    if (fits)
-      for (uint32_t i = 0; i < nc; ++i) {
-        P.stage_tid[sbase + i] = tt[i * BLOCK + tx];
-        P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)tc[i * BLOCK + tx]);
-      }
-  }
-  if (P.work) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
-      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
-      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
-    }
-    if (lane == 0) { atomicAdd(&s_work[0], wq); atomicAdd(&s_work[1], wh); atomicAdd(&s_work[2], wp); }
-    __syncthreads();
-    if (tx < 3 && s_work[tx]) atomicAdd(P.work + tx, (unsigned long long)s_work[tx]);
-  }
-}
-
-// ------------------------------------------------------------------ 4 lanes per read (short reads)
-// Middle ground between one thread and one warp per read: a QUAD of 4 lanes owns a read, a warp 8 reads.
-// The read's hashes, the elements of each posting list and the table slots are dealt to the 4 lanes by
-// index (j % 4), so those loops run ceil(n/4) times with little spread; the two phases whose work differs most
-// from read to read (voting the posting elements, ranking the candidates) are dealt across the whole warp by
-// a prefix sum over the 8 reads.  The per-warp shared memory is small enough (4.9 KB) for 44+ warps per SM.  (A warp-per-32-reads variant with every loop
-// flattened over the tile by prefix sums was tried and was slower: 12 KB of tables per warp capped the
-// occupancy at 25 %, see profiles/r01_notes.md.)  Tables are [slot][quad]: lane g scanning slots g, g+4, ... is bank-conflict free.
-// Reads with several items, more than kQuadMaxHashes hashes for a k, more than kQuadMaxLists distinct lists
-// or more than kQuadMaxFill distinct transcripts go to the warp-per-read kernel (slow_list).  nk <= 4.
-static constexpr int kQuadWarps = 4;
-static constexpr uint32_t kQuadSlots = 32;
-static constexpr uint32_t kQuadMaxFill = 24;
-static constexpr uint32_t kQuadMaxHashes = 16;
-static constexpr uint32_t kQuadMaxLists = 8;
-
-struct QuadSmem {
-  uint32_t key[kQuadSlots][8];
-  uint32_t cnt[kQuadSlots][8];
-  uint32_t ct[kQuadMaxFill][8];        // surviving candidates: transcript
-  uint32_t cs[kQuadMaxFill][8];        // surviving candidates: 0x7FFFFFFF - score
-  uint32_t ho[kQuadMaxHashes][8];      // posting offset per hash (SQ_EMPTY: miss, 0xFFFFFFFE: duplicate hash)
-  uint32_t lo[kQuadMaxLists][8];       // distinct posting lists: offset
-  uint32_t llw[kQuadMaxLists][8];      // distinct posting lists: length (low 16 bits) | weight (high 16 bits)
-  uint32_t fill[8];                    // distinct transcripts in each read's table
-  uint16_t hh[kQuadMaxHashes][8];      // low 16 bits of each hash (duplicate pre-filter)
-};
-
-template <int NK, bool LISTED>  // LISTED: only the reads the bit-mask kernel left in mid_list
-__global__ void __launch_bounds__(kQuadWarps * 32) vote_quad_kernel(const __grid_constant__ VoteParams P) {
-  extern __shared__ __align__(16) unsigned char quad_smem_raw[];
-  QuadSmem& S = reinterpret_cast<QuadSmem*>(quad_smem_raw)[threadIdx.x >> 5];
-  const uint32_t lane = lane_id(), q = lane >> 2, g = lane & 3;
-  const uint32_t qmask = 0xFu << (q * 4);
-  constexpr uint32_t nk = NK;
-  const uint32_t n_in = LISTED ? *P.mid_count : P.n_reads;
-  const uint32_t n_oct = (n_in + 7) / 8;
-  uint32_t wq = 0, wh = 0, wp = 0;
-
-  for (uint32_t oct = blockIdx.x * kQuadWarps + (threadIdx.x >> 5); oct < n_oct; oct += gridDim.x * kQuadWarps) {
-    const bool valid = oct * 8 + q < n_in;
-    const uint32_t r = valid ? (LISTED ? P.mid_list[oct * 8 + q] : oct * 8 + q) : 0u;
-#pragma unroll
-    for (uint32_t sl = g; sl < kQuadSlots; sl += 4) { S.key[sl][q] = SQ_EMPTY; S.cnt[sl][q] = 0; }
-    if (g == 0) S.fill[q] = 0;
-    bool defer = false;
-    uint32_t item0 = 0, boff = 0, fill = 0, tq = 0, th = 0;
-    if (valid) {
-      item0 = P.item_start[r];
-      if (P.item_start[r + 1] - item0 != 1) defer = true;
-      boff = P.base_off[r] - P.bias;
-    }
-    __syncwarp();
-    for (uint32_t ki = 0; ki < nk; ++ki) {
-      const IndexTable& tb = P.tab[ki];
-      if (!tb.present) continue;
-      uint32_t n = 0;
-      if (valid && !defer) {
-        n = P.cnt[(uint64_t)ki * P.n_items_ub + item0];
-        if (n > kQuadMaxHashes) { defer = true; n = 0; }
-      }
-      const uint32_t* hs = P.sel + (uint64_t)ki * P.slot_stride + boff;
-      // ---- probe: lane g takes hashes g, g+4, ...
-      unsigned long long m1 = 0, m2 = 0;  // which of 64 buckets (two independent 6-bit fields) my hashes fall in
-      bool maybe_dup = false;
-      for (uint32_t j = g; j < n; j += 4) {
-        const uint32_t h = hs[j];
-        S.hh[j][q] = (uint16_t)h;
-        S.ho[j][q] = probe(tb, h);
-        const unsigned long long b1 = 1ull << (h & 63), b2 = 1ull << ((h >> 6) & 63);
-        maybe_dup |= (m1 & b1) && (m2 & b2);
-        m1 |= b1;
-        m2 |= b2;
-      }
-      // the sketch is a set: a hash that already occurred earlier in the read must not vote twice.  Equal
-      // hashes share both buckets, so the exact check runs only when some pair of hashes of the read does
-      // (about 1 % of the reads).
-#pragma unroll
-      for (int d = 1; d <= 2; d <<= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, d), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, d);
-        maybe_dup |= (m1 & o1) && (m2 & o2);
-        if (d == 1) { m1 |= o1; m2 |= o2; }  // pairs (0,1) and (2,3) merged, then compared across
-      }
-      maybe_dup = __ballot_sync(0xFFFFFFFFu, maybe_dup) & qmask;
-      __syncwarp();
-      if (maybe_dup) {
-        for (uint32_t j = g; j < n; j += 4) {
-          const uint16_t h16 = S.hh[j][q];
-          bool dup = false;
-          for (uint32_t jj = 0; jj < j; ++jj)
-            if (S.hh[jj][q] == h16) dup |= hs[jj] == hs[j];
-          if (dup) S.ho[j][q] = 0xFFFFFFFEu;
-        }
-      }
-      __syncwarp();
-      // ---- group hits that share a posting list (equal offsets).  Lane g looks at hits g, g+4, ...: a hit is
-      //      the FIRST of its list when no earlier hit has the same offset, and then its weight is the number of
-      //      hits with that offset.  The firsts are compacted into (lo, llw) by a prefix inside the quad.
-      uint32_t first_off[kQuadMaxHashes / 4], first_w[kQuadMaxHashes / 4];
-      uint32_t my_first = 0;
-#pragma unroll
-      for (uint32_t m = 0; m < kQuadMaxHashes / 4; ++m) {
-        const uint32_t j = g + 4 * m;
-        first_w[m] = 0;
-        first_off[m] = 0;
-        if (j < n) {
-          const uint32_t off = S.ho[j][q];
-          if (off != 0xFFFFFFFEu) {  // not a duplicate hash
-            ++tq;
-            if (off != SQ_EMPTY) {
-              ++th;
-              bool seen = false;
-              for (uint32_t jj = 0; jj < j; ++jj) seen |= S.ho[jj][q] == off;
-              if (!seen) {
-                uint32_t w = 1;
-                for (uint32_t jj = j + 1; jj < n; ++jj) w += S.ho[jj][q] == off ? 1u : 0u;
-                first_off[m] = off;
-                first_w[m] = w;
-                ++my_first;
-              }
-            }
-          }
-        }
-      }
-      uint32_t fpre = my_first;  // inclusive prefix of the firsts inside the quad
-      {
-        const uint32_t a1 = __shfl_up_sync(0xFFFFFFFFu, fpre, 1);
-        if (g >= 1) fpre += a1;
-        const uint32_t a2 = __shfl_up_sync(0xFFFFFFFFu, fpre, 2);
-        if (g >= 2) fpre += a2;
-      }
-      uint32_t nd = __shfl_sync(0xFFFFFFFFu, fpre, q * 4 + 3);
-      if (nd > kQuadMaxLists) { defer = true; nd = 0; }
-      uint32_t nel = 0;  // posting elements of my lists
-      if (nd) {
-        uint32_t pos = fpre - my_first;
-#pragma unroll
-        for (uint32_t m = 0; m < kQuadMaxHashes / 4; ++m)
-          if (first_w[m]) {
-            const uint32_t len = __ldg(tb.postings + first_off[m]);  // header word: list length
-            S.lo[pos][q] = first_off[m];
-            S.llw[pos][q] = (first_w[m] << 16) | (len & 0xFFFFu);
-            if (len > 0xFFFFu) nel = 0x40000000u;  // absurdly long list: leave the read to the warp kernel
-            nel += len;
-            ++pos;
-          }
-      }
-      nel += __shfl_xor_sync(0xFFFFFFFFu, nel, 1);
-      nel += __shfl_xor_sync(0xFFFFFFFFu, nel, 2);
-      if (nel >= 0x40000000u) { defer = true; nel = 0; }
-      // ---- vote: the posting elements of the warp's 8 reads are dealt to the 32 lanes evenly (prefix sum of the
-      //      per-read element counts); each goes into its read's hash table with shared-memory atomics
-      uint32_t eincl = g == 0 ? nel : 0;
-#pragma unroll
-      for (int d = 4; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, eincl, d);
-        if ((int)lane >= d) eincl += t;
-      }
-      eincl = __shfl_sync(0xFFFFFFFFu, eincl, q * 4);  // inclusive prefix of my quad, on all its lanes
-      const uint32_t etot = __shfl_sync(0xFFFFFFFFu, eincl, 28);
-      __syncwarp();
-      for (uint32_t e0 = 0; e0 < etot; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        uint32_t qq = 0;  // owner quad = number of quads whose inclusive prefix is <= e
-#pragma unroll
-        for (int step = 4; step; step >>= 1) {
-          const uint32_t t = __shfl_sync(0xFFFFFFFFu, eincl, ((qq + step - 1) & 7) * 4);
-          if (t <= e) qq += step;
-        }
-        const uint32_t qel = __shfl_sync(0xFFFFFFFFu, nel, (qq & 7) * 4);
-        const uint32_t qex = __shfl_sync(0xFFFFFFFFu, eincl, (qq & 7) * 4) - qel;
-        if (e < etot) {
-          uint32_t idx = e - qex, i = 0, lw = S.llw[0][qq];
-          while (idx >= (lw & 0xFFFFu)) { idx -= lw & 0xFFFFu; lw = S.llw[++i][qq]; }
-          const uint32_t tid = __ldg(tb.postings + S.lo[i][qq] + SQ_LIST_HDR + idx) & ~SQ_LAST;
-          const uint32_t add = (lw >> 16) << (8 * ki);
-          uint32_t sl = (tid * kHashMul) >> 27;
-          uint32_t tries = 0;
-          for (; tries < kQuadSlots; ++tries) {
-            const uint32_t old = atomicCAS(&S.key[sl][qq], SQ_EMPTY, tid);
-            if (old == SQ_EMPTY) atomicAdd(&S.fill[qq], 1u);
-            if (old == SQ_EMPTY || old == tid) { atomicAdd(&S.cnt[sl][qq], add); break; }
-            sl = (sl + 1) & (kQuadSlots - 1);
-          }
-          if (tries == kQuadSlots) S.fill[qq] = 1000;  // table full
-          wp += lw >> 16;
-        }
-      }
-      __syncwarp();
-    }
-    fill = S.fill[q];
-    if (fill > kQuadMaxFill) defer = true;  // too many distinct transcripts for the table
-    // ---- per-k maximum over the table: lane g scans slots g, g+4, ...; combine inside the quad
-    uint32_t mx = 0;
-#pragma unroll
-    for (uint32_t sl = g; sl < kQuadSlots; sl += 4) {
-      const uint32_t c = S.cnt[sl][q];
-      uint32_t m2 = 0;
-#pragma unroll
-      for (int ki = 0; ki < NK; ++ki) {
-        const uint32_t a = (c >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
-        m2 |= (a > b ? a : b) << (8 * ki);
-      }
-      mx = m2;
-    }
-#pragma unroll
-    for (int d = 1; d <= 2; d <<= 1) {
-      const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
-      uint32_t m2 = 0;
-#pragma unroll
-      for (int ki = 0; ki < NK; ++ki) {
-        const uint32_t a = (o >> (8 * ki)) & 255, b = (mx >> (8 * ki)) & 255;
-        m2 |= (a > b ? a : b) << (8 * ki);
-      }
-      mx = m2;
-    }
-    // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an integer
-    // count, count < x  <=>  count < ceil(x)
-    uint32_t ithr[NK];
-#pragma unroll
-    for (int ki = 0; ki < NK; ++ki) {
-      const double t = ceil(P.fraction * (double)(int)((mx >> (8 * ki)) & 255));
-      ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
-    }
-    // ---- survivors of my slots, compacted into the quad's candidate list (positions by a 4-lane prefix)
-    uint32_t mine = 0;  // bit m set: slot g+4m passes
-    uint32_t my_n = 0;
-    if (valid && !defer) {
-#pragma unroll
-      for (uint32_t m = 0; m < kQuadSlots / 4; ++m) {
-        const uint32_t sl = g + 4 * m;
-        const uint32_t c = S.cnt[sl][q];
-        bool ok = S.key[sl][q] != SQ_EMPTY;
-#pragma unroll
-        for (int ki = 0; ki < NK; ++ki)
-          if (((c >> (8 * ki)) & 255) < ithr[ki]) ok = false;
-        if (ok) { mine |= 1u << m; ++my_n; }
-      }
-    }
-    uint32_t pre = my_n;  // inclusive prefix inside the quad
-    {
-      const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, pre, 1);
-      if (g >= 1) pre += a;
-      const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, pre, 2);
-      if (g >= 2) pre += b;
-    }
-    const uint32_t nc = __shfl_sync(0xFFFFFFFFu, pre, q * 4 + 3);
-    {
-      uint32_t pos = pre - my_n;
-      for (uint32_t m = 0; m < kQuadSlots / 4; ++m)
-        if (mine & (1u << m)) {
-          const uint32_t sl = g + 4 * m;
-          const uint32_t c = S.cnt[sl][q];
-          uint32_t score = 0;
-#pragma unroll
-          for (int ki = 0; ki < NK; ++ki) score += (c >> (8 * ki)) & 255;
-          S.ct[pos][q] = S.key[sl][q];
-          S.cs[pos][q] = 0x7FFFFFFFu - score;
-          ++pos;
-        }
-    }
-    if (valid && !defer) { wq += tq; wh += th; }  // every lane counted its own hashes
-    // hand reads that did not fit (long reads, many hashes, many lists, many transcripts) to the
-    // warp-per-read kernel: they are the heavy ones, a whole warp suits them better than one thread
-    const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer && g == 0);
-    if (dmask) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(P.slow_count, (uint32_t)__popc(dmask));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      if (valid && defer && g == 0) P.slow_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
-    }
-    // one staging allocation per warp (8 reads): exclusive prefix of nc over the quads
-    uint32_t qincl = g == 0 ? nc : 0;
-#pragma unroll
-    for (int d = 4; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, qincl, d);
-      if ((int)lane >= d) qincl += t;
-    }
-    qincl = __shfl_sync(0xFFFFFFFFu, qincl, q * 4);      // inclusive prefix of my quad, on all its lanes
-    const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, qincl, 28);
-    unsigned long long wbase = 0;
-    if (lane == 0 && wtot) wbase = atomicAdd(P.stage_cursor, (unsigned long long)wtot);
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-    const bool fits = wbase + wtot <= P.stage_cap;
-    const unsigned long long rbase = wbase + (qincl - nc);
-    if (valid && g == 0) {
-      P.read_soff[r] = (uint32_t)rbase;
-      P.read_cnt[r] = (fits && !defer) ? nc : 0u;
-    }
-    __syncwarp();
-    // ---- order (score desc, transcript asc).  The candidates of the warp's 8 reads are dealt to the 32 lanes
-    //      evenly (lists differ a lot in size); each is ranked against its own read's list and written at its
-    //      rank, which is its position in the ordered output.
-    if (fits)
-      for (uint32_t e0 = 0; e0 < wtot; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        uint32_t qq = 0;  // owner quad = number of quads whose inclusive prefix is <= e
-#pragma unroll
-        for (int step = 4; step; step >>= 1) {
-          const uint32_t t = __shfl_sync(0xFFFFFFFFu, qincl, ((qq + step - 1) & 7) * 4);
-          if (t <= e) qq += step;
-        }
-        const uint32_t qn = __shfl_sync(0xFFFFFFFFu, nc, (qq & 7) * 4);
-        const uint32_t qex = __shfl_sync(0xFFFFFFFFu, qincl, (qq & 7) * 4) - qn;
-        if (e < wtot) {
-          const uint32_t idx = e - qex;
-          const uint32_t inv = S.cs[idx][qq], tid = S.ct[idx][qq];
-          uint32_t rank = 0;
-          for (uint32_t j = 0; j < qn; ++j) {
-            const uint32_t pi = S.cs[j][qq], pt = S.ct[j][qq];
-            rank += (pi < inv || (pi == inv && pt < tid)) ? 1u : 0u;
-          }
-          P.stage_tid[wbase + qex + rank] = tid;
-          P.stage_score[wbase + qex + rank] = (int32_t)(0x7FFFFFFFu - inv);
-        }
-      }
-    __syncwarp();
-  }
-  if (P.work) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
-      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
-      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
-    }
-    if (lane == 0) {
-      if (wq) atomicAdd(P.work + 0, (unsigned long long)wq);
-      if (wh) atomicAdd(P.work + 1, (unsigned long long)wh);
-      if (wp) atomicAdd(P.work + 2, (unsigned long long)wp);
-    }
-  }
-}
-
-// ------------------------------------------------------------------ bit-mask path (short reads, one k)
-// The isoforms of a gene have neighbouring ids, so the posting lists a short read hits almost always fit a
-// window of 64 transcripts.  The index keeps, per distinct list, the window base and a 64-bit membership mask,
-// and for one-k indexes a second, "direct" hash table whose entries carry that header next to the key: a probe
-// is one 32-byte bucket and nothing else.  One THREAD votes for a read without any table of its own: every hit
-// adds 1 at the list's positions of a bit-sliced counter (5 planes of 64 bits = a count 0..31 per window
-// position, a ripple-carry over whole words).  Per-position maximum, the `count < ceil(fraction*max)` filter
-// and the (score desc, transcript asc) order are word operations too.  The block first deals its reads to the
-// threads in order of hash count, so that the probe loop of a warp diverges little.
+// ------------------------------------------------------------------ bit-sliced path (short reads, 1..4 k values)
+// The isoforms of a gene have neighbouring (internal) ids, so the posting lists a short read hits almost always
+// fit a window of 32 transcripts, and nine list descriptors in ten carry the list itself (base + mask).  One
+// THREAD votes for a read without any table of its own and -- for those nine in ten -- without touching memory
+// beyond the read's descriptors: every hit adds 1 at the list's positions of a bit-sliced counter (per k-index NP
+// planes of 32 bits = a count 0..2^NP-1 per window position, a ripple-carry over whole words).  Per-k maximum,
+// the `count < ceil(fraction*max)` filter for every k, the score (sum over k, a bit-sliced adder) and the
+// (score desc, transcript asc) order are word operations too.
 //
 // 32-bit hashes below the 5 % threshold collide: about one list in 70 joins the k-mers of two unrelated genes
-// and one read in seven meets such a list (real annotations add paralogues).  A list header therefore holds
-// up to two (base, mask) ranges, and the thread keeps a second, 2-plane window (counts up to 3) for an id
-// range away from the first; the two windows never overlap, so maximum, filter and order stay word operations.
-// Reads that still do not fit (several items, > 16 hashes, > 4 two-range lists, a list that needs three
-// ranges, a third id range, a distant count above 3) are handed to the 4-lanes-per-read kernel through mid_list.
+// and one read in seven meets such a list (real annotations add paralogues).  A range that does not fit the
+// window is counted as "outside": with n_out of them no transcript out there has more than n_out votes for that
+// k, so when n_out is below some k's threshold (and not above any k's maximum) they can neither pass the filter
+// nor move a maximum, and are ignored.  Lists of two ranges wait until the single-range ones have anchored the
+// window.  Reads that still do not fit (several items, more hashes than the counters hold, a list that needs
+// three ranges, outside ranges that could matter) are handed to the warp-per-read window kernel through mid_list.
 static constexpr int kBitsBlock = 128;
-static constexpr uint32_t kBitsMaxHashes = 16;
-static constexpr uint32_t kBitsMaxInd = 4;  // two-range lists per read
+static constexpr uint32_t kBitsMaxInd = 4;    // two-range lists per (read, k)
 
-// bit-sliced counters: NP planes of 64 positions
-template <int NP>
+// bit-sliced counters: per k-index NP planes of 32 positions
+template <int NK, int NP>
 struct BitWin {
-  unsigned long long pl[NP];
-  unsigned long long orm;  // positions with a count
-  uint32_t base;
-  bool have;
+  uint32_t pl[NK][NP];
+  uint32_t orm;   // positions with a count for some k
+  uint32_t base;  // transcript id of position 0 (valid once orm != 0)
 };
 
-// make room for a list part (window base `base`, membership `mask`) in W without touching the id range of the
-// other window O; on success `mask` is aligned to W.  Nothing is modified on failure.
-template <int NP, int NO>
-__device__ __forceinline__ bool win_place(BitWin<NP>& W, const BitWin<NO>& O, uint32_t base, unsigned long long& mask) {
-  if (!W.have || base < W.base) {
-    if (W.have) {
-      const uint32_t d = W.base - base;
-      if (d >= 64 || (W.orm >> (64 - d)) != 0) return false;
-    }
-    if (O.have && base < O.base + 64 && O.base < base + 64) return false;  // ranges would overlap
-    if (W.have) {
-      const uint32_t d = W.base - base;
-#pragma unroll
-      for (int b = 0; b < NP; ++b) W.pl[b] <<= d;
-      W.orm <<= d;
-    }
+// Align a list part (first transcript `base`, 64-bit membership `mask`, bit 0 set) with the window, moving the
+// window down when the part starts below it.  Returns the part's 32-bit mask in window coordinates, or 0 when
+// it does not fit (nothing is modified then).
+template <int NK, int NP>
+__device__ __forceinline__ uint32_t win_place(BitWin<NK, NP>& W, uint32_t base, unsigned long long mask) {
+  if (mask >> 32) return 0u;
+  const uint32_t m = (uint32_t)mask;
+  if (W.orm == 0) {
     W.base = base;
-    W.have = true;
-    return true;
+    return m;
   }
-  const uint32_t d2 = base - W.base;
-  if (d2 >= 64 || (d2 && (mask >> (64 - d2)) != 0)) return false;
-  mask <<= d2;
-  return true;
+  if (base >= W.base) {
+    const uint32_t d = base - W.base;
+    if (d >= 32 || (d && (m >> (32 - d)))) return 0u;
+    return m << d;
+  }
+  const uint32_t d = W.base - base;
+  if (d >= 32 || (W.orm >> (32 - d))) return 0u;
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int b = 0; b < NP; ++b) W.pl[k][b] <<= d;
+  W.orm <<= d;
+  W.base = base;
+  return m;
 }
 
-// add weight w at the positions of mask; false if a counter would pass 2^NP - 1
-template <int NP>
-__device__ __forceinline__ bool win_add(BitWin<NP>& W, unsigned long long mask, uint32_t w) {
-  if (w >> NP) return false;
-  unsigned long long carry = 0, npl[NP];
+// add 1 at the positions of m for k-index K (a constant after unrolling); false (nothing changed) if a counter
+// would pass 2^NP - 1
+template <int NK, int NP>
+__device__ __forceinline__ bool win_add(BitWin<NK, NP>& W, int K, uint32_t m) {
+  uint32_t carry = m, npl[NP];
 #pragma unroll
   for (int b = 0; b < NP; ++b) {
-    const unsigned long long a = ((w >> b) & 1u) ? mask : 0ull;
-    npl[b] = W.pl[b] ^ a ^ carry;
-    carry = (W.pl[b] & a) | (W.pl[b] & carry) | (a & carry);
+    npl[b] = W.pl[K][b] ^ carry;
+    carry &= W.pl[K][b];
   }
   if (carry) return false;
 #pragma unroll
-  for (int b = 0; b < NP; ++b) W.pl[b] = npl[b];
-  W.orm |= mask;
+  for (int b = 0; b < NP; ++b) W.pl[K][b] = npl[b];
+  W.orm |= m;
   return true;
 }
 
 template <int NP>
-__device__ __forceinline__ uint32_t win_max(const BitWin<NP>& W) {  // MSB first
-  uint32_t mx = 0;
-  unsigned long long cand = W.orm;
+__device__ __forceinline__ uint32_t planes_max(const uint32_t (&pl)[NP], uint32_t among) {  // MSB first
+  uint32_t mx = 0, cand = among;
 #pragma unroll
   for (int b = NP - 1; b >= 0; --b) {
-    const unsigned long long t = cand & W.pl[b];
+    const uint32_t t = cand & pl[b];
     if (t) { cand = t; mx |= 1u << b; }
   }
   return mx;
 }
 
+// positions of `among` whose count is >= thr
 template <int NP>
-__device__ __forceinline__ unsigned long long win_at_least(const BitWin<NP>& W, uint32_t thr) {
-  if (thr >> NP) return 0ull;
-  unsigned long long gt = 0, eq = W.orm;  // positions with count > / == the bits of thr seen so far
+__device__ __forceinline__ uint32_t planes_at_least(const uint32_t (&pl)[NP], uint32_t among, uint32_t thr) {
+  if (thr >> NP) return 0u;
+  uint32_t gt = 0, eq = among;  // positions with count > / == the bits of thr seen so far
 #pragma unroll
   for (int b = NP - 1; b >= 0; --b) {
-    const unsigned long long tbit = ((thr >> b) & 1u) ? ~0ull : 0ull;
-    gt |= eq & W.pl[b] & ~tbit;
-    eq &= ~(W.pl[b] ^ tbit);
+    const uint32_t tbit = ((thr >> b) & 1u) ? ~0u : 0u;
+    gt |= eq & pl[b] & ~tbit;
+    eq &= ~(pl[b] ^ tbit);
   }
   return gt | eq;
 }
 
 template <int NP>
-__device__ __forceinline__ unsigned long long win_equal(const BitWin<NP>& W, unsigned long long among, uint32_t c) {
-  if (c >> NP) return 0ull;
-  unsigned long long e = among;
+__device__ __forceinline__ uint32_t planes_equal(const uint32_t (&pl)[NP], uint32_t among, uint32_t c) {
+  if (c >> NP) return 0u;
+  uint32_t e = among;
 #pragma unroll
-  for (int b = 0; b < NP; ++b) e &= ((c >> b) & 1u) ? W.pl[b] : ~W.pl[b];
+  for (int b = 0; b < NP; ++b) e &= ((c >> b) & 1u) ? pl[b] : ~pl[b];
   return e;
 }
 
-// first bucket of the direct table already loaded: the entry of h, or .y == SQ_DIRECT_EMPTY when h is not a key
-__device__ __forceinline__ uint4 direct_resolve(const IndexTable& tb, uint32_t h, uint32_t b, uint4 a, uint4 c) {
-  for (uint32_t tries = 0;; ++tries) {
-    if (a.x == h && a.y != SQ_DIRECT_EMPTY) return a;
-    if (c.x == h && c.y != SQ_DIRECT_EMPTY) return c;
-    if (a.y == SQ_DIRECT_EMPTY || c.y == SQ_DIRECT_EMPTY || tries >= tb.dmask) break;
-    b = (b + 1) & tb.dmask;  // full bucket without the key: next one (rare)
-    ld_bucket(tb.direct + 2 * (size_t)b, a, c);
+// score planes = sum over k of the count planes (bit-sliced ripple adders); NS >= NP + 2 planes hold 4 x (2^NP - 1)
+template <int NK, int NP, int NS>
+__device__ __forceinline__ void planes_sum(const BitWin<NK, NP>& W, uint32_t (&s)[NS]) {
+#pragma unroll
+  for (int b = 0; b < NS; ++b) s[b] = b < NP ? W.pl[0][b] : 0u;
+#pragma unroll
+  for (int k = 1; k < NK; ++k) {
+    uint32_t carry = 0;
+#pragma unroll
+    for (int b = 0; b < NS; ++b) {
+      const uint32_t a = b < NP ? W.pl[k][b] : 0u;
+      const uint32_t t = s[b] ^ a ^ carry;
+      carry = (s[b] & a) | (s[b] & carry) | (a & carry);
+      s[b] = t;
+    }
   }
-  return make_uint4(h, SQ_DIRECT_EMPTY, 0u, 0u);
 }
 
-__global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_constant__ VoteParams P) {
-  __shared__ uint32_t s_h[kBitsMaxHashes][kBitsBlock];  // the read's hashes so far (exact duplicate check)
-  __shared__ uint32_t s_ind[kBitsMaxInd][kBitsBlock];   // posting offsets of the two-range lists it met
-  __shared__ uint32_t s_work[4];
-  __shared__ uint32_t s_hist[kBitsMaxHashes + 2];
-  __shared__ uint32_t s_perm[kBitsBlock];
-  const uint32_t tx = threadIdx.x, lane = lane_id(), warp = tx >> 5;
-  uint32_t r = blockIdx.x * kBitsBlock + tx;
-  bool valid = r < P.n_reads;
-  const IndexTable& tb = P.tab[0];
-  if (tx < 4) s_work[tx] = 0;
-  bool defer = false;
-  uint32_t wq = 0, wh = 0, wp = 0;
-  BitWin<5> A = {{0, 0, 0, 0, 0}, 0, 0, false};  // the read's own gene: counts up to 31
-  BitWin<2> B = {{0, 0}, 0, 0, false};           // a second, distant id range (hash collisions, paralogs): up to 3
-  unsigned long long sa = 0, sb = 0;             // survivors
-  uint32_t mx = 0, ithr = 0, nc = 0;
-  uint32_t n = 0;
-  // Every per-thread loop below runs for the longest lane of its warp, and the hash count of a read varies
-  // 2..14: deal the block's reads to the threads in order of hash count (counting sort in shared memory), so
-  // that a warp holds reads of similar size.  `r` is the read this thread works for from here on.
-  if (tx < kBitsMaxHashes + 2) s_hist[tx] = 0;
+template <int NK, int NP>
+__global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_kernel(const __grid_constant__ VoteParams P) {
+  __shared__ uint32_t s_ind[kBitsMaxInd][kBitsBlock];   // posting offsets of the two-range lists a (read, k) met
+  __shared__ uint32_t s_work[2];
+  constexpr uint32_t kMaxCount = (1u << NP) - 1;  // hashes per (read, k) the counters can take
+  const uint32_t tx = threadIdx.x, lane = lane_id();
+  const uint32_t r = blockIdx.x * kBitsBlock + tx;
+  const bool valid = r < P.n_reads;
+  if (tx < 2) s_work[tx] = 0;
   __syncthreads();
-  {
-    uint32_t key = kBitsMaxHashes + 1;  // beyond the batch, several items or too many hashes: no work, go last
-    if (valid && tb.present) {
-      const uint32_t item0 = P.item_start[r];
-      if (P.item_start[r + 1] - item0 == 1) key = min((uint32_t)P.cnt[item0], kBitsMaxHashes + 1);
-    }
-    // The read's hashes go into this thread's shared-memory column now (one or two 256-bit loads when the slot
-    // is 32-byte aligned, as it is for reads packed at a fixed stride): their DRAM latency passes behind the
-    // deal's barriers, and the vote loop below never waits on global memory for a hash.
-    if (key <= kBitsMaxHashes && key) {
-      const uint32_t* hp = P.sel + (P.base_off[r] - P.bias);
-      if ((reinterpret_cast<uintptr_t>(hp) & 31) == 0 && P.len[r] >= kBitsMaxHashes) {  // the slot is len words long
-        for (uint32_t j0 = 0; j0 < key; j0 += 8) {
-          uint4 a, c;
-          asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                       : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
-                       : "l"(hp + j0));
-          s_h[j0 + 0][tx] = a.x; s_h[j0 + 1][tx] = a.y; s_h[j0 + 2][tx] = a.z; s_h[j0 + 3][tx] = a.w;
-          s_h[j0 + 4][tx] = c.x; s_h[j0 + 5][tx] = c.y; s_h[j0 + 6][tx] = c.z; s_h[j0 + 7][tx] = c.w;
-        }
-      } else {
-        for (uint32_t j = 0; j < key; ++j) s_h[j][tx] = __ldg(hp + j);
-      }
-    }
-    const uint32_t rank = atomicAdd(&s_hist[key], 1u);
-    __syncthreads();
-    if (tx == 0) {
-      uint32_t acc = 0;
-      for (uint32_t i = 0; i < kBitsMaxHashes + 2; ++i) { const uint32_t c = s_hist[i]; s_hist[i] = acc; acc += c; }
-    }
-    __syncthreads();
-    s_perm[s_hist[key] + rank] = tx;
-    __syncthreads();
-  }
-  const uint32_t col = s_perm[tx];  // the thread that loaded the hashes of the read this thread votes for
-  r = blockIdx.x * kBitsBlock + col;
-  valid = r < P.n_reads;
-  if (valid && tb.present) {
+  bool defer = false;
+  uint32_t wp = 0;
+  BitWin<NK, NP> A;
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int b = 0; b < NP; ++b) A.pl[k][b] = 0;
+  A.orm = 0;
+  A.base = 0;
+  uint32_t n_out[NK];
+#pragma unroll
+  for (int ki = 0; ki < NK; ++ki) n_out[ki] = 0;
+  if (valid) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
-    n = defer ? 0u : (uint32_t)P.cnt[item0];
-    if (n > kBitsMaxHashes) { defer = true; n = 0; }
-  }
-  if (valid && tb.present) {
-    // ---- probe the read's hashes two at a time (independent loads in flight) and vote hit by hit.  After
-    // the deal above the lanes of a warp have about the same number of hashes, so this loop diverges little.
-    uint32_t m1 = 0, m2 = 0, nind = 0;
-    auto seen = [&](uint32_t h, uint32_t upto) {  // is h one of the read's first `upto` hashes?
-      const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
-      bool dup = false;
-      if ((m1 & b1) && (m2 & b2))  // an equal hash would share both filter bits: exact check (rare)
-        for (uint32_t jj = 0; jj < upto; ++jj) dup |= s_h[jj][col] == h;
-      m1 |= b1;
-      m2 |= b2;
-      return dup;
-    };
-    auto vote = [&](const uint4& e) {
-      ++wq;
-      if (e.y == SQ_DIRECT_EMPTY) return;
-      ++wh;
-      if (e.y == SQ_NOMASK) { defer = true; return; }
-      if (e.y >> 31) {  // two-range list: after the single-range ones (they fix window A)
-        if (nind < kBitsMaxInd) s_ind[nind++][tx] = e.z; else defer = true;
-        return;
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) {
+      const IndexTable& tb = P.tab[ki];
+      if (!tb.present || defer) continue;
+      const uint32_t n = (uint32_t)P.cnt[(uint64_t)ki * P.n_items_ub + item0];  // flagged counts are > kMaxCount
+      if (n > kMaxCount) { defer = true; continue; }
+      const uint32_t* pp = P.pay + (uint64_t)ki * P.hstride + P.hoff[(uint64_t)ki * P.n_items_ub + item0];
+      uint32_t nind = 0;
+      auto place_add = [&](uint32_t base, unsigned long long mask) {
+        const uint32_t m = win_place(A, base, mask);
+        if (!m) ++n_out[ki];
+        else if (!win_add(A, ki, m)) defer = true;
+      };
+      auto vote = [&](uint32_t d) {
+        if (d == SQ_EMPTY) return;
+        if (desc_inline(d)) {
+          const unsigned long long mask = desc_mask(tb, d);
+          wp += (uint32_t)__popcll(mask);
+          place_add(desc_base(tb, d), mask);
+          return;
+        }
+        const uint4 hd = ld_hdr(tb.lhdr + (d & 0x7FFFFFFFu));
+        if (hd.x == SQ_NOMASK) { defer = true; return; }
+        if (hd.x >> 31) {  // two-range list: after the single-range ones (they anchor the window)
+          if (nind < kBitsMaxInd) s_ind[nind++][tx] = hd.w; else defer = true;
+          return;
+        }
+        const unsigned long long mask = ((unsigned long long)hd.z << 32) | hd.y;
+        wp += (uint32_t)__popcll(mask);
+        place_add(hd.x, mask);
+      };
+      // the read's descriptors are consecutive words: four loads in flight, then the votes (no dependent access
+      // for an inline descriptor)
+      for (uint32_t j = 0; j < n && !defer; j += 4) {
+        uint32_t d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d[u] = j + u < n ? __ldg(pp + j + u) : SQ_EMPTY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (!defer) vote(d[u]);
       }
-      unsigned long long mask = ((unsigned long long)e.w << 32) | e.z;
-      wp += (uint32_t)__popcll(mask);
-      if (win_place(A, B, e.y, mask)) win_add(A, mask, 1u);
-      else if (!(win_place(B, A, e.y, mask) && win_add(B, mask, 1u))) defer = true;
-    };
-    for (uint32_t j = 0; j < n && !defer; j += 2) {
-      const bool two = j + 1 < n;
-      const uint32_t h1 = s_h[j][col], h2 = two ? s_h[j + 1][col] : 0u;
-      const bool v1 = !seen(h1, j);
-      const bool v2 = two && !seen(h2, j + 1);
-      const uint32_t b1 = (h1 * kHashMul) >> tb.dshift, b2 = (h2 * kHashMul) >> tb.dshift;
-      uint4 a1 = make_uint4(0, 0, 0, 0), c1 = a1, a2 = a1, c2 = a1;
-      if (v1) ld_bucket(tb.direct + 2 * (size_t)b1, a1, c1);
-      if (v2) ld_bucket(tb.direct + 2 * (size_t)b2, a2, c2);
-      if (v1) vote(direct_resolve(tb, h1, b1, a1, c1));
-      if (v2 && !defer) vote(direct_resolve(tb, h2, b2, a2, c2));
-    }
-    for (uint32_t i = 0; i < nind && !defer; ++i) {  // two-range lists: both ranges from the list header
-      const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + s_ind[i][tx]);
-      const uint4 hd = __ldg(hp), h2 = __ldg(hp + 1);
-      unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
-      unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
-      wp += hd.x;
-      if (win_place(A, B, hd.y & 0x7FFFFFFFu, mask)) win_add(A, mask, 1u);
-      else if (!(win_place(B, A, hd.y & 0x7FFFFFFFu, mask) && win_add(B, mask, 1u))) { defer = true; break; }
-      if (win_place(A, B, h2.x, mask2)) win_add(A, mask2, 1u);
-      else if (!(win_place(B, A, h2.x, mask2) && win_add(B, mask2, 1u))) { defer = true; break; }
-    }
-    if (!defer && (A.orm | B.orm)) {
-      // ---- maximum over the positions (sparse_chaining.cpp:76-82)
-      mx = max(win_max(A), win_max(B));
-      // thresholds[i] = fraction * max_counts[i] (:84-87), test (double)count < threshold (:95); for an
-      // integer count, count < x  <=>  count < ceil(x)
-      const double t = ceil(P.fraction * (double)(int)mx);
-      ithr = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
-      sa = win_at_least(A, ithr);
-      sb = win_at_least(B, ithr);
-      nc = (uint32_t)(__popcll(sa) + __popcll(sb));
+      for (uint32_t i = 0; i < nind && !defer; ++i) {  // two-range lists: both ranges from the list's posting header
+        const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + s_ind[i][tx]);
+        const uint4 hd = __ldg(hp), h2 = __ldg(hp + 1);
+        const unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
+        const unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
+        wp += hd.x;
+        // a list with both ranges outside the window still gives a transcript out there one vote at most
+        const uint32_t before = n_out[ki];
+        place_add(hd.y & 0x7FFFFFFFu, mask);
+        if (!defer) place_add(h2.x, mask2);
+        if (n_out[ki] == before + 2) --n_out[ki];
+      }
     }
   }
-  // hand reads that did not fit to the 4-lanes-per-read kernel
+  // ---- per-k maximum over the positions (sparse_chaining.cpp:76-82), thresholds[i] = fraction * max_counts[i]
+  // (:84-87), test (double)count < threshold (:95): for an integer count, count < x  <=>  count < ceil(x)
+  uint32_t sa = 0;  // survivors
+  uint32_t nc = 0;
+  if (valid && !defer) {
+    sa = A.orm;
+    bool any_out = false, out_fails = false, out_above_max = false;
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) {
+      const uint32_t mx = planes_max(A.pl[ki], A.orm);
+      const double t = ceil(P.fraction * (double)(int)mx);
+      const uint32_t ithr = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+      sa &= planes_at_least(A.pl[ki], A.orm, ithr);
+      any_out |= n_out[ki] != 0;
+      out_fails |= n_out[ki] < ithr;
+      out_above_max |= n_out[ki] > mx;
+    }
+    if (any_out && (!out_fails || out_above_max)) defer = true;  // transcripts outside the window could matter
+    else nc = (uint32_t)__popc(sa);
+  }
+  // hand reads that did not fit to the warp-per-read window kernel
   {
     const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, valid && defer);
     if (dmask) {
@@ -1121,7 +635,7 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
       if (valid && defer) {
         P.mid_list[base + __popc(dmask & ((1u << lane) - 1))] = r;
-        wq = wh = wp = 0;
+        wp = 0;
         nc = 0;
       }
     }
@@ -1138,28 +652,19 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     P.read_soff[r] = (uint32_t)sbase;
     P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
     if (fits && nc) {
-      // ---- order: score descending (:108-109), transcript ascending inside a score; the two windows
-      // cover disjoint id ranges, so inside a score the lower window goes first
-      const uint32_t lowest = ithr > 1 ? ithr : 1;
-      const bool b_first = B.have && B.base < A.base;
-      for (uint32_t c = mx; c >= lowest; --c) {
-        unsigned long long e1 = win_equal(A, sa, c), e2 = win_equal(B, sb, c);
-        uint32_t base1 = A.base, base2 = B.base;
-        if (b_first) {
-          const unsigned long long te = e1; e1 = e2; e2 = te;
-          base1 = B.base; base2 = A.base;
-        }
+      // ---- score = sum of the counts over k (:100); order: score descending (:108-109), transcript ascending
+      // inside a score
+      constexpr int NS = NK == 1 ? NP : NP + 2;
+      uint32_t SA[NS];
+      planes_sum(A, SA);
+      while (sa) {
+        const uint32_t c = planes_max(SA, sa);
+        uint32_t e1 = planes_equal(SA, sa, c);
+        sa &= ~e1;
         while (e1) {
-          const uint32_t p = (uint32_t)__ffsll((long long)e1) - 1;
+          const uint32_t p = (uint32_t)__ffs((int)e1) - 1;
           e1 &= e1 - 1;
-          P.stage_tid[sbase] = base1 + p;
-          P.stage_score[sbase] = (int32_t)c;
-          ++sbase;
-        }
-        while (e2) {
-          const uint32_t p = (uint32_t)__ffsll((long long)e2) - 1;
-          e2 &= e2 - 1;
-          P.stage_tid[sbase] = base2 + p;
+          P.stage_tid[sbase] = A.base + p;
           P.stage_score[sbase] = (int32_t)c;
           ++sbase;
         }
@@ -1167,90 +672,294 @@ __global__ void __launch_bounds__(kBitsBlock, 8) vote_bits_kernel(const __grid_c
     }
   }
   if (P.work) {
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      wq += __shfl_xor_sync(0xFFFFFFFFu, wq, d);
-      wh += __shfl_xor_sync(0xFFFFFFFFu, wh, d);
-      wp += __shfl_xor_sync(0xFFFFFFFFu, wp, d);
-    }
-    if (lane == 0) {  // the last warp to arrive flushes the block's sums: no barrier at the exit
-      atomicAdd(&s_work[0], wq);
-      atomicAdd(&s_work[1], wh);
-      atomicAdd(&s_work[2], wp);
+    wp = __reduce_add_sync(0xFFFFFFFFu, wp);
+    if (lane == 0) {  // the last warp to arrive flushes the block's sum: no barrier at the exit
+      atomicAdd(&s_work[0], wp);
       __threadfence_block();
-      if (atomicAdd(&s_work[3], 1u) == kBitsBlock / 32 - 1) {
+      if (atomicAdd(&s_work[1], 1u) == kBitsBlock / 32 - 1) {
         __threadfence_block();
-        for (int i = 0; i < 3; ++i) {
-          const uint32_t v = *(volatile uint32_t*)&s_work[i];
-          if (v) atomicAdd(P.work + i, (unsigned long long)v);
-        }
+        const uint32_t v = *(volatile uint32_t*)&s_work[0];
+        if (v) atomicAdd(P.work + 2, (unsigned long long)v);
       }
     }
   }
 }
 
-template <typename CT>
-static cudaStream_t launch_fast_tiers(const VoteParams& p, cudaStream_t s, cudaEvent_t ev_b, cudaStream_t tail,
-                                      cudaEvent_t fork) {
-  constexpr int capA = 16, blkA = 256, capB = 48, blkB = 128;
-  constexpr size_t smA = (size_t)capA * blkA * (4 + sizeof(CT)), smB = (size_t)capB * blkB * (4 + sizeof(CT));
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(vote_fast_kernel<CT, capA, blkA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
-    cudaFuncSetAttribute(vote_fast_kernel<CT, capB, blkB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smB);
-    attr = true;
-  }
-  if (p.nk <= 4) {
-    // 4-lanes-per-read kernel first (persistent grid), what does not fit goes to the CAP=48 thread tier
-    static int quad_grid[5] = {0, 0, 0, 0, 0};
-    const int nkq = p.nk < 4 ? (int)p.nk : 4;
-    const size_t qsm = sizeof(QuadSmem) * kQuadWarps;
-    if (!quad_grid[nkq]) {
-      int dev = 0, sms = 0, per_sm = 1;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      switch (nkq) {
-        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<1, true>, kQuadWarps * 32, qsm); break;
-        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<2, false>, kQuadWarps * 32, qsm); break;
-        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<3, false>, kQuadWarps * 32, qsm); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_quad_kernel<4, false>, kQuadWarps * 32, qsm); break;
-      }
-      quad_grid[nkq] = sms * (per_sm < 1 ? 1 : per_sm);
-    }
-    const uint32_t need = ((p.n_reads + 7) / 8 + kQuadWarps - 1) / kQuadWarps;
-    const uint32_t qgrid = need < (uint32_t)quad_grid[nkq] ? need : (uint32_t)quad_grid[nkq];
-    switch (nkq) {
-      case 1:
-        if (p.tab[0].direct && (uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4) {
-          // one k, mean read length up to ~320: the bit-mask kernel takes every read it can, the quad kernel
-          // the rest (mid_list); the profiling events bracket the first, dominant kernel of the chain
-          vote_bits_kernel<<<(p.n_reads + kBitsBlock - 1) / kBitsBlock, kBitsBlock, 0, s>>>(p);
-          if (ev_b) cudaEventRecord(ev_b, s);
-          if (tail && fork) {  // the rest is a few latency-bound launches for ~2 % of the reads: off the main stream
-            cudaEventRecord(fork, s);
-            cudaStreamWaitEvent(tail, fork, 0);
-            s = tail;
+// ------------------------------------------------------------------ warp per read on window counters
+// A long read (several items, hundreds of selected hashes) is voted by one WARP, and so are the short reads the
+// bit-sliced kernel hands on (LISTED).  Most descriptors of an error-prone read are SQ_EMPTY; the hits are
+// collected in shared memory as (hash, descriptor).  The sketch is a SET (include/sketch.h:15) and the sketch
+// kernel only removed the repeats inside an item: in a read of several items a hit whose hash already occurred is
+// dropped -- among the hits only, two small bitmaps tell which hits can have a twin at all.  The lists a read
+// hits belong to one gene, i.e. one window of 64 internal transcript ids: the warp picks the window (the most
+// common base among the lanes' first hits anchors it), and every list inside it adds 1 at its positions of a
+// per-warp counter array in shared memory (64 positions per k-index, native shared-memory atomics).  Hits
+// outside the window are hash collisions with unrelated genes; each can give a transcript there at most one
+// vote, so with n_out of them no outside transcript has more than n_out votes: when that is below the
+// threshold of some k-index (and not above any k's inside maximum) they can neither pass the filter nor move a
+// maximum, and are ignored.  Everything else (a list straddling the window edge or needing three ranges, too
+// many hits, outside hits that could matter) goes to the warp-per-read kernel with the general hash table
+// (slow_list).  Maximum, filter, score and order over the 64 positions are done two positions per lane.
+static constexpr int kLongWarps = 4;
+static constexpr uint32_t kLongMaxHits = 1024;
+
+struct LongSmem {
+  uint32_t hh[kLongMaxHits];  // hash of each hit
+  uint32_t hd[kLongMaxHits];  // descriptor of each hit (SQ_EMPTY: dropped duplicate)
+  uint32_t cnt[4][64];        // votes per k-index and window position
+  uint32_t bm1[64], bm2[64];  // 2048-bit filters of the duplicate test
+  unsigned long long cand[64];
+};
+
+template <int NK, bool LISTED>
+__global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid_constant__ VoteParams P) {
+  extern __shared__ __align__(16) unsigned char long_smem_raw[];
+  LongSmem& S = reinterpret_cast<LongSmem*>(long_smem_raw)[threadIdx.x >> 5];
+  const uint32_t lane = lane_id();
+  const uint32_t lt = (1u << lane) - 1;
+  const uint32_t n_in = LISTED ? *P.mid_count : P.n_reads;
+  uint32_t wp = 0;
+  for (uint32_t ri = blockIdx.x * kLongWarps + (threadIdx.x >> 5); ri < n_in; ri += gridDim.x * kLongWarps) {
+    const uint32_t r = LISTED ? P.mid_list[ri] : ri;
+    const uint32_t item0 = P.item_start[r];
+    const uint32_t n_it = P.item_start[r + 1] - item0;
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) { S.cnt[ki][lane] = 0; S.cnt[ki][lane + 32] = 0; }
+    bool defer = false;
+    bool have_win = false;
+    uint32_t abase = 0;
+    uint32_t n_out[NK];
+    uint32_t tp = 0;
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) {
+      n_out[ki] = 0;
+      const IndexTable& tb = P.tab[ki];
+      if (!tb.present || defer) continue;
+      // ---- collect the hits (items are walked 32 at a time, their descriptors flattened)
+      uint32_t nh = 0;
+      bool need_set = n_it > 1;
+      for (uint32_t g = 0; g < n_it; g += 32) {
+        const uint32_t it = g + lane;
+        const uint32_t craw = it < n_it ? P.cnt[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+        const uint32_t c = craw & SQ_CNT_MASK;
+        const uint32_t my_off = it < n_it ? P.hoff[(uint64_t)ki * P.n_items_ub + item0 + it] : 0u;
+        if (__any_sync(0xFFFFFFFFu, (craw & SQ_CNT_RAW) != 0)) need_set = true;
+        const uint32_t incl = warp_incl_scan(c);
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const uint32_t excl = incl - c;
+        for (uint32_t f = 0; f < tot; f += 32) {
+          const uint32_t idx = f + lane;
+          uint32_t j = 0;  // item (within this group) holding entry idx: number of lanes with incl <= idx
+#pragma unroll
+          for (int step = 16; step; step >>= 1) {
+            const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (j + step - 1) & 31);
+            if (t <= idx) j += step;
           }
-          vote_quad_kernel<1, true><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
-        } else {  // long reads span several items: straight to the quad kernel
-          vote_quad_kernel<1, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p);
-          if (ev_b) cudaEventRecord(ev_b, s);
+          const uint32_t exj = __shfl_sync(0xFFFFFFFFu, excl, j & 31);
+          const uint32_t ofj = __shfl_sync(0xFFFFFFFFu, my_off, j & 31);
+          const uint64_t at = (uint64_t)ki * P.hstride + ofj + (idx - exj);
+          const uint32_t d = idx < tot ? __ldg(P.pay + at) : SQ_EMPTY;
+          const uint32_t hit = __ballot_sync(0xFFFFFFFFu, d != SQ_EMPTY);
+          if (d != SQ_EMPTY) {
+            const uint32_t pos = nh + __popc(hit & lt);
+            if (pos < kLongMaxHits) {
+              S.hd[pos] = d;
+              if (need_set) S.hh[pos] = __ldg(P.hsel + at);
+            }
+          }
+          nh += __popc(hit);
         }
-        break;
-      case 2: vote_quad_kernel<2, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
-      case 3: vote_quad_kernel<3, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
-      default: vote_quad_kernel<4, false><<<qgrid, kQuadWarps * 32, qsm, s>>>(p); break;
+      }
+      if (nh > kLongMaxHits) { defer = true; continue; }
+      __syncwarp();
+      // ---- set semantics: a hit is dropped when an equal hash sits at a smaller index.  Filter 1 takes every
+      // hit; a hit that finds its bit taken marks filter 2; only hits whose bit is in filter 2 can have a twin.
+      if (need_set) {
+        S.bm1[lane] = 0; S.bm1[lane + 32] = 0; S.bm2[lane] = 0; S.bm2[lane + 32] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < nh; i += 32) {
+          const uint32_t b = (S.hh[i] * kHashMul) >> 21;
+          if (atomicOr(&S.bm1[b >> 5], 1u << (b & 31)) & (1u << (b & 31))) atomicOr(&S.bm2[b >> 5], 1u << (b & 31));
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nh; i += 32) {
+          const uint32_t h = S.hh[i], b = (h * kHashMul) >> 21;
+          if (S.bm2[b >> 5] & (1u << (b & 31))) {
+            bool dup = false;
+            for (uint32_t j = 0; j < i; ++j) dup |= S.hh[j] == h;
+            if (dup) S.hd[i] = SQ_EMPTY;
+          }
+        }
+        __syncwarp();
+      }
+      // first range of a hit: (base, mask); SQ_NOMASK in base when the list needs three ranges
+      auto first_range = [&](uint32_t d, uint32_t& base, unsigned long long& mask, uint32_t& post) {
+        if (desc_inline(d)) {
+          base = desc_base(tb, d);
+          mask = desc_mask(tb, d);
+          post = SQ_EMPTY;
+        } else {
+          const uint4 hd = ld_hdr(tb.lhdr + (d & 0x7FFFFFFFu));
+          base = hd.x == SQ_NOMASK ? SQ_NOMASK : hd.x & 0x7FFFFFFFu;
+          mask = ((unsigned long long)hd.z << 32) | hd.y;
+          post = (hd.x != SQ_NOMASK && (hd.x >> 31)) ? hd.w : SQ_EMPTY;  // a second range follows in the posting header
+        }
+      };
+      // ---- window: anchored at the most common base (in 64-id granules) among the lanes' first hits
+      if (!have_win) {
+        uint32_t b0 = SQ_EMPTY;
+        for (uint32_t i = lane; i < nh && b0 == SQ_EMPTY; i += 32) {
+          const uint32_t d = S.hd[i];
+          if (d == SQ_EMPTY) continue;
+          uint32_t base, post;
+          unsigned long long mask;
+          first_range(d, base, mask, post);
+          if (base != SQ_NOMASK) b0 = base;
+        }
+        const uint32_t havem = __ballot_sync(0xFFFFFFFFu, b0 != SQ_EMPTY);
+        if (havem) {
+          const uint32_t peers = __match_any_sync(0xFFFFFFFFu, b0 == SQ_EMPTY ? SQ_EMPTY : b0 >> 6);
+          uint32_t best = b0 == SQ_EMPTY ? 0u : ((uint32_t)__popc(peers) << 8) | (31u - lane);  // most peers, lowest lane
+#pragma unroll
+          for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, d));
+          const uint32_t anchor = __shfl_sync(0xFFFFFFFFu, b0, 31u - (best & 255u));
+          // window base = smallest range base within 64 ids below the anchor
+          uint32_t mn = anchor;
+          for (uint32_t i = lane; i < nh; i += 32) {
+            const uint32_t d = S.hd[i];
+            if (d == SQ_EMPTY) continue;
+            uint32_t base, post;
+            unsigned long long mask;
+            first_range(d, base, mask, post);
+            if (base == SQ_NOMASK) continue;
+            if (base + 64 > anchor && base < mn) mn = base;
+            if (post != SQ_EMPTY) {
+              const uint32_t b2 = __ldg(tb.postings + post + 4);
+              if (b2 + 64 > anchor && b2 < mn) mn = b2;
+            }
+          }
+#pragma unroll
+          for (int d = 16; d; d >>= 1) mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, d));
+          abase = mn;
+          have_win = true;
+        }
+      }
+      // ---- votes: every range of every remaining hit goes into the window counters, is counted as outside,
+      // or (straddling the window edge / three-range list) sends the read to the general kernel
+      uint32_t outside = 0;
+      bool bad = false;
+      auto range = [&](uint32_t b, unsigned long long m) {
+        const uint32_t hi = b + 63u - (uint32_t)__clzll((long long)m);
+        if (b >= abase && hi < abase + 64u) {
+          const uint32_t sh = b - abase;
+          while (m) {
+            const uint32_t q = (uint32_t)__ffsll((long long)m) - 1;
+            m &= m - 1;
+            atomicAdd(&S.cnt[ki][sh + q], 1u);
+          }
+        } else if (hi < abase || b >= abase + 64u) {
+          ++outside;
+        } else {
+          bad = true;
+        }
+      };
+      for (uint32_t i = lane; i < nh; i += 32) {
+        const uint32_t d = S.hd[i];
+        if (d == SQ_EMPTY) continue;
+        uint32_t base, post;
+        unsigned long long m1;
+        first_range(d, base, m1, post);
+        if (base == SQ_NOMASK) { bad = true; continue; }
+        tp += (uint32_t)__popcll(m1);
+        const uint32_t before = outside;
+        range(base, m1);
+        if (post != SQ_EMPTY) {
+          const uint4 h2 = __ldg(reinterpret_cast<const uint4*>(tb.postings + post) + 1);
+          const unsigned long long m2 = ((unsigned long long)h2.z << 32) | h2.y;
+          tp += (uint32_t)__popcll(m2);
+          range(h2.x, m2);
+          if (outside == before + 2) --outside;  // both ranges outside: still one vote per transcript there
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, bad)) defer = true;
+      n_out[ki] = __reduce_add_sync(0xFFFFFFFFu, outside);
+      __syncwarp();
     }
-    if (ev_b && nkq != 1) cudaEventRecord(ev_b, s);
-  } else {
-    // more than 4 k values: 64-bit packed counters, thread-per-read tiers (16 then 48 table entries)
-    vote_fast_kernel<CT, capA, blkA, false><<<(p.n_reads + blkA - 1) / blkA, blkA, smA, s>>>(p);
-    if (ev_b) cudaEventRecord(ev_b, s);
-    vote_fast_kernel<CT, capB, blkB, true><<<(p.n_reads + blkB - 1) / blkB, blkB, smB, s>>>(p);
+    // ---- per-k maximum (sparse_chaining.cpp:76-82), thresholds (:84-87), filter for every k (:90-98), score (:100)
+    bool ok0 = false, ok1 = false;
+    uint32_t s0 = 0, s1 = 0;
+    if (!defer) {
+      uint32_t c0[NK], c1[NK], ithr[NK];
+      bool any_out = false, out_fails = false, out_above_max = false;
+#pragma unroll
+      for (int ki = 0; ki < NK; ++ki) {
+        c0[ki] = S.cnt[ki][lane];
+        c1[ki] = S.cnt[ki][lane + 32];
+        const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, max(c0[ki], c1[ki]));
+        const double t = ceil(P.fraction * (double)(int)mx);
+        ithr[ki] = t >= 2147483647.0 ? 0x7FFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+        s0 += c0[ki];
+        s1 += c1[ki];
+        any_out |= n_out[ki] != 0;
+        out_fails |= n_out[ki] < ithr[ki];
+        out_above_max |= n_out[ki] > mx;
+      }
+      // transcripts outside the window have at most n_out votes per k: ignorable only if that cannot pass
+      // some k's threshold and cannot raise any k's maximum
+      if (any_out && (!out_fails || out_above_max)) defer = true;
+      ok0 = s0 != 0;
+      ok1 = s1 != 0;
+#pragma unroll
+      for (int ki = 0; ki < NK; ++ki) {
+        ok0 &= c0[ki] >= ithr[ki];
+        ok1 &= c1[ki] >= ithr[ki];
+      }
+    }
+    if (defer) {
+      if (lane == 0) {
+        P.slow_list[atomicAdd(P.slow_count, 1u)] = r;
+        P.read_cnt[r] = 0;
+        P.read_soff[r] = 0;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- order: score descending (:108-109), transcript ascending inside a score; rank by counting
+    const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, ok0), m1 = __ballot_sync(0xFFFFFFFFu, ok1);
+    const uint32_t nc = (uint32_t)(__popc(m0) + __popc(m1));
+    if (ok0) S.cand[__popc(m0 & lt)] = ((unsigned long long)(0x7FFFFFFFu - s0) << 32) | (abase + lane);
+    if (ok1) S.cand[__popc(m0) + __popc(m1 & lt)] = ((unsigned long long)(0x7FFFFFFFu - s1) << 32) | (abase + lane + 32);
+    unsigned long long sbase = 0;
+    if (lane == 0) {
+      sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
+      P.read_soff[r] = (uint32_t)sbase;
+      P.read_cnt[r] = sbase + nc <= P.stage_cap ? nc : 0u;  // the host re-runs the vote with a staging area of the reported size
+    }
+    sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
+    __syncwarp();
+    if (sbase + nc <= P.stage_cap)
+      for (uint32_t i = lane; i < nc; i += 32) {
+        const unsigned long long key = S.cand[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < nc; ++j) rank += S.cand[j] < key ? 1u : 0u;
+        P.stage_tid[sbase + rank] = (uint32_t)key;
+        P.stage_score[sbase + rank] = (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32));
+      }
+    wp += tp;
+    __syncwarp();
   }
-  return s;
+  if (P.work) {
+    wp = __reduce_add_sync(0xFFFFFFFFu, wp);
+    if (lane == 0 && wp) atomicAdd(P.work + 2, (unsigned long long)wp);
+  }
 }
 
+// every read of the batch to the general warp-per-read kernel (more than 4 k values)
+__global__ void all_to_slow_kernel(const VoteParams P) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < P.n_reads) P.slow_list[r] = r;
+  if (r == 0) *P.slow_count = P.n_reads;
+}
 
 // large-table path: one warp per worker, scratch in global memory
 __global__ void __launch_bounds__(32) vote_overflow_kernel(const __grid_constant__ VoteParams P) {
@@ -1298,31 +1007,95 @@ size_t vote_smem_bytes(uint32_t nk) {
   return (size_t)kVoteWarps * (tab + tab * nk + tab + set + 4) * sizeof(uint32_t);
 }
 
-cudaStream_t launch_vote(const VoteParams& p, cudaStream_t s, uint64_t* launches, cudaEvent_t ev_a, cudaEvent_t ev_b,
-                         cudaStream_t tail, cudaEvent_t fork) {
-  if (p.n_reads == 0) return s;
-  static int sm_count = 0, configured_nk = -1;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const size_t smem = vote_smem_bytes(p.nk);
-  if (configured_nk != (int)p.nk) {
-    cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured_nk = (int)p.nk;
-  }
+
+// Per-device launch configuration (function attributes and occupancy-derived persistent grids).  Function
+// attributes belong to the CURRENT device, so this runs once per engine, on the engine's device (sq_create):
+// one process may drive several GPUs from several host threads.
+template <int NK>
+static cudaError_t long_occupancy(int* per_sm) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, vote_long_kernel<NK, false>, kLongWarps * 32,
+                                                        sizeof(LongSmem) * kLongWarps);
+}
+
+cudaError_t vote_configure(uint32_t nk, VoteDeviceCfg* cfg) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if ((err = cudaDeviceGetAttribute(&cfg->sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+  cfg->nk = nk;
+  const size_t smem = vote_smem_bytes(nk);
+  if ((err = cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_kernel, kVoteWarps * 32, smem);
-  if (per_sm < 1) per_sm = 1;
-  uint32_t grid = (uint32_t)(sm_count * per_sm);
+  if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vote_kernel, kVoteWarps * 32, smem)) != cudaSuccess) return err;
+  cfg->vote_grid = cfg->sm_count * (per_sm < 1 ? 1 : per_sm);
+  per_sm = 1;
+  switch (nk) {
+    case 1: err = long_occupancy<1>(&per_sm); break;
+    case 2: err = long_occupancy<2>(&per_sm); break;
+    case 3: err = long_occupancy<3>(&per_sm); break;
+    default: err = long_occupancy<4>(&per_sm); break;
+  }
+  if (err != cudaSuccess) return err;
+  cfg->long_grid = cfg->sm_count * (per_sm < 1 ? 1 : per_sm);
+  cfg->lookup_grid = cfg->sm_count * 8;
+  return cudaSuccess;
+}
+
+void launch_lookup(const VoteParams& p, const VoteDeviceCfg& cfg, uint32_t ki, cudaStream_t s, uint64_t* launches) {
+  if (!p.tab[ki].present) return;
+  lookup_kernel<<<cfg.lookup_grid, kLookupBlock, 0, s>>>(p.hsel + (uint64_t)ki * p.hstride, p.pay + (uint64_t)ki * p.hstride,
+                                                         p.hcursor + ki, p.tab[ki], p.work);
+  if (launches) ++*launches;
+}
+
+template <int NK>
+static cudaStream_t launch_tiers(const VoteParams& p, const VoteDeviceCfg& cfg, cudaStream_t s, cudaEvent_t ev_b,
+                                 cudaStream_t tail, cudaEvent_t fork) {
+  const size_t lsm = sizeof(LongSmem) * kLongWarps;
+  const bool short_reads = (uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4;
+  if (short_reads) {
+    // mean read length up to ~320: the bit-sliced kernel takes every read it can, the window kernel the rest
+    // (mid_list); the profiling events bracket the first, dominant kernel of the chain
+    const uint32_t grid = (p.n_reads + kBitsBlock - 1) / kBitsBlock;
+    if (p.count_bits <= 5) vote_bits_kernel<NK, 5><<<grid, kBitsBlock, 0, s>>>(p);
+    else vote_bits_kernel<NK, 7><<<grid, kBitsBlock, 0, s>>>(p);
+    if (ev_b) cudaEventRecord(ev_b, s);
+    if (tail && fork) {  // the rest is a few latency-bound launches for ~2 % of the reads: off the main stream
+      cudaEventRecord(fork, s);
+      cudaStreamWaitEvent(tail, fork, 0);
+      s = tail;
+    }
+    const uint32_t lgrid = (uint32_t)std::min<uint64_t>((uint64_t)cfg.long_grid, (p.n_reads / 16 + kLongWarps) / kLongWarps);
+    vote_long_kernel<NK, true><<<lgrid, kLongWarps * 32, lsm, s>>>(p);
+  } else {  // long reads span several items: one warp per read on the window counters
+    const uint32_t lneed = (p.n_reads + kLongWarps - 1) / kLongWarps;
+    const uint32_t lgrid = lneed < (uint32_t)cfg.long_grid ? lneed : (uint32_t)cfg.long_grid;
+    vote_long_kernel<NK, false><<<lgrid, kLongWarps * 32, lsm, s>>>(p);
+    if (ev_b) cudaEventRecord(ev_b, s);
+  }
+  return s;
+}
+
+cudaStream_t launch_vote(const VoteParams& p, const VoteDeviceCfg& cfg, cudaStream_t s, uint64_t* launches,
+                         cudaEvent_t ev_a, cudaEvent_t ev_b, cudaStream_t tail, cudaEvent_t fork) {
+  if (p.n_reads == 0) return s;
+  const size_t smem = vote_smem_bytes(p.nk);
+  uint32_t grid = (uint32_t)cfg.vote_grid;
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
   if (ev_a) cudaEventRecord(ev_a, s);
-  s = p.nk <= 4 ? launch_fast_tiers<uint32_t>(p, s, ev_b, tail, fork)
-                : launch_fast_tiers<unsigned long long>(p, s, ev_b, tail, fork);
+  switch (p.nk) {
+    case 1: s = launch_tiers<1>(p, cfg, s, ev_b, tail, fork); break;
+    case 2: s = launch_tiers<2>(p, cfg, s, ev_b, tail, fork); break;
+    case 3: s = launch_tiers<3>(p, cfg, s, ev_b, tail, fork); break;
+    case 4: s = launch_tiers<4>(p, cfg, s, ev_b, tail, fork); break;
+    default:  // more than 4 k values: every read to the general kernel
+      all_to_slow_kernel<<<(p.n_reads + 255) / 256, 256, 0, s>>>(p);
+      if (ev_b) cudaEventRecord(ev_b, s);
+      break;
+  }
   vote_kernel<<<grid, kVoteWarps * 32, smem, s>>>(p);
-  vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
+  if (p.n_workers) vote_overflow_kernel<<<p.n_workers, 32, 0, s>>>(p);
   if (launches) *launches += 4;
   return s;
 }

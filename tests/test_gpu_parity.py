@@ -398,3 +398,53 @@ def test_engine_reuse_stream_and_errors(gpu_lib, sqb, port):
         sqb.Engine([31] * 9, 10)
     with pytest.raises(sqb.SketchQuantError):
         sqb.Engine([31], 0)
+
+
+@pytest.mark.parametrize("ks", [[31], [21, 25, 31]])
+def test_scrambled_transcript_ids(gpu_lib, sqb, port, ks):
+    """A reference-written index stores its transcripts in unordered_map order (src/data_io.cpp:185-196): the
+    engine renumbers them internally, results come back in the caller's numbering whatever it is."""
+    d = dataset(n_genes=80, n_reads=2000, seed=31)
+    T = len(d["tseqs"])
+    perm = np.random.default_rng(4).permutation(T)          # new id of transcript i
+    inv = np.argsort(perm)
+    d2 = {"tseqs": [d["tseqs"][i] for i in inv], "names": [d["names"][i] for i in inv], "reads": d["reads"]}
+    thr = port.threshold(SKETCH)
+    p1 = port.postings_from_sequences(d["tseqs"], ks, thr)
+    p2 = port.postings_from_sequences(d2["tseqs"], ks, thr)
+    off1, tid1, score1, pi1, nr1, pr1, it1, st1 = _gpu_quant(sqb, d, ks, p1)
+    off2, tid2, score2, pi2, nr2, pr2, it2, st2 = _gpu_quant(sqb, d2, ks, p2)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, p2, d2["reads"])
+    assert off2.tolist() == ooff.tolist() and tid2.tolist() == otid.tolist() and score2.tolist() == oscore.tolist()
+    opi, oit = port.em(ooff, otid, oscore, R, T)
+    onr, opres = port.assign(ooff, otid, oscore, T, opi)
+    np.testing.assert_allclose(pi2, opi, rtol=RTOL)
+    np.testing.assert_allclose(nr2, onr, rtol=RTOL, atol=1e-12)
+    assert pr2.tolist() == opres.tolist() and it2 == oit
+    # the same quantification under another labelling
+    np.testing.assert_allclose(pi2[perm], pi1, rtol=RTOL)
+    np.testing.assert_allclose(nr2[perm], nr1, rtol=RTOL, atol=1e-12)
+    assert csr_to_lists(off2, perm[tid1].astype(np.uint32), score1) == csr_to_lists(off2, tid2, score2)
+    # scrambling must not push reads off the bit-mask kernel
+    assert st2["mid_reads"] <= st1["mid_reads"] + 0.02 * len(d["reads"])
+
+
+def test_repeated_id_in_a_posting_list(gpu_lib, sqb, port):
+    """a hand-made index may name a transcript twice under one hash: the reference votes once per posting
+    (src/sparse_chaining.cpp:64-69), and so does every vote kernel"""
+    d = dataset()
+    ks = [31]
+    thr = port.threshold(SKETCH)
+    keys, off, tids = port.postings_from_sequences(d["tseqs"], ks, thr)[31]
+    # double the first transcript of every third list
+    new_off, new_tids = [0], []
+    for i in range(len(keys)):
+        seg = tids[int(off[i]):int(off[i + 1])].tolist()
+        if i % 3 == 0:
+            seg = [seg[0]] + seg
+        new_tids += seg
+        new_off.append(len(new_tids))
+    post = {31: (keys, np.asarray(new_off, dtype=np.uint64), np.asarray(new_tids, dtype=np.uint32))}
+    off_g, tid_g, score_g, pi, nr, *_ = _gpu_quant(sqb, d, ks, post)
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, post, d["reads"])
+    assert off_g.tolist() == ooff.tolist() and tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
