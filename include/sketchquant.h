@@ -120,6 +120,10 @@ int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_w
 int sq_push_reads_device(sq_engine* e, const uint32_t* d_packed_words, uint64_t n_words,
                          const uint32_t* d_base_off, const uint32_t* d_len, uint32_t n_reads,
                          uint64_t n_bases_hint);
+/* Page-locked host memory for the buffers handed to sq_push_reads*(): copies from it are asynchronous and run at the
+ * full PCIe rate (from pageable memory they are staged).  NULL when the allocation fails. */
+void* sq_host_alloc(size_t bytes);
+void sq_host_free(void* p);
 /* Wait until every pushed batch has been voted. */
 int sq_sync(sq_engine* e);
 /* Forget all pushed reads (keeps the index). */

@@ -16,7 +16,7 @@ EXPORTS = [
     "sq_version", "sq_device_count", "sq_last_error", "sq_threshold_from_fraction", "sq_create", "sq_destroy",
     "sq_set_stream", "sq_set_profiling", "sq_set_option", "sq_load_index", "sq_push_reads", "sq_push_reads_fixed", "sq_push_reads_device",
     "sq_sync", "sq_reset_reads", "sq_finish", "sq_sketch", "sq_num_pairs", "sq_get_candidates", "sq_build_postings",
-    "sq_nccl_unique_id", "sq_comm_init", "sq_get_stats", "sq_set_candidates",
+    "sq_nccl_unique_id", "sq_comm_init", "sq_get_stats", "sq_set_candidates", "sq_host_alloc", "sq_host_free",
 ]
 
 

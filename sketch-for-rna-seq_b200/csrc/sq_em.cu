@@ -90,15 +90,56 @@ struct ListHash {
   }
 };
 
-// ------------------------------------------------------------------ candidate compaction
-// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store.  The read's
-// EM class key and list fingerprint are computed on the way (the list is in flight anyway).
+// ------------------------------------------------------------------ read classes, built while the batches arrive
+// EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
+// contribute identical terms, so they are collapsed into one class with a weight.  The compaction
+// of every batch (tail stream, idle most of the time) folds a 128-bit fingerprint of each list -- two independent
+// 64-bit non-cryptographic hashes over length, transcripts and scores -- and enters it in a lock-free open-addressing
+// table: slot = {h, g, weight, smallest read index of the class}.  A slot's h is claimed first, then its g; an
+// arrival with the same h and another g moves on like any other mismatch, so no thread ever waits for another.
+// When the last batch is in, the classes are all there: sq_finish only orders them (by best candidate and
+// fingerprint, which makes the order -- and every floating-point sum over classes -- independent of the order
+// of insertion) instead of sorting all the reads.  Element-wise comparison of the lists (option exact_classes), a
+// full table or a missing table fall back to sorting the reads by (best candidate, list hash).
+struct ClassSlot {
+  unsigned long long h, g;  // fingerprint; h == 0: free
+  uint32_t w, rep;          // reads in the class; smallest read index (its list is the class's list)
+  uint32_t pad0, pad1;
+};
+static constexpr uint32_t kClassMaxProbe = 256;
+
+// counters: [0] classes, [1] (class, transcript) pairs, then a u32 overflow flag
+__device__ __forceinline__ void class_insert(ClassSlot* tab, uint32_t mask, unsigned long long h, unsigned long long g,
+                                             uint32_t w, uint32_t rep, uint32_t len, unsigned long long* counters) {
+  uint32_t s = (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+  for (uint32_t tries = 0; tries < kClassMaxProbe; ++tries, s = (s + 1) & mask) {
+    unsigned long long cur = tab[s].h;
+    if (cur == 0) {
+      const unsigned long long old = atomicCAS(&tab[s].h, 0ull, h);
+      cur = old == 0 ? h : old;
+    }
+    if (cur != h) continue;
+    const unsigned long long og = atomicCAS(&tab[s].g, 0ull, g);
+    if (og != 0 && og != g) continue;
+    atomicAdd(&tab[s].w, w);
+    atomicMin(&tab[s].rep, rep);
+    if (og == 0) {  // this thread created the class
+      atomicAdd(counters + 0, 1ull);
+      atomicAdd(counters + 1, (unsigned long long)len);
+    }
+    return;
+  }
+  *reinterpret_cast<uint32_t*>(counters + 2) = 1;  // table too full: sq_finish takes the sort path
+}
+
+// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store.  The read's list
+// fingerprint is folded on the way (the list is in flight anyway) and entered in the class table.
 __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uint32_t* __restrict__ read_cnt,
                                const uint32_t* __restrict__ batch_off, uint32_t n_reads,
                                const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
                                uint64_t pbase, uint64_t read_base, uint32_t* __restrict__ cand_tid,
-                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off, uint32_t T,
-                               uint32_t hash_bits, uint64_t* __restrict__ rkey, ulonglong2* __restrict__ rfp) {
+                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off,
+                               ClassSlot* __restrict__ ctab, uint32_t cmask, unsigned long long* __restrict__ ccnt) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint64_t dst = pbase + batch_off[r];
@@ -107,7 +148,6 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
   const uint32_t c = read_cnt[r], so = read_soff[r];
   ListHash lh;
   lh.init(c);
-  uint32_t top = T;  // reads without candidates go last (one empty class)
   // blocks of 4 candidates: the eight loads go out together (the kernel waits on latency, the fold is serial)
   for (uint32_t i0 = 0; i0 < c; i0 += 4) {
     uint32_t t[4];
@@ -117,7 +157,6 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
       t[u] = i0 + u < c ? stage_tid[so + i0 + u] : 0u;
       sc[u] = i0 + u < c ? stage_score[so + i0 + u] : 0;
     }
-    if (i0 == 0) top = t[0];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (i0 + u < c) {
@@ -126,31 +165,108 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
         lh.add(t[u], sc[u]);
       }
   }
-  rkey[read_base + r] = lh.key(top, hash_bits, read_base + r);
-  rfp[read_base + r] = make_ulonglong2(lh.h, lh.g);
+  // a read without candidates adds nothing to any EM sum (isoform_assignment.cpp:36-45): it needs no class
+  if (ctab && c) class_insert(ctab, cmask, lh.h ? lh.h : 1ull, lh.g ? lh.g : 1ull, 1u, (uint32_t)(read_base + r), c, ccnt);
 }
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, uint32_t T, uint32_t hash_bits,
-                    uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches) {
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t cmask,
+                    unsigned long long* ccnt, cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
                                                        stage_score, pbase, read_base, cand_tid, cand_score, read_off,
-                                                       T, hash_bits, rkey, static_cast<ulonglong2*>(rfp));
+                                                       static_cast<ClassSlot*>(ctab), cmask, ccnt);
   if (launches) ++*launches;
 }
 
-// ------------------------------------------------------------------ EM equivalence classes
-// EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
-// contribute identical terms, so they are collapsed into one class with a weight.  Reads are
+// a grown table takes over the classes of the old one
+__global__ void class_rehash_kernel(const ClassSlot* __restrict__ old, uint32_t old_cap, ClassSlot* __restrict__ tab,
+                                    uint32_t mask, unsigned long long* __restrict__ scratch_counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= old_cap) return;
+  const ClassSlot sl = old[i];
+  if (sl.h) class_insert(tab, mask, sl.h, sl.g, sl.w, sl.rep, 0u, scratch_counters);
+}
+
+__global__ void class_clear_kernel(ClassSlot* tab, uint32_t cap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) { ClassSlot z; z.h = 0; z.g = 0; z.w = 0; z.rep = 0xFFFFFFFFu; z.pad0 = z.pad1 = 0; tab[i] = z; }
+}
+
+void launch_class_clear(void* tab, uint32_t cap, cudaStream_t s, uint64_t* launches) {
+  if (!cap) return;
+  class_clear_kernel<<<(cap + 255) / 256, 256, 0, s>>>(static_cast<ClassSlot*>(tab), cap);
+  if (launches) ++*launches;
+}
+
+// scratch_counters: 3 u64 the rehash may scribble on (the class counts do not change)
+void launch_class_rehash(const void* old, uint32_t old_cap, void* tab, uint32_t cap, unsigned long long* scratch_counters,
+                         cudaStream_t s, uint64_t* launches) {
+  launch_class_clear(tab, cap, s, launches);
+  if (!old_cap) return;
+  class_rehash_kernel<<<(old_cap + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(old), old_cap,
+                                                            static_cast<ClassSlot*>(tab), cap - 1, scratch_counters);
+  if (launches) ++*launches;
+}
+
+// occupied slots -> (order key, slot): key = best candidate of the class in the high bits, fingerprint below
+__global__ void class_collect_kernel(const ClassSlot* __restrict__ tab, uint32_t cap, const uint32_t* __restrict__ read_off,
+                                     const uint32_t* __restrict__ cand_tid, uint32_t tbits,
+                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+                                     uint32_t* __restrict__ counter) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool occ = i < cap && tab[i].h != 0;
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+  if (!m) return;
+  uint32_t base = 0;
+  if (lane_id() == (uint32_t)__ffs(m) - 1) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+  if (!occ) return;
+  const uint32_t pos = base + __popc(m & ((1u << lane_id()) - 1));
+  const unsigned long long top = cand_tid[read_off[tab[i].rep]];
+  keys[pos] = (top << (64 - tbits)) | (tab[i].h >> tbits);
+  vals[pos] = i;
+}
+
+// classes in their final order: representative read, list length, weight
+__global__ void class_from_sorted_kernel(const uint32_t* __restrict__ slot_of, uint32_t n_classes,
+                                         const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ read_off,
+                                         uint32_t* __restrict__ class_read, uint32_t* __restrict__ class_cnt,
+                                         double* __restrict__ weight) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_classes) return;
+  const ClassSlot sl = tab[slot_of[c]];
+  class_read[c] = sl.rep;
+  class_cnt[c] = read_off[sl.rep + 1] - read_off[sl.rep];
+  weight[c] = (double)sl.w;
+}
+
+void launch_class_collect(const void* tab, uint32_t cap, const uint32_t* read_off, const uint32_t* cand_tid, uint32_t tbits,
+                          uint64_t* keys, uint32_t* vals, uint32_t* counter, cudaStream_t s, uint64_t* launches) {
+  cudaMemsetAsync(counter, 0, 4, s);
+  if (!cap) return;
+  class_collect_kernel<<<(cap + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(tab), cap, read_off, cand_tid, tbits,
+                                                         reinterpret_cast<unsigned long long*>(keys), vals, counter);
+  if (launches) ++*launches;
+}
+
+void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* read_off,
+                              uint32_t* class_read, uint32_t* class_cnt, double* weight, cudaStream_t s, uint64_t* launches) {
+  if (!n_classes) return;
+  class_from_sorted_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(slot_of, n_classes, static_cast<const ClassSlot*>(tab),
+                                                                   read_off, class_read, class_cnt, weight);
+  if (launches) ++*launches;
+}
+
+// ------------------------------------------------------------------ EM equivalence classes, sort path
+// (option exact_classes, candidates set through sq_set_candidates, or a class table that ran full.)  Reads are
 // sorted by (best candidate, hash of the list); a read starts a class when its list differs from its
-// predecessor's.  "Differs" is decided on a 128-bit fingerprint of the list (two independent 64-bit hashes
-// over length, transcripts and scores): comparing the lists themselves costs ~10 random sectors per read
-// (2.8 ms at 20 M reads), the fingerprint one; two different lists collide with probability 2^-128, and a
-// collision would only merge two EM terms.  Sorting by best candidate
-// first also keeps the classes of one gene adjacent, which makes the 1/den gathers of the transcript-major
-// pass local.  Summing w identical terms becomes one multiplication by w: a re-association only.
+// predecessor's: element-wise with exact_classes (~10 random sectors per read, 2.8 ms at 20 M reads), else by
+// the same 128-bit non-cryptographic fingerprint the class table uses (an accidental match of two different
+// lists would merge two EM terms and nothing else).  Ordering by best candidate keeps the classes of one gene
+// adjacent, which makes the 1/den gathers of the transcript-major pass local.  Summing w identical terms
+// becomes one multiplication by w: a re-association only.
 __global__ void class_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
                                  uint32_t T, uint32_t hash_bits, uint64_t* __restrict__ keys,
@@ -233,7 +349,7 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
     out_tid[d + j] = cand_tid[b + j];
     out_score[d + j] = cand_score[b + j];
   }
-  weight[c] = (double)(class_pos[c + 1] - class_pos[c]);
+  if (class_pos) weight[c] = (double)(class_pos[c + 1] - class_pos[c]);  // sort path; the table path wrote it already
 }
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
@@ -383,13 +499,13 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
 // transcript has a few dozen pairs on average, so 8-lane groups keep the lanes busy; G = 32 for deep data.
 template <int G>
 __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
-                                  const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
+                                  const uint32_t* __restrict__ toff, const uint32_t* __restrict__ n_seg_ptr, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
                                   const double* __restrict__ inv_den, const double* __restrict__ pi,
                                   double* __restrict__ partial, const uint32_t* __restrict__ state) {
   if (state[0]) return;
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G, gl = threadIdx.x & (G - 1);
-  const bool valid = w < n_seg;
+  const bool valid = w < *n_seg_ptr;  // the grid covers an upper bound (no host round trip for the exact count)
   double acc = 0.0;
   if (valid) {
     const uint32_t t = seg_tid[w];
@@ -523,13 +639,13 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
 // ------------------------------------------------------------------ assignment (:70-97)
 template <int G>
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
-                                  const uint32_t* __restrict__ toff, uint32_t n_seg, uint32_t seg,
+                                  const uint32_t* __restrict__ toff, const uint32_t* __restrict__ n_seg_ptr, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
                                   const double* __restrict__ tot, const double* __restrict__ weight,
                                   const double* __restrict__ pi, double* __restrict__ partial,
                                   uint32_t* __restrict__ present_u32) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / G, gl = threadIdx.x & (G - 1);
-  const bool valid = w < n_seg;
+  const bool valid = w < *n_seg_ptr;
   uint32_t t = 0;
   double acc = 0.0;
   bool any = false;
@@ -600,7 +716,7 @@ void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uin
 }
 
 // lanes per segment: a transcript-major run averages n_pairs / n_seg pairs
-static inline bool narrow_groups(const EmView& v) { return v.n_seg && v.n_pairs / v.n_seg < 96; }
+static inline bool narrow_groups(const EmView& v) { return v.n_pairs / (v.T ? v.T : 1) < 96; }  // ~pairs per transcript
 
 void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum) {
   if (v.n_reads) {
@@ -611,10 +727,10 @@ void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool w
   if (v.n_seg) {
     if (narrow_groups(v))
       em_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
     else
       em_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
     if (launches) ++*launches;
   }
   if (with_sum) {
@@ -647,11 +763,11 @@ void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cud
   if (v.n_seg) {
     if (narrow_groups(v))
       as_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
+          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
           present_u32);
     else
       as_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.n_seg, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
+          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
           present_u32);
     if (launches) ++*launches;
   }

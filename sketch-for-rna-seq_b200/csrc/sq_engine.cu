@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -139,9 +140,12 @@ struct sq_engine {
   uint32_t* cand_tid = nullptr;
   int32_t* cand_score = nullptr;
   uint32_t* read_off = nullptr;
-  uint64_t* rkey = nullptr;   // per read: EM class sort key (computed by the compaction)
-  void* rfp = nullptr;        // per read: 128-bit list fingerprint
-  bool keys_valid = true;
+  // read classes, built by the compactions (see sq_em.cu): table of 32-byte slots; retired tables wait for reset/destroy
+  DevBuf ctab;
+  uint32_t ct_cap = 0;
+  std::vector<DevBuf> ct_retired;
+  unsigned long long* d_ccnt = nullptr;  // [0] classes, [1] class pairs, [2] low word: table-full flag
+  bool keys_valid = true;                // false: the store was filled by sq_set_candidates, no table
   uint32_t class_hash_bits = 14;
   uint64_t cand_cap = 0, read_cap = 0;
   uint64_t n_reads = 0, n_bases = 0, n_batches = 0;  // n_reads: all enqueued batches
@@ -266,25 +270,15 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
   if (need_reads > e->read_cap) {
     uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
     uint32_t* p = nullptr;
-    uint64_t* pk = nullptr;
-    void* pf = nullptr;
     SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
-    SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
-    SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
     if (e->read_off) {
       SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
-      SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
-      SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
       SQ_CUDA(e, cudaStreamSynchronize(cs));
       SQ_CUDA(e, cudaFree(e->read_off));
-      SQ_CUDA(e, cudaFree(e->rkey));
-      SQ_CUDA(e, cudaFree(e->rfp));
     } else {
       SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), cs));
     }
     e->read_off = p;
-    e->rkey = pk;
-    e->rfp = pf;
     e->read_cap = cap;
   }
   const uint64_t need_pairs = e->P + pairs;
@@ -325,6 +319,29 @@ int ensure_big_scratch(sq_engine* e) {
   SQ_CUDA(e, cudaMemsetAsync(e->big_cnt.p, 0, w * tab * e->nk * 4, e->stream));
   e->launches += 2;
   e->big_ready = true;
+  return SQ_OK;
+}
+
+// The class table must keep its load low: it grows (classes re-entered by a kernel on the tail stream) when the
+// class count last reported by a compaction plus the reads of two more batches passes half of it.  Should
+// it fill up anyway, the kernels raise a flag and sq_finish takes the sort path.
+int ensure_class_table(sq_engine* e, uint32_t batch_reads) {
+  cudaStream_t cs = e->tail_stream;
+  const uint64_t known = e->h_mirror[8];
+  const uint64_t bound = known + 2ull * std::max<uint32_t>(batch_reads, 1u << 16);  // reports lag a batch or two
+  if (e->ct_cap && bound * 2 <= e->ct_cap) return SQ_OK;
+  uint64_t cap = std::max<uint64_t>(e->ct_cap, 1u << 22);
+  while (bound * 2 > cap && cap < (1ull << 30)) cap <<= 1;
+  if (cap == e->ct_cap) return SQ_OK;
+  DevBuf old;
+  std::swap(old, e->ctab);
+  const uint32_t old_cap = e->ct_cap;
+  SQ_CUDA(e, e->ctab.ensure((size_t)cap * 32));
+  e->ct_cap = (uint32_t)cap;
+  SQ_CUDA(e, e->misc.ensure(256));
+  launch_class_rehash(old.p, old_cap, e->ctab.p, e->ct_cap, reinterpret_cast<unsigned long long*>(e->misc.as<char>() + 64), cs,
+                      &e->launches);
+  if (old.p) e->ct_retired.push_back(old);  // still read by the kernel just enqueued: freed at reset / destroy
   return SQ_OK;
 }
 
@@ -396,10 +413,12 @@ int finalize_slot(sq_engine* e, Slot& s) {
     StageScope st(e, 2, cs);
     launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads, s.scan_tmp.as<uint32_t>(),
                           cs, &e->launches);
+    SQ_TRY(ensure_class_table(e, s.n_reads));
     launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
                    s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
-                   e->cand_score, e->read_off, (uint32_t)e->T, e->class_hash_bits, e->rkey, e->rfp, cs,
-                   &e->launches);
+                   e->cand_score, e->read_off, e->ctab.p, e->ct_cap - 1, e->d_ccnt, cs, &e->launches);
+    // the class counts so far reach the host behind the compaction: table growth and sq_finish read them there
+    SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 8, e->d_ccnt, 24, cudaMemcpyDeviceToHost, cs));
     SQ_CUDA(e, cudaGetLastError());
     SQ_CUDA(e, cudaEventRecord(s.done, cs));
   }
@@ -652,8 +671,9 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 16);          // byte 128
   e->d_fail = e->d_flags + 1;                                          // byte 132
   e->d_hcur = reinterpret_cast<uint32_t*>(e->d_totals + 20);           // bytes 160..255 (3 x 8 counters)
-  if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 64, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
-  memset(e->h_mirror, 0, 64);
+  e->d_ccnt = e->d_totals + 17;                                        // bytes 136..159
+  if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 128, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
+  memset(e->h_mirror, 0, 128);
   *out = e;
   return SQ_OK;
 }
@@ -689,8 +709,8 @@ void sq_destroy(sq_engine* e) {
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
   if (e->read_off) cudaFree(e->read_off);
-  if (e->rkey) cudaFree(e->rkey);
-  if (e->rfp) cudaFree(e->rfp);
+  e->ctab.release();
+  for (auto& b : e->ct_retired) b.release();
   if (e->d_totals) cudaFree(e->d_totals);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -742,6 +762,15 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
     if (post_tid[i] >= e->T) return fail(e, SQ_ERR_ARG, "posting %llu names transcript %u >= T", (unsigned long long)i, post_tid[i]);
   KTab& t = e->tab[kidx];
   const uint32_t T = (uint32_t)e->T;
+  const bool trace = getenv("SQ_TRACE") != nullptr;
+  auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_lap = wall();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const double n = wall();
+    fprintf(stderr, "[sq trace] load_index k-index %u: %-22s %.3f s\n", kidx, what, n - t_lap);
+    t_lap = n;
+  };
   // Posting lists with identical content are stored once (all k-mers of an exon shared by the same isoforms
   // have the same list): the table maps a key to the id of its DISTINCT list, so equal ids mean equal lists and
   // a read whose hits share a list merges it once with a weight.  Host threads: (1) sort the lists that are not
@@ -786,6 +815,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
       lh[i] = h ? h : 1;
     }
   });
+  lap("sort check + hashes");
   // (2) per-partition de-duplication: rep = first key of each distinct list, support = keys that share it
   std::vector<std::vector<uint32_t>> rep(nth), support(nth);
   std::vector<uint32_t> loc(nkeys, SQ_EMPTY);  // distinct-list number inside the partition
@@ -834,6 +864,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
     for (uint64_t i = i0; i < i1; ++i)
       if (loc[i] != SQ_EMPTY) lid[i] = (uint32_t)(lbase[part_of(lh[i])] + loc[i]);
   });
+  lap("list de-duplication");
   // (3) Internal transcript numbering.  The vote kernels want the transcripts that share posting lists (the
   // isoforms of a gene) to have neighbouring ids, whatever order the caller's ids came in: a reference-written
   // index stores its transcripts in unordered_map order (src/data_io.cpp:185-196).  Union-find over the lists
@@ -870,6 +901,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
     SQ_CUDA(e, cudaMemcpy(e->d_ext_of.p, e->ext_of.data(), (size_t)T * 4, cudaMemcpyHostToDevice));
     e->perm_ready = true;
   }
+  lap("renumbering");
   // (4) per distinct list: 8 header words + the internal ids ascending (last one flagged), 32-byte aligned; and
   // the 16-byte entry of the header table
   std::vector<uint32_t> loff(n_lists + 1, 0);
@@ -926,6 +958,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
     }
   });
   if (n_lists >= 0x7FFFFFFFull) return fail(e, SQ_ERR_CAPACITY, "more than 2^31 distinct posting lists for one k");
+  lap("headers + id lists");
   // keys with a list, in ascending order, each once: the reference's loader does mapping[kmer] = vec
   // (src/data_io.cpp:297), so of a key that a hand-made index repeats the LAST occurrence counts
   std::vector<uint32_t> k2, d2;
@@ -955,6 +988,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
       d2.swap(ds);
     }
   }
+  lap("key order");
   const uint64_t n2 = k2.size();
   const uint32_t n_sectors = n2 ? k2.back() / SQ_BMAP_BITS + 1 : 1;
   SQ_CUDA(e, t.bmap.ensure((size_t)n_sectors * 32));
@@ -985,6 +1019,7 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   dcnt.release();
   dexcl.release();
   dtmp.release();
+  lap("upload + bitmap");
   t.present = true;
   return SQ_OK;
 }
@@ -1095,6 +1130,16 @@ int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_w
   return SQ_OK;
 }
 
+void* sq_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void sq_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int sq_sync(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_CUDA(e, cudaSetDevice(e->device));
@@ -1115,7 +1160,10 @@ int sq_reset_reads(sq_engine* e) {
   SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 256, e->stream));
   if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
-  memset(e->h_mirror, 0, 64);
+  memset(e->h_mirror, 0, 128);
+  if (e->ct_cap) launch_class_clear(e->ctab.p, e->ct_cap, e->stream, &e->launches);
+  for (auto& b : e->ct_retired) b.release();
+  e->ct_retired.clear();
   e->P = 0;
   e->ovf_total = 0;
   e->slow_total = 0;
@@ -1267,7 +1315,31 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_CUDA(e, e->cls_read.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_pos.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_weight.ensure((R + 2) * 8));
-    if (R) {
+    const bool use_table = R && e->keys_valid && !e->exact_classes && e->ct_cap && (e->h_mirror[10] & 0xFFFFFFFFull) == 0;
+    if (use_table) {
+      // the classes were collected while the batches arrived: order them and copy their lists
+      n_classes = (uint32_t)e->h_mirror[8];
+      n_cpairs = (uint32_t)e->h_mirror[9];
+      const uint64_t nmax = std::max<uint64_t>(std::max<uint64_t>(P, n_classes), 1);
+      SQ_CUDA(e, e->keys_a.ensure((nmax + 1) * 8));
+      SQ_CUDA(e, e->keys_b.ensure((nmax + 1) * 8));
+      SQ_CUDA(e, e->vals_a.ensure((nmax + 1) * 4));
+      SQ_CUDA(e, e->vals_b.ensure((nmax + 1) * 4));
+      SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(nmax) * 4));
+      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, (uint64_t)n_classes + 1)) * 4));
+      const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(T));
+      launch_class_collect(e->ctab.p, e->ct_cap, e->read_off, e->cand_tid, tbits, e->keys_a.as<uint64_t>(),
+                           e->vals_a.as<uint32_t>(), reinterpret_cast<uint32_t*>(e->misc.as<char>() + 96), st, &e->launches);
+      uint64_t* skeys = nullptr;
+      uint32_t* slot_of = nullptr;
+      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(), e->vals_b.as<uint32_t>(),
+                        n_classes, 64, e->sort_tmp.as<uint32_t>(), &skeys, &slot_of, st, &e->launches);
+      launch_class_from_sorted(slot_of, n_classes, e->ctab.p, e->read_off, e->cls_read.as<uint32_t>(),
+                               e->em_cnt.as<uint32_t>(), e->cls_weight.as<double>(), st, &e->launches);
+      launch_class_gather(e->cls_read.as<uint32_t>(), nullptr, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(),
+                          n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid, e->cand_score,
+                          e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->cls_weight.as<double>(), st, &e->launches);
+    } else if (R) {
       SQ_CUDA(e, e->keys_a.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->keys_b.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->vals_a.ensure((std::max(P, R) + 1) * 4));
@@ -1276,16 +1348,10 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R + 1)) * 4));
       const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1));
       const uint32_t hash_bits = e->class_hash_bits;
-      const void* fp = e->rfp;
-      if (e->keys_valid) {
-        // keys and fingerprints were produced batch by batch by the compaction (the sort works on a copy)
-        SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));
-      } else {
-        SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
-        launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
-                          e->cls_fp.p, st, &e->launches);
-        fp = e->cls_fp.p;
-      }
+      SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
+      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
+                        e->cls_fp.p, st, &e->launches);
+      const void* fp = e->cls_fp.p;
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
@@ -1316,8 +1382,9 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
                       &e->launches);
     launch_tmajor(keys, n_cpairs, T, e->em_seg, e->toff.as<uint32_t>(), e->tm_read.as<uint32_t>(),
                   e->nseg.as<uint32_t>(), e->seg_off.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), st, &e->launches);
-    SQ_CUDA(e, cudaMemcpyAsync(&n_seg, e->seg_off.as<uint32_t>() + T, 4, cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(e, cudaStreamSynchronize(st));
+    // segments: at most one per em_seg pairs plus one per transcript; the exact count stays on the device
+    // (seg_off[T]), the kernels that walk the segments read it there
+    n_seg = (uint32_t)(n_cpairs / e->em_seg + T + 1);
     SQ_CUDA(e, e->seg_tid.ensure(((size_t)n_seg + 1) * 4));
     SQ_CUDA(e, e->seg_begin.ensure(((size_t)n_seg + 1) * 4));
     SQ_CUDA(e, e->partial.ensure(((size_t)n_seg + 1) * 8));

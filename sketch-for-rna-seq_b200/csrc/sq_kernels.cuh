@@ -18,7 +18,7 @@ struct EmView {
   const uint32_t* seg_off;    // per transcript: first segment (T+1 entries)
   const uint32_t* seg_tid;
   const uint32_t* seg_begin;
-  uint32_t n_seg;
+  uint32_t n_seg;             // upper bound (grids); the exact count is seg_off[T] on the device
   uint32_t seg;
   uint64_t n_pairs;           // rows of the transcript-major copy
   uint32_t T;
@@ -43,8 +43,16 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, uint32_t T, uint32_t hash_bits,
-                    uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches);
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t cmask,
+                    unsigned long long* ccnt, cudaStream_t s, uint64_t* launches);
+// read-class table (32-byte slots), see sq_em.cu
+void launch_class_clear(void* tab, uint32_t cap, cudaStream_t s, uint64_t* launches);
+void launch_class_rehash(const void* old, uint32_t old_cap, void* tab, uint32_t cap, unsigned long long* scratch_counters,
+                         cudaStream_t s, uint64_t* launches);
+void launch_class_collect(const void* tab, uint32_t cap, const uint32_t* read_off, const uint32_t* cand_tid, uint32_t tbits,
+                          uint64_t* keys, uint32_t* vals, uint32_t* counter, cudaStream_t s, uint64_t* launches);
+void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* read_off,
+                              uint32_t* class_read, uint32_t* class_cnt, double* weight, cudaStream_t s, uint64_t* launches);
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
                        uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);

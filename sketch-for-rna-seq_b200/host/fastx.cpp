@@ -216,6 +216,161 @@ std::vector<FastqFile::Rec> FastqFile::admitted_records(uint32_t max_k, int n_th
   return out;
 }
 
+bool FastqScanner::next(size_t max_records, uint64_t max_seq_bytes, RawChunk* out) {
+  out->recs.clear();
+  out->seq_bytes = 0;
+  const char* d = d_;
+  const size_t n = n_;
+  auto line_end = [&](size_t p) {  // position of the line's '\n', or n
+    const void* q = p < n ? memchr(d + p, '\n', n - p) : nullptr;
+    return q ? (size_t)(static_cast<const char*>(q) - d) : n;
+  };
+  while (pos_ < n && out->recs.size() < max_records && out->seq_bytes < max_seq_bytes) {
+    const size_t b = pos_, e = line_end(b);
+    pos_ = e + 1;
+    if (e == b || d[b] != '@') continue;  // main.cpp:121-123
+    FastqFile::Rec r;
+    r.id_off = b + 1;
+    r.id_len = (uint32_t)(e - b - 1);
+    if (pos_ < n) {
+      const size_t se = line_end(pos_);
+      r.seq_off = pos_;
+      r.seq_len = (uint32_t)(se - pos_);
+      pos_ = se + 1;
+    } else {
+      r.seq_off = n;
+      r.seq_len = 0;  // getline on EOF leaves an empty sequence
+    }
+    for (int skip = 0; skip < 2 && pos_ < n; ++skip) pos_ = line_end(pos_) + 1;  // '+', quality
+    out->recs.push_back(r);
+    out->seq_bytes += r.seq_len;
+    ++seen_;
+  }
+  if (pos_ > n) pos_ = n;
+  return !out->recs.empty() || pos_ < n;
+}
+
+IdSet::IdSet(uint64_t expected) {
+  uint64_t cap = 1024;
+  while (cap < expected * 2 + 16) cap <<= 1;
+  mask_ = cap - 1;
+  limit_ = cap - cap / 4;
+  slots_ = calloc(cap, sizeof(uint64_t));
+  count_ = calloc(1, sizeof(uint64_t));
+  if (!slots_ || !count_) throw std::runtime_error("IdSet: out of memory");
+}
+IdSet::~IdSet() {
+  free(slots_);
+  free(count_);
+}
+void IdSet::prefetch(uint64_t h) const {
+  if (h == 0) h = 0x9E3779B97F4A7C15ull;
+  __builtin_prefetch(static_cast<const uint64_t*>(slots_) + (((h * 0x9E3779B97F4A7C15ull) >> 20) & mask_), 1, 0);
+}
+bool IdSet::insert(uint64_t h) {
+  if (h == 0) h = 0x9E3779B97F4A7C15ull;  // 0 marks a free slot
+  uint64_t* slots = static_cast<uint64_t*>(slots_);
+  uint64_t* count = static_cast<uint64_t*>(count_);
+  if (__atomic_load_n(count, __ATOMIC_RELAXED) >= limit_) return false;
+  for (uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> 20;; ++s) {
+    uint64_t* slot = slots + (s & mask_);
+    uint64_t cur = __atomic_load_n(slot, __ATOMIC_RELAXED);
+    if (cur == 0) {
+      if (__atomic_compare_exchange_n(slot, &cur, h, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        __atomic_fetch_add(count, 1, __ATOMIC_RELAXED);
+        return true;
+      }
+    }
+    if (cur == h) return false;
+  }
+}
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+// 32 bases -> 8 packed bytes; returns false when a byte is not one of A C G T.  code = x ^ (x >> 1) with
+// x = (c >> 1) & 3 maps A C G T to 0 1 2 3; maddubs / madd fold four 2-bit codes into one byte.
+__attribute__((target("avx2"))) static inline bool pack32_avx2(const unsigned char* s, uint8_t* dst) {
+  const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s));
+  const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(c, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(c, _mm256_set1_epi8('C'))),
+                                     _mm256_or_si256(_mm256_cmpeq_epi8(c, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(c, _mm256_set1_epi8('T'))));
+  if (_mm256_movemask_epi8(ok) != -1) return false;
+  const __m256i x = _mm256_and_si256(_mm256_srli_epi16(c, 1), _mm256_set1_epi8(3));
+  const __m256i code = _mm256_xor_si256(x, _mm256_and_si256(_mm256_srli_epi16(x, 1), _mm256_set1_epi8(1)));
+  const __m256i p16 = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x0401));    // c0 + 4*c1 per 16-bit lane
+  const __m256i p32 = _mm256_madd_epi16(p16, _mm256_set1_epi32(0x00100001));    // + 16*(c2 + 4*c3) per 32-bit lane
+  const __m256i sh = _mm256_shuffle_epi8(p32, _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                               0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+  const uint32_t lo = (uint32_t)_mm256_extract_epi32(sh, 0), hi = (uint32_t)_mm256_extract_epi32(sh, 4);
+  memcpy(dst, &lo, 4);
+  memcpy(dst + 4, &hi, 4);
+  return true;
+}
+static const bool kHaveAvx2 = __builtin_cpu_supports("avx2");
+#else
+static const bool kHaveAvx2 = false;
+static inline bool pack32_avx2(const unsigned char*, uint8_t*) { return false; }
+#endif
+
+bool admit_and_pack(const char* d, const RawChunk& c, uint32_t max_k, IdSet* ids, PackedView* out) {
+  // code table with an "invalid" bit: anything but upper-case ACGT refuses the read (data_io.cpp:17-34)
+  static const struct Adm {
+    uint8_t code[256];
+    Adm() {
+      memset(code, 0x80, sizeof(code));
+      code[(int)'A'] = 0; code[(int)'C'] = 1; code[(int)'G'] = 2; code[(int)'T'] = 3;
+    }
+  } adm;
+  bool unique = true;
+  std::vector<uint64_t> hs;  // id hashes of the admitted reads: inserted at the end, slots prefetched ahead
+  if (ids) hs.reserve(c.recs.size());
+  uint64_t pos = 0;  // next free base (multiple of 4)
+  uint32_t nr = 0;
+  uint8_t* bytes = reinterpret_cast<uint8_t*>(out->words);
+  for (const FastqFile::Rec& r : c.recs) {
+    const uint32_t L = r.seq_len;
+    if (L < max_k) continue;  // main.cpp:136-138
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(d + r.seq_off);
+    uint8_t* dst = bytes + pos / 4;
+    uint32_t bad = 0, j = 0;
+    if (kHaveAvx2)
+      for (; j + 32 <= L; j += 32)
+        if (!pack32_avx2(s + j, dst + j / 4)) { bad = 0x80; break; }
+    for (; j + 4 <= L && !(bad & 0x80); j += 4) {
+      const uint32_t a = adm.code[s[j]], b = adm.code[s[j + 1]], cc = adm.code[s[j + 2]], e = adm.code[s[j + 3]];
+      bad |= a | b | cc | e;
+      dst[j / 4] = (uint8_t)(a | b << 2 | cc << 4 | e << 6);
+    }
+    if (j < L && !(bad & 0x80)) {
+      uint32_t v = 0;
+      for (uint32_t q = 0; j + q < L; ++q) { const uint32_t a = adm.code[s[j + q]]; bad |= a; v |= (a & 3) << (2 * q); }
+      dst[j / 4] = (uint8_t)v;
+    }
+    if (bad & 0x80) continue;  // refused: the bytes written are overwritten by the next read
+    if (ids) {
+      uint64_t h = 0xcbf29ce484222325ull;
+      const unsigned char* p = reinterpret_cast<const unsigned char*>(d + r.id_off);
+      for (uint32_t q = 0; q < r.id_len; ++q) { h ^= p[q]; h *= 0x100000001b3ull; }
+      hs.push_back(h ^ (h >> 29));
+    }
+    out->base_off[nr] = (uint32_t)pos;
+    out->len[nr] = L;
+    ++nr;
+    out->n_bases = pos + L;
+    pos += ((uint64_t)L + 3) & ~3ull;
+  }
+  for (size_t i = 0; i < hs.size(); ++i) {
+    if (i + 12 < hs.size()) ids->prefetch(hs[i + 12]);
+    if (!ids->insert(hs[i])) unique = false;
+  }
+  // zero the tail so that the word count can be rounded up to a multiple of 4 (+4 of padding)
+  const uint64_t used_bytes = pos / 4;
+  out->n_words = (((out->n_bases + 15) / 16 + 3) & ~(uint64_t)3) + 4;
+  memset(bytes + used_bytes, 0, out->n_words * 4 - used_bytes);
+  out->n_reads = nr;
+  if (nr == 0) { out->n_bases = 0; }
+  return unique;
+}
+
 void pack_sequences(const char* const* seqs, const uint32_t* lens, size_t n, int n_threads, PackedBatch* out) {
   out->base_off.resize(n);
   out->len.assign(lens, lens + n);

@@ -40,6 +40,58 @@ class FastqFile {
   size_t size_ = 0;
 };
 
+// ---- streaming ingest: the file is cut into chunks of records while it is being scanned, every chunk is
+// admitted + packed by a worker into a caller-supplied (page-locked) buffer and can be pushed to a GPU right
+// away.  Duplicate read ids (last one wins, main.cpp:147) are a whole-file property: the chunks only RECORD every
+// id in a concurrent set and report whether any id came twice; the caller then redoes the file through
+// admitted_records().  (FASTQ ids are unique in practice; the exact path stays for files where they are not.)
+struct RawChunk {
+  std::vector<FastqFile::Rec> recs;
+  uint64_t seq_bytes = 0;
+};
+// Sequential record scanner over a mapped FASTQ file (same state machine as admitted_records()).
+class FastqScanner {
+ public:
+  explicit FastqScanner(const FastqFile& f) : d_(f.data()), n_(f.size()) {}
+  // next chunk of at most max_records records / max_seq_bytes sequence bytes; false when the file is exhausted
+  bool next(size_t max_records, uint64_t max_seq_bytes, RawChunk* out);
+  uint64_t records_seen() const { return seen_; }
+
+ private:
+  const char* d_;
+  size_t n_, pos_ = 0;
+  uint64_t seen_ = 0;
+};
+
+// concurrent set of 64-bit id hashes (open addressing, lock-free)
+class IdSet {
+ public:
+  explicit IdSet(uint64_t expected);
+  ~IdSet();
+  // false when h was already there (duplicate id, or a 64-bit collision: the caller falls back to the exact path
+  // either way) or when the set is full
+  bool insert(uint64_t h);
+  void prefetch(uint64_t h) const;  // pull h's slot towards the cache ahead of insert()
+
+ private:
+  void* slots_;
+  uint64_t mask_, limit_;
+  void* count_;
+};
+
+// admitted reads of a chunk, packed into caller-supplied buffers (capacity: words for `seq_bytes` bases + 8,
+// one base_off / len entry per record)
+struct PackedView {
+  uint32_t* words = nullptr;
+  uint32_t* base_off = nullptr;
+  uint32_t* len = nullptr;
+  uint64_t n_words = 0, n_bases = 0;
+  uint32_t n_reads = 0;
+};
+// admission (ACGT only, length >= max_k) + packing in one pass over the sequence bytes; ids of admitted reads go
+// into `ids` (may be NULL).  Returns false if an admitted id was already in the set.
+bool admit_and_pack(const char* file_data, const RawChunk& c, uint32_t max_k, IdSet* ids, PackedView* out);
+
 // 2-bit packing (A=0 C=1 G=2 T=3, 16 bases per uint32, include/sketchquant.h).  Sequence i starts at base
 // base_off[i] = next multiple of 4 after the previous one.  Lower-case acgt/u pack like upper case (the hash
 // treats them alike); callers split sequences at other characters first.

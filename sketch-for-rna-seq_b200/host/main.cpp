@@ -12,6 +12,7 @@
 // src/main.cpp:43,185,188), --report FILE (JSON timing report), --index-cache / SQ_INDEX_CACHE=1 (keep a
 // parsed copy of the index next to it as <index>.sqidx, used only while the index file is unchanged).
 #include <getopt.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -19,7 +20,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <iostream>
 #include <memory>
 #include <mutex>
@@ -71,9 +74,10 @@ void print_help(const std::string& program_name) {  // main.cpp:24-40, verbatim 
   std::cout << "  " << program_name << " quant <index_file> <reads.fastq> <output>" << std::endl;
 }
 
-[[noreturn]] void die(sq_engine* e, int rc, const char* what) {
+[[noreturn]] void die(sq_engine* e, int rc, const char* what) {  // may be called from a worker thread
   std::cerr << "sketchquant: " << what << " failed (" << rc << "): " << sq_last_error(e) << std::endl;
-  std::exit(2);
+  std::cout.flush();
+  _exit(2);
 }
 #define SQ(e, call)                    \
   do {                                 \
@@ -168,6 +172,61 @@ void output_to_csv(const std::string& path, const std::vector<std::string>& name
   out.close();
 }
 
+// small blocking queue for the ingest pipeline
+template <class T>
+class Channel {
+ public:
+  explicit Channel(size_t cap) : cap_(cap) {}
+  bool push(T v) {  // false when the channel was aborted
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return q_.size() < cap_ || abort_; });
+    if (abort_) return false;
+    q_.push_back(std::move(v));
+    cv_.notify_all();
+    return true;
+  }
+  bool pop(T* out) {  // false when closed and drained, or aborted
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !q_.empty() || closed_ || abort_; });
+    if (abort_ || q_.empty()) return false;
+    *out = std::move(q_.front());
+    q_.pop_front();
+    cv_.notify_all();
+    return true;
+  }
+  void close() { std::lock_guard<std::mutex> lk(mu_); closed_ = true; cv_.notify_all(); }
+  void abort() { std::lock_guard<std::mutex> lk(mu_); abort_ = true; cv_.notify_all(); }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<T> q_;
+  size_t cap_;
+  bool closed_ = false, abort_ = false;
+};
+
+// a chunk of admitted, packed reads in page-locked memory (sq_host_alloc)
+struct PinnedBatch {
+  void* mem = nullptr;
+  size_t cap = 0;
+  PackedView v;
+  void ensure(uint64_t seq_bytes, size_t n_recs) {
+    const size_t words = (size_t)((seq_bytes + 4 * n_recs) / 16 + 16);
+    const size_t need = words * 4 + n_recs * 8 + 256;
+    if (need > cap) {
+      if (mem) sq_host_free(mem);
+      cap = need + need / 4;
+      mem = sq_host_alloc(cap);
+      if (!mem) throw std::runtime_error("cannot allocate page-locked host memory");
+    }
+    v = PackedView();
+    v.words = static_cast<uint32_t*>(mem);
+    v.base_off = v.words + words;
+    v.len = v.base_off + n_recs;
+  }
+  void release() { if (mem) sq_host_free(mem); mem = nullptr; cap = 0; }
+};
+
 // quantification (main.cpp:165-197)
 void quantification(const std::string& index_path, const std::string& reads_path, const std::string& output_path,
                     std::vector<unsigned>& kmer_lengths, const Options& opt) {
@@ -179,8 +238,9 @@ void quantification(const std::string& index_path, const std::string& reads_path
   const double t_index = now();
   if (kmer_lengths.empty()) throw std::runtime_error("no k-mer length available");
   const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
+  const bool trace = getenv("SQ_TRACE") != nullptr;
 
-  if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] index file parsed            %.3f s\n", now() - t_start);
+  if (trace) fprintf(stderr, "[sq trace] index file parsed            %.3f s\n", now() - t_start);
   int threads = opt.threads > 0 ? opt.threads : (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   const size_t T = idx.names.size();
   std::vector<double> pi(T, 0.0), numreads(T, 0.0);
@@ -189,6 +249,7 @@ void quantification(const std::string& index_path, const std::string& reads_path
   sq_stats stats;
   memset(&stats, 0, sizeof(stats));
   uint64_t n_seen = 0, R = 0;
+  bool exact_path = false;
 
   if (T == 0) {
     // unreadable/empty index: upstream carries on with empty maps and writes a header-only CSV
@@ -211,27 +272,67 @@ void quantification(const std::string& index_path, const std::string& reads_path
     std::vector<sq_engine*> eng(G, nullptr);
     uint8_t uid[SQ_NCCL_ID_BYTES];
     if (G > 1) SQ(nullptr, sq_nccl_unique_id(uid));
-    // One host thread per GPU.  Each creates its engine and index replica right away (CUDA context, table
-    // build) while the main thread scans the FASTQ; then it packs and pushes its contiguous share of records.
-    const size_t chunk_reads = 1u << 21;
+    FastqFile fq(reads_path);  // an unopenable file throws like upstream
+
+    // ---- pipeline: one scanner cuts the file into chunks of records (by reads AND by bases: a chunk of long
+    // reads stays far below the engine's batch limits); workers admit + pack each chunk into a page-locked
+    // buffer; one pusher per GPU creates its engine and index replica, then hands ready chunks to sq_push_reads
+    // while scanning and packing go on.
+    const size_t chunk_reads = 1u << 18;
+    const uint64_t chunk_bases = 1ull << 26;
+    const int W = std::max(1, threads - 1);
+    Channel<RawChunk> raw((size_t)W + 2);
+    Channel<PinnedBatch*> ready((size_t)2 * G + 2);
+    Channel<PinnedBatch*> pool((size_t)W + 2 * G + 4);
+    std::vector<PinnedBatch> buffers((size_t)W + 2 * G + 2);
+    for (auto& bf : buffers) pool.push(&bf);
+    IdSet ids(fq.size() / 150 + 1024);
+    std::atomic<bool> ids_unique{true};
+    std::atomic<uint64_t> admitted{0}, seen{0};
+    std::mutex err_mu;
+    std::string first_error;
+    auto fail_all = [&](const std::string& what) {
+      { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = what; }
+      raw.abort(); ready.abort(); pool.abort();
+    };
+    std::thread scanner([&] {
+      try {
+        FastqScanner sc(fq);
+        RawChunk c;
+        while (sc.next(chunk_reads, chunk_bases, &c)) {
+          if (!c.recs.empty() && !raw.push(std::move(c))) break;
+          c = RawChunk();
+        }
+        seen = sc.records_seen();
+      } catch (const std::exception& ex) { fail_all(ex.what()); }
+      raw.close();
+    });
+    std::atomic<int> workers_left{W};
     std::vector<std::thread> workers;
-    std::vector<double> tr(G, 0), tc(G, 0), te(G, 0);
-    std::vector<std::vector<double>> pis(G), nrs(G);
-    std::vector<std::vector<uint8_t>> prs(G);
-    std::vector<sq_stats> sts(G);
-    std::mutex mu;
-    std::condition_variable cv;
-    bool reads_ready = false, reads_failed = false;
-    const FastqFile* fqp = nullptr;
-    std::vector<FastqFile::Rec> recs;
-    for (int g = 0; g < G; ++g) {
-      workers.emplace_back([&, g] {
+    for (int w = 0; w < W; ++w)
+      workers.emplace_back([&] {
+        try {
+          RawChunk c;
+          while (raw.pop(&c)) {
+            PinnedBatch* bf = nullptr;
+            if (!pool.pop(&bf)) break;
+            bf->ensure(c.seq_bytes, c.recs.size());
+            if (!admit_and_pack(fq.data(), c, kmax, &ids, &bf->v)) ids_unique = false;
+            admitted += bf->v.n_reads;
+            if (bf->v.n_reads == 0) { pool.push(bf); continue; }
+            if (!ready.push(bf)) break;
+          }
+        } catch (const std::exception& ex) { fail_all(ex.what()); }
+        if (--workers_left == 0) ready.close();
+      });
+    std::vector<std::thread> pushers;
+    for (int g = 0; g < G; ++g)
+      pushers.emplace_back([&, g] {
         sq_engine* e = nullptr;
         int rc = sq_create(&e, g, (uint32_t)k32.size(), k32.data(), sq_threshold_from_fraction((double)opt.sketch_size),
                            opt.chain_fraction, T);
         if (rc != SQ_OK) die(nullptr, rc, "sq_create");
         eng[g] = e;
-        if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] gpu %d engine created           %.3f s since start\n", g, now() - t_start);
         if (opt.report.size()) sq_set_profiling(e, 1);
         for (size_t ki = 0; ki < k32.size(); ++ki) {
           auto it = idx.maps.find(k32[ki]);
@@ -240,69 +341,78 @@ void quantification(const std::string& index_path, const std::string& reads_path
           SQ(e, sq_load_index(e, (uint32_t)ki, P.keys.size(), P.keys.data(), P.off.data(), P.tid.data()));
         }
         if (G > 1) SQ(e, sq_comm_init(e, G, g, uid));
-        if (getenv("SQ_TRACE")) fprintf(stderr, "[sq trace] gpu %d engine+index ready      %.3f s since start\n", g, now() - t_start);
-        {
-          std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return reads_ready || reads_failed; });
-          if (reads_failed) return;
+        if (trace) fprintf(stderr, "[sq trace] gpu %d engine+index ready      %.3f s since start\n", g, now() - t_start);
+        PinnedBatch* bf = nullptr;
+        while (ready.pop(&bf)) {
+          SQ(e, sq_push_reads(e, bf->v.words, bf->v.n_words, bf->v.base_off, bf->v.len, bf->v.n_reads));
+          pool.push(bf);
         }
-        const FastqFile& fq = *fqp;
+      });
+    scanner.join();
+    for (auto& w : workers) w.join();
+    for (auto& p : pushers) p.join();
+    if (!first_error.empty()) throw std::runtime_error(first_error);
+    n_seen = seen;
+    R = admitted;
+    if (trace) fprintf(stderr, "[sq trace] streamed %llu reads              %.3f s since start\n", (unsigned long long)R, now() - t_start);
+
+    auto on_all_gpus = [&](auto&& fn) {
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; ++g) th.emplace_back([&, g] { fn(g); });
+      for (auto& t : th) t.join();
+    };
+    if (!ids_unique) {
+      // some read id came twice (or the id set overflowed): later duplicates replace earlier ones
+      // (read_sketches[read.id] = ..., main.cpp:147), a whole-file rule -- redo the reads through the exact scan
+      exact_path = true;
+      if (trace) fprintf(stderr, "[sq trace] duplicate read ids: exact path\n");
+      std::vector<FastqFile::Rec> recs = fq.admitted_records(kmax, threads, &n_seen);
+      R = recs.size();
+      on_all_gpus([&](int g) {
+        sq_engine* e = eng[g];
+        SQ(e, sq_reset_reads(e));
         const uint64_t per = (R + G - 1) / G, lo = std::min<uint64_t>(R, g * per), hi = std::min<uint64_t>(R, lo + per);
-        PackedBatch pb[2];
+        PackedBatch pb;
         std::vector<const char*> ptr;
         std::vector<uint32_t> len;
-        int which = 0;
-        for (uint64_t b = lo; b < hi; b += chunk_reads) {
-          const uint64_t n = std::min<uint64_t>(chunk_reads, hi - b);
-          ptr.resize(n);
-          len.resize(n);
-          for (uint64_t i = 0; i < n; ++i) {
-            ptr[i] = fq.data() + recs[b + i].seq_off;
-            len[i] = recs[b + i].seq_len;
+        for (uint64_t b = lo; b < hi;) {
+          ptr.clear();
+          len.clear();
+          uint64_t bases = 0;
+          while (b < hi && ptr.size() < chunk_reads && bases < chunk_bases) {  // chunks by reads and by bases
+            ptr.push_back(fq.data() + recs[b].seq_off);
+            len.push_back(recs[b].seq_len);
+            bases += recs[b].seq_len;
+            ++b;
           }
-          PackedBatch& P = pb[which];
-          which ^= 1;
-          pack_sequences(ptr.data(), len.data(), n, std::max(1, threads / G), &P);
-          SQ(e, sq_push_reads(e, P.words.data(), P.words.size(), P.base_off.data(), P.len.data(), (uint32_t)n));
+          pack_sequences(ptr.data(), len.data(), ptr.size(), std::max(1, threads / G), &pb);
+          SQ(e, sq_push_reads(e, pb.words.data(), pb.words.size(), pb.base_off.data(), pb.len.data(), (uint32_t)ptr.size()));
         }
-        tr[g] = now();
-        SQ(e, sq_sync(e));
-        tc[g] = now();
-        pis[g].resize(T);
-        nrs[g].resize(T);
-        prs[g].resize(T);
-        int iters = 0;
-        SQ(e, sq_finish(e, G > 1 ? 0 : R, opt.em_iters, opt.em_tol, pis[g].data(), nrs[g].data(), prs[g].data(), &iters));
-        te[g] = now();
-        sq_get_stats(e, &sts[g]);
       });
     }
-    // main thread: FASTQ scan (an unopenable file throws like upstream; release the workers first)
-    std::unique_ptr<FastqFile> fq;
-    try {
-      fq.reset(new FastqFile(reads_path));
-      recs = fq->admitted_records(kmax, threads, &n_seen);
-    } catch (...) {
-      { std::lock_guard<std::mutex> lk(mu); reads_failed = true; }
-      cv.notify_all();
-      for (auto& w : workers) w.join();
-      throw;
-    }
-    R = recs.size();
-    fqp = fq.get();
-    { std::lock_guard<std::mutex> lk(mu); reads_ready = true; }
-    cv.notify_all();
-    for (auto& w : workers) w.join();
-    std::cout << "Loading read completed" << std::endl;
+    for (auto& bf : buffers) bf.release();
+    std::cout << "Loading read completed" << std::endl;  // upstream's read stage includes the sketching (main.cpp:182)
+    t_reads = now();
+    on_all_gpus([&](int g) { SQ(eng[g], sq_sync(eng[g])); });
     std::cout << "Sparse chaining completed" << std::endl;
+    t_chain = now();
+    std::vector<std::vector<double>> pis(G), nrs(G);
+    std::vector<std::vector<uint8_t>> prs(G);
+    std::vector<sq_stats> sts(G);
+    on_all_gpus([&](int g) {
+      pis[g].resize(T);
+      nrs[g].resize(T);
+      prs[g].resize(T);
+      int iters = 0;
+      SQ(eng[g], sq_finish(eng[g], G > 1 ? 0 : R, opt.em_iters, opt.em_tol, pis[g].data(), nrs[g].data(), prs[g].data(), &iters));
+      sq_get_stats(eng[g], &sts[g]);
+    });
     std::cout << "EM estimation completed" << std::endl;
     std::cout << "Read assignment completed" << std::endl;
+    t_em = now();
     pi = pis[0];
     numreads = nrs[0];
     present = prs[0];
-    t_reads = *std::max_element(tr.begin(), tr.end());
-    t_chain = *std::max_element(tc.begin(), tc.end());
-    t_em = *std::max_element(te.begin(), te.end());
     stats = sts[0];
     for (int g = 1; g < G; ++g) {
       stats.reads += sts[g].reads; stats.bases += sts[g].bases; stats.sketch_hashes += sts[g].sketch_hashes;
@@ -316,7 +426,7 @@ void quantification(const std::string& index_path, const std::string& reads_path
     std::ofstream r(opt.report);
     const double t_end = now();
     r << "{\"records_seen\": " << n_seen << ", \"reads_admitted\": " << R << ", \"transcripts\": " << T
-      << ", \"gpus\": " << opt.gpus << ", \"host_threads\": " << threads
+      << ", \"gpus\": " << opt.gpus << ", \"host_threads\": " << threads << ", \"duplicate_id_path\": " << (exact_path ? "true" : "false")
       << ", \"s_load_index\": " << (t_index - t_start) << ", \"s_parse_pack_push\": " << (t_reads - t_index)
       << ", \"s_vote_drain\": " << (t_chain - t_reads) << ", \"s_em_assign\": " << (t_em - t_chain)
       << ", \"s_total\": " << (t_end - t_start) << ", \"reads_per_s_quant\": " << (R / std::max(1e-9, t_em - t_index))
@@ -395,6 +505,79 @@ int main(int argc, char* argv[]) {
     std::cout << "records " << seen << " admitted " << recs.size() << "\n";
     for (auto& r : recs)
       std::cout << std::string(fq.data() + r.id_off, r.id_len) << "\t" << std::string(fq.data() + r.seq_off, r.seq_len) << "\n";
+  } else if (mode == "selftest-stream" && optind + 1 <= argc) {
+    // the streaming scanner + admission + packing of quant mode, chunked small on purpose (no GPU needed)
+    FastqFile fq(argv[optind]);
+    FastqScanner sc(fq);
+    IdSet ids(fq.size() / 150 + 1024);
+    const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
+    RawChunk c;
+    bool unique = true;
+    uint64_t admitted = 0;
+    std::ostringstream body;
+    while (sc.next(3, 200, &c)) {
+      if (c.recs.empty()) continue;
+      std::vector<uint32_t> mem((c.seq_bytes + 4 * c.recs.size()) / 16 + 16 + 2 * c.recs.size());
+      PackedView v;
+      v.words = mem.data();
+      v.base_off = mem.data() + (c.seq_bytes + 4 * c.recs.size()) / 16 + 16;
+      v.len = v.base_off + c.recs.size();
+      unique &= admit_and_pack(fq.data(), c, kmax, &ids, &v);
+      admitted += v.n_reads;
+      for (uint32_t i = 0; i < v.n_reads; ++i) {
+        std::string sq(v.len[i], '?');
+        for (uint32_t j = 0; j < v.len[i]; ++j) {
+          const uint64_t b = (uint64_t)v.base_off[i] + j;
+          sq[j] = "ACGT"[(v.words[b >> 4] >> (2 * (b & 15))) & 3];
+        }
+        body << sq << "\n";
+      }
+    }
+    std::cout << "records " << sc.records_seen() << " admitted " << admitted << " unique " << (unique ? 1 : 0) << "\n" << body.str();
+  } else if (mode == "selftest-ingest" && optind + 1 <= argc) {
+    // host side of quant mode's ingest pipeline alone (scan -> admit + pack in workers, batches dropped): reads/s
+    const double t0 = now();
+    FastqFile fq(argv[optind]);
+    const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
+    const int W = std::max(1, (opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency()) - 1);
+    Channel<RawChunk> raw((size_t)W + 2);
+    IdSet ids(fq.size() / 150 + 1024);
+    std::atomic<uint64_t> admitted{0}, bases{0};
+    std::atomic<bool> unique{true};
+    uint64_t seen = 0;
+    std::thread scanner([&] {
+      FastqScanner sc(fq);
+      RawChunk c;
+      while (sc.next(1u << 18, 1ull << 26, &c)) {
+        if (!c.recs.empty()) raw.push(std::move(c));
+        c = RawChunk();
+      }
+      seen = sc.records_seen();
+      raw.close();
+    });
+    std::vector<std::thread> workers;
+    for (int w = 0; w < W; ++w)
+      workers.emplace_back([&] {
+        RawChunk c;
+        std::vector<uint32_t> mem;
+        while (raw.pop(&c)) {
+          if (getenv("SQ_SCAN_ONLY")) { admitted += c.recs.size(); continue; }
+          const size_t words = (c.seq_bytes + 4 * c.recs.size()) / 16 + 16;
+          mem.resize(words + 2 * c.recs.size());
+          PackedView v;
+          v.words = mem.data();
+          v.base_off = mem.data() + words;
+          v.len = v.base_off + c.recs.size();
+          if (!admit_and_pack(fq.data(), c, kmax, &ids, &v)) unique = false;
+          admitted += v.n_reads;
+          bases += v.n_bases;
+        }
+      });
+    scanner.join();
+    for (auto& w : workers) w.join();
+    const double dt = now() - t0;
+    std::cout << "records " << seen << " admitted " << admitted << " unique " << (unique ? 1 : 0) << " threads " << (W + 1)
+              << " seconds " << dt << " reads_per_s " << (admitted / dt) << " MB_per_s " << (fq.size() / dt / 1e6) << "\n";
   } else if (mode == "selftest-fasta" && optind + 1 <= argc) {
     for (auto& r : load_fasta(argv[optind])) std::cout << r.id << "\t" << r.sequence << "\n";
   } else if (mode == "selftest-index" && optind + 1 <= argc) {

@@ -109,3 +109,32 @@ def test_unopenable_inputs(tmp_path):
     rc, out, err = run(OURS, "-o", "quant", str(tmp_path / "none.idx"), str(tmp_path / "none.fq"), str(tmp_path / "o.csv"))
     assert "Unable to open file for reading" in err and "Loading index completed" in out
     assert rc != 0 and "Could not open FASTQ file" in err  # uncaught runtime_error -> terminate, like upstream
+
+
+def test_streaming_scan_equals_whole_file_scan(tmp_path):
+    """quant mode's streaming scanner + admission + 2-bit packing sees the records the whole-file scan sees"""
+    rng = np.random.default_rng(8)
+    recs = []
+    for i in range(400):
+        n = int(rng.integers(20, 300))
+        s = bytes(rng.choice(list(b"ACGT"), n).tolist())
+        if i % 17 == 0:
+            s = s[:5] + b"N" + s[6:]
+        if i % 29 == 0:
+            s = s.lower()
+        recs.append(b"@id%d extra\n" % i + s + b"\n+\n" + b"I" * n + b"\n")
+        if i % 50 == 0:
+            recs.append(b"\nstray line\n")
+    fq = tmp_path / "s.fq"
+    fq.write_bytes(b"".join(recs))
+    rc, out, _ = run(OURS, "-k", "21,31", "-o", "selftest-admit", str(fq))
+    rc2, out2, _ = run(OURS, "-k", "21,31", "-o", "selftest-stream", str(fq))
+    assert rc == 0 and rc2 == 0
+    whole = [l.split("\t")[1] for l in out.strip().split("\n")[1:]]
+    stream = out2.strip().split("\n")
+    assert stream[0] == out.split("\n")[0] + " unique 1"
+    assert stream[1:] == whole
+    # duplicate ids are reported (quant mode then takes the exact whole-file path)
+    fq.write_bytes(TRICKY_FASTQ)
+    rc3, out3, _ = run(OURS, "-k", "21,31", "-o", "selftest-stream", str(fq))
+    assert rc3 == 0 and out3.split("\n")[0].endswith("unique 0")

@@ -103,3 +103,44 @@ def test_index_sidecar_cache(gpu_lib, tmp_path):
     subprocess.run([OURS, "--index-cache", "-o", "quant", idx, fq, csv2], check=True, capture_output=True)
     subprocess.run([REF, "-o", "quant", idx, fq, ref2], check=True, capture_output=True)
     assert_csv_equal(read_csv(csv2), read_csv(ref2))
+
+
+def test_repeated_key_in_index_file_last_wins(gpu_lib, sqb, tmp_path):
+    """the reference's loader does mapping[kmer] = vec (src/data_io.cpp:297): of a key that a hand-made index file
+    repeats, the last record counts; and duplicate read ids take the exact whole-file path"""
+    import numpy as np
+    d = dataset(n_genes=30, n_reads=600, seed=21)
+    fa, fq = write_inputs(tmp_path, d, TRICKY_FASTQ)
+    idx, idx2 = str(tmp_path / "a.idx"), str(tmp_path / "b.idx")
+    subprocess.run([OURS, "-k", "31", "-o", "index", fa, idx], check=True, capture_output=True)
+    ks, names, seqs, post = sqb.index_io.read_index(idx)
+    keys, off, tids = post[31]
+    # append every 5th key once more with another posting list (the first transcript only)
+    ek, eo, et = list(keys), list(off), list(tids)
+    for i in range(0, len(keys), 5):
+        ek.append(int(keys[i]))
+        et.append(0)
+        eo.append(len(et))
+    post2 = {31: (np.asarray(ek, dtype=np.uint32), np.asarray(eo, dtype=np.uint64), np.asarray(et, dtype=np.uint32))}
+    sqb.index_io.write_index(idx2, ks, names, seqs, post2)
+    a, b = str(tmp_path / "ours.csv"), str(tmp_path / "ref.csv")
+    rep = str(tmp_path / "rep.json")
+    r = subprocess.run([OURS, "--report", rep, "-o", "quant", idx2, fq, a], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    subprocess.run([REF, "-o", "quant", idx2, fq, b], check=True, capture_output=True)
+    assert_csv_equal(read_csv(a), read_csv(b))
+    import json
+    assert json.load(open(rep))["duplicate_id_path"] is True  # TRICKY_FASTQ repeats the id r1
+
+
+def test_cli_long_reads_chunked_by_bases(gpu_lib, tmp_path):
+    """long reads: the ingest pipeline cuts chunks by bases as well as by reads"""
+    d = dataset(n_genes=60, n_reads=150, long_reads=(1000, 10000), err=0.05, exon_median=400, seed=9)
+    fa, fq = write_inputs(tmp_path, d)
+    idx = str(tmp_path / "i.idx")
+    subprocess.run([OURS, "-k", "31", "-o", "index", fa, idx], check=True, capture_output=True)
+    a, b = str(tmp_path / "ours.csv"), str(tmp_path / "ref.csv")
+    r = subprocess.run([OURS, "-o", "quant", idx, fq, a], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    subprocess.run([REF, "-o", "quant", idx, fq, b], check=True, capture_output=True)
+    assert_csv_equal(read_csv(a), read_csv(b))

@@ -53,3 +53,17 @@ def test_sketch_is_a_sorted_set(port):
     assert len(sk) == 4 and sorted(set(sk.tolist())) == sk.tolist()
     assert not port.lib.orc_is_valid_sequence(b"ACGN", 4) and port.lib.orc_is_valid_sequence(b"ACGT", 4)
     assert not port.lib.orc_is_valid_sequence(b"acgt", 4)
+
+
+def test_upstream_canonical_known_answer_vector(port):
+    """The upstream ntHash/btllib test vector NtHash("ACATGCATGCA", 3, 5): the base (canonical) hash of the first
+    three 5-mers.  ntHash2's canonical hash is forward + reverse (mod 2^64) and the reverse-strand hash of a
+    k-mer is the forward hash of its reverse complement, so this pins seeds, rotation and orientation of the
+    forward hash the reference uses (src/sketch.cpp:33) independently of the survey-derived forward KATs."""
+    seq = b"ACATGCATGCA"
+    want = [0xf59ecb45f0e22b9c, 0x38cc00f940aebdae, 0x603a48c5a11c794a]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    for p, w in enumerate(want):
+        kmer = seq[p:p + 5]
+        rc = kmer.translate(comp)[::-1]
+        assert (port.fwd_hash64(kmer) + port.fwd_hash64(rc)) & 0xFFFFFFFFFFFFFFFF == w, (p, kmer)
