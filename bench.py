@@ -429,16 +429,22 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     # vote kernels (whatever their internal encoding): per read item_start/cnt/base_off in and soff/cnt out, 4 B per
     # sketch hash, 12 B per probe (hash + table slot: key, list), 4 B per posting of a hit list (4 B x deg;
     # the bit-mask kernels get them as 64-bit masks, the information is the same), 8 B per candidate
-    vote_name = st.get("vote_kernel_name") or ("vote_bits_kernel" if kind != "long" else "vote_long_kernel")
-    b_vote = (12 + 2 * nk) * n_reads + 4 * st["sketch_hashes"] + (4 + 8) * st["queries"] + 4 * st["postings"] \
-        + 8 * st["pairs"] + 8 * n_reads
+    # The lookup kernel: per probe the hash in (4 B), one table slot (8 B: key + descriptor) and the descriptor out
+    # (4 B).  The first vote kernel (bit-sliced thread-per-read for short reads, warp-per-read window kernel for long
+    # ones): per read item_start/cnt/hoff in and soff/cnt out, 4 B per descriptor, 4 B per posting of a hit list
+    # (4 B x deg; nine in ten arrive inside the descriptor, the information is the same), 8 B per candidate.
+    vote_name = "vote_bits_kernel" if kind != "long" else "vote_long_kernel"
+    b_lookup = 16 * st["queries"]
+    b_vote = (12 + 6 * nk) * n_reads + 4 * st["queries"] + 4 * st["postings"] + 8 * st["pairs"] + 8 * n_reads
     # EM: per iteration the class CSR and its transcript-major copy are read once each (12 B + 8 B gathered per
     # class pair, twice) plus the per-class and per-transcript vectors
     b_em = iters * (40 * st["em_class_pairs"] + 20 * st["em_classes"] + 16 * T)
     S = steps
+    n_batches = max(int(st["batches"]), 1)
     kern = {
         "sketch_kernel": {"ms": stage.get("ms_sketch", 0) / S, "bytes": b_sketch, "launches": stage.get("sketch_launches", 0) // S},
-        vote_name: {"ms": stage.get("ms_vote_main" if st.get("vote_main_is_first", kind != "long") else "ms_vote", 0) / S, "bytes": b_vote, "launches": stage.get("vote_launches", 0) // S},
+        "lookup_kernel": {"ms": stage.get("ms_lookup", 0) / S, "bytes": b_lookup, "launches": n_batches * nk},
+        vote_name: {"ms": stage.get("ms_vote_main", 0) / S, "bytes": b_vote, "launches": stage.get("vote_launches", 0) // S},
         "em_iterations": {"ms": stage.get("ms_em", 0) / S, "bytes": b_em, "launches": iters},
     }
     for kname, kv in kern.items():
@@ -589,7 +595,9 @@ def summary(r):
             "e2e_ms_per_step": r["e2e"]["ms_per_step"], "e2e_reads_per_s": r["e2e"]["value"],
             "steps": r["steps"], "kernels": k,
             "hashing_frac": k["sketch_kernel"]["frac"],
-            "lookup_frac": next((v["frac"] for n, v in k.items() if n.startswith("vote")), None),
+            "lookup_frac": k["lookup_kernel"]["frac"],
+            "lookup_gprobes_per_s": (r["work"]["queries"] / (k["lookup_kernel"]["ms_per_step"] / 1e3) / 1e9) if k["lookup_kernel"]["ms_per_step"] else None,
+            "vote_frac": next((v["frac"] for n, v in k.items() if n.startswith("vote")), None),
             "sketch_gkmers_per_s": r["roofline"]["sketch_gkmers_per_s"],
             "stage_ms_per_step": r["roofline"]["stage_ms_per_step"], "work": r["work"],
             "config": {k2: r["config"][k2] for k2 in ("workload", "reads_per_gpu", "k", "sketch_scale", "threshold", "index_keys")},
@@ -676,8 +684,9 @@ def run_ours(args):
                        "lookup_frac": sweep["s=%g" % s].get("lookup_frac"),
                        "index_keys": (sweep["s=%g" % s].get("config", {}).get("index_keys") or [None] * 3)[i]}
                       for s in SCALES for i, k in enumerate([21, 25, 31])],
-            "note": "one fused pass hashes all three k per read and one vote kernel looks all three tables up, so "
-                    "hashing/lookup fractions are per scale; the per-k rows repeat them next to that k's index size"}
+            "note": "one fused sketch pass hashes all three k per read, the lookup kernel then runs once per k-index; "
+                    "hashing/lookup fractions are measured per scale (all k together), the per-k rows repeat them next to "
+                    "that k's index size"}
     if want in ("all", "long"):
         short_chunks = None  # free the short reads before the long ones are made
         import gc

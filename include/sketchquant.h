@@ -93,7 +93,9 @@ int sq_set_profiling(sq_engine* e, int enabled);
  * "overflow_workers", "max_read_len", "em_segment", "sub_batch_reads" (reads per internal batch of
  * sq_push_reads_fixed, default 2^20): set before the first push.  "exact_classes" (any time):
  * 1 = reads are merged into one EM term only after comparing their candidate lists element by element,
- * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads). */
+ * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads).
+ * "vote_tier" (any time, tests): 0 = automatic, 1 = every read through the warp-per-read window kernel, 2 = every
+ * read through the general warp-per-read kernel; the results do not depend on it. */
 int sq_set_option(sq_engine* e, const char* name, int64_t value);
 
 /* Replaces the TranscriptMapping for k-index kidx that load_index() fills (src/data_io.cpp:274-300,

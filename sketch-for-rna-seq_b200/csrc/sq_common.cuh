@@ -114,6 +114,7 @@ struct VoteParams {
   const uint16_t* cnt;
   const uint32_t* hcursor;           // [nk] selected hashes of the batch per k-index
   uint32_t count_bits;               // planes of the bit-sliced counters (5: up to 31 hashes per read and k, 7: 127)
+  uint32_t force_tier;               // tests: 0 = automatic, 1 = every read to the window kernel, 2 = every read to the general kernel
   IndexTable tab[SQ_MAXK];
   // staging output (batch local)
   uint32_t* stage_tid;

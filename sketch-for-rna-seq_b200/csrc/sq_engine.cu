@@ -120,6 +120,7 @@ struct sq_engine {
   uint32_t em_seg = 1024;
   uint32_t sub_batch_reads = 1u << 20;  // sq_push_reads_fixed: reads per internal batch
   bool exact_classes = false;  // compare candidate lists element-wise instead of by 128-bit fingerprint
+  uint32_t vote_tier = 0;      // tests: force every read through one vote tier (see VoteParams::force_tier)
   // batch slots
   Slot slot[2];
   int next_slot = 0;
@@ -552,6 +553,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.cnt = s.cnt.as<uint16_t>();
     vp.hcursor = e->d_hcur + 8 * s.id;
     vp.count_bits = item_hash_bound(e, n_bases, n_reads) <= 31 ? 5 : 7;
+    vp.force_tier = e->vote_tier;
     const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(e->T));
     for (uint32_t i = 0; i < e->nk; ++i) {
       vp.tab[i].bmap = e->tab[i].bmap.as<uint4>();
@@ -737,6 +739,7 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   if (!e || !name) return SQ_ERR_ARG;
   const std::string n(name);
   if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
+  if (n == "vote_tier") { e->vote_tier = (uint32_t)value; return SQ_OK; }
   if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);

@@ -546,6 +546,7 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
   A.orm = 0;
   A.base = 0;
   uint32_t n_out[NK];
+  uint32_t out_below_end = 0;  // largest end of a part counted as outside below the window
 #pragma unroll
   for (int ki = 0; ki < NK; ++ki) n_out[ki] = 0;
   if (valid) {
@@ -561,8 +562,17 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
       uint32_t nind = 0;
       auto place_add = [&](uint32_t base, unsigned long long mask) {
         const uint32_t m = win_place(A, base, mask);
-        if (!m) ++n_out[ki];
-        else if (!win_add(A, ki, m)) defer = true;
+        if (m) {
+          if (!win_add(A, ki, m)) defer = true;
+          return;
+        }
+        // does not fit: it may be counted as "outside" only if it lies entirely beside the window's 32 ids -- above
+        // them (the window only ever moves down), or below them now AND when the read is done (checked at the end)
+        const uint32_t end = base + 64u - (uint32_t)__clzll((long long)mask);  // one past the last id of the part
+        if (A.orm == 0) defer = true;  // wider than a window
+        else if (base >= A.base + 32u) ++n_out[ki];
+        else if (end <= A.base) { ++n_out[ki]; out_below_end = max(out_below_end, end); }
+        else defer = true;
       };
       auto vote = [&](uint32_t d) {
         if (d == SQ_EMPTY) return;
@@ -623,7 +633,8 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
       out_fails |= n_out[ki] < ithr;
       out_above_max |= n_out[ki] > mx;
     }
-    if (any_out && (!out_fails || out_above_max)) defer = true;  // transcripts outside the window could matter
+    // transcripts outside the window could matter, or the window moved onto a part counted as outside
+    if (any_out && (!out_fails || out_above_max || out_below_end > A.base)) defer = true;
     else nc = (uint32_t)__popc(sa);
   }
   // hand reads that did not fit to the warp-per-read window kernel
@@ -747,18 +758,7 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
         const uint32_t incl = warp_incl_scan(c);
         const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         const uint32_t excl = incl - c;
-        for (uint32_t f = 0; f < tot; f += 32) {
-          const uint32_t idx = f + lane;
-          uint32_t j = 0;  // item (within this group) holding entry idx: number of lanes with incl <= idx
-#pragma unroll
-          for (int step = 16; step; step >>= 1) {
-            const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (j + step - 1) & 31);
-            if (t <= idx) j += step;
-          }
-          const uint32_t exj = __shfl_sync(0xFFFFFFFFu, excl, j & 31);
-          const uint32_t ofj = __shfl_sync(0xFFFFFFFFu, my_off, j & 31);
-          const uint64_t at = (uint64_t)ki * P.hstride + ofj + (idx - exj);
-          const uint32_t d = idx < tot ? __ldg(P.pay + at) : SQ_EMPTY;
+        auto take = [&](uint32_t d, uint64_t at) {  // warp-wide: append the hits among 32 descriptors
           const uint32_t hit = __ballot_sync(0xFFFFFFFFu, d != SQ_EMPTY);
           if (d != SQ_EMPTY) {
             const uint32_t pos = nh + __popc(hit & lt);
@@ -768,6 +768,33 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
             }
           }
           nh += __popc(hit);
+        };
+        // the items of a sketch warp lie back to back in the dense arrays: a group's descriptors are then one run
+        // and are read as such (coalesced, two loads in flight); otherwise entry by entry through the item offsets
+        const uint32_t first_off = __shfl_sync(0xFFFFFFFFu, my_off, 0);
+        if (__all_sync(0xFFFFFFFFu, c == 0 || my_off == first_off + excl)) {
+          const uint64_t run = (uint64_t)ki * P.hstride + first_off;
+          for (uint32_t f = 0; f < tot; f += 64) {
+            const uint32_t i0 = f + lane, i1 = f + 32 + lane;
+            const uint32_t d0 = i0 < tot ? __ldg(P.pay + run + i0) : SQ_EMPTY;
+            const uint32_t d1 = i1 < tot ? __ldg(P.pay + run + i1) : SQ_EMPTY;
+            take(d0, run + i0);
+            if (f + 32 < tot) take(d1, run + i1);
+          }
+        } else {
+          for (uint32_t f = 0; f < tot; f += 32) {
+            const uint32_t idx = f + lane;
+            uint32_t j = 0;  // item (within this group) holding entry idx: number of lanes with incl <= idx
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+              const uint32_t t = __shfl_sync(0xFFFFFFFFu, incl, (j + step - 1) & 31);
+              if (t <= idx) j += step;
+            }
+            const uint32_t exj = __shfl_sync(0xFFFFFFFFu, excl, j & 31);
+            const uint32_t ofj = __shfl_sync(0xFFFFFFFFu, my_off, j & 31);
+            const uint64_t at = (uint64_t)ki * P.hstride + ofj + (idx - exj);
+            take(idx < tot ? __ldg(P.pay + at) : SQ_EMPTY, at);
+          }
         }
       }
       if (nh > kLongMaxHits) { defer = true; continue; }
@@ -1052,7 +1079,7 @@ template <int NK>
 static cudaStream_t launch_tiers(const VoteParams& p, const VoteDeviceCfg& cfg, cudaStream_t s, cudaEvent_t ev_b,
                                  cudaStream_t tail, cudaEvent_t fork) {
   const size_t lsm = sizeof(LongSmem) * kLongWarps;
-  const bool short_reads = (uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4;
+  const bool short_reads = p.force_tier != 1 && (uint64_t)(p.n_items_ub - p.n_reads) <= (uint64_t)p.n_reads + p.n_reads / 4;
   if (short_reads) {
     // mean read length up to ~320: the bit-sliced kernel takes every read it can, the window kernel the rest
     // (mid_list); the profiling events bracket the first, dominant kernel of the chain
@@ -1084,7 +1111,7 @@ cudaStream_t launch_vote(const VoteParams& p, const VoteDeviceCfg& cfg, cudaStre
   const uint32_t need = (p.n_reads + kVoteWarps - 1) / kVoteWarps;
   if (grid > need) grid = need;
   if (ev_a) cudaEventRecord(ev_a, s);
-  switch (p.nk) {
+  switch (p.force_tier == 2 ? 99u : p.nk) {
     case 1: s = launch_tiers<1>(p, cfg, s, ev_b, tail, fork); break;
     case 2: s = launch_tiers<2>(p, cfg, s, ev_b, tail, fork); break;
     case 3: s = launch_tiers<3>(p, cfg, s, ev_b, tail, fork); break;

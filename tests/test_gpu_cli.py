@@ -26,12 +26,12 @@ def read_csv(path):
     return {l.split(",")[0]: (float(l.split(",")[1]), float(l.split(",")[2])) for l in lines[1:]}
 
 
-def assert_csv_equal(a, b):
-    assert set(a) == set(b)
+def assert_csv_equal(a, b, what=""):
+    assert set(a) == set(b), what
     for k in a:
         # both programs print 6 significant digits
-        assert a[k][0] == pytest.approx(b[k][0], rel=2e-5), k
-        assert a[k][1] == pytest.approx(b[k][1], rel=2e-5), k
+        assert a[k][0] == pytest.approx(b[k][0], rel=2e-5), (what, k)
+        assert a[k][1] == pytest.approx(b[k][1], rel=2e-5), (what, k)
 
 
 def write_inputs(tmp_path, d, extra_fastq=b""):
@@ -66,7 +66,7 @@ def test_cli_matches_reference_program(gpu_lib, tmp_path, klist):
     ref = read_csv(p["rr.csv"])
     assert len(ref) > 20
     for csv in ("oo.csv", "or.csv", "ro.csv"):
-        assert_csv_equal(read_csv(p[csv]), ref)
+        assert_csv_equal(read_csv(p[csv]), ref, csv)
 
 
 def test_cli_report_and_default_mode(gpu_lib, tmp_path):
