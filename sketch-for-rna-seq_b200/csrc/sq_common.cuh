@@ -152,7 +152,8 @@ cudaError_t sketch_configure();  // per device
 // list descriptor (see IndexTable) of every selected hash of the batch, one k-index at a time
 struct VoteDeviceCfg;
 void launch_lookup(const VoteParams& p, const VoteDeviceCfg& cfg, uint32_t ki, cudaStream_t s, uint64_t* launches);
-void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, cudaStream_t s,
+void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, uint32_t* item_start,
+                         uint32_t* item_read, const KList& ks, unsigned long long* stats, cudaStream_t s,
                          uint64_t* launches);
 void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp, uint32_t* base_off, uint32_t* scan_tmp,
                            cudaStream_t s, uint64_t* launches);

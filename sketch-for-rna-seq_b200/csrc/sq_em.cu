@@ -103,30 +103,42 @@ struct ListHash {
 // full table or a missing table fall back to sorting the reads by (best candidate, list hash).
 struct ClassSlot {
   unsigned long long h, g;  // fingerprint; h == 0: free
-  uint32_t w, rep;          // reads in the class; smallest read index (its list is the class's list)
-  uint32_t pad0, pad1;
+  uint32_t rep;             // a read of the class (its list is the class's list), written once by the creator
+  uint32_t pad0, pad1, pad2;
 };
 static constexpr uint32_t kClassMaxProbe = 256;
 
-// counters: [0] classes, [1] (class, transcript) pairs, then a u32 overflow flag
-__device__ __forceinline__ void class_insert(ClassSlot* tab, uint32_t mask, unsigned long long h, unsigned long long g,
-                                             uint32_t w, uint32_t rep, uint32_t len, unsigned long long* counters) {
+// Seven reads in eight meet their class: one 16-byte load finds it (the table is only written when a class is
+// created, so its sectors stay clean), one atomic on the separate, eight times smaller and therefore L2-resident
+// array of weights counts the read.  counters: [0] classes, [1] (class, transcript) pairs, then a u32 overflow
+// flag; slots[i] = slot of the i-th class created.
+__device__ __forceinline__ void class_insert(ClassSlot* tab, uint32_t* cw, uint32_t mask, unsigned long long h,
+                                             unsigned long long g, uint32_t rep, uint32_t len,
+                                             unsigned long long* counters, uint32_t* slots) {
   uint32_t s = (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> 32) & mask;
   for (uint32_t tries = 0; tries < kClassMaxProbe; ++tries, s = (s + 1) & mask) {
-    unsigned long long cur = tab[s].h;
+    uint4 lo;  // h and g in one load that bypasses L1 (other SMs write these slots)
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(&tab[s]));
+    unsigned long long cur = ((unsigned long long)lo.y << 32) | lo.x;
+    unsigned long long og = ((unsigned long long)lo.w << 32) | lo.z;
     if (cur == 0) {
       const unsigned long long old = atomicCAS(&tab[s].h, 0ull, h);
       cur = old == 0 ? h : old;
+      og = 0;
     }
     if (cur != h) continue;
-    const unsigned long long og = atomicCAS(&tab[s].g, 0ull, g);
-    if (og != 0 && og != g) continue;
-    atomicAdd(&tab[s].w, w);
-    atomicMin(&tab[s].rep, rep);
-    if (og == 0) {  // this thread created the class
-      atomicAdd(counters + 0, 1ull);
-      atomicAdd(counters + 1, (unsigned long long)len);
+    if (og == 0) {
+      og = atomicCAS(&tab[s].g, 0ull, g);
+      if (og == 0) {  // this thread created the class
+        og = g;
+        tab[s].rep = rep;
+        const unsigned long long c = atomicAdd(counters + 0, 1ull);
+        atomicAdd(counters + 1, (unsigned long long)len);
+        if (slots) slots[c] = s;
+      }
     }
+    if (og != g) continue;
+    atomicAdd(&cw[s], 1u);
     return;
   }
   *reinterpret_cast<uint32_t*>(counters + 2) = 1;  // table too full: sq_finish takes the sort path
@@ -139,7 +151,9 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
                                const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
                                uint64_t pbase, uint64_t read_base, uint32_t* __restrict__ cand_tid,
                                int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off,
-                               ClassSlot* __restrict__ ctab, uint32_t cmask, unsigned long long* __restrict__ ccnt) {
+                               ClassSlot* ctab, uint32_t* cw, uint32_t cmask, unsigned long long* __restrict__ ccnt,
+                               uint32_t* __restrict__ cslots, uint32_t T, uint32_t hash_bits,
+                               uint64_t* __restrict__ rkey, ulonglong2* __restrict__ rfp) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint64_t dst = pbase + batch_off[r];
@@ -148,6 +162,7 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
   const uint32_t c = read_cnt[r], so = read_soff[r];
   ListHash lh;
   lh.init(c);
+  uint32_t top = T;  // sort path: reads without candidates go last (one empty class)
   // blocks of 4 candidates: the eight loads go out together (the kernel waits on latency, the fold is serial)
   for (uint32_t i0 = 0; i0 < c; i0 += 4) {
     uint32_t t[4];
@@ -157,6 +172,7 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
       t[u] = i0 + u < c ? stage_tid[so + i0 + u] : 0u;
       sc[u] = i0 + u < c ? stage_score[so + i0 + u] : 0;
     }
+    if (i0 == 0) top = t[0];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
       if (i0 + u < c) {
@@ -165,96 +181,108 @@ __global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uin
         lh.add(t[u], sc[u]);
       }
   }
+  if (rkey) {  // sort path of sq_finish: the read's class sort key and list fingerprint
+    rkey[read_base + r] = lh.key(top, hash_bits, read_base + r);
+    rfp[read_base + r] = make_ulonglong2(lh.h, lh.g);
+  }
   // a read without candidates adds nothing to any EM sum (isoform_assignment.cpp:36-45): it needs no class
-  if (ctab && c) class_insert(ctab, cmask, lh.h ? lh.h : 1ull, lh.g ? lh.g : 1ull, 1u, (uint32_t)(read_base + r), c, ccnt);
+  if (ctab && c) class_insert(ctab, cw, cmask, lh.h ? lh.h : 1ull, lh.g ? lh.g : 1ull, (uint32_t)(read_base + r), c, ccnt, cslots);
 }
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t cmask,
-                    unsigned long long* ccnt, cudaStream_t s, uint64_t* launches) {
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t* cw, uint32_t cmask,
+                    unsigned long long* ccnt, uint32_t* cslots, uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp,
+                    cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
                                                        stage_score, pbase, read_base, cand_tid, cand_score, read_off,
-                                                       static_cast<ClassSlot*>(ctab), cmask, ccnt);
+                                                       static_cast<ClassSlot*>(ctab), cw, cmask, ccnt, cslots, T, hash_bits,
+                                                       rkey, static_cast<ulonglong2*>(rfp));
   if (launches) ++*launches;
 }
 
-// a grown table takes over the classes of the old one
-__global__ void class_rehash_kernel(const ClassSlot* __restrict__ old, uint32_t old_cap, ClassSlot* __restrict__ tab,
-                                    uint32_t mask, unsigned long long* __restrict__ scratch_counters) {
+// a grown table takes over the classes of the old one (in creation order: the slot list is rewritten in place)
+__global__ void class_rehash_kernel(const ClassSlot* __restrict__ old, const uint32_t* __restrict__ old_cw, ClassSlot* tab,
+                                    uint32_t* __restrict__ cw, uint32_t mask, uint32_t* __restrict__ slots,
+                                    unsigned long long* __restrict__ counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= old_cap) return;
-  const ClassSlot sl = old[i];
-  if (sl.h) class_insert(tab, mask, sl.h, sl.g, sl.w, sl.rep, 0u, scratch_counters);
+  if (i >= (uint32_t)counters[0]) return;
+  const uint32_t os = slots[i];
+  const ClassSlot sl = old[os];
+  uint32_t s = (uint32_t)((sl.h * 0x9E3779B97F4A7C15ull) >> 32) & mask;
+  for (uint32_t tries = 0; tries < kClassMaxProbe; ++tries, s = (s + 1) & mask) {
+    if (atomicCAS(&tab[s].h, 0ull, sl.h) != 0ull) continue;  // classes are distinct: a taken slot is someone else's
+    tab[s].g = sl.g;
+    tab[s].rep = sl.rep;
+    cw[s] = old_cw[os];
+    slots[i] = s;
+    return;
+  }
+  *reinterpret_cast<uint32_t*>(counters + 2) = 1;
 }
 
-__global__ void class_clear_kernel(ClassSlot* tab, uint32_t cap) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < cap) { ClassSlot z; z.h = 0; z.g = 0; z.w = 0; z.rep = 0xFFFFFFFFu; z.pad0 = z.pad1 = 0; tab[i] = z; }
-}
-
-void launch_class_clear(void* tab, uint32_t cap, cudaStream_t s, uint64_t* launches) {
+void launch_class_clear(void* tab, uint32_t* cw, uint32_t cap, cudaStream_t s, uint64_t* launches) {
+  (void)launches;
   if (!cap) return;
-  class_clear_kernel<<<(cap + 255) / 256, 256, 0, s>>>(static_cast<ClassSlot*>(tab), cap);
+  cudaMemsetAsync(tab, 0, (size_t)cap * sizeof(ClassSlot), s);
+  cudaMemsetAsync(cw, 0, (size_t)cap * 4, s);
+}
+
+// counters: the live class counters (number of classes to move; a full new table raises their flag)
+void launch_class_rehash(const void* old, const uint32_t* old_cw, void* tab, uint32_t* cw, uint32_t cap, uint32_t* slots,
+                         unsigned long long* counters, uint64_t n_classes_ub, cudaStream_t s, uint64_t* launches) {
+  launch_class_clear(tab, cw, cap, s, launches);
+  if (!old || !n_classes_ub) return;
+  class_rehash_kernel<<<(uint32_t)((n_classes_ub + 255) / 256), 256, 0, s>>>(static_cast<const ClassSlot*>(old), old_cw,
+                                                                             static_cast<ClassSlot*>(tab), cw, cap - 1, slots,
+                                                                             counters);
   if (launches) ++*launches;
 }
 
-// scratch_counters: 3 u64 the rehash may scribble on (the class counts do not change)
-void launch_class_rehash(const void* old, uint32_t old_cap, void* tab, uint32_t cap, unsigned long long* scratch_counters,
-                         cudaStream_t s, uint64_t* launches) {
-  launch_class_clear(tab, cap, s, launches);
-  if (!old_cap) return;
-  class_rehash_kernel<<<(old_cap + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(old), old_cap,
-                                                            static_cast<ClassSlot*>(tab), cap - 1, scratch_counters);
-  if (launches) ++*launches;
-}
-
-// occupied slots -> (order key, slot): key = best candidate of the class in the high bits, fingerprint below
-__global__ void class_collect_kernel(const ClassSlot* __restrict__ tab, uint32_t cap, const uint32_t* __restrict__ read_off,
+// classes -> (order key, slot): key = best candidate of the class in the high bits, fingerprint below
+__global__ void class_collect_kernel(const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ slots,
+                                     uint32_t n_classes, const uint32_t* __restrict__ read_off,
                                      const uint32_t* __restrict__ cand_tid, uint32_t tbits,
-                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
-                                     uint32_t* __restrict__ counter) {
+                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool occ = i < cap && tab[i].h != 0;
-  const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
-  if (!m) return;
-  uint32_t base = 0;
-  if (lane_id() == (uint32_t)__ffs(m) - 1) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
-  if (!occ) return;
-  const uint32_t pos = base + __popc(m & ((1u << lane_id()) - 1));
-  const unsigned long long top = cand_tid[read_off[tab[i].rep]];
-  keys[pos] = (top << (64 - tbits)) | (tab[i].h >> tbits);
-  vals[pos] = i;
+  if (i >= n_classes) return;
+  const uint32_t s = slots[i];
+  const ClassSlot sl = tab[s];
+  const unsigned long long top = cand_tid[read_off[sl.rep]];
+  keys[i] = (top << (64 - tbits)) | (sl.h >> tbits);
+  vals[i] = s;
 }
 
 // classes in their final order: representative read, list length, weight
 __global__ void class_from_sorted_kernel(const uint32_t* __restrict__ slot_of, uint32_t n_classes,
-                                         const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ read_off,
+                                         const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ cw,
+                                         const uint32_t* __restrict__ read_off,
                                          uint32_t* __restrict__ class_read, uint32_t* __restrict__ class_cnt,
                                          double* __restrict__ weight) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_classes) return;
-  const ClassSlot sl = tab[slot_of[c]];
-  class_read[c] = sl.rep;
-  class_cnt[c] = read_off[sl.rep + 1] - read_off[sl.rep];
-  weight[c] = (double)sl.w;
+  const uint32_t s = slot_of[c];
+  const uint32_t rep = tab[s].rep;
+  class_read[c] = rep;
+  class_cnt[c] = read_off[rep + 1] - read_off[rep];
+  weight[c] = (double)cw[s];
 }
 
-void launch_class_collect(const void* tab, uint32_t cap, const uint32_t* read_off, const uint32_t* cand_tid, uint32_t tbits,
-                          uint64_t* keys, uint32_t* vals, uint32_t* counter, cudaStream_t s, uint64_t* launches) {
-  cudaMemsetAsync(counter, 0, 4, s);
-  if (!cap) return;
-  class_collect_kernel<<<(cap + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(tab), cap, read_off, cand_tid, tbits,
-                                                         reinterpret_cast<unsigned long long*>(keys), vals, counter);
+void launch_class_collect(const void* tab, const uint32_t* slots, uint32_t n_classes, const uint32_t* read_off,
+                          const uint32_t* cand_tid, uint32_t tbits, uint64_t* keys, uint32_t* vals, cudaStream_t s,
+                          uint64_t* launches) {
+  if (!n_classes) return;
+  class_collect_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(tab), slots, n_classes, read_off,
+                                                               cand_tid, tbits, reinterpret_cast<unsigned long long*>(keys), vals);
   if (launches) ++*launches;
 }
 
-void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* read_off,
-                              uint32_t* class_read, uint32_t* class_cnt, double* weight, cudaStream_t s, uint64_t* launches) {
+void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* cw,
+                              const uint32_t* read_off, uint32_t* class_read, uint32_t* class_cnt, double* weight,
+                              cudaStream_t s, uint64_t* launches) {
   if (!n_classes) return;
-  class_from_sorted_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(slot_of, n_classes, static_cast<const ClassSlot*>(tab),
+  class_from_sorted_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(slot_of, n_classes, static_cast<const ClassSlot*>(tab), cw,
                                                                    read_off, class_read, class_cnt, weight);
   if (launches) ++*launches;
 }
@@ -340,15 +368,24 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
                                     const uint32_t* __restrict__ class_off, uint32_t n_classes,
                                     const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ cand_tid,
                                     const int32_t* __restrict__ cand_score, uint32_t* __restrict__ out_tid,
-                                    int32_t* __restrict__ out_score, double* __restrict__ weight) {
+                                    int32_t* __restrict__ out_score, uint32_t* __restrict__ out_pack,
+                                    uint32_t* __restrict__ pack_bad, double* __restrict__ weight) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_classes) return;
   const uint32_t r = class_read[c];
   const uint32_t b = read_off[r], n = read_off[r + 1] - b, d = class_off[c];
+  bool bad = false;
   for (uint32_t j = 0; j < n; ++j) {
-    out_tid[d + j] = cand_tid[b + j];
-    out_score[d + j] = cand_score[b + j];
+    const uint32_t t = cand_tid[b + j];
+    const int32_t sc = cand_score[b + j];
+    out_tid[d + j] = t;
+    out_score[d + j] = sc;
+    // packed copy for the EM iterations: transcript in 24 bits, score in 8 (half the bytes per pair: the 20 x 2
+    // passes over the pairs then run out of L2); a score above 255 or an id above 2^24 keeps the unpacked arrays
+    out_pack[d + j] = (t & 0xFFFFFFu) | ((uint32_t)sc << 24);
+    bad |= (uint32_t)sc > 255u || t > 0xFFFFFFu;
   }
+  if (bad) *pack_bad = 1;
   if (class_pos) weight[c] = (double)(class_pos[c + 1] - class_pos[c]);  // sort path; the table path wrote it already
 }
 
@@ -377,21 +414,27 @@ void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* 
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
                          uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
                          const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
-                         double* weight, cudaStream_t s, uint64_t* launches) {
+                         uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches) {
   launch_exclusive_scan(class_cnt, class_off, n_classes, scan_tmp, s, launches);
+  cudaMemsetAsync(pack_bad, 0, 4, s);
   if (!n_classes) return;
   class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, read_off,
-                                                              cand_tid, cand_score, out_tid, out_score, weight);
+                                                              cand_tid, cand_score, out_tid, out_score, out_pack, pack_bad,
+                                                              weight);
   if (launches) ++*launches;
 }
 
 // ------------------------------------------------------------------ transcript-major view
+// packed: cand_tid holds transcript | score << 24; the score moves to the top 8 bits of the class word
 __global__ void make_sort_keys_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
-                                      const uint32_t* __restrict__ cand_tid, uint64_t* __restrict__ keys) {
+                                      const uint32_t* __restrict__ cand_tid, uint64_t* __restrict__ keys, bool packed) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = read_off[r], e = read_off[r + 1];
-  for (uint32_t j = b; j < e; ++j) keys[j] = ((uint64_t)r << 32) | cand_tid[j];
+  for (uint32_t j = b; j < e; ++j) {
+    const uint32_t t = cand_tid[j];
+    keys[j] = packed ? ((uint64_t)((uint32_t)r | (t & 0xFF000000u)) << 32) | (t & 0xFFFFFFu) : ((uint64_t)r << 32) | t;
+  }
 }
 
 // keys sorted by transcript (low 32 bits): toff[t] = first pair of transcript t, toff[T] = P
@@ -404,6 +447,7 @@ __global__ void seg_offsets_kernel(const uint64_t* __restrict__ keys, uint64_t P
   for (int64_t t = prev + 1; t <= cur; ++t) toff[t] = (uint32_t)j;
 }
 
+// tm_read[j] = class of the j-th pair in transcript order (packed: with its score in the top 8 bits)
 __global__ void split_keys_kernel(const uint64_t* __restrict__ keys, uint64_t P, uint32_t* __restrict__ tm_read) {
   const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (j < P) tm_read[j] = (uint32_t)(keys[j] >> 32);
@@ -450,7 +494,7 @@ __device__ __forceinline__ int32_t ld_stream(const int32_t* p) {
 // own row in order (same sums as a plain per-thread loop, without the strided global reads).
 static constexpr uint32_t kDenCap = 3072;
 
-template <bool ASSIGN>
+template <bool ASSIGN, bool PACKED>  // PACKED: cand_tid holds transcript | score << 24, cand_score is not read
 __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
                                                      const uint32_t* __restrict__ cand_tid,
                                                      const int32_t* __restrict__ cand_score,
@@ -472,7 +516,12 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
       for (int u = 0; u < 4; ++u) {
         const uint32_t q = j + 256 * u;
         t[u] = q < np ? ld_stream(cand_tid + b0 + q) : 0u;
-        sc[u] = q < np ? ld_stream(cand_score + b0 + q) : 0;
+        if (PACKED) {
+          sc[u] = (int32_t)(t[u] >> 24);
+          t[u] &= 0xFFFFFFu;
+        } else {
+          sc[u] = q < np ? ld_stream(cand_score + b0 + q) : 0;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) p[u] = j + 256 * u < np ? pi[t[u]] : 0.0;
@@ -489,7 +538,10 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
   if (staged) {
     for (uint32_t j = b; j < e; ++j) den += s_term[j - b0];
   } else {
-    for (uint32_t j = b; j < e; ++j) den += pi[cand_tid[j]] * (double)cand_score[j];
+    for (uint32_t j = b; j < e; ++j) {
+      const uint32_t t = cand_tid[j];
+      den += PACKED ? pi[t & 0xFFFFFFu] * (double)(t >> 24) : pi[t] * (double)cand_score[j];
+    }
   }
   // a class of w identical reads adds w identical posteriors: fold w into the reciprocal (exact for w = 1)
   out[r] = ASSIGN ? den : (den > 1e-10 ? (1.0 / den) * weight[r] : 0.0);
@@ -497,7 +549,7 @@ __global__ void __launch_bounds__(256) em_den_kernel(const uint32_t* __restrict_
 
 // one group of G lanes per segment of <= seg pairs of one transcript: partial posterior sum (:46-49).  A
 // transcript has a few dozen pairs on average, so 8-lane groups keep the lanes busy; G = 32 for deep data.
-template <int G>
+template <int G, bool PACKED>  // PACKED: tm_read holds class | score << 24, tm_score is not read
 __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, const uint32_t* __restrict__ n_seg_ptr, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
@@ -516,13 +568,20 @@ __global__ void em_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
       uint32_t sc[4], c[4];
       double iv[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { sc[u] = ld_stream(tm_score + j + u * G); c[u] = ld_stream(tm_read + j + u * G); }
+      for (int u = 0; u < 4; ++u) {
+        c[u] = ld_stream(tm_read + j + u * G);
+        if (PACKED) { sc[u] = c[u] >> 24; c[u] &= 0xFFFFFFu; } else { sc[u] = ld_stream(tm_score + j + u * G); }
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) iv[u] = inv_den[c[u]];
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc += (p * (double)(int32_t)sc[u]) * iv[u];
     }
-    for (; j < e; j += G) acc += (p * (double)(int32_t)ld_stream(tm_score + j)) * inv_den[ld_stream(tm_read + j)];
+    for (; j < e; j += G) {
+      uint32_t c = ld_stream(tm_read + j), sc;
+      if (PACKED) { sc = c >> 24; c &= 0xFFFFFFu; } else { sc = ld_stream(tm_score + j); }
+      acc += (p * (double)(int32_t)sc) * inv_den[c];
+    }
   }
 #pragma unroll
   for (int d = G / 2; d; d >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, d, G);
@@ -637,7 +696,7 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
 }
 
 // ------------------------------------------------------------------ assignment (:70-97)
-template <int G>
+template <int G, bool PACKED>
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
                                   const uint32_t* __restrict__ toff, const uint32_t* __restrict__ n_seg_ptr, uint32_t seg,
                                   const uint32_t* __restrict__ tm_read, const uint32_t* __restrict__ tm_score,
@@ -658,7 +717,10 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
       uint32_t c[4], sc[4];
       double tt[4], wt[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { c[u] = ld_stream(tm_read + j + u * G); sc[u] = ld_stream(tm_score + j + u * G); }
+      for (int u = 0; u < 4; ++u) {
+        c[u] = ld_stream(tm_read + j + u * G);
+        if (PACKED) { sc[u] = c[u] >> 24; c[u] &= 0xFFFFFFu; } else { sc[u] = ld_stream(tm_score + j + u * G); }
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { tt[u] = tot[c[u]]; wt[u] = weight[c[u]]; }
 #pragma unroll
@@ -669,10 +731,11 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
         }
     }
     for (; j < e; j += G) {
-      const uint32_t c = tm_read[j];
+      uint32_t c = tm_read[j], sc;
+      if (PACKED) { sc = c >> 24; c &= 0xFFFFFFu; } else { sc = tm_score[j]; }
       const double tt = tot[c];
       if (tt > 0.0) {
-        acc += ((p * (double)(int32_t)tm_score[j]) / tt) * weight[c];  // :90 divides per term; w identical reads
+        acc += ((p * (double)(int32_t)sc) / tt) * weight[c];  // :90 divides per term; w identical reads
         any = true;
       }
     }
@@ -688,10 +751,10 @@ __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const ui
 }
 
 // ------------------------------------------------------------------ host-side launch helpers
-void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
-                           cudaStream_t s, uint64_t* launches) {
+void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, bool packed,
+                           uint64_t* keys, cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
-  make_sort_keys_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, keys);
+  make_sort_keys_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, keys, packed);
   if (launches) ++*launches;
 }
 
@@ -720,17 +783,24 @@ static inline bool narrow_groups(const EmView& v) { return v.n_pairs / (v.T ? v.
 
 void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum) {
   if (v.n_reads) {
-    em_den_kernel<false><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
-        v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
+    if (v.packed)
+      em_den_kernel<false, true><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+          v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
+    else
+      em_den_kernel<false, false><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+          v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, v.weight, v.read_tmp, v.state);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
-    if (narrow_groups(v))
-      em_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
-    else
-      em_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state);
+#define SQ_EM_PARTIAL(G, PK)                                                                                   \
+  em_partial_kernel<G, PK><<<(uint32_t)(((uint64_t)v.n_seg * G + 255) / 256), 256, 0, s>>>(                    \
+      v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.pi, v.partial, v.state)
+    if (narrow_groups(v)) {
+      if (v.packed) SQ_EM_PARTIAL(8, true); else SQ_EM_PARTIAL(8, false);
+    } else {
+      if (v.packed) SQ_EM_PARTIAL(32, true); else SQ_EM_PARTIAL(32, false);
+    }
+#undef SQ_EM_PARTIAL
     if (launches) ++*launches;
   }
   if (with_sum) {
@@ -756,19 +826,25 @@ void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double t
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches) {
   cudaMemsetAsync(present_u32, 0, sizeof(uint32_t) * v.T, s);
   if (v.n_reads) {
-    em_den_kernel<true><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
-        v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, nullptr, v.read_tmp, nullptr);
+    if (v.packed)
+      em_den_kernel<true, true><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+          v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, nullptr, v.read_tmp, nullptr);
+    else
+      em_den_kernel<true, false><<<(uint32_t)((v.n_reads + 255) / 256), 256, 0, s>>>(
+          v.read_off, v.n_reads, v.cand_tid, v.cand_score, v.pi, nullptr, v.read_tmp, nullptr);
     if (launches) ++*launches;
   }
   if (v.n_seg) {
-    if (narrow_groups(v))
-      as_partial_kernel<8><<<(uint32_t)(((uint64_t)v.n_seg * 8 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
-          present_u32);
-    else
-      as_partial_kernel<32><<<(uint32_t)(((uint64_t)v.n_seg * 32 + 255) / 256), 256, 0, s>>>(
-          v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi, v.partial,
-          present_u32);
+#define SQ_AS_PARTIAL(G, PK)                                                                                   \
+  as_partial_kernel<G, PK><<<(uint32_t)(((uint64_t)v.n_seg * G + 255) / 256), 256, 0, s>>>(                    \
+      v.seg_tid, v.seg_begin, v.toff, v.seg_off + v.T, v.seg, v.tm_read, v.tm_score, v.read_tmp, v.weight, v.pi,   \
+      v.partial, present_u32)
+    if (narrow_groups(v)) {
+      if (v.packed) SQ_AS_PARTIAL(8, true); else SQ_AS_PARTIAL(8, false);
+    } else {
+      if (v.packed) SQ_AS_PARTIAL(32, true); else SQ_AS_PARTIAL(32, false);
+    }
+#undef SQ_AS_PARTIAL
     if (launches) ++*launches;
   }
   seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, numreads, nullptr);

@@ -121,6 +121,9 @@ struct sq_engine {
   uint32_t sub_batch_reads = 1u << 20;  // sq_push_reads_fixed: reads per internal batch
   bool exact_classes = false;  // compare candidate lists element-wise instead of by 128-bit fingerprint
   uint32_t vote_tier = 0;      // tests: force every read through one vote tier (see VoteParams::force_tier)
+  bool class_table = false;    // collect the read classes in the compactions instead of sorting the reads in sq_finish
+                               // (measured: 0.5 ms less after the last copy of a host-fed pass, but its random traffic
+                               // costs a device-resident pass 3 ms: it competes with the index for L2)
   // batch slots
   Slot slot[2];
   int next_slot = 0;
@@ -142,17 +145,19 @@ struct sq_engine {
   int32_t* cand_score = nullptr;
   uint32_t* read_off = nullptr;
   // read classes, built by the compactions (see sq_em.cu): table of 32-byte slots; retired tables wait for reset/destroy
-  DevBuf ctab;
+  DevBuf ctab, ct_w, ct_slots;           // slots, reads per slot, slot of the i-th class created
   uint32_t ct_cap = 0;
   std::vector<DevBuf> ct_retired;
   unsigned long long* d_ccnt = nullptr;  // [0] classes, [1] class pairs, [2] low word: table-full flag
-  bool keys_valid = true;                // false: the store was filled by sq_set_candidates, no table
+  uint64_t* rkey = nullptr;              // sort path: per read class sort key and 128-bit list fingerprint, written by
+  void* rfp = nullptr;                   // the compactions when the class table is off
+  bool keys_valid = true;                // false: the store was filled by sq_set_candidates
   uint32_t class_hash_bits = 14;
   uint64_t cand_cap = 0, read_cap = 0;
   uint64_t n_reads = 0, n_bases = 0, n_batches = 0;  // n_reads: all enqueued batches
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
-      read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score,
+      read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score, em_pack,
       cls_head, cls_id, cls_read, cls_pos, cls_weight, cls_fp, out_pi, out_nr, out_present;
   uint64_t n_classes_last = 0, n_cpairs_last = 0;
   int em_iterations = 0;
@@ -271,15 +276,29 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
   if (need_reads > e->read_cap) {
     uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
     uint32_t* p = nullptr;
+    uint64_t* pk = nullptr;
+    void* pf = nullptr;
     SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
+    if (!e->class_table) {
+      SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
+      SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
+    }
     if (e->read_off) {
       SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+      if (pk && e->rkey) {
+        SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
+        SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
+      }
       SQ_CUDA(e, cudaStreamSynchronize(cs));
       SQ_CUDA(e, cudaFree(e->read_off));
     } else {
       SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), cs));
     }
+    if (e->rkey) SQ_CUDA(e, cudaFree(e->rkey));
+    if (e->rfp) SQ_CUDA(e, cudaFree(e->rfp));
     e->read_off = p;
+    e->rkey = pk;
+    e->rfp = pf;
     e->read_cap = cap;
   }
   const uint64_t need_pairs = e->P + pairs;
@@ -324,25 +343,32 @@ int ensure_big_scratch(sq_engine* e) {
 }
 
 // The class table must keep its load low: it grows (classes re-entered by a kernel on the tail stream) when the
-// class count last reported by a compaction plus the reads of two more batches passes half of it.  Should
-// it fill up anyway, the kernels raise a flag and sq_finish takes the sort path.
+// class count last reported by a compaction plus the reads of the coming batch passes 60 % of it.  The reports lag
+// a batch or two; should the table fill up anyway, the kernels raise a flag and sq_finish takes the sort path.
 int ensure_class_table(sq_engine* e, uint32_t batch_reads) {
   cudaStream_t cs = e->tail_stream;
   const uint64_t known = e->h_mirror[8];
-  const uint64_t bound = known + 2ull * std::max<uint32_t>(batch_reads, 1u << 16);  // reports lag a batch or two
-  if (e->ct_cap && bound * 2 <= e->ct_cap) return SQ_OK;
+  const uint64_t bound = known + std::max<uint64_t>((uint64_t)batch_reads + batch_reads / 4, 1u << 16);
+  if (e->ct_cap && bound * 8 <= (uint64_t)e->ct_cap * 5) return SQ_OK;
   uint64_t cap = std::max<uint64_t>(e->ct_cap, 1u << 22);
-  while (bound * 2 > cap && cap < (1ull << 30)) cap <<= 1;
+  while (bound * 8 > cap * 5 && cap < (1ull << 30)) cap <<= 1;
   if (cap == e->ct_cap) return SQ_OK;
-  DevBuf old;
+  DevBuf old, old_w, old_slots;
   std::swap(old, e->ctab);
+  std::swap(old_w, e->ct_w);
+  std::swap(old_slots, e->ct_slots);
   const uint32_t old_cap = e->ct_cap;
   SQ_CUDA(e, e->ctab.ensure((size_t)cap * 32));
+  SQ_CUDA(e, e->ct_w.ensure((size_t)cap * 4));
+  SQ_CUDA(e, e->ct_slots.ensure((size_t)cap * 4));
   e->ct_cap = (uint32_t)cap;
-  SQ_CUDA(e, e->misc.ensure(256));
-  launch_class_rehash(old.p, old_cap, e->ctab.p, e->ct_cap, reinterpret_cast<unsigned long long*>(e->misc.as<char>() + 64), cs,
-                      &e->launches);
-  if (old.p) e->ct_retired.push_back(old);  // still read by the kernel just enqueued: freed at reset / destroy
+  if (old_slots.p) SQ_CUDA(e, cudaMemcpyAsync(e->ct_slots.p, old_slots.p, (size_t)old_cap * 4, cudaMemcpyDeviceToDevice, cs));
+  launch_class_rehash(old.p, old_w.as<uint32_t>(), e->ctab.p, e->ct_w.as<uint32_t>(), e->ct_cap, e->ct_slots.as<uint32_t>(),
+                      e->d_ccnt, old_cap, cs, &e->launches);
+  // the old buffers are still read by what was just enqueued: freed at reset / destroy
+  if (old.p) e->ct_retired.push_back(old);
+  if (old_w.p) e->ct_retired.push_back(old_w);
+  if (old_slots.p) e->ct_retired.push_back(old_slots);
   return SQ_OK;
 }
 
@@ -414,10 +440,12 @@ int finalize_slot(sq_engine* e, Slot& s) {
     StageScope st(e, 2, cs);
     launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads, s.scan_tmp.as<uint32_t>(),
                           cs, &e->launches);
-    SQ_TRY(ensure_class_table(e, s.n_reads));
+    if (e->class_table) SQ_TRY(ensure_class_table(e, s.n_reads));
     launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
                    s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
-                   e->cand_score, e->read_off, e->ctab.p, e->ct_cap - 1, e->d_ccnt, cs, &e->launches);
+                   e->cand_score, e->read_off, e->class_table ? e->ctab.p : nullptr, e->ct_w.as<uint32_t>(), e->ct_cap - 1,
+                   e->d_ccnt, e->ct_slots.as<uint32_t>(), (uint32_t)e->T, e->class_hash_bits, e->class_table ? nullptr : e->rkey,
+                   e->class_table ? nullptr : e->rfp, cs, &e->launches);
     // the class counts so far reach the host behind the compaction: table growth and sq_finish read them there
     SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 8, e->d_ccnt, 24, cudaMemcpyDeviceToHost, cs));
     SQ_CUDA(e, cudaGetLastError());
@@ -486,20 +514,23 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
     SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
   }
+  KList kl;
+  kl.nk = e->nk;
+  for (uint32_t i = 0; i < e->nk; ++i) kl.k[i] = e->ks[i];
+  const bool one_item_each = derive_boff && fixed_len && fixed_len <= SQ_CHUNK;
   if (derive_boff && fixed_len) {  // equal lengths: offsets and lengths are written on the GPU, nothing was copied
     StageScope st(e, 6);
-    launch_fixed_layout(const_cast<uint32_t*>(d_len), derive_boff, n_reads, fixed_len, e->stream, &e->launches);
+    launch_fixed_layout(const_cast<uint32_t*>(d_len), derive_boff, n_reads, fixed_len,
+                        one_item_each ? s.item_start.as<uint32_t>() : nullptr,
+                        one_item_each ? s.item_read.as<uint32_t>() : nullptr, kl, e->d_totals + 4, e->stream, &e->launches);
   } else if (derive_boff) {  // offsets not supplied: reads are packed back to back on 4-base boundaries
     StageScope st(e, 6);
     launch_derive_offsets(d_len, n_reads, s.nit.as<uint32_t>(), derive_boff, s.scan_tmp.as<uint32_t>(), e->stream,
                           &e->launches);
   }
 
-  {
+  if (!one_item_each) {
     StageScope st(e, 6);
-    KList kl;
-    kl.nk = e->nk;
-    for (uint32_t i = 0; i < e->nk; ++i) kl.k[i] = e->ks[i];
     launch_items(d_len, n_reads, s.nit.as<uint32_t>(), s.item_start.as<uint32_t>(), s.item_read.as<uint32_t>(),
                  items_ub, s.scan_tmp.as<uint32_t>(), e->stream, &e->launches, kl, e->d_totals + 4);
     // cnt needs no clearing: the sketch kernel writes the count of every item that exists, for every k
@@ -704,14 +735,18 @@ void sq_destroy(sq_engine* e) {
   DevBuf* all[] = {&e->big_keys, &e->big_cnt, &e->big_list, &e->big_set, &e->big_cand, &e->keys_a, &e->keys_b,
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
-                   &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score,
+                   &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score, &e->em_pack,
                    &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->cls_fp, &e->out_pi,
                    &e->out_nr, &e->out_present};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
   if (e->read_off) cudaFree(e->read_off);
+  if (e->rkey) cudaFree(e->rkey);
+  if (e->rfp) cudaFree(e->rfp);
   e->ctab.release();
+  e->ct_w.release();
+  e->ct_slots.release();
   for (auto& b : e->ct_retired) b.release();
   if (e->d_totals) cudaFree(e->d_totals);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
@@ -740,6 +775,11 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
   if (n == "vote_tier") { e->vote_tier = (uint32_t)value; return SQ_OK; }
+  if (n == "class_table") {
+    if (e->n_batches) return fail(e, SQ_ERR_STATE, "option class_table must be set before the first push (or after sq_reset_reads)");
+    e->class_table = value != 0;
+    return SQ_OK;
+  }
   if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
@@ -1164,7 +1204,7 @@ int sq_reset_reads(sq_engine* e) {
   if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   memset(e->h_mirror, 0, 128);
-  if (e->ct_cap) launch_class_clear(e->ctab.p, e->ct_cap, e->stream, &e->launches);
+  if (e->ct_cap) launch_class_clear(e->ctab.p, e->ct_w.as<uint32_t>(), e->ct_cap, e->stream, &e->launches);
   for (auto& b : e->ct_retired) b.release();
   e->ct_retired.clear();
   e->P = 0;
@@ -1295,7 +1335,9 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   // ---- transcript-major copy of the pairs: stable radix sort on the transcript id ----
   uint64_t* keys = nullptr;
   uint32_t* vals = nullptr;
-  uint32_t n_seg = 0, n_classes = 0, n_cpairs = 0;
+  uint32_t n_seg = 0, n_classes = 0, n_cpairs = 0, pack_bad = 0;
+  bool packed = false;
+  uint32_t* d_pack_bad = reinterpret_cast<uint32_t*>(e->misc.as<char>() + 128);
   {
     StageScope sc(e, 3);
     SQ_CUDA(e, e->toff.ensure(((size_t)T + 1) * 4));
@@ -1313,12 +1355,13 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_CUDA(e, e->em_cnt.ensure((R + 2) * 4));
     SQ_CUDA(e, e->em_tid.ensure((P + 1) * 4));
     SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
+    SQ_CUDA(e, e->em_pack.ensure((P + 1) * 4));
     SQ_CUDA(e, e->cls_head.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_id.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_read.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_pos.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_weight.ensure((R + 2) * 8));
-    const bool use_table = R && e->keys_valid && !e->exact_classes && e->ct_cap && (e->h_mirror[10] & 0xFFFFFFFFull) == 0;
+    const bool use_table = R && e->class_table && e->keys_valid && !e->exact_classes && e->ct_cap && (e->h_mirror[10] & 0xFFFFFFFFull) == 0;
     if (use_table) {
       // the classes were collected while the batches arrived: order them and copy their lists
       n_classes = (uint32_t)e->h_mirror[8];
@@ -1331,17 +1374,21 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(nmax) * 4));
       SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, (uint64_t)n_classes + 1)) * 4));
       const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(T));
-      launch_class_collect(e->ctab.p, e->ct_cap, e->read_off, e->cand_tid, tbits, e->keys_a.as<uint64_t>(),
-                           e->vals_a.as<uint32_t>(), reinterpret_cast<uint32_t*>(e->misc.as<char>() + 96), st, &e->launches);
+      launch_class_collect(e->ctab.p, e->ct_slots.as<uint32_t>(), n_classes, e->read_off, e->cand_tid, tbits,
+                           e->keys_a.as<uint64_t>(), e->vals_a.as<uint32_t>(), st, &e->launches);
       uint64_t* skeys = nullptr;
       uint32_t* slot_of = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(), e->vals_b.as<uint32_t>(),
                         n_classes, 64, e->sort_tmp.as<uint32_t>(), &skeys, &slot_of, st, &e->launches);
-      launch_class_from_sorted(slot_of, n_classes, e->ctab.p, e->read_off, e->cls_read.as<uint32_t>(),
-                               e->em_cnt.as<uint32_t>(), e->cls_weight.as<double>(), st, &e->launches);
+      launch_class_from_sorted(slot_of, n_classes, e->ctab.p, e->ct_w.as<uint32_t>(), e->read_off,
+                               e->cls_read.as<uint32_t>(), e->em_cnt.as<uint32_t>(), e->cls_weight.as<double>(), st,
+                               &e->launches);
       launch_class_gather(e->cls_read.as<uint32_t>(), nullptr, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(),
                           n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid, e->cand_score,
-                          e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->cls_weight.as<double>(), st, &e->launches);
+                          e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(), d_pack_bad,
+                          e->cls_weight.as<double>(), st, &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(&pack_bad, d_pack_bad, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaStreamSynchronize(st));
     } else if (R) {
       SQ_CUDA(e, e->keys_a.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->keys_b.ensure((std::max(P, R) + 1) * 8));
@@ -1351,10 +1398,16 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, R + 1)) * 4));
       const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1));
       const uint32_t hash_bits = e->class_hash_bits;
-      SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
-      launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
-                        e->cls_fp.p, st, &e->launches);
-      const void* fp = e->cls_fp.p;
+      const void* fp = e->rfp;
+      if (e->keys_valid && !e->class_table && e->rkey) {
+        // keys and fingerprints were produced batch by batch by the compaction (the sort works on a copy)
+        SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));
+      } else {
+        SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
+        launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
+                          e->cls_fp.p, st, &e->launches);
+        fp = e->cls_fp.p;
+      }
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
@@ -1367,22 +1420,27 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       SQ_CUDA(e, cudaStreamSynchronize(st));
       launch_class_gather(e->cls_read.as<uint32_t>(), e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(),
                           e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid,
-                          e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(),
-                          e->cls_weight.as<double>(), st, &e->launches);
+                          e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(),
+                          d_pack_bad, e->cls_weight.as<double>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_cpairs, e->em_off.as<uint32_t>() + n_classes, 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(e, cudaMemcpyAsync(&pack_bad, d_pack_bad, 4, cudaMemcpyDeviceToHost, st));
       SQ_CUDA(e, cudaStreamSynchronize(st));
     } else {
       SQ_CUDA(e, cudaMemsetAsync(e->em_off.p, 0, 4, st));
     }
+    // transcript and score of a pair in one word (24 + 8 bits) when every score, id and class index fits: the two
+    // copies of the pairs the EM iterations stream are then half the size (and the sort below carries no values)
+    packed = n_cpairs && !pack_bad && T <= (1u << 24) && n_classes <= (1u << 24);
     if (n_cpairs) {
-      launch_make_sort_keys(e->em_off.as<uint32_t>(), n_classes, e->em_tid.as<uint32_t>(), e->keys_a.as<uint64_t>(),
-                            st, &e->launches);
-      SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->em_score.p, (size_t)n_cpairs * 4, cudaMemcpyDeviceToDevice, st));
+      launch_make_sort_keys(e->em_off.as<uint32_t>(), n_classes, packed ? e->em_pack.as<uint32_t>() : e->em_tid.as<uint32_t>(),
+                            packed, e->keys_a.as<uint64_t>(), st, &e->launches);
+      if (!packed)
+        SQ_CUDA(e, cudaMemcpyAsync(e->vals_a.p, e->em_score.p, (size_t)n_cpairs * 4, cudaMemcpyDeviceToDevice, st));
     }
     const int nbits = (int)std::max<uint32_t>(1, log2_ceil(T));
-    launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(),
-                      e->vals_b.as<uint32_t>(), n_cpairs, nbits, e->sort_tmp.as<uint32_t>(), &keys, &vals, st,
-                      &e->launches);
+    launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), packed ? nullptr : e->vals_a.as<uint32_t>(),
+                      packed ? nullptr : e->vals_b.as<uint32_t>(), n_cpairs, nbits, e->sort_tmp.as<uint32_t>(), &keys, &vals,
+                      st, &e->launches);
     launch_tmajor(keys, n_cpairs, T, e->em_seg, e->toff.as<uint32_t>(), e->tm_read.as<uint32_t>(),
                   e->nseg.as<uint32_t>(), e->seg_off.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), st, &e->launches);
     // segments: at most one per em_seg pairs plus one per transcript; the exact count stays on the device
@@ -1406,8 +1464,9 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
 
   EmView v;
   v.read_off = e->em_off.as<uint32_t>();
-  v.cand_tid = e->em_tid.as<uint32_t>();
+  v.cand_tid = packed ? e->em_pack.as<uint32_t>() : e->em_tid.as<uint32_t>();
   v.cand_score = e->em_score.as<int32_t>();
+  v.packed = packed;
   v.n_reads = n_classes;
   v.weight = e->cls_weight.as<double>();
   v.toff = e->toff.as<uint32_t>();

@@ -7,13 +7,14 @@ namespace sq {
 struct EmView {
   // read-major CSR
   const uint32_t* read_off;
-  const uint32_t* cand_tid;
+  const uint32_t* cand_tid;   // packed: transcript | score << 24 (cand_score unused)
   const int32_t* cand_score;
+  bool packed;                // both copies of the pairs carry the score in the top 8 bits of their 32-bit word
   uint64_t n_reads;           // rows of the CSR = equivalence classes of reads
   const double* weight;       // reads per class
   // transcript-major copy, split into segments of <= seg pairs
   const uint32_t* toff;
-  const uint32_t* tm_read;
+  const uint32_t* tm_read;    // packed: class | score << 24 (tm_score unused)
   const uint32_t* tm_score;
   const uint32_t* seg_off;    // per transcript: first segment (T+1 entries)
   const uint32_t* seg_tid;
@@ -43,16 +44,19 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
 
 void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
                     const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t cmask,
-                    unsigned long long* ccnt, cudaStream_t s, uint64_t* launches);
+                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t* cw, uint32_t cmask,
+                    unsigned long long* ccnt, uint32_t* cslots, uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp,
+                    cudaStream_t s, uint64_t* launches);
 // read-class table (32-byte slots), see sq_em.cu
-void launch_class_clear(void* tab, uint32_t cap, cudaStream_t s, uint64_t* launches);
-void launch_class_rehash(const void* old, uint32_t old_cap, void* tab, uint32_t cap, unsigned long long* scratch_counters,
-                         cudaStream_t s, uint64_t* launches);
-void launch_class_collect(const void* tab, uint32_t cap, const uint32_t* read_off, const uint32_t* cand_tid, uint32_t tbits,
-                          uint64_t* keys, uint32_t* vals, uint32_t* counter, cudaStream_t s, uint64_t* launches);
-void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* read_off,
-                              uint32_t* class_read, uint32_t* class_cnt, double* weight, cudaStream_t s, uint64_t* launches);
+void launch_class_clear(void* tab, uint32_t* cw, uint32_t cap, cudaStream_t s, uint64_t* launches);
+void launch_class_rehash(const void* old, const uint32_t* old_cw, void* tab, uint32_t* cw, uint32_t cap, uint32_t* slots,
+                         unsigned long long* counters, uint64_t n_classes_ub, cudaStream_t s, uint64_t* launches);
+void launch_class_collect(const void* tab, const uint32_t* slots, uint32_t n_classes, const uint32_t* read_off,
+                          const uint32_t* cand_tid, uint32_t tbits, uint64_t* keys, uint32_t* vals, cudaStream_t s,
+                          uint64_t* launches);
+void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* cw,
+                              const uint32_t* read_off, uint32_t* class_read, uint32_t* class_cnt, double* weight,
+                              cudaStream_t s, uint64_t* launches);
 
 void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
                        uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);
@@ -63,9 +67,9 @@ void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* 
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
                          uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
                          const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
-                         double* weight, cudaStream_t s, uint64_t* launches);
-void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, uint64_t* keys,
-                           cudaStream_t s, uint64_t* launches);
+                         uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches);
+void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, bool packed,
+                           uint64_t* keys, cudaStream_t s, uint64_t* launches);
 void launch_tmajor(const uint64_t* keys, uint64_t P, uint32_t T, uint32_t seg, uint32_t* toff, uint32_t* tm_read,
                    uint32_t* nseg, uint32_t* seg_off, uint32_t* scan_tmp, cudaStream_t s, uint64_t* launches);
 void launch_seg_expand(const uint32_t* toff, const uint32_t* seg_off, uint32_t T, uint32_t seg, uint32_t* seg_tid,

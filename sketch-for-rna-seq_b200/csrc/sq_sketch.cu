@@ -371,17 +371,35 @@ void launch_derive_offsets(const uint32_t* len, uint32_t n_reads, uint32_t* tmp,
   launch_exclusive_scan(tmp, base_off, n_reads, scan_tmp, s, launches);
 }
 
+// equal-length reads packed back to back, each starting at the next multiple of 4 bases: nothing to scan.  A read
+// of up to SQ_CHUNK bases is one item, so the item tables are written here too (item i = read i) and the three
+// item kernels are not needed.
 __global__ void fixed_layout_kernel(uint32_t* __restrict__ len, uint32_t* __restrict__ base_off, uint32_t n,
-                                    uint32_t L, uint32_t stride) {
+                                    uint32_t L, uint32_t stride, uint32_t* __restrict__ item_start,
+                                    uint32_t* __restrict__ item_read, KList ks, unsigned long long* __restrict__ stats) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n) len[r] = L;
-  if (r <= n) base_off[r] = r * stride;
+  if (r < n) {
+    len[r] = L;
+    if (item_read) item_read[r] = r;
+  }
+  if (r <= n) {
+    base_off[r] = r * stride;
+    if (item_start) item_start[r] = r;
+  }
+  if (r == 0 && stats && item_start) {
+    unsigned long long km = 0;
+    for (uint32_t i = 0; i < ks.nk; ++i) km += L >= ks.k[i] ? L - ks.k[i] + 1 : 0;
+    atomicAdd(stats + 0, km * n);
+    atomicAdd(stats + 1, (unsigned long long)L * n);
+  }
 }
 
-// equal-length reads packed back to back, each starting at the next multiple of 4 bases: nothing to scan
-void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, cudaStream_t s,
+// with_items: also write item_start / item_read (read_len <= SQ_CHUNK) and add the batch to the k-mer / base counters
+void launch_fixed_layout(uint32_t* len, uint32_t* base_off, uint32_t n_reads, uint32_t read_len, uint32_t* item_start,
+                         uint32_t* item_read, const KList& ks, unsigned long long* stats, cudaStream_t s,
                          uint64_t* launches) {
-  fixed_layout_kernel<<<n_reads / 256 + 1, 256, 0, s>>>(len, base_off, n_reads, read_len, (read_len + 3u) & ~3u);
+  fixed_layout_kernel<<<n_reads / 256 + 1, 256, 0, s>>>(len, base_off, n_reads, read_len, (read_len + 3u) & ~3u, item_start,
+                                                        item_read, ks, stats);
   if (launches) ++*launches;
 }
 

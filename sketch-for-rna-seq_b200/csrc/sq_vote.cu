@@ -552,13 +552,26 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
   if (valid) {
     const uint32_t item0 = P.item_start[r];
     if (P.item_start[r + 1] - item0 != 1) defer = true;
+    // counts, offsets and the first descriptors of every k-index are independent loads: all in flight at once
+    uint32_t nn[NK], oo[NK], d0[NK][4];
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) {
+      nn[ki] = P.tab[ki].present ? (uint32_t)P.cnt[(uint64_t)ki * P.n_items_ub + item0] : 0u;
+      oo[ki] = P.tab[ki].present ? P.hoff[(uint64_t)ki * P.n_items_ub + item0] : 0u;
+    }
+#pragma unroll
+    for (int ki = 0; ki < NK; ++ki) {
+      const uint32_t* pp = P.pay + (uint64_t)ki * P.hstride + oo[ki];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d0[ki][u] = (uint32_t)u < nn[ki] && nn[ki] <= kMaxCount ? __ldg(pp + u) : SQ_EMPTY;
+    }
 #pragma unroll
     for (int ki = 0; ki < NK; ++ki) {
       const IndexTable& tb = P.tab[ki];
       if (!tb.present || defer) continue;
-      const uint32_t n = (uint32_t)P.cnt[(uint64_t)ki * P.n_items_ub + item0];  // flagged counts are > kMaxCount
+      const uint32_t n = nn[ki];  // flagged counts are > kMaxCount
       if (n > kMaxCount) { defer = true; continue; }
-      const uint32_t* pp = P.pay + (uint64_t)ki * P.hstride + P.hoff[(uint64_t)ki * P.n_items_ub + item0];
+      const uint32_t* pp = P.pay + (uint64_t)ki * P.hstride + oo[ki];
       uint32_t nind = 0;
       auto place_add = [&](uint32_t base, unsigned long long mask) {
         const uint32_t m = win_place(A, base, mask);
@@ -594,7 +607,10 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
       };
       // the read's descriptors are consecutive words: four loads in flight, then the votes (no dependent access
       // for an inline descriptor)
-      for (uint32_t j = 0; j < n && !defer; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (!defer) vote(d0[ki][u]);
+      for (uint32_t j = 4; j < n && !defer; j += 4) {
         uint32_t d[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) d[u] = j + u < n ? __ldg(pp + j + u) : SQ_EMPTY;
@@ -712,7 +728,7 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
 // many hits, outside hits that could matter) goes to the warp-per-read kernel with the general hash table
 // (slow_list).  Maximum, filter, score and order over the 64 positions are done two positions per lane.
 static constexpr int kLongWarps = 4;
-static constexpr uint32_t kLongMaxHits = 1024;
+static constexpr uint32_t kLongMaxHits = 512;
 
 struct LongSmem {
   uint32_t hh[kLongMaxHits];  // hash of each hit
@@ -878,12 +894,9 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
       auto range = [&](uint32_t b, unsigned long long m) {
         const uint32_t hi = b + 63u - (uint32_t)__clzll((long long)m);
         if (b >= abase && hi < abase + 64u) {
-          const uint32_t sh = b - abase;
-          while (m) {
-            const uint32_t q = (uint32_t)__ffsll((long long)m) - 1;
-            m &= m - 1;
-            atomicAdd(&S.cnt[ki][sh + q], 1u);
-          }
+          uint32_t* c = &S.cnt[ki][b - abase];
+          for (uint32_t lo = (uint32_t)m; lo; lo &= lo - 1) atomicAdd(c + __ffs((int)lo) - 1, 1u);
+          for (uint32_t up = (uint32_t)(m >> 32); up; up &= up - 1) atomicAdd(c + 31 + __ffs((int)up), 1u);
         } else if (hi < abase || b >= abase + 64u) {
           ++outside;
         } else {
