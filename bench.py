@@ -334,8 +334,6 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     nk = len(ks)
     eng = sqb.Engine(ks, T, sketch_fraction=scale, chain_fraction=0.9, device=local)
     eng.set_option("batch_bases", 1 << 29)
-    if os.environ.get("SQ_BENCH_CLASS_TABLE"):
-        eng.set_option("class_table", int(os.environ["SQ_BENCH_CLASS_TABLE"]))
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     t0 = time.time()

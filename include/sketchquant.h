@@ -94,9 +94,6 @@ int sq_set_profiling(sq_engine* e, int enabled);
  * sq_push_reads_fixed, default 2^20): set before the first push.  "exact_classes" (any time):
  * 1 = reads are merged into one EM term only after comparing their candidate lists element by element,
  * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads).
- * "class_table" (before the first push): 1 = the compaction of every batch enters each read's list fingerprint in a
- * hash table of read classes, sq_finish then orders the classes instead of sorting the reads (default 0: its random
- * memory traffic competes with the index for L2, see profiles/r02_notes.md).
  * "vote_tier" (any time, tests): 0 = automatic, 1 = every read through the warp-per-read window kernel, 2 = every
  * read through the general warp-per-read kernel; the results do not depend on it. */
 int sq_set_option(sq_engine* e, const char* name, int64_t value);

@@ -116,13 +116,14 @@ struct VoteParams {
   uint32_t count_bits;               // planes of the bit-sliced counters (5: up to 31 hashes per read and k, 7: 127)
   uint32_t force_tier;               // tests: 0 = automatic, 1 = every read to the window kernel, 2 = every read to the general kernel
   IndexTable tab[SQ_MAXK];
-  // staging output (batch local)
-  uint32_t* stage_tid;
+  // output: the free tail of the engine's candidate store (no staging: what the vote writes is final)
+  uint32_t* stage_tid;               // store + stage_base
   int32_t* stage_score;
-  uint64_t stage_cap;
-  unsigned long long* stage_cursor;  // device counter
-  uint32_t* read_soff;               // per read: staging offset
-  uint32_t* read_cnt;                // per read: candidates
+  uint64_t stage_cap;                // free pairs behind stage_base
+  uint32_t stage_base;               // pairs of the earlier batches
+  unsigned long long* stage_cursor;  // device counter: pairs of this batch
+  uint32_t* read_soff;               // per read of the batch: start of its list in the store (absolute)
+  uint32_t* read_cnt;                // per read of the batch: candidates
   uint32_t* mid_list;                // reads the bit-sliced kernel hands to the warp-per-read window kernel
   uint32_t* mid_count;
   uint32_t* slow_list;               // reads the window kernel hands to the general warp-per-read kernel

@@ -90,224 +90,80 @@ struct ListHash {
   }
 };
 
-// ------------------------------------------------------------------ read classes, built while the batches arrive
-// EM does not care which read is which: reads with the same candidate list (same transcripts, same scores)
-// contribute identical terms, so they are collapsed into one class with a weight.  The compaction
-// of every batch (tail stream, idle most of the time) folds a 128-bit fingerprint of each list -- two independent
-// 64-bit non-cryptographic hashes over length, transcripts and scores -- and enters it in a lock-free open-addressing
-// table: slot = {h, g, weight, smallest read index of the class}.  A slot's h is claimed first, then its g; an
-// arrival with the same h and another g moves on like any other mismatch, so no thread ever waits for another.
-// When the last batch is in, the classes are all there: sq_finish only orders them (by best candidate and
-// fingerprint, which makes the order -- and every floating-point sum over classes -- independent of the order
-// of insertion) instead of sorting all the reads.  Element-wise comparison of the lists (option exact_classes), a
-// full table or a missing table fall back to sorting the reads by (best candidate, list hash).
-struct ClassSlot {
-  unsigned long long h, g;  // fingerprint; h == 0: free
-  uint32_t rep;             // a read of the class (its list is the class's list), written once by the creator
-  uint32_t pad0, pad1, pad2;
-};
-static constexpr uint32_t kClassMaxProbe = 256;
-
-// Seven reads in eight meet their class: one 16-byte load finds it (the table is only written when a class is
-// created, so its sectors stay clean), one atomic on the separate, eight times smaller and therefore L2-resident
-// array of weights counts the read.  counters: [0] classes, [1] (class, transcript) pairs, then a u32 overflow
-// flag; slots[i] = slot of the i-th class created.
-__device__ __forceinline__ void class_insert(ClassSlot* tab, uint32_t* cw, uint32_t mask, unsigned long long h,
-                                             unsigned long long g, uint32_t rep, uint32_t len,
-                                             unsigned long long* counters, uint32_t* slots) {
-  uint32_t s = (uint32_t)((h * 0x9E3779B97F4A7C15ull) >> 32) & mask;
-  for (uint32_t tries = 0; tries < kClassMaxProbe; ++tries, s = (s + 1) & mask) {
-    uint4 lo;  // h and g in one load that bypasses L1 (other SMs write these slots)
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(&tab[s]));
-    unsigned long long cur = ((unsigned long long)lo.y << 32) | lo.x;
-    unsigned long long og = ((unsigned long long)lo.w << 32) | lo.z;
-    if (cur == 0) {
-      const unsigned long long old = atomicCAS(&tab[s].h, 0ull, h);
-      cur = old == 0 ? h : old;
-      og = 0;
-    }
-    if (cur != h) continue;
-    if (og == 0) {
-      og = atomicCAS(&tab[s].g, 0ull, g);
-      if (og == 0) {  // this thread created the class
-        og = g;
-        tab[s].rep = rep;
-        const unsigned long long c = atomicAdd(counters + 0, 1ull);
-        atomicAdd(counters + 1, (unsigned long long)len);
-        if (slots) slots[c] = s;
-      }
-    }
-    if (og != g) continue;
-    atomicAdd(&cw[s], 1u);
-    return;
-  }
-  *reinterpret_cast<uint32_t*>(counters + 2) = 1;  // table too full: sq_finish takes the sort path
-}
-
-// staging (arbitrary order) -> final CSR in read order; pbase = pairs already in the store.  The read's list
-// fingerprint is folded on the way (the list is in flight anyway) and entered in the class table.
-__global__ void compact_kernel(const uint32_t* __restrict__ read_soff, const uint32_t* __restrict__ read_cnt,
-                               const uint32_t* __restrict__ batch_off, uint32_t n_reads,
-                               const uint32_t* __restrict__ stage_tid, const int32_t* __restrict__ stage_score,
-                               uint64_t pbase, uint64_t read_base, uint32_t* __restrict__ cand_tid,
-                               int32_t* __restrict__ cand_score, uint32_t* __restrict__ read_off,
-                               ClassSlot* ctab, uint32_t* cw, uint32_t cmask, unsigned long long* __restrict__ ccnt,
-                               uint32_t* __restrict__ cslots, uint32_t T, uint32_t hash_bits,
-                               uint64_t* __restrict__ rkey, ulonglong2* __restrict__ rfp) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const uint64_t dst = pbase + batch_off[r];
-  read_off[read_base + r] = (uint32_t)dst;
-  if (r == n_reads - 1) read_off[read_base + n_reads] = (uint32_t)(pbase + batch_off[n_reads]);
-  const uint32_t c = read_cnt[r], so = read_soff[r];
+// ------------------------------------------------------------------ candidate store and read classes
+// The vote kernels write a read's candidates straight into the engine's store (one atomic cursor; rd_start / rd_cnt
+// say where): nothing is staged, scanned or moved afterwards.  EM does not care which read is which: reads with
+// the same candidate list (same transcripts, same scores) contribute identical terms, so they are collapsed into
+// one class with a weight.  Behind every batch's vote a kernel folds a 128-bit fingerprint of each
+// list -- two independent 64-bit non-cryptographic hashes over length, transcripts and scores -- and the read's
+// class sort key (best candidate, a few hash bits, read index).  sq_finish sorts the keys; a read starts a class
+// when its list differs from its predecessor's: by fingerprint (an accidental 128-bit match of two different
+// lists would merge two EM terms and nothing else), or element-wise with option exact_classes (~10 random
+// sectors per read, 2.8 ms at 20 M reads).  Ordering by best candidate keeps the classes of one gene adjacent,
+// which makes the 1/den gathers of the transcript-major pass local.  Summing w identical terms becomes one
+// multiplication by w: a re-association only.
+__global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restrict__ rd_start,
+                                                        const uint32_t* __restrict__ rd_cnt, uint64_t r0, uint32_t n,
+                                                        const uint32_t* __restrict__ cand_tid,
+                                                        const int32_t* __restrict__ cand_score, uint32_t T,
+                                                        uint32_t hash_bits, uint64_t* __restrict__ rkey,
+                                                        ulonglong2* __restrict__ rfp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t r = r0 + i;
+  const uint32_t c = rd_cnt[r], so = rd_start[r];
   ListHash lh;
   lh.init(c);
-  uint32_t top = T;  // sort path: reads without candidates go last (one empty class)
+  uint32_t top = T;  // reads without candidates go last (one empty class)
   // blocks of 4 candidates: the eight loads go out together (the kernel waits on latency, the fold is serial)
   for (uint32_t i0 = 0; i0 < c; i0 += 4) {
     uint32_t t[4];
     int32_t sc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      t[u] = i0 + u < c ? stage_tid[so + i0 + u] : 0u;
-      sc[u] = i0 + u < c ? stage_score[so + i0 + u] : 0;
+      t[u] = i0 + u < c ? cand_tid[so + i0 + u] : 0u;
+      sc[u] = i0 + u < c ? cand_score[so + i0 + u] : 0;
     }
     if (i0 == 0) top = t[0];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + u < c) {
-        cand_tid[dst + i0 + u] = t[u];
-        cand_score[dst + i0 + u] = sc[u];
-        lh.add(t[u], sc[u]);
-      }
+      if (i0 + u < c) lh.add(t[u], sc[u]);
   }
-  if (rkey) {  // sort path of sq_finish: the read's class sort key and list fingerprint
-    rkey[read_base + r] = lh.key(top, hash_bits, read_base + r);
-    rfp[read_base + r] = make_ulonglong2(lh.h, lh.g);
-  }
-  // a read without candidates adds nothing to any EM sum (isoform_assignment.cpp:36-45): it needs no class
-  if (ctab && c) class_insert(ctab, cw, cmask, lh.h ? lh.h : 1ull, lh.g ? lh.g : 1ull, (uint32_t)(read_base + r), c, ccnt, cslots);
+  rkey[r] = lh.key(top, hash_bits, r);
+  rfp[r] = make_ulonglong2(lh.h, lh.g);
 }
 
-void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
-                    const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t* cw, uint32_t cmask,
-                    unsigned long long* ccnt, uint32_t* cslots, uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp,
-                    cudaStream_t s, uint64_t* launches) {
-  if (!n_reads) return;
-  compact_kernel<<<(n_reads + 255) / 256, 256, 0, s>>>(read_soff, read_cnt, batch_off, n_reads, stage_tid,
-                                                       stage_score, pbase, read_base, cand_tid, cand_score, read_off,
-                                                       static_cast<ClassSlot*>(ctab), cw, cmask, ccnt, cslots, T, hash_bits,
-                                                       rkey, static_cast<ulonglong2*>(rfp));
+void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n,
+                      const uint32_t* cand_tid, const int32_t* cand_score, uint32_t T, uint32_t hash_bits, uint64_t* rkey,
+                      void* rfp, cudaStream_t s, uint64_t* launches) {
+  if (!n) return;
+  read_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, r0, (uint32_t)n, cand_tid, cand_score, T,
+                                                               hash_bits, rkey, static_cast<ulonglong2*>(rfp));
   if (launches) ++*launches;
 }
 
-// a grown table takes over the classes of the old one (in creation order: the slot list is rewritten in place)
-__global__ void class_rehash_kernel(const ClassSlot* __restrict__ old, const uint32_t* __restrict__ old_cw, ClassSlot* tab,
-                                    uint32_t* __restrict__ cw, uint32_t mask, uint32_t* __restrict__ slots,
-                                    unsigned long long* __restrict__ counters) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (uint32_t)counters[0]) return;
-  const uint32_t os = slots[i];
-  const ClassSlot sl = old[os];
-  uint32_t s = (uint32_t)((sl.h * 0x9E3779B97F4A7C15ull) >> 32) & mask;
-  for (uint32_t tries = 0; tries < kClassMaxProbe; ++tries, s = (s + 1) & mask) {
-    if (atomicCAS(&tab[s].h, 0ull, sl.h) != 0ull) continue;  // classes are distinct: a taken slot is someone else's
-    tab[s].g = sl.g;
-    tab[s].rep = sl.rep;
-    cw[s] = old_cw[os];
-    slots[i] = s;
-    return;
-  }
-  *reinterpret_cast<uint32_t*>(counters + 2) = 1;
-}
-
-void launch_class_clear(void* tab, uint32_t* cw, uint32_t cap, cudaStream_t s, uint64_t* launches) {
-  (void)launches;
-  if (!cap) return;
-  cudaMemsetAsync(tab, 0, (size_t)cap * sizeof(ClassSlot), s);
-  cudaMemsetAsync(cw, 0, (size_t)cap * 4, s);
-}
-
-// counters: the live class counters (number of classes to move; a full new table raises their flag)
-void launch_class_rehash(const void* old, const uint32_t* old_cw, void* tab, uint32_t* cw, uint32_t cap, uint32_t* slots,
-                         unsigned long long* counters, uint64_t n_classes_ub, cudaStream_t s, uint64_t* launches) {
-  launch_class_clear(tab, cw, cap, s, launches);
-  if (!old || !n_classes_ub) return;
-  class_rehash_kernel<<<(uint32_t)((n_classes_ub + 255) / 256), 256, 0, s>>>(static_cast<const ClassSlot*>(old), old_cw,
-                                                                             static_cast<ClassSlot*>(tab), cw, cap - 1, slots,
-                                                                             counters);
-  if (launches) ++*launches;
-}
-
-// classes -> (order key, slot): key = best candidate of the class in the high bits, fingerprint below
-__global__ void class_collect_kernel(const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ slots,
-                                     uint32_t n_classes, const uint32_t* __restrict__ read_off,
-                                     const uint32_t* __restrict__ cand_tid, uint32_t tbits,
-                                     unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_classes) return;
-  const uint32_t s = slots[i];
-  const ClassSlot sl = tab[s];
-  const unsigned long long top = cand_tid[read_off[sl.rep]];
-  keys[i] = (top << (64 - tbits)) | (sl.h >> tbits);
-  vals[i] = s;
-}
-
-// classes in their final order: representative read, list length, weight
-__global__ void class_from_sorted_kernel(const uint32_t* __restrict__ slot_of, uint32_t n_classes,
-                                         const ClassSlot* __restrict__ tab, const uint32_t* __restrict__ cw,
-                                         const uint32_t* __restrict__ read_off,
-                                         uint32_t* __restrict__ class_read, uint32_t* __restrict__ class_cnt,
-                                         double* __restrict__ weight) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_classes) return;
-  const uint32_t s = slot_of[c];
-  const uint32_t rep = tab[s].rep;
-  class_read[c] = rep;
-  class_cnt[c] = read_off[rep + 1] - read_off[rep];
-  weight[c] = (double)cw[s];
-}
-
-void launch_class_collect(const void* tab, const uint32_t* slots, uint32_t n_classes, const uint32_t* read_off,
-                          const uint32_t* cand_tid, uint32_t tbits, uint64_t* keys, uint32_t* vals, cudaStream_t s,
-                          uint64_t* launches) {
-  if (!n_classes) return;
-  class_collect_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(static_cast<const ClassSlot*>(tab), slots, n_classes, read_off,
-                                                               cand_tid, tbits, reinterpret_cast<unsigned long long*>(keys), vals);
-  if (launches) ++*launches;
-}
-
-void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* cw,
-                              const uint32_t* read_off, uint32_t* class_read, uint32_t* class_cnt, double* weight,
-                              cudaStream_t s, uint64_t* launches) {
-  if (!n_classes) return;
-  class_from_sorted_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(slot_of, n_classes, static_cast<const ClassSlot*>(tab), cw,
-                                                                   read_off, class_read, class_cnt, weight);
-  if (launches) ++*launches;
-}
-
-// ------------------------------------------------------------------ EM equivalence classes, sort path
-// (option exact_classes, candidates set through sq_set_candidates, or a class table that ran full.)  Reads are
-// sorted by (best candidate, hash of the list); a read starts a class when its list differs from its
-// predecessor's: element-wise with exact_classes (~10 random sectors per read, 2.8 ms at 20 M reads), else by
-// the same 128-bit non-cryptographic fingerprint the class table uses (an accidental match of two different
-// lists would merge two EM terms and nothing else).  Ordering by best candidate keeps the classes of one gene
-// adjacent, which makes the 1/den gathers of the transcript-major pass local.  Summing w identical terms
-// becomes one multiplication by w: a re-association only.
-__global__ void class_key_kernel(const uint32_t* __restrict__ read_off, uint64_t n_reads,
-                                 const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                 uint32_t T, uint32_t hash_bits, uint64_t* __restrict__ keys,
-                                 ulonglong2* __restrict__ fp) {
+// the store in read order (sq_get_candidates): off = exclusive scan of rd_cnt
+__global__ void csr_gather_kernel(const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
+                                  const uint32_t* __restrict__ off, uint64_t n_reads,
+                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                  uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
-  const uint32_t b = read_off[r], e = read_off[r + 1];
-  ListHash lh;
-  lh.init(e - b);
-  for (uint32_t j = b; j < e; ++j) lh.add(cand_tid[j], cand_score[j]);
-  fp[r] = make_ulonglong2(lh.h, lh.g);
-  const uint64_t top = b < e ? cand_tid[b] : T;  // reads without candidates go last (one empty class)
-  keys[r] = lh.key(top, hash_bits, r);
+  const uint32_t b = rd_start[r], n = rd_cnt[r], d = off[r];
+  for (uint32_t j = 0; j < n; ++j) {
+    out_tid[d + j] = cand_tid[b + j];
+    out_score[d + j] = cand_score[b + j];
+  }
+}
+
+void launch_csr_gather(const uint32_t* rd_start, const uint32_t* rd_cnt, uint32_t* off, uint64_t n_reads,
+                       uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid,
+                       int32_t* out_score, cudaStream_t s, uint64_t* launches) {
+  launch_exclusive_scan(rd_cnt, off, (uint32_t)n_reads, scan_tmp, s, launches);
+  if (!n_reads) return;
+  csr_gather_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, off, n_reads, cand_tid, cand_score,
+                                                                      out_tid, out_score);
+  if (launches) ++*launches;
 }
 
 __global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
@@ -331,15 +187,16 @@ __global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_
 
 // exact variant (option exact_classes): equal key AND element-wise equal lists; ~10 random sectors per read
 __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
-                                        const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ cand_tid,
-                                        const int32_t* __restrict__ cand_score, uint32_t* __restrict__ head) {
+                                        const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
+                                        const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                        uint32_t* __restrict__ head) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   uint32_t h = 1;
   if (i > 0 && (keys[i] >> 32) == (keys[i - 1] >> 32)) {
     const uint32_t r = (uint32_t)keys[i], q = (uint32_t)keys[i - 1];
-    const uint32_t b = read_off[r], n = read_off[r + 1] - b, bq = read_off[q];
-    if (read_off[q + 1] - bq == n) {
+    const uint32_t b = rd_start[r], n = rd_cnt[r], bq = rd_start[q];
+    if (rd_cnt[q] == n) {
       h = 0;
       for (uint32_t j = 0; j < n; ++j)
         if (cand_tid[b + j] != cand_tid[bq + j] || cand_score[b + j] != cand_score[bq + j]) { h = 1; break; }
@@ -351,7 +208,7 @@ __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint6
 // class c = run of sorted positions starting at a head: its list is the head's, its weight the run length
 __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ cid,
                                   const uint64_t* __restrict__ keys, uint64_t n_reads,
-                                  const uint32_t* __restrict__ read_off, uint32_t* __restrict__ class_read,
+                                  const uint32_t* __restrict__ rd_cnt, uint32_t* __restrict__ class_read,
                                   uint32_t* __restrict__ class_pos, uint32_t* __restrict__ class_cnt) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
@@ -359,21 +216,22 @@ __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint3
     const uint32_t c = cid[i], r = (uint32_t)keys[i];
     class_read[c] = r;
     class_pos[c] = (uint32_t)i;
-    class_cnt[c] = read_off[r + 1] - read_off[r];
+    class_cnt[c] = rd_cnt[r];
   }
   if (i == n_reads - 1) class_pos[cid[n_reads]] = (uint32_t)n_reads;  // cid[n_reads] = number of classes
 }
 
 __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, const uint32_t* __restrict__ class_pos,
                                     const uint32_t* __restrict__ class_off, uint32_t n_classes,
-                                    const uint32_t* __restrict__ read_off, const uint32_t* __restrict__ cand_tid,
-                                    const int32_t* __restrict__ cand_score, uint32_t* __restrict__ out_tid,
-                                    int32_t* __restrict__ out_score, uint32_t* __restrict__ out_pack,
+                                    const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
+                                    const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
+                                    uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score,
+                                    uint32_t* __restrict__ out_pack,
                                     uint32_t* __restrict__ pack_bad, double* __restrict__ weight) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_classes) return;
   const uint32_t r = class_read[c];
-  const uint32_t b = read_off[r], n = read_off[r + 1] - b, d = class_off[c];
+  const uint32_t b = rd_start[r], n = rd_cnt[r], d = class_off[c];
   bool bad = false;
   for (uint32_t j = 0; j < n; ++j) {
     const uint32_t t = cand_tid[b + j];
@@ -386,39 +244,31 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
     bad |= (uint32_t)sc > 255u || t > 0xFFFFFFu;
   }
   if (bad) *pack_bad = 1;
-  if (class_pos) weight[c] = (double)(class_pos[c + 1] - class_pos[c]);  // sort path; the table path wrote it already
-}
-
-void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
-                       uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches) {
-  if (!n_reads) return;
-  class_key_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(read_off, n_reads, cand_tid, cand_score, T,
-                                                                     hash_bits, keys, static_cast<ulonglong2*>(fp));
-  if (launches) ++*launches;
+  weight[c] = (double)(class_pos[c + 1] - class_pos[c]);
 }
 
 // heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + class table (read, position, count)
-void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
-                        const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
+                        const void* fp, const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, read_off, cand_tid, cand_score, head);
+  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, rd_start, rd_cnt, cand_tid, cand_score, head);
   else class_head_kernel<<<grid, 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
   launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
-  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, read_off, class_read, class_pos, class_cnt);
+  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, rd_cnt, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;
 }
 
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
-                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
-                         const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* rd_start,
+                         const uint32_t* rd_cnt, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
                          uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches) {
   launch_exclusive_scan(class_cnt, class_off, n_classes, scan_tmp, s, launches);
   cudaMemsetAsync(pack_bad, 0, 4, s);
   if (!n_classes) return;
-  class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, read_off,
+  class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, rd_start, rd_cnt,
                                                               cand_tid, cand_score, out_tid, out_score, out_pack, pack_bad,
                                                               weight);
   if (launches) ++*launches;

@@ -42,19 +42,17 @@ struct DevBuf {
 
 struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
-  DevBuf nit, item_start, item_read, cnt, hsel, pay, hoff, read_soff, read_cnt, batch_off, ovf_list, slow_list, mid_list,
-      stage_tid, stage_score, scan_tmp;
+  DevBuf nit, item_start, item_read, cnt, hsel, pay, hoff, ovf_list, slow_list, mid_list, scan_tmp;
   cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr, fork = nullptr;
-  bool in_flight = false;   // compaction enqueued, `done` recorded
-  bool pending = false;     // vote enqueued, compaction not yet (needs the exact candidate count)
-  uint64_t stage_cap = 0;
+  bool in_flight = false;   // class keys enqueued, `done` recorded
+  bool pending = false;     // vote enqueued, its exact candidate count not yet seen by the host
   uint32_t n_reads = 0;
   uint64_t read_base = 0;
   VoteParams vp;
   int id = 0;
   void release() {
-    DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &hsel, &pay, &hoff, &read_soff, &read_cnt,
-                     &batch_off, &ovf_list, &slow_list, &mid_list, &stage_tid, &stage_score, &scan_tmp};
+    DevBuf* all[] = {&packed, &base_off, &len, &nit, &item_start, &item_read, &cnt, &hsel, &pay, &hoff,
+                     &ovf_list, &slow_list, &mid_list, &scan_tmp};
     for (DevBuf* b : all) b->release();
   }
 };
@@ -121,9 +119,6 @@ struct sq_engine {
   uint32_t sub_batch_reads = 1u << 20;  // sq_push_reads_fixed: reads per internal batch
   bool exact_classes = false;  // compare candidate lists element-wise instead of by 128-bit fingerprint
   uint32_t vote_tier = 0;      // tests: force every read through one vote tier (see VoteParams::force_tier)
-  bool class_table = false;    // collect the read classes in the compactions instead of sorting the reads in sq_finish
-                               // (measured: 0.5 ms less after the last copy of a host-fed pass, but its random traffic
-                               // costs a device-resident pass 3 ms: it competes with the index for L2)
   // batch slots
   Slot slot[2];
   int next_slot = 0;
@@ -140,17 +135,14 @@ struct sq_engine {
   DevBuf big_keys, big_cnt, big_list, big_set, big_cand;
   uint32_t big_cap_log2 = 0, big_set_log2 = 0;
   bool big_ready = false;
-  // candidate store (CSR over all pushed reads)
+  // candidate store over all pushed reads: the vote kernels append a read's list at an atomic cursor (read r:
+  // cand_*[rd_start[r] .. +rd_cnt[r])), so the lists of a batch are contiguous but not in read order
   uint32_t* cand_tid = nullptr;
   int32_t* cand_score = nullptr;
-  uint32_t* read_off = nullptr;
-  // read classes, built by the compactions (see sq_em.cu): table of 32-byte slots; retired tables wait for reset/destroy
-  DevBuf ctab, ct_w, ct_slots;           // slots, reads per slot, slot of the i-th class created
-  uint32_t ct_cap = 0;
-  std::vector<DevBuf> ct_retired;
-  unsigned long long* d_ccnt = nullptr;  // [0] classes, [1] class pairs, [2] low word: table-full flag
-  uint64_t* rkey = nullptr;              // sort path: per read class sort key and 128-bit list fingerprint, written by
-  void* rfp = nullptr;                   // the compactions when the class table is off
+  uint32_t* rd_start = nullptr;
+  uint32_t* rd_cnt = nullptr;
+  uint64_t* rkey = nullptr;              // per read: class sort key and 128-bit list fingerprint (see sq_em.cu), written
+  void* rfp = nullptr;                   // behind every batch's vote
   bool keys_valid = true;                // false: the store was filled by sq_set_candidates
   uint32_t class_hash_bits = 14;
   uint64_t cand_cap = 0, read_cap = 0;
@@ -267,36 +259,34 @@ int check_flags(sq_engine* e) {
   return SQ_OK;
 }
 
-// make sure the CSR store can take `reads` more reads (beyond read_base) and `pairs` more pairs (beyond P);
-// contents are preserved
+// make sure the store can take `reads` more reads (beyond read_base) and `pairs` more pairs (beyond P); contents
+// are preserved.  Growth is geometric; a steady-state pass (sq_reset_reads between passes) never reallocates.
 int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pairs) {
-  // the store is written by the compactions, which run on the tail stream
+  // earlier batches' class-key kernels (tail stream) may still read the store and write the per-read arrays
   cudaStream_t cs = e->tail_stream;
   const uint64_t need_reads = read_base + reads + 1;
   if (need_reads > e->read_cap) {
-    uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
-    uint32_t* p = nullptr;
+    const uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
+    uint32_t *ps = nullptr, *pc = nullptr;
     uint64_t* pk = nullptr;
     void* pf = nullptr;
-    SQ_CUDA(e, cudaMalloc(&p, cap * sizeof(uint32_t)));
-    if (!e->class_table) {
-      SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
-      SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
+    SQ_CUDA(e, cudaMalloc(&ps, cap * sizeof(uint32_t)));
+    SQ_CUDA(e, cudaMalloc(&pc, cap * sizeof(uint32_t)));
+    SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
+    SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
+    if (e->rd_start && read_base) {
+      SQ_CUDA(e, cudaMemcpyAsync(ps, e->rd_start, read_base * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(pc, e->rd_cnt, read_base * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
+      SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
     }
-    if (e->read_off) {
-      SQ_CUDA(e, cudaMemcpyAsync(p, e->read_off, (read_base + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
-      if (pk && e->rkey) {
-        SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
-        SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
-      }
-      SQ_CUDA(e, cudaStreamSynchronize(cs));
-      SQ_CUDA(e, cudaFree(e->read_off));
-    } else {
-      SQ_CUDA(e, cudaMemsetAsync(p, 0, sizeof(uint32_t), cs));
-    }
+    SQ_CUDA(e, cudaStreamSynchronize(cs));
+    if (e->rd_start) SQ_CUDA(e, cudaFree(e->rd_start));
+    if (e->rd_cnt) SQ_CUDA(e, cudaFree(e->rd_cnt));
     if (e->rkey) SQ_CUDA(e, cudaFree(e->rkey));
     if (e->rfp) SQ_CUDA(e, cudaFree(e->rfp));
-    e->read_off = p;
+    e->rd_start = ps;
+    e->rd_cnt = pc;
     e->rkey = pk;
     e->rfp = pf;
     e->read_cap = cap;
@@ -310,18 +300,28 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
     int32_t* sc = nullptr;
     SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint32_t)));
     SQ_CUDA(e, cudaMalloc(&sc, cap * sizeof(int32_t)));
-    if (e->cand_tid) {
+    if (e->cand_tid && e->P) {
       SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, e->P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
       SQ_CUDA(e, cudaMemcpyAsync(sc, e->cand_score, e->P * sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
-      SQ_CUDA(e, cudaStreamSynchronize(cs));
-      SQ_CUDA(e, cudaFree(e->cand_tid));
-      SQ_CUDA(e, cudaFree(e->cand_score));
     }
+    SQ_CUDA(e, cudaStreamSynchronize(cs));
+    if (e->cand_tid) SQ_CUDA(e, cudaFree(e->cand_tid));
+    if (e->cand_score) SQ_CUDA(e, cudaFree(e->cand_score));
     e->cand_tid = t;
     e->cand_score = sc;
     e->cand_cap = cap;
   }
   return SQ_OK;
+}
+
+// point a batch's vote at the free tail of the store (called with the exact P of all earlier batches)
+void aim_vote_at_store(sq_engine* e, Slot& s) {
+  s.vp.stage_tid = e->cand_tid + e->P;
+  s.vp.stage_score = e->cand_score + e->P;
+  s.vp.stage_cap = e->cand_cap - e->P;
+  s.vp.stage_base = (uint32_t)e->P;
+  s.vp.read_soff = e->rd_start + s.read_base;
+  s.vp.read_cnt = e->rd_cnt + s.read_base;
 }
 
 int ensure_big_scratch(sq_engine* e) {
@@ -339,36 +339,6 @@ int ensure_big_scratch(sq_engine* e) {
   SQ_CUDA(e, cudaMemsetAsync(e->big_cnt.p, 0, w * tab * e->nk * 4, e->stream));
   e->launches += 2;
   e->big_ready = true;
-  return SQ_OK;
-}
-
-// The class table must keep its load low: it grows (classes re-entered by a kernel on the tail stream) when the
-// class count last reported by a compaction plus the reads of the coming batch passes 60 % of it.  The reports lag
-// a batch or two; should the table fill up anyway, the kernels raise a flag and sq_finish takes the sort path.
-int ensure_class_table(sq_engine* e, uint32_t batch_reads) {
-  cudaStream_t cs = e->tail_stream;
-  const uint64_t known = e->h_mirror[8];
-  const uint64_t bound = known + std::max<uint64_t>((uint64_t)batch_reads + batch_reads / 4, 1u << 16);
-  if (e->ct_cap && bound * 8 <= (uint64_t)e->ct_cap * 5) return SQ_OK;
-  uint64_t cap = std::max<uint64_t>(e->ct_cap, 1u << 22);
-  while (bound * 8 > cap * 5 && cap < (1ull << 30)) cap <<= 1;
-  if (cap == e->ct_cap) return SQ_OK;
-  DevBuf old, old_w, old_slots;
-  std::swap(old, e->ctab);
-  std::swap(old_w, e->ct_w);
-  std::swap(old_slots, e->ct_slots);
-  const uint32_t old_cap = e->ct_cap;
-  SQ_CUDA(e, e->ctab.ensure((size_t)cap * 32));
-  SQ_CUDA(e, e->ct_w.ensure((size_t)cap * 4));
-  SQ_CUDA(e, e->ct_slots.ensure((size_t)cap * 4));
-  e->ct_cap = (uint32_t)cap;
-  if (old_slots.p) SQ_CUDA(e, cudaMemcpyAsync(e->ct_slots.p, old_slots.p, (size_t)old_cap * 4, cudaMemcpyDeviceToDevice, cs));
-  launch_class_rehash(old.p, old_w.as<uint32_t>(), e->ctab.p, e->ct_w.as<uint32_t>(), e->ct_cap, e->ct_slots.as<uint32_t>(),
-                      e->d_ccnt, old_cap, cs, &e->launches);
-  // the old buffers are still read by what was just enqueued: freed at reset / destroy
-  if (old.p) e->ct_retired.push_back(old);
-  if (old_w.p) e->ct_retired.push_back(old_w);
-  if (old_slots.p) e->ct_retired.push_back(old_slots);
   return SQ_OK;
 }
 
@@ -394,26 +364,22 @@ int enqueue_vote(sq_engine* e, Slot& s) {
   return SQ_OK;
 }
 
-// The vote of a batch reports the exact number of candidate pairs; only then can they be moved into the
-// CSR store (grown exactly) in read order.  If the staging area was too small the vote is simply re-run
-// with a staging area of the reported size (the batch inputs are still in the slot).
+// The vote of a batch writes into the free tail of the store and reports the exact number of candidate pairs.
+// If the tail was too short the store grows and the vote is simply re-run (the batch's descriptors are still in
+// the slot); otherwise nothing is left to do but the reads' class keys.
 int finalize_slot(sq_engine* e, Slot& s) {
   if (!s.pending) return SQ_OK;
   SQ_CUDA(e, cudaEventSynchronize(s.voted));
   uint64_t needed = e->h_mirror[4 * s.id];
-  // Re-run the vote chain (the batch's descriptors are still in the slot) when the staging area was too small, or
-  // when a read needs the large-table scratch for the first time.  The work counters were complete after the
-  // first pass (every read was voted, only not stored), so the re-runs do not count.
+  // Re-run the vote chain when the store's tail was too short, or when a read needs the large-table scratch for
+  // the first time.  The work counters were complete after the first pass (every read was voted, only not
+  // stored), so the re-runs do not count.
   for (;;) {
     const bool need_big = (e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull) != 0 && s.vp.n_workers == 0;
-    if (needed <= s.stage_cap && !need_big) break;
-    if (needed > s.stage_cap) {
-      s.stage_cap = needed + needed / 8;
-      SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
-      SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
-      s.vp.stage_tid = s.stage_tid.as<uint32_t>();
-      s.vp.stage_score = s.stage_score.as<int32_t>();
-      s.vp.stage_cap = s.stage_cap;
+    if (needed <= s.vp.stage_cap && !need_big) break;
+    if (needed > s.vp.stage_cap) {
+      SQ_TRY(ensure_store(e, s.read_base, s.n_reads, needed + needed / 8));
+      aim_vote_at_store(e, s);
     }
     if (need_big) {
       SQ_TRY(ensure_big_scratch(e));
@@ -432,22 +398,13 @@ int finalize_slot(sq_engine* e, Slot& s) {
     needed = e->h_mirror[4 * s.id];
   }
   const uint64_t ovf = e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull;
-  SQ_TRY(ensure_store(e, s.read_base, s.n_reads, needed));
   {
-    // on the tail stream, behind this batch's vote follow-ups (the host has seen `voted`): the compaction is
-    // latency-bound and overlaps the next batch's sketch and vote on the engine stream
+    // on the tail stream, behind this batch's vote follow-ups (the host has seen `voted`): latency-bound, overlaps
+    // the next batch's sketch and vote on the engine stream
     cudaStream_t cs = e->tail_stream;
     StageScope st(e, 2, cs);
-    launch_exclusive_scan(s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads, s.scan_tmp.as<uint32_t>(),
-                          cs, &e->launches);
-    if (e->class_table) SQ_TRY(ensure_class_table(e, s.n_reads));
-    launch_compact(s.read_soff.as<uint32_t>(), s.read_cnt.as<uint32_t>(), s.batch_off.as<uint32_t>(), s.n_reads,
-                   s.stage_tid.as<uint32_t>(), s.stage_score.as<int32_t>(), e->P, s.read_base, e->cand_tid,
-                   e->cand_score, e->read_off, e->class_table ? e->ctab.p : nullptr, e->ct_w.as<uint32_t>(), e->ct_cap - 1,
-                   e->d_ccnt, e->ct_slots.as<uint32_t>(), (uint32_t)e->T, e->class_hash_bits, e->class_table ? nullptr : e->rkey,
-                   e->class_table ? nullptr : e->rfp, cs, &e->launches);
-    // the class counts so far reach the host behind the compaction: table growth and sq_finish read them there
-    SQ_CUDA(e, cudaMemcpyAsync(e->h_mirror + 8, e->d_ccnt, 24, cudaMemcpyDeviceToHost, cs));
+    launch_read_keys(e->rd_start, e->rd_cnt, s.read_base, s.n_reads, e->cand_tid, e->cand_score, (uint32_t)e->T,
+                     e->class_hash_bits, e->rkey, e->rfp, cs, &e->launches);
     SQ_CUDA(e, cudaGetLastError());
     SQ_CUDA(e, cudaEventRecord(s.done, cs));
   }
@@ -489,7 +446,6 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   if (items_ub64 >= 0xFFFFFFFFull || n_bases >= 0xFFFFFFFFull) return fail(e, SQ_ERR_ARG, "batch too large");
   const uint32_t items_ub = (uint32_t)items_ub64;
   const uint64_t hstride = ((n_bases + 3) & ~3ull) + 4;  // capacity per k: every k-mer of the batch (+ lookup padding)
-  s.stage_cap = std::max<uint64_t>((uint64_t)e->cand_per_read * n_reads, 4096);
   SQ_CUDA(e, s.nit.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.item_start.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.item_read.ensure((size_t)items_ub * 4));
@@ -497,14 +453,9 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.hsel.ensure((size_t)hstride * e->nk * 4));
   SQ_CUDA(e, s.pay.ensure((size_t)hstride * e->nk * 4));
   SQ_CUDA(e, s.hoff.ensure((size_t)items_ub * e->nk * 4));
-  SQ_CUDA(e, s.read_soff.ensure((size_t)n_reads * 4));
-  SQ_CUDA(e, s.read_cnt.ensure((size_t)n_reads * 4));
-  SQ_CUDA(e, s.batch_off.ensure(((size_t)n_reads + 1) * 4));
   SQ_CUDA(e, s.ovf_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.slow_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.mid_list.ensure((size_t)n_reads * 4));
-  SQ_CUDA(e, s.stage_tid.ensure((size_t)s.stage_cap * 4));
-  SQ_CUDA(e, s.stage_score.ensure((size_t)s.stage_cap * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
   // The batch before this one (other slot) must be finalized (host waits for its vote, then enqueues its
   // compaction).  Host batches: now, before the engine stream starts waiting for our copy, so the compaction
@@ -595,12 +546,15 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
       vp.tab[i].present = e->tab[i].present ? 1u : 0u;
       vp.tab[i].tbits = tbits;
     }
-    vp.stage_tid = s.stage_tid.as<uint32_t>();
-    vp.stage_score = s.stage_score.as<int32_t>();
-    vp.stage_cap = s.stage_cap;
+    // the vote writes into the free tail of the store (the batch before this one is finalized: P is exact); room
+    // for the expected pairs is made here, a batch that needs more is re-run by finalize_slot
+    s.n_reads = n_reads;
+    s.read_base = e->n_reads;
+    uint64_t expect = (uint64_t)e->cand_per_read * n_reads;
+    if (e->n_reads && e->P) expect = std::min<uint64_t>(expect, 2 * (e->P / e->n_reads + 1) * n_reads);  // twice the rate so far
+    SQ_TRY(ensure_store(e, s.read_base, n_reads, std::max<uint64_t>(expect, 4096)));
+    aim_vote_at_store(e, s);
     vp.stage_cursor = e->d_slot_ctr + 4 * s.id;
-    vp.read_soff = s.read_soff.as<uint32_t>();
-    vp.read_cnt = s.read_cnt.as<uint32_t>();
     vp.ovf_list = s.ovf_list.as<uint32_t>();
     vp.ovf_count = reinterpret_cast<uint32_t*>(e->d_slot_ctr + 4 * s.id + 1);
     vp.slow_list = s.slow_list.as<uint32_t>();
@@ -617,8 +571,6 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     vp.big_set_log2 = e->big_set_log2;
     vp.n_workers = e->big_ready ? e->n_workers : 0;  // the large-table scratch is made when a read first needs it
     vp.work = e->d_totals + 1;
-    s.n_reads = n_reads;
-    s.read_base = e->n_reads;
     {
       StageScope st(e, 8);  // seed lookup, one k-index at a time (each table L2-resident during its pass)
       for (uint32_t i = 0; i < e->nk; ++i) launch_lookup(vp, e->vote_cfg, i, e->stream, &e->launches);
@@ -704,7 +656,6 @@ int sq_create(sq_engine** out, int device, uint32_t nk, const uint32_t* ks, uint
   e->d_flags = reinterpret_cast<uint32_t*>(e->d_totals + 16);          // byte 128
   e->d_fail = e->d_flags + 1;                                          // byte 132
   e->d_hcur = reinterpret_cast<uint32_t*>(e->d_totals + 20);           // bytes 160..255 (3 x 8 counters)
-  e->d_ccnt = e->d_totals + 17;                                        // bytes 136..159
   if ((ce = cudaHostAlloc(reinterpret_cast<void**>(&e->h_mirror), 128, cudaHostAllocMapped)) != cudaSuccess) return bail(ce, "cudaHostAlloc");
   memset(e->h_mirror, 0, 128);
   *out = e;
@@ -741,13 +692,10 @@ void sq_destroy(sq_engine* e) {
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
   if (e->cand_score) cudaFree(e->cand_score);
-  if (e->read_off) cudaFree(e->read_off);
+  if (e->rd_start) cudaFree(e->rd_start);
+  if (e->rd_cnt) cudaFree(e->rd_cnt);
   if (e->rkey) cudaFree(e->rkey);
   if (e->rfp) cudaFree(e->rfp);
-  e->ctab.release();
-  e->ct_w.release();
-  e->ct_slots.release();
-  for (auto& b : e->ct_retired) b.release();
   if (e->d_totals) cudaFree(e->d_totals);
   if (e->h_mirror) cudaFreeHost(e->h_mirror);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -775,11 +723,6 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
   if (n == "vote_tier") { e->vote_tier = (uint32_t)value; return SQ_OK; }
-  if (n == "class_table") {
-    if (e->n_batches) return fail(e, SQ_ERR_STATE, "option class_table must be set before the first push (or after sq_reset_reads)");
-    e->class_table = value != 0;
-    return SQ_OK;
-  }
   if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
@@ -1201,12 +1144,8 @@ int sq_reset_reads(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
   SQ_CUDA(e, cudaMemsetAsync(e->d_totals, 0, 256, e->stream));
-  if (e->read_off) SQ_CUDA(e, cudaMemsetAsync(e->read_off, 0, 4, e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   memset(e->h_mirror, 0, 128);
-  if (e->ct_cap) launch_class_clear(e->ctab.p, e->ct_w.as<uint32_t>(), e->ct_cap, e->stream, &e->launches);
-  for (auto& b : e->ct_retired) b.release();
-  e->ct_retired.clear();
   e->P = 0;
   e->ovf_total = 0;
   e->slow_total = 0;
@@ -1229,12 +1168,23 @@ int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* 
   if (!e) return SQ_ERR_ARG;
   SQ_TRY(sq_sync(e));
   const uint64_t R = e->n_reads, P = e->P;
+  // the store keeps the lists in the order the vote kernels finished them: gather them in read order
   std::vector<uint32_t> tmp(R + 1, 0);
-  if (R) SQ_CUDA(e, cudaMemcpy(tmp.data(), e->read_off, (R + 1) * 4, cudaMemcpyDeviceToHost));
+  SQ_CUDA(e, e->em_off.ensure((R + 2) * 4));
+  SQ_CUDA(e, e->em_tid.ensure((P + 1) * 4));
+  SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
+  SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)(R + 1)) * 4));
+  if (R) {
+    launch_csr_gather(e->rd_start, e->rd_cnt, e->em_off.as<uint32_t>(), R, e->scan_tmp.as<uint32_t>(), e->cand_tid,
+                      e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->stream, &e->launches);
+    SQ_CUDA(e, cudaMemcpyAsync(tmp.data(), e->em_off.p, R * 4, cudaMemcpyDeviceToHost, e->stream));
+    SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+    tmp[R] = (uint32_t)P;
+  }
   if (read_off)
     for (uint64_t i = 0; i <= R; ++i) read_off[i] = tmp[i];
-  if (P && tid) SQ_CUDA(e, cudaMemcpy(tid, e->cand_tid, P * 4, cudaMemcpyDeviceToHost));
-  if (P && score) SQ_CUDA(e, cudaMemcpy(score, e->cand_score, P * 4, cudaMemcpyDeviceToHost));
+  if (P && tid) SQ_CUDA(e, cudaMemcpy(tid, e->em_tid.p, P * 4, cudaMemcpyDeviceToHost));
+  if (P && score) SQ_CUDA(e, cudaMemcpy(score, e->em_score.p, P * 4, cudaMemcpyDeviceToHost));
   if (P && tid && e->perm_ready && !e->perm_identity) {
     // the store holds internal ids, ordered (score desc, internal id asc): hand out the caller's ids, equal
     // scores in ascending order of those
@@ -1242,7 +1192,7 @@ int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* 
     const int32_t* sc = score;
     if (!sc) {
       sc_own.resize(P);
-      SQ_CUDA(e, cudaMemcpy(sc_own.data(), e->cand_score, P * 4, cudaMemcpyDeviceToHost));
+      SQ_CUDA(e, cudaMemcpy(sc_own.data(), e->em_score.p, P * 4, cudaMemcpyDeviceToHost));
       sc = sc_own.data();
     }
     for (uint64_t i = 0; i < P; ++i) tid[i] = e->ext_of[tid[i]];
@@ -1277,12 +1227,16 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
     e->perm_ready = true;
   }
   SQ_TRY(ensure_store(e, 0, n_reads, P));
-  std::vector<uint32_t> off32(n_reads + 1, 0);
-  for (uint64_t i = 0; i <= n_reads && n_reads; ++i) {
-    if (i && read_off[i] < read_off[i - 1]) return fail(e, SQ_ERR_ARG, "read_off must be non-decreasing");
-    off32[i] = (uint32_t)read_off[i];
+  std::vector<uint32_t> start32(n_reads + 1, 0), cnt32(n_reads + 1, 0);
+  for (uint64_t i = 0; i < n_reads; ++i) {
+    if (read_off[i + 1] < read_off[i]) return fail(e, SQ_ERR_ARG, "read_off must be non-decreasing");
+    start32[i] = (uint32_t)read_off[i];
+    cnt32[i] = (uint32_t)(read_off[i + 1] - read_off[i]);
   }
-  SQ_CUDA(e, cudaMemcpy(e->read_off, off32.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice));
+  if (n_reads) {
+    SQ_CUDA(e, cudaMemcpy(e->rd_start, start32.data(), n_reads * 4, cudaMemcpyHostToDevice));
+    SQ_CUDA(e, cudaMemcpy(e->rd_cnt, cnt32.data(), n_reads * 4, cudaMemcpyHostToDevice));
+  }
   if (P) {
     if (e->perm_identity) {
       SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
@@ -1295,7 +1249,7 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
   }
   e->P = P;
   e->n_reads = n_reads;
-  e->keys_valid = false;  // no compaction ran: sq_finish computes the class keys itself
+  e->keys_valid = false;  // no vote ran: sq_finish computes the class keys itself
   return SQ_OK;
 }
 
@@ -1361,35 +1315,7 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
     SQ_CUDA(e, e->cls_read.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_pos.ensure((R + 2) * 4));
     SQ_CUDA(e, e->cls_weight.ensure((R + 2) * 8));
-    const bool use_table = R && e->class_table && e->keys_valid && !e->exact_classes && e->ct_cap && (e->h_mirror[10] & 0xFFFFFFFFull) == 0;
-    if (use_table) {
-      // the classes were collected while the batches arrived: order them and copy their lists
-      n_classes = (uint32_t)e->h_mirror[8];
-      n_cpairs = (uint32_t)e->h_mirror[9];
-      const uint64_t nmax = std::max<uint64_t>(std::max<uint64_t>(P, n_classes), 1);
-      SQ_CUDA(e, e->keys_a.ensure((nmax + 1) * 8));
-      SQ_CUDA(e, e->keys_b.ensure((nmax + 1) * 8));
-      SQ_CUDA(e, e->vals_a.ensure((nmax + 1) * 4));
-      SQ_CUDA(e, e->vals_b.ensure((nmax + 1) * 4));
-      SQ_CUDA(e, e->sort_tmp.ensure(radix_tmp_words(nmax) * 4));
-      SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)std::max<uint64_t>(T, (uint64_t)n_classes + 1)) * 4));
-      const uint32_t tbits = std::max<uint32_t>(1, log2_ceil(T));
-      launch_class_collect(e->ctab.p, e->ct_slots.as<uint32_t>(), n_classes, e->read_off, e->cand_tid, tbits,
-                           e->keys_a.as<uint64_t>(), e->vals_a.as<uint32_t>(), st, &e->launches);
-      uint64_t* skeys = nullptr;
-      uint32_t* slot_of = nullptr;
-      launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), e->vals_a.as<uint32_t>(), e->vals_b.as<uint32_t>(),
-                        n_classes, 64, e->sort_tmp.as<uint32_t>(), &skeys, &slot_of, st, &e->launches);
-      launch_class_from_sorted(slot_of, n_classes, e->ctab.p, e->ct_w.as<uint32_t>(), e->read_off,
-                               e->cls_read.as<uint32_t>(), e->em_cnt.as<uint32_t>(), e->cls_weight.as<double>(), st,
-                               &e->launches);
-      launch_class_gather(e->cls_read.as<uint32_t>(), nullptr, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(),
-                          n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid, e->cand_score,
-                          e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(), d_pack_bad,
-                          e->cls_weight.as<double>(), st, &e->launches);
-      SQ_CUDA(e, cudaMemcpyAsync(&pack_bad, d_pack_bad, 4, cudaMemcpyDeviceToHost, st));
-      SQ_CUDA(e, cudaStreamSynchronize(st));
-    } else if (R) {
+    if (R) {
       SQ_CUDA(e, e->keys_a.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->keys_b.ensure((std::max(P, R) + 1) * 8));
       SQ_CUDA(e, e->vals_a.ensure((std::max(P, R) + 1) * 4));
@@ -1399,27 +1325,23 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       const uint32_t top_bits = std::max<uint32_t>(1, log2_ceil((uint64_t)T + 1));
       const uint32_t hash_bits = e->class_hash_bits;
       const void* fp = e->rfp;
-      if (e->keys_valid && !e->class_table && e->rkey) {
-        // keys and fingerprints were produced batch by batch by the compaction (the sort works on a copy)
-        SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));
-      } else {
-        SQ_CUDA(e, e->cls_fp.ensure((R + 1) * 16));
-        launch_class_keys(e->read_off, R, e->cand_tid, e->cand_score, T, hash_bits, e->keys_a.as<uint64_t>(),
-                          e->cls_fp.p, st, &e->launches);
-        fp = e->cls_fp.p;
-      }
+      // keys and fingerprints were produced batch by batch behind the votes (sq_set_candidates: here)
+      if (!e->keys_valid)
+        launch_read_keys(e->rd_start, e->rd_cnt, 0, R, e->cand_tid, e->cand_score, T, hash_bits, e->rkey, e->rfp, st,
+                         &e->launches);
+      SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));  // the sort works on a copy
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
                         (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
-      launch_class_heads(skeys, R, e->read_off, fp, e->cand_tid, e->cand_score, e->exact_classes,
+      launch_class_heads(skeys, R, e->rd_start, e->rd_cnt, fp, e->cand_tid, e->cand_score, e->exact_classes,
                          e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
       SQ_CUDA(e, cudaStreamSynchronize(st));
       launch_class_gather(e->cls_read.as<uint32_t>(), e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(),
-                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->read_off, e->cand_tid,
+                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->rd_start, e->rd_cnt, e->cand_tid,
                           e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(),
                           d_pack_bad, e->cls_weight.as<double>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_cpairs, e->em_off.as<uint32_t>() + n_classes, 4, cudaMemcpyDeviceToHost, st));

@@ -42,31 +42,20 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
                         uint32_t T, double* pi_out, double* nr_out, uint8_t* present_out, cudaStream_t s,
                         uint64_t* launches);
 
-void launch_compact(const uint32_t* read_soff, const uint32_t* read_cnt, const uint32_t* batch_off, uint32_t n_reads,
-                    const uint32_t* stage_tid, const int32_t* stage_score, uint64_t pbase, uint64_t read_base,
-                    uint32_t* cand_tid, int32_t* cand_score, uint32_t* read_off, void* ctab, uint32_t* cw, uint32_t cmask,
-                    unsigned long long* ccnt, uint32_t* cslots, uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp,
-                    cudaStream_t s, uint64_t* launches);
-// read-class table (32-byte slots), see sq_em.cu
-void launch_class_clear(void* tab, uint32_t* cw, uint32_t cap, cudaStream_t s, uint64_t* launches);
-void launch_class_rehash(const void* old, const uint32_t* old_cw, void* tab, uint32_t* cw, uint32_t cap, uint32_t* slots,
-                         unsigned long long* counters, uint64_t n_classes_ub, cudaStream_t s, uint64_t* launches);
-void launch_class_collect(const void* tab, const uint32_t* slots, uint32_t n_classes, const uint32_t* read_off,
-                          const uint32_t* cand_tid, uint32_t tbits, uint64_t* keys, uint32_t* vals, cudaStream_t s,
-                          uint64_t* launches);
-void launch_class_from_sorted(const uint32_t* slot_of, uint32_t n_classes, const void* tab, const uint32_t* cw,
-                              const uint32_t* read_off, uint32_t* class_read, uint32_t* class_cnt, double* weight,
-                              cudaStream_t s, uint64_t* launches);
-
-void launch_class_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, const int32_t* cand_score,
-                       uint32_t T, uint32_t hash_bits, uint64_t* keys, void* fp, cudaStream_t s, uint64_t* launches);
-void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* read_off, const void* fp,
-                        const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
+// candidate store: per-read class keys + fingerprints behind a batch's vote; the store in read order (taps)
+void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n,
+                      const uint32_t* cand_tid, const int32_t* cand_score, uint32_t T, uint32_t hash_bits, uint64_t* rkey,
+                      void* rfp, cudaStream_t s, uint64_t* launches);
+void launch_csr_gather(const uint32_t* rd_start, const uint32_t* rd_cnt, uint32_t* off, uint64_t n_reads,
+                       uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid,
+                       int32_t* out_score, cudaStream_t s, uint64_t* launches);
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
+                        const void* fp, const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches);
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
-                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* read_off,
-                         const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* rd_start,
+                         const uint32_t* rd_cnt, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
                          uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches);
 void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, bool packed,
                            uint64_t* keys, cudaStream_t s, uint64_t* launches);

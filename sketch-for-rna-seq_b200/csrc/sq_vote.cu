@@ -339,7 +339,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
     sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
     uint32_t kept = nc;
     if (sbase + nc > P.stage_cap) kept = 0;  // the host re-runs the vote with a staging area of the reported size
-    P.read_soff[r] = (uint32_t)sbase;
+    P.read_soff[r] = P.stage_base + (uint32_t)sbase;
     P.read_cnt[r] = kept;
   }
   sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
   const bool fits = sbase + wtot <= P.stage_cap;
   sbase += incl - nc;
   if (valid) {
-    P.read_soff[r] = (uint32_t)sbase;
+    P.read_soff[r] = P.stage_base + (uint32_t)sbase;
     P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
     if (fits && nc) {
       // ---- score = sum of the counts over k (:100); order: score descending (:108-109), transcript ascending
@@ -972,7 +972,7 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
     unsigned long long sbase = 0;
     if (lane == 0) {
       sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
-      P.read_soff[r] = (uint32_t)sbase;
+      P.read_soff[r] = P.stage_base + (uint32_t)sbase;
       P.read_cnt[r] = sbase + nc <= P.stage_cap ? nc : 0u;  // the host re-runs the vote with a staging area of the reported size
     }
     sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
