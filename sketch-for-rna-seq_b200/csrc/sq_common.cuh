@@ -98,6 +98,30 @@ struct IndexTable {
   uint32_t tbits;           // bits of a transcript id inside an inline descriptor
 };
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ list fingerprint (EM read classes, see sq_em.cu)
+// Two independent 64-bit hashes over (length, transcripts, scores) of a candidate list, folded step by step.
+struct ListHash {
+  uint64_t h, g;
+  __device__ __forceinline__ void init(uint32_t n) {
+    h = 0xcbf29ce484222325ull ^ n;
+    g = 0x9E3779B97F4A7C15ull + n;
+  }
+  __device__ __forceinline__ void add(uint32_t tid, int32_t score) {
+    const uint64_t x = ((uint64_t)tid << 32) | (uint32_t)score;
+    h ^= x;
+    h *= 0x100000001b3ull;
+    h ^= h >> 31;
+    g = (g ^ (x * 0xC2B2AE3D27D4EB4Full)) * 0xD6E8FEB86659FD93ull;
+    g ^= g >> 29;
+  }
+  // sort key in the high word (best candidate, then a few hash bits), read index in the low word
+  __device__ __forceinline__ uint64_t key(uint64_t top, uint32_t hash_bits, uint64_t r) const {
+    return (((top << hash_bits) | ((h ^ (h >> 32)) & ((1ull << hash_bits) - 1))) << 32) | r;
+  }
+};
+#endif
+
 struct VoteParams {
   const uint32_t* base_off;
   uint32_t bias;
@@ -124,6 +148,11 @@ struct VoteParams {
   unsigned long long* stage_cursor;  // device counter: pairs of this batch
   uint32_t* read_soff;               // per read of the batch: start of its list in the store (absolute)
   uint32_t* read_cnt;                // per read of the batch: candidates
+  // per read of the batch: class sort key and 128-bit list fingerprint, folded by whichever kernel emits the list
+  uint64_t* rkey;
+  void* rfp;                         // ulonglong2
+  uint64_t read_base;                // index of the batch's first read among all pushed reads (low word of the key)
+  uint32_t key_T, key_hash_bits;
   uint32_t* mid_list;                // reads the bit-sliced kernel hands to the warp-per-read window kernel
   uint32_t* mid_count;
   uint32_t* slow_list;               // reads the window kernel hands to the general warp-per-read kernel

@@ -68,28 +68,6 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
   if (launches) ++*launches;
 }
 
-// ------------------------------------------------------------------ list fingerprint (EM classes, see below)
-// Two independent 64-bit hashes over (length, transcripts, scores) of a candidate list, folded step by step.
-struct ListHash {
-  uint64_t h, g;
-  __device__ __forceinline__ void init(uint32_t n) {
-    h = 0xcbf29ce484222325ull ^ n;
-    g = 0x9E3779B97F4A7C15ull + n;
-  }
-  __device__ __forceinline__ void add(uint32_t tid, int32_t score) {
-    const uint64_t x = ((uint64_t)tid << 32) | (uint32_t)score;
-    h ^= x;
-    h *= 0x100000001b3ull;
-    h ^= h >> 31;
-    g = (g ^ (x * 0xC2B2AE3D27D4EB4Full)) * 0xD6E8FEB86659FD93ull;
-    g ^= g >> 29;
-  }
-  // sort key in the high word (best candidate, then a few hash bits), read index in the low word
-  __device__ __forceinline__ uint64_t key(uint64_t top, uint32_t hash_bits, uint64_t r) const {
-    return (((top << hash_bits) | ((h ^ (h >> 32)) & ((1ull << hash_bits) - 1))) << 32) | r;
-  }
-};
-
 // ------------------------------------------------------------------ candidate store and read classes
 // The vote kernels write a read's candidates straight into the engine's store (one atomic cursor; rd_start / rd_cnt
 // say where): nothing is staged, scanned or moved afterwards.  EM does not care which read is which: reads with

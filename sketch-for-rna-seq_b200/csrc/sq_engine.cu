@@ -43,8 +43,7 @@ struct DevBuf {
 struct Slot {
   DevBuf packed, base_off, len;  // only used for host pushes
   DevBuf nit, item_start, item_read, cnt, hsel, pay, hoff, ovf_list, slow_list, mid_list, scan_tmp;
-  cudaEvent_t done = nullptr, copied = nullptr, voted = nullptr, fork = nullptr;
-  bool in_flight = false;   // class keys enqueued, `done` recorded
+  cudaEvent_t copied = nullptr, voted = nullptr, fork = nullptr;
   bool pending = false;     // vote enqueued, its exact candidate count not yet seen by the host
   uint32_t n_reads = 0;
   uint64_t read_base = 0;
@@ -262,7 +261,7 @@ int check_flags(sq_engine* e) {
 // make sure the store can take `reads` more reads (beyond read_base) and `pairs` more pairs (beyond P); contents
 // are preserved.  Growth is geometric; a steady-state pass (sq_reset_reads between passes) never reallocates.
 int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pairs) {
-  // earlier batches' class-key kernels (tail stream) may still read the store and write the per-read arrays
+  // called with every earlier batch finalized, i.e. with no kernel in flight that touches the store
   cudaStream_t cs = e->tail_stream;
   const uint64_t need_reads = read_base + reads + 1;
   if (need_reads > e->read_cap) {
@@ -322,6 +321,11 @@ void aim_vote_at_store(sq_engine* e, Slot& s) {
   s.vp.stage_base = (uint32_t)e->P;
   s.vp.read_soff = e->rd_start + s.read_base;
   s.vp.read_cnt = e->rd_cnt + s.read_base;
+  s.vp.rkey = e->rkey;
+  s.vp.rfp = e->rfp;
+  s.vp.read_base = s.read_base;
+  s.vp.key_T = (uint32_t)e->T;
+  s.vp.key_hash_bits = e->class_hash_bits;
 }
 
 int ensure_big_scratch(sq_engine* e) {
@@ -366,7 +370,7 @@ int enqueue_vote(sq_engine* e, Slot& s) {
 
 // The vote of a batch writes into the free tail of the store and reports the exact number of candidate pairs.
 // If the tail was too short the store grows and the vote is simply re-run (the batch's descriptors are still in
-// the slot); otherwise nothing is left to do but the reads' class keys.
+// the slot).
 int finalize_slot(sq_engine* e, Slot& s) {
   if (!s.pending) return SQ_OK;
   SQ_CUDA(e, cudaEventSynchronize(s.voted));
@@ -398,17 +402,7 @@ int finalize_slot(sq_engine* e, Slot& s) {
     needed = e->h_mirror[4 * s.id];
   }
   const uint64_t ovf = e->h_mirror[4 * s.id + 1] & 0xFFFFFFFFull;
-  {
-    // on the tail stream, behind this batch's vote follow-ups (the host has seen `voted`): latency-bound, overlaps
-    // the next batch's sketch and vote on the engine stream
-    cudaStream_t cs = e->tail_stream;
-    StageScope st(e, 2, cs);
-    launch_read_keys(e->rd_start, e->rd_cnt, s.read_base, s.n_reads, e->cand_tid, e->cand_score, (uint32_t)e->T,
-                     e->class_hash_bits, e->rkey, e->rfp, cs, &e->launches);
-    SQ_CUDA(e, cudaGetLastError());
-    SQ_CUDA(e, cudaEventRecord(s.done, cs));
-  }
-  s.in_flight = true;
+  // nothing is left to do for the batch: its lists, class keys and fingerprints were written by the vote kernels
   s.pending = false;
   e->P += needed;
   e->ovf_total += ovf;
@@ -422,17 +416,12 @@ int acquire_slot(sq_engine* e, Slot** out) {
   Slot& s = e->slot[e->next_slot];
   s.id = e->next_slot;
   e->next_slot ^= 1;
-  if (!s.done) {
-    SQ_CUDA(e, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  if (!s.copied) {
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.voted, cudaEventDisableTiming));
     SQ_CUDA(e, cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
   }
   SQ_TRY(finalize_slot(e, s));
-  if (s.in_flight) {
-    SQ_CUDA(e, cudaEventSynchronize(s.done));
-    s.in_flight = false;
-  }
   *out = &s;
   return SQ_OK;
 }
@@ -670,7 +659,6 @@ void sq_destroy(sq_engine* e) {
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto& s : e->slot) {
     s.release();
-    if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.voted) cudaEventDestroy(s.voted);
     if (s.fork) cudaEventDestroy(s.fork);
@@ -1135,7 +1123,6 @@ int sq_sync(sq_engine* e) {
   SQ_TRY(finalize_slot(e, e->slot[e->next_slot ^ 1]));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   SQ_CUDA(e, cudaStreamSynchronize(e->tail_stream));
-  for (auto& s : e->slot) s.in_flight = false;
   resolve_events(e);
   return check_flags(e);
 }

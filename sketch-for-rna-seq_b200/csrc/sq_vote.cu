@@ -20,6 +20,14 @@
 
 namespace sq {
 
+// the read's class sort key and list fingerprint (see ListHash) leave with its list: no later pass over the store
+__device__ __forceinline__ void store_read_key(const VoteParams& P, uint32_t r, const ListHash& lh, uint32_t top) {
+  const uint64_t g = P.read_base + r;
+  P.rkey[g] = lh.key(top, P.key_hash_bits, g);
+  reinterpret_cast<ulonglong2*>(P.rfp)[g] = make_ulonglong2(lh.h, lh.g);
+}
+
+
 size_t vote_smem_bytes(uint32_t nk);
 
 static constexpr int kVoteWarps = 8;
@@ -341,6 +349,13 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
     if (sbase + nc > P.stage_cap) kept = 0;  // the host re-runs the vote with a staging area of the reported size
     P.read_soff[r] = P.stage_base + (uint32_t)sbase;
     P.read_cnt[r] = kept;
+    ListHash lh;  // rare tier: one lane folds the ordered list
+    lh.init(nc);
+    for (uint32_t i = 0; i < nc; ++i) {
+      const unsigned long long key = S.cand[i];
+      lh.add((uint32_t)key, (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32)));
+    }
+    store_read_key(P, r, lh, nc ? (uint32_t)S.cand[0] : P.key_T);
   }
   sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
   if (sbase + nc <= P.stage_cap)
@@ -678,12 +693,16 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
   if (valid) {
     P.read_soff[r] = P.stage_base + (uint32_t)sbase;
     P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
+    ListHash lh;
+    lh.init(nc);
+    uint32_t top = P.key_T;
     if (fits && nc) {
       // ---- score = sum of the counts over k (:100); order: score descending (:108-109), transcript ascending
       // inside a score
       constexpr int NS = NK == 1 ? NP : NP + 2;
       uint32_t SA[NS];
       planes_sum(A, SA);
+      top = 0xFFFFFFFFu;
       while (sa) {
         const uint32_t c = planes_max(SA, sa);
         uint32_t e1 = planes_equal(SA, sa, c);
@@ -693,10 +712,13 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
           e1 &= e1 - 1;
           P.stage_tid[sbase] = A.base + p;
           P.stage_score[sbase] = (int32_t)c;
+          lh.add(A.base + p, (int32_t)c);
+          if (top == 0xFFFFFFFFu) top = A.base + p;
           ++sbase;
         }
       }
     }
+    if (!defer) store_read_key(P, r, lh, top);  // a deferred read gets its key from the kernel that takes it
   }
   if (P.work) {
     wp = __reduce_add_sync(0xFFFFFFFFu, wp);
@@ -977,14 +999,25 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
     }
     sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
     __syncwarp();
-    if (sbase + nc <= P.stage_cap)
-      for (uint32_t i = lane; i < nc; i += 32) {
-        const unsigned long long key = S.cand[i];
-        uint32_t rank = 0;
-        for (uint32_t j = 0; j < nc; ++j) rank += S.cand[j] < key ? 1u : 0u;
+    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(S.bm1);  // 64 entries over bm1 + bm2 (done with)
+    const bool fits = sbase + nc <= P.stage_cap;
+    for (uint32_t i = lane; i < nc; i += 32) {
+      const unsigned long long key = S.cand[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nc; ++j) rank += S.cand[j] < key ? 1u : 0u;
+      sorted[rank] = key;
+      if (fits) {
         P.stage_tid[sbase + rank] = (uint32_t)key;
         P.stage_score[sbase + rank] = (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32));
       }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      ListHash lh;
+      lh.init(nc);
+      for (uint32_t i = 0; i < nc; ++i) lh.add((uint32_t)sorted[i], (int32_t)(0x7FFFFFFFu - (uint32_t)(sorted[i] >> 32)));
+      store_read_key(P, r, lh, nc ? (uint32_t)sorted[0] : P.key_T);
+    }
     wp += tp;
     __syncwarp();
   }
