@@ -72,54 +72,58 @@ __device__ __forceinline__ void emit_room(Emitter& E, uint32_t x) {
   }
 }
 
-// every window end in [c0, c1) of the read at bases [boff, boff+L): hashes <= thr are emitted in window order
+// every window end in [c0, c1) of the read at bases [boff, boff+L): hashes <= thr are emitted in window order.
+// Neither phase cares where the read starts inside a packed word: the bases are brought to bit 0 with one funnel
+// shift per 16 (the word pair is carried from block to block), so every lane of a warp runs the same number of
+// unrolled blocks whatever its alignment, and only the last (end - pos) mod 16 steps go one at a time.
 template <bool GLOBAL>
 __device__ __forceinline__ void roll_item(const uint32_t* wp, uint32_t tb, uint32_t k, uint32_t L, uint32_t boff,
                                           uint32_t c0, uint32_t c1, uint32_t thr, Emitter& E) {
   const uint32_t e_first = max(c0, k - 1);  // first window end that lies in this item
   if (L < k || e_first >= c1) return;
-  uint32_t x = 0, y = 0;  // lane value s: x = s[31:0], y = s[32:1]
-  // ---- fill the first window (k bases, no output): one base to reach an even position, then two bases
-  //      per table lookup (a nibble of the packed word), then a last single base if k is left odd
+  const uint32_t end = boff + c1;
+  const uint32_t last_w = (end - 1) >> 4;  // last packed word this item reads (words up to it belong to the read)
+  uint32_t x = 0, y = 0;                   // lane value s: x = s[31:0], y = s[32:1]
   uint32_t pos = boff + e_first - (k - 1);
-  const uint32_t wend = pos + k;
-  if (pos & 1) {
-    const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
-    x = d.x;
-    y = d.y;
-    ++pos;
-  }
-  while (pos + 2 <= wend) {
-    uint32_t w = wp[pos >> 4] >> ((pos & 15) * 2);
-    uint32_t n2 = min((wend - pos) >> 1, (16 - (pos & 15)) >> 1);  // pairs left in this word
-    pos += 2 * n2;
-    for (; n2; --n2) {
-      const uint2 d = lds_v2(tb + 128 + (w & 15) * 8);
-      const uint32_t nx = __funnelshift_l(y, x, 2) ^ d.x;
-      y = __funnelshift_l(y, x, 1) ^ d.y;
-      x = nx;
-      w >>= 4;
+  // ---- fill the first window (k bases, no output): 16 bases per funnel shift, two bases per table lookup (a
+  //      nibble of the packed word), a last single base when the count is odd
+  {
+    const uint32_t sh = 2 * (pos & 15);
+    uint32_t iw = pos >> 4, lo = wp[iw];
+    for (uint32_t left = k; left;) {
+      const uint32_t hi = iw + 1 <= last_w ? wp[iw + 1] : 0u;
+      uint32_t w = __funnelshift_r(lo, hi, sh);
+      lo = hi;
+      ++iw;
+      const uint32_t n = min(left, 16u);
+      left -= n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (2 * i + 1 < (int)n) {  // warp-uniform: k is
+          const uint2 d = lds_v2(tb + 128 + ((w >> (4 * i)) & 15) * 8);
+          const uint32_t nx = __funnelshift_l(y, x, 2) ^ d.x;
+          y = __funnelshift_l(y, x, 1) ^ d.y;
+          x = nx;
+        }
+      if (n & 1) {
+        const uint2 d = lds_v2(tb + 256 + ((w >> (2 * (n - 1))) & 3) * 8);
+        const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
+        y = x ^ d.y;
+        x = nx;
+      }
     }
-  }
-  if (pos < wend) {
-    const uint2 d = lds_v2(tb + 256 + code_at(wp, pos) * 8);
-    const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
-    y = x ^ d.y;
-    x = nx;
-    ++pos;
+    pos += k;
   }
   if (x <= thr) emit_checked<GLOBAL>(E, x);
+  if (pos >= end) return;
   // ---- roll: pos = absolute index of the incoming base, the outgoing one is k behind
-  const uint32_t end = boff + c1;
-  const uint32_t q = k >> 4, dr = k & 15;
-  auto partial = [&](uint32_t stop) {  // steps pos .. stop-1, all inside one incoming word
-    const uint32_t iw = pos >> 4, j0 = pos & 15;
-    uint32_t win = wp[iw] >> (2 * j0);
-    uint32_t wout = wp[iw - q];
-    // the word before is only needed for steps j < dr; when j0 >= dr it may lie before the read
-    if (dr) wout = __funnelshift_r(dr > j0 ? wp[iw - q - 1] : 0u, wout, 32 - 2 * dr);
-    wout >>= 2 * j0;
-    for (; pos < stop; ++pos) {
+  const uint32_t sh_i = 2 * (pos & 15), sh_o = 2 * ((pos - k) & 15);
+  uint32_t iw = pos >> 4, ow = (pos - k) >> 4;
+  uint32_t ilo = wp[iw], olo = wp[ow];
+  auto careful = [&](uint32_t n) {  // n <= 16 steps, one at a time, with the staging capacity test
+    const uint32_t ihi = iw + 1 <= last_w ? wp[iw + 1] : 0u, ohi = ow + 1 <= last_w ? wp[ow + 1] : 0u;
+    uint32_t win = __funnelshift_r(ilo, ihi, sh_i), wout = __funnelshift_r(olo, ohi, sh_o);
+    for (uint32_t j = 0; j < n; ++j) {
       const uint2 d = lds_v2(tb + ((win & 3) << 5) + ((wout & 3) << 3));
       const uint32_t nx = __funnelshift_l(y, x, 1) ^ d.x;
       y = x ^ d.y;
@@ -128,18 +132,23 @@ __device__ __forceinline__ void roll_item(const uint32_t* wp, uint32_t tb, uint3
       win >>= 2;
       wout >>= 2;
     }
+    pos += n;
+    ++iw;
+    ++ow;
+    ilo = ihi;
+    olo = ohi;
   };
-  if ((pos & 15) && pos < end) partial(min(end, (pos + 15) & ~15u));
-  // aligned blocks of 16 steps: one incoming word, the outgoing stream re-aligned by a funnel shift
   while (pos + 16 <= end) {
-    if (!GLOBAL && E.sp + 16 * 128 > E.sp_end) {  // the staging column may fill up inside this block: careful steps
-      partial(pos + 16);
+    if (!GLOBAL && E.sp + 16 * 128 > E.sp_end) {  // the staging column may fill up inside this block
+      careful(16);
       continue;
     }
-    const uint32_t iw = pos >> 4;
-    const uint32_t win = wp[iw];
-    uint32_t wout = wp[iw - q];
-    if (dr) wout = __funnelshift_r(wp[iw - q - 1], wout, 32 - 2 * dr);
+    const uint32_t ihi = iw + 1 <= last_w ? wp[iw + 1] : 0u, ohi = wp[ow + 1];  // ow + 1 <= iw: inside the read
+    const uint32_t win = __funnelshift_r(ilo, ihi, sh_i), wout = __funnelshift_r(olo, ohi, sh_o);
+    ilo = ihi;
+    olo = ohi;
+    ++iw;
+    ++ow;
     const uint32_t xe = ((win & 0x33333333u) << 2) | (wout & 0x33333333u);
     const uint32_t xo = (win & 0xCCCCCCCCu) | ((wout >> 2) & 0x33333333u);
 #pragma unroll
@@ -163,7 +172,7 @@ __device__ __forceinline__ void roll_item(const uint32_t* wp, uint32_t tb, uint3
     }
     pos += 16;
   }
-  if (pos < end) partial(end);
+  if (pos < end) careful(end - pos);
 }
 
 __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_constant__ SketchParams p) {
