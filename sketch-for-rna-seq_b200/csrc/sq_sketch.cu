@@ -186,7 +186,14 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   uint32_t* ostage = smem + p.nk * kLutWords + (kSketchBlock / 32) * kStageWordsPerWarp + warp * (p.cap * 32);
   // statistics: warps add their selected-hash counts here, the last one to arrive flushes (no exit barrier)
   __shared__ uint32_t s_sel, s_arrived;
-  if (threadIdx.x == 0) { s_sel = 0; s_arrived = 0; }
+  __shared__ __align__(8) unsigned long long s_bar[kSketchBlock / 32];  // one mbarrier per warp (used once: phase 0)
+  if (threadIdx.x == 0) {
+    s_sel = 0;
+    s_arrived = 0;
+    for (int w = 0; w < kSketchBlock / 32; ++w)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_bar[w])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   auto arrive = [&](uint32_t v) {  // called by one lane per warp
     if (!p.stats) return;
@@ -235,9 +242,29 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
     if (nw <= (uint32_t)kStageWordsPerWarp) {
       const uint32_t n4 = (nw + 3) >> 2;
       const uint4* src = reinterpret_cast<const uint4*>(p.packed + base4);
-      uint4* dst = reinterpret_cast<uint4*>(stage);
-      for (uint32_t i = lane; i < n4; i += 32) dst[i] = __ldg(src + i);
-      __syncwarp();
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        // the warp's span is one contiguous piece of the packed stream: one bulk copy (TMA engine, no register
+        // round trip, no per-lane load/store instructions) that signals the warp's mbarrier when the bytes landed
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[warp]);
+        if (lane == 0) {
+          const uint32_t bytes = n4 * 16;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           (uint32_t)__cvta_generic_to_shared(stage)),
+                       "l"(src), "r"(bytes), "r"(bar)
+                       : "memory");
+        }
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(done)
+                       : "r"(bar)
+                       : "memory");
+      } else {  // a caller's device buffer that is not 16-byte aligned
+        uint32_t* dst = stage;
+        for (uint32_t i = lane; i < nw; i += 32) dst[i] = __ldg(p.packed + base4 + i);
+        __syncwarp();
+      }
       wp = stage - base4;  // generic pointer: word index w lives at stage[w - base4]
     }
   }
