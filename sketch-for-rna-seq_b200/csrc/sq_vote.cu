@@ -602,47 +602,58 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
         else if (end <= A.base) { ++n_out[ki]; out_below_end = max(out_below_end, end); }
         else defer = true;
       };
+      // One call site of place_add per loop: with several k values the kernel's code would otherwise pass the
+      // instruction cache (6 000 instructions at three k values: two warps in three were waiting for instructions).
       auto vote = [&](uint32_t d) {
         if (d == SQ_EMPTY) return;
+        uint32_t base;
+        unsigned long long mask;
         if (desc_inline(d)) {
-          const unsigned long long mask = desc_mask(tb, d);
-          wp += (uint32_t)__popcll(mask);
-          place_add(desc_base(tb, d), mask);
-          return;
+          mask = desc_mask(tb, d);
+          base = desc_base(tb, d);
+        } else {
+          const uint4 hd = ld_hdr(tb.lhdr + (d & 0x7FFFFFFFu));
+          if (hd.x == SQ_NOMASK) { defer = true; return; }
+          if (hd.x >> 31) {  // two-range list: after the single-range ones (they anchor the window)
+            if (nind < kBitsMaxInd) s_ind[nind++][tx] = hd.w; else defer = true;
+            return;
+          }
+          mask = ((unsigned long long)hd.z << 32) | hd.y;
+          base = hd.x;
         }
-        const uint4 hd = ld_hdr(tb.lhdr + (d & 0x7FFFFFFFu));
-        if (hd.x == SQ_NOMASK) { defer = true; return; }
-        if (hd.x >> 31) {  // two-range list: after the single-range ones (they anchor the window)
-          if (nind < kBitsMaxInd) s_ind[nind++][tx] = hd.w; else defer = true;
-          return;
-        }
-        const unsigned long long mask = ((unsigned long long)hd.z << 32) | hd.y;
         wp += (uint32_t)__popcll(mask);
-        place_add(hd.x, mask);
+        place_add(base, mask);
       };
       // the read's descriptors are consecutive words: four loads in flight, then the votes (no dependent access
-      // for an inline descriptor)
+      // for an inline descriptor); the first four were loaded above
+      uint32_t d[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (!defer) vote(d0[ki][u]);
-      for (uint32_t j = 4; j < n && !defer; j += 4) {
-        uint32_t d[4];
+      for (int u = 0; u < 4; ++u) d[u] = d0[ki][u];
+      for (uint32_t j = 0; j < n && !defer; j += 4) {
+        if (j) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d[u] = j + u < n ? __ldg(pp + j + u) : SQ_EMPTY;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (!defer) vote(d[u]);
+          for (int u = 0; u < 4; ++u) d[u] = j + u < n ? __ldg(pp + j + u) : SQ_EMPTY;
+        }
+#pragma unroll(NK == 1 ? 4 : 1)
+        for (int u = 0; u < 4; ++u) {
+          if (!defer) vote(d[0]);
+          d[0] = d[1]; d[1] = d[2]; d[2] = d[3];
+        }
       }
       for (uint32_t i = 0; i < nind && !defer; ++i) {  // two-range lists: both ranges from the list's posting header
         const uint4* hp = reinterpret_cast<const uint4*>(tb.postings + s_ind[i][tx]);
         const uint4 hd = __ldg(hp), h2 = __ldg(hp + 1);
-        const unsigned long long mask = ((unsigned long long)hd.w << 32) | hd.z;
-        const unsigned long long mask2 = ((unsigned long long)h2.z << 32) | h2.y;
         wp += hd.x;
         // a list with both ranges outside the window still gives a transcript out there one vote at most
         const uint32_t before = n_out[ki];
-        place_add(hd.y & 0x7FFFFFFFu, mask);
-        if (!defer) place_add(h2.x, mask2);
+        uint32_t b0 = hd.y & 0x7FFFFFFFu, b1 = h2.x;
+        unsigned long long m0 = ((unsigned long long)hd.w << 32) | hd.z, m1 = ((unsigned long long)h2.z << 32) | h2.y;
+#pragma unroll(NK == 1 ? 2 : 1)
+        for (int h = 0; h < 2; ++h) {
+          if (!defer) place_add(b0, m0);
+          b0 = b1;
+          m0 = m1;
+        }
         if (n_out[ki] == before + 2) --n_out[ki];
       }
     }
