@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
     return;
   }
 
-  uint32_t L = 0, boff = 0, c0 = 0, c1 = 0;
+  uint32_t L = 0, boff = 0, c0 = 0, c1 = 0, nit = 1;
   if (valid) {
     const uint32_t r = p.item_read[item];
     const uint32_t ci = item - p.item_start[r];
     L = p.len[r];
     boff = p.base_off[r] - p.bias;
-    const uint32_t nit = items_of(L);
+    nit = items_of(L);
     const uint32_t clen = (L + nit - 1) / nit;
     c0 = ci * clen;
     c1 = min(L, c0 + clen);
@@ -286,8 +286,10 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
     n_sel += c;
     const bool raw = c > p.cap;  // did not fit: this lane rolls again, straight to global memory
     __syncwarp();
-    // ---- the sketch is a set: drop the repeats inside the item (a two-word filter says when to look at all)
-    if (p.dedup && !raw && c > 1) {
+    // ---- the sketch is a set: drop the repeats inside the item (a two-word filter says when to look at all).
+    // A read of several items is voted through a per-read set of hashes anyway (the same hash may sit in two of
+    // its items): its items keep their repeats.
+    if (p.dedup && !raw && c > 1 && nit == 1) {
       uint32_t m1 = 0, m2 = 0;
       for (uint32_t i = 0; i < c; ++i) {
         const uint32_t h = lds_u32(col + 128 * i);

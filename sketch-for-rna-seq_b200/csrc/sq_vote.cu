@@ -1156,6 +1156,11 @@ static cudaStream_t launch_tiers(const VoteParams& p, const VoteDeviceCfg& cfg, 
     const uint32_t lgrid = lneed < (uint32_t)cfg.long_grid ? lneed : (uint32_t)cfg.long_grid;
     vote_long_kernel<NK, false><<<lgrid, kLongWarps * 32, lsm, s>>>(p);
     if (ev_b) cudaEventRecord(ev_b, s);
+    if (tail && fork) {  // the general kernel sees ~1 % of the reads and waits on their longest: off the main stream
+      cudaEventRecord(fork, s);
+      cudaStreamWaitEvent(tail, fork, 0);
+      s = tail;
+    }
   }
   return s;
 }
