@@ -370,6 +370,14 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
                 eng.push_reads_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), 0, c["h_len"].data_ptr(), c["n"])
         return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), 0, 20, 0.01)
 
+    # the same pinned buffers copied to the device and nothing else: the host->device ceiling of `e2e` on this box
+    # (with N ranks: all ranks copy at the same time, as they do in the e2e leg)
+    d_sink = torch.empty(max(c["h_words"].numel() for c in chunks), dtype=chunks[0]["h_words"].dtype, device=dev)
+
+    def step_copy_only():
+        for c in chunks:
+            d_sink[:c["h_words"].numel()].copy_(c["h_words"], non_blocking=True)
+
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
             fn()
@@ -414,6 +422,7 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     # `value`); `roofline` is computed from these
     ms_prof, _, _, stage = timed(step_device, steps, 1, profile=True)
     ms_e2e, wall_e2e, _, _ = timed(step_host, steps, max(min(warmup, 3), 1))
+    ms_copy, _, _, _ = timed(step_copy_only, steps, 1)
     log("[bench] rank %d %s k=%s s=%g: device-resident %.2f ms/step, profiled %.2f, host-buffer e2e %.2f" % (
         rank, kind, ks, scale, ms / steps, ms_prof / steps, ms_e2e / steps))
     total_reads = n_reads * world
@@ -432,10 +441,11 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     # The lookup kernel: per probe the hash in (4 B), one table slot (8 B: key + descriptor) and the descriptor out
     # (4 B).  The first vote kernel (bit-sliced thread-per-read for short reads, warp-per-read window kernel for long
     # ones): per read item_start/cnt/hoff in and soff/cnt out, 4 B per descriptor, 4 B per posting of a hit list
-    # (4 B x deg; nine in ten arrive inside the descriptor, the information is the same), 8 B per candidate.
+    # (4 B x deg; nine in ten arrive inside the descriptor, the information is the same), 8 B per candidate,
+    # 24 B per read for the class sort key and list fingerprint the kernel folds while it emits the list.
     vote_name = "vote_bits_kernel" if kind != "long" else "vote_long_kernel"
     b_lookup = 16 * st["queries"]
-    b_vote = (12 + 6 * nk) * n_reads + 4 * st["queries"] + 4 * st["postings"] + 8 * st["pairs"] + 8 * n_reads
+    b_vote = (12 + 6 * nk) * n_reads + 4 * st["queries"] + 4 * st["postings"] + 8 * st["pairs"] + (8 + 24) * n_reads
     # EM: per iteration the class CSR and its transcript-major copy are read once each (12 B + 8 B gathered per
     # class pair, twice) plus the per-class and per-transcript vectors
     b_em = iters * (40 * st["em_class_pairs"] + 20 * st["em_classes"] + 16 * T)
@@ -485,6 +495,7 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
         "e2e": {"value": e2e_value, "unit": "reads/s",
                 "h2d_bytes_per_step": int(sum(c["h_words"].numel() * 4 + (0 if fixed_len else 4 * c["n"]) for c in chunks)),
                 "d2h_bytes_per_step": int(T * 17), "ms_per_step": ms_e2e / steps, "wall_ms_per_step": wall_e2e / steps,
+                "h2d_copy_only_ms_per_step": ms_copy / steps,
                 "input": "2-bit packed reads of one length in pinned host memory (sq_push_reads_fixed: lengths and offsets written on the GPU)"
                 if fixed_len else "2-bit packed reads + lengths in pinned host memory (sq_push_reads, offsets derived on the GPU)"},
         "gpu_launches": int(launches), "wall_ms_per_step": wall / steps, "clocks": clk, "roofline": roofline,

@@ -450,9 +450,9 @@ def test_repeated_id_in_a_posting_list(gpu_lib, sqb, port):
     assert off_g.tolist() == ooff.tolist() and tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
 
 
-def test_device_push_from_unaligned_buffer(gpu_lib, sqb, port):
-    """sq_push_reads_device with packed words that start 4, 8 or 12 bytes past a 16-byte boundary: the sketch kernel
-    stages a warp's span with one bulk copy only when the source is 16-byte aligned, otherwise lane by lane"""
+def test_device_push_alignment_contract(gpu_lib, sqb, port):
+    """sq_push_reads_device: packed words on a 16-byte boundary go through (the sketch kernel stages a warp's span
+    with one bulk copy, which needs that alignment); any other start is refused, not silently mis-read"""
     import torch
     d = dataset()
     ks = [21, 31]
@@ -461,20 +461,21 @@ def test_device_push_from_unaligned_buffer(gpu_lib, sqb, port):
     reads = d["reads"][:300] + [d["tseqs"][2][:2000]]
     words, off, ln = sqb.packing.pack_reads(reads)
     nb = int(sum(len(r) for r in reads))
-    res = []
-    for shift in (0, 1, 2, 3):
-        with sqb.Engine(ks, len(d["names"])) as e:
-            for i, k in enumerate(ks):
-                e.load_index(i, *postings[k])
-            buf = torch.zeros(words.shape[0] + 8, dtype=torch.int32, device="cuda")
+    with sqb.Engine(ks, len(d["names"])) as e:
+        for i, k in enumerate(ks):
+            e.load_index(i, *postings[k])
+        buf = torch.zeros(words.shape[0] + 8, dtype=torch.int32, device="cuda")
+        b = torch.from_numpy(off.astype(np.uint32).view(np.int32)).cuda()
+        l = torch.from_numpy(ln.astype(np.uint32).view(np.int32)).cuda()
+        for shift in (1, 2, 3):
             w = buf[shift:shift + words.shape[0]]
-            w.copy_(torch.from_numpy(words.view(np.int32)))
             assert w.data_ptr() % 16 == 4 * shift
-            b = torch.from_numpy(off.astype(np.uint32).view(np.int32)).cuda()
-            l = torch.from_numpy(ln.astype(np.uint32).view(np.int32)).cuda()
-            e.push_reads_device(w.data_ptr(), w.numel(), b.data_ptr(), l.data_ptr(), l.numel(), nb + 4 * l.numel())
-            res.append(e.candidates())
+            with pytest.raises(sqb.SketchQuantError):
+                e.push_reads_device(w.data_ptr(), w.numel(), b.data_ptr(), l.data_ptr(), l.numel(), nb + 4 * l.numel())
+        w = buf[4:4 + words.shape[0]]
+        w.copy_(torch.from_numpy(words.view(np.int32)))
+        e.push_reads_device(w.data_ptr(), w.numel(), b.data_ptr(), l.data_ptr(), l.numel(), nb + 4 * l.numel())
+        off_g, tid_g, score_g = e.candidates()
     _, ooff, otid, oscore, _ = port.chain_batch(ks, thr, 0.9, postings, reads)
-    for off_g, tid_g, score_g in res:
-        assert off_g.tolist() == ooff.tolist()
-        assert tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
+    assert off_g.tolist() == ooff.tolist()
+    assert tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
