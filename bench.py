@@ -334,6 +334,8 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     nk = len(ks)
     eng = sqb.Engine(ks, T, sketch_fraction=scale, chain_fraction=0.9, device=local)
     eng.set_option("batch_bases", 1 << 29)
+    if os.environ.get("SQ_BENCH_PEER_EXCHANGE"):  # A/B of the EM exchange at N > 1 (0: ncclAllReduce per iteration)
+        eng.set_option("peer_exchange", int(os.environ["SQ_BENCH_PEER_EXCHANGE"]))
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     t0 = time.time()
@@ -491,7 +493,8 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
                    "transcript_ids": "scrambled (--permute-ids)" if permute is not None else "generator order",
                    "l2_policy": "inputs (%.0f MB packed reads per pass) larger than the 126 MB L2; the index tables "
                                 "are meant to stay L2-resident" % (n_bases / 4 / 1e6),
-                   "parallelism": "reads sharded across %d GPU(s), index replicated, NCCL all-reduce of T-vectors" % world},
+                   "parallelism": "reads sharded across %d GPU(s), index replicated; EM sums per iteration: %s; NumReads/presence: one NCCL all-reduce each" % (
+                       world, "none (one GPU)" if world == 1 else ("exchanged over peer memory inside the M-step kernel" if st.get("peer_exchange") else "ncclAllReduce"))},
         "e2e": {"value": e2e_value, "unit": "reads/s",
                 "h2d_bytes_per_step": int(sum(c["h_words"].numel() * 4 + (0 if fixed_len else 4 * c["n"]) for c in chunks)),
                 "d2h_bytes_per_step": int(T * 17), "ms_per_step": ms_e2e / steps, "wall_ms_per_step": wall_e2e / steps,

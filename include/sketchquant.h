@@ -48,7 +48,8 @@ typedef struct sq_stats {
   uint64_t overflow_reads; /* reads that needed the large-table path */
   uint64_t batches;
   int32_t em_iterations;   /* executed by the last sq_finish */
-  int32_t reserved;
+  int32_t peer_exchange;   /* 1: the last sq_finish exchanged the EM sums over peer memory inside the M-step kernel,
+                            * 0: one GPU, or ncclAllReduce per iteration */
   /* device time of the kernels of each stage, ms, accumulated over batches (CUDA events on the engine stream;
    * only filled when profiling was enabled with sq_set_profiling) */
   float ms_sketch, ms_vote, ms_compact, ms_sort, ms_em, ms_assign;
@@ -94,6 +95,8 @@ int sq_set_profiling(sq_engine* e, int enabled);
  * sq_push_reads_fixed, default 2^20): set before the first push.  "exact_classes" (any time):
  * 1 = reads are merged into one EM term only after comparing their candidate lists element by element,
  * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads).
+ * "peer_exchange" (any time, every rank alike): 1 (default) = with a communicator the ranks' EM sums are exchanged over
+ * peer memory inside the M-step kernel when all ranks could map each other's buffers, 0 = ncclAllReduce per iteration.
  * "vote_tier" (any time, tests): 0 = automatic, 1 = every read through the warp-per-read window kernel, 2 = every
  * read through the general warp-per-read kernel; the results do not depend on it. */
 int sq_set_option(sq_engine* e, const char* name, int64_t value);

@@ -29,7 +29,7 @@ class SketchQuantError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("bases", C.c_uint64), ("kmers", C.c_uint64), ("sketch_hashes", C.c_uint64),
                 ("pairs", C.c_uint64), ("overflow_reads", C.c_uint64), ("batches", C.c_uint64),
-                ("em_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("em_iterations", C.c_int32), ("peer_exchange", C.c_int32),
                 ("ms_sketch", C.c_float), ("ms_vote", C.c_float), ("ms_compact", C.c_float), ("ms_sort", C.c_float),
                 ("ms_em", C.c_float), ("ms_assign", C.c_float), ("launches", C.c_uint64),
                 ("queries", C.c_uint64), ("hits", C.c_uint64), ("postings", C.c_uint64), ("ms_items", C.c_float),

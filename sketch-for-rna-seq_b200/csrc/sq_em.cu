@@ -523,6 +523,81 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
   }
 }
 
+// ------------------------------------------------------------------ several GPUs: exchange fused into the M-step
+// Reads are sharded, so every rank holds partial posterior sums of all T transcripts.  Instead of seg_sum ->
+// ncclAllReduce -> update -> converge (a collective and three launches per iteration), every rank writes its sums
+// into a buffer its peers have mapped (CUDA IPC over NVLink / NVSwitch), raises a flag in every peer's memory, and
+// the M-step kernel itself waits for the peers' flags and adds the N vectors in rank order while it updates pi: one
+// pass over peer memory, the same bits on every rank (the order of the sum is the rank order everywhere), no
+// collective.  The buffers are double-buffered by iteration parity: a rank can only be one iteration ahead of the
+// slowest one, because its next M-step waits for everybody's flag.
+__global__ void peer_signal_kernel(unsigned long long* const* __restrict__ peer_flags, uint32_t slot, uint32_t rank,
+                                   uint32_t nranks, unsigned long long epoch) {
+  // the sums were written by the kernels before this one on the stream; make them visible system-wide first
+  __threadfence_system();
+  if (threadIdx.x < nranks) {
+    unsigned long long* f = peer_flags[threadIdx.x] + (size_t)slot * nranks + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+  }
+}
+
+__device__ __forceinline__ double ld_peer(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) em_mstep_peer_kernel(const double* const* __restrict__ peer_ps,
+                                                            const unsigned long long* my_flags, uint32_t slot,
+                                                            uint32_t nranks, unsigned long long epoch, double* ps,
+                                                            double* pi, uint32_t T, double add_a, double add_b,
+                                                            double* __restrict__ block_change, double tol,
+                                                            uint32_t* state, double* last_change, uint32_t* err) {
+  if (state[0]) return;
+  __shared__ double sh[8], sh2[8];
+  __shared__ uint32_t s_last;
+  if (threadIdx.x < nranks) {  // every peer's sums of this iteration have landed (a dead peer must not hang the GPU)
+    const unsigned long long* f = my_flags + (size_t)slot * nranks + threadIdx.x;
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > 8000000000ll) { atomicOr(err, 1u); break; }  // ~4 s
+    }
+  }
+  __syncthreads();
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  double ch = 0.0;
+  if (t < T) {
+    double sum = 0.0;
+    for (uint32_t r = 0; r < nranks; ++r) sum += ld_peer(peer_ps[r] + (size_t)slot * T + t);  // rank order everywhere
+    ps[t] = sum;
+    const double np = (sum + add_a) + add_b;
+    ch = fabs(np - pi[t]);
+    pi[t] = np;
+  }
+  const double bsum = block_sum_256(ch, sh);
+  if (threadIdx.x == 0) {
+    block_change[blockIdx.x] = bsum;
+    __threadfence();
+    s_last = atomicAdd(&state[2], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (uint32_t i = threadIdx.x; i < gridDim.x; i += 256) s += *(volatile double*)&block_change[i];
+  const double tot = block_sum_256(s, sh2);
+  if (threadIdx.x == 0) {
+    state[2] = 0;
+    *last_change = tot;
+    __threadfence();
+    state[1] += 1;
+    if (tot < tol) state[0] = 1;  // :62-64
+  }
+}
+
 // ------------------------------------------------------------------ assignment (:70-97)
 template <int G, bool PACKED>
 __global__ void as_partial_kernel(const uint32_t* __restrict__ seg_tid, const uint32_t* __restrict__ seg_begin,
@@ -649,6 +724,22 @@ void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double t
   em_mstep_fused_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.partial, v.ps, v.pi, v.T, add_a, add_b,
                                                          v.block_change, tol, v.state, v.last_change);
   if (launches) ++*launches;
+}
+
+// per-transcript sums of this rank into `out` (the peer-visible exchange slot)
+void launch_seg_sum(const EmView& v, double* out, cudaStream_t s, uint64_t* launches) {
+  seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, out, v.state);
+  if (launches) ++*launches;
+}
+
+void launch_em_mstep_peer(const EmView& v, const double* const* peer_ps, unsigned long long* const* peer_flags,
+                          const unsigned long long* my_flags, uint32_t slot, uint32_t rank, uint32_t nranks,
+                          unsigned long long epoch, double add_a, double add_b, double tol, uint32_t* err, cudaStream_t s,
+                          uint64_t* launches) {
+  peer_signal_kernel<<<1, 32, 0, s>>>(peer_flags, slot, rank, nranks, epoch);
+  em_mstep_peer_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(peer_ps, my_flags, slot, nranks, epoch, v.ps, v.pi, v.T, add_a,
+                                                        add_b, v.block_change, tol, v.state, v.last_change, err);
+  if (launches) *launches += 2;
 }
 
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches) {

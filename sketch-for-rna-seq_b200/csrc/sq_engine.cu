@@ -71,6 +71,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load(std::string* err) {
@@ -81,6 +82,7 @@ struct NcclApi {
     GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
     CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
     if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { *err = "libnccl lacks required symbols"; return false; }
@@ -166,6 +168,15 @@ struct sq_engine {
   // NCCL
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  // EM exchange over peer memory (see sq_em.cu): this rank's two slots of T sums and 2 x nranks flags, the peers'
+  // mappings of theirs (CUDA IPC), the same as device arrays of pointers; epoch counts iterations over the
+  // engine's life (slot = epoch & 1, flags only ever grow)
+  bool peer_ok = false, peer_wanted = true, peer_used = false;
+  double* xbuf = nullptr;
+  unsigned long long* xflags = nullptr;
+  std::vector<void*> peer_mapped;  // what cudaIpcOpenMemHandle returned (closed in sq_destroy)
+  DevBuf d_peer_ps, d_peer_flags, d_peer_err;
+  unsigned long long epoch = 0;
 };
 
 namespace {
@@ -656,6 +667,12 @@ void sq_destroy(sq_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   resolve_events(e);
+  for (void* m : e->peer_mapped) cudaIpcCloseMemHandle(m);
+  if (e->xbuf) cudaFree(e->xbuf);
+  if (e->xflags) cudaFree(e->xflags);
+  e->d_peer_ps.release();
+  e->d_peer_flags.release();
+  e->d_peer_err.release();
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   for (auto& s : e->slot) {
     s.release();
@@ -711,6 +728,7 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
   if (n == "vote_tier") { e->vote_tier = (uint32_t)value; return SQ_OK; }
+  if (n == "peer_exchange") { e->peer_wanted = value != 0; return SQ_OK; }
   if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
@@ -1403,8 +1421,19 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   {
     StageScope sc(e, 4);
     launch_em_init(v.pi, T, state, st, &e->launches);
+    const bool peer = e->comm && e->peer_ok && e->peer_wanted;
+    e->peer_used = peer;
     for (int it = 0; it < em_iters; ++it) {
-      if (e->comm) {
+      if (peer) {
+        // this rank's sums go to its exchange slot; the M-step kernel adds all ranks' slots over peer memory
+        const unsigned long long epoch = ++e->epoch;
+        const uint32_t slot = (uint32_t)(epoch & 1);
+        launch_em_estep(v, st, &e->launches, false);
+        launch_seg_sum(v, e->xbuf + (size_t)slot * T, st, &e->launches);
+        launch_em_mstep_peer(v, e->d_peer_ps.as<const double*>(), e->d_peer_flags.as<unsigned long long*>(), e->xflags, slot,
+                             (uint32_t)e->rank, (uint32_t)e->nranks, epoch, add_a, add_b, em_tol,
+                             e->d_peer_err.as<uint32_t>(), st, &e->launches);
+      } else if (e->comm) {
         launch_em_estep(v, st, &e->launches, true);
         SQ_TRY(allreduce(e, v.ps, T, ncclDouble));
         launch_em_mstep(v, add_a, add_b, em_tol, st, &e->launches);
@@ -1432,8 +1461,11 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   SQ_CUDA(e, cudaMemcpyAsync(numreads, e->out_nr.p, (size_t)T * 8, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaMemcpyAsync(present, e->out_present.p, (size_t)T, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaMemcpyAsync(st_host, state, 8, cudaMemcpyDeviceToHost, st));
+  uint32_t peer_err = 0;
+  if (e->peer_ok) SQ_CUDA(e, cudaMemcpyAsync(&peer_err, e->d_peer_err.p, 4, cudaMemcpyDeviceToHost, st));
   SQ_CUDA(e, cudaStreamSynchronize(st));
   SQ_CUDA(e, cudaGetLastError());
+  if (peer_err) return fail(e, SQ_ERR_NCCL, "a peer rank did not deliver its sums within the exchange time-out");
   e->em_iterations = (int)st_host[1];
   if (iters_done) *iters_done = e->em_iterations;
   resolve_events(e);
@@ -1454,6 +1486,7 @@ int sq_get_stats(sq_engine* e, sq_stats* out) {
   out->overflow_reads = e->ovf_total;
   out->batches = e->n_batches;
   out->em_iterations = e->em_iterations;
+  out->peer_exchange = e->peer_used ? 1 : 0;
   out->ms_sketch = e->ms[0]; out->ms_vote = e->ms[1]; out->ms_compact = e->ms[2];
   out->ms_sort = e->ms[3]; out->ms_em = e->ms[4]; out->ms_assign = e->ms[5];
   out->launches = e->launches;
@@ -1480,6 +1513,73 @@ int sq_nccl_unique_id(uint8_t id[SQ_NCCL_ID_BYTES]) {
   return SQ_OK;
 }
 
+// Map every rank's exchange buffers into every other rank (CUDA IPC handles travel through the communicator).  Not
+// being able to (ranks that are threads of one process cannot open each other's handles, no peer access, an old
+// libnccl) is not an error: all ranks agree, by a min all-reduce, to keep the per-iteration ncclAllReduce then.
+static int setup_peer_exchange(sq_engine* e) {
+  const int N = e->nranks;
+  e->peer_ok = false;
+  if (N < 2 || N > 32 || !g_nccl.AllGather) return SQ_OK;
+  struct Card { cudaIpcMemHandle_t ps, flags; int ok; int pad; };
+  const size_t T = (size_t)e->T;
+  Card mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = 1;
+  if (cudaMalloc(&e->xbuf, 2 * T * sizeof(double)) != cudaSuccess || cudaMalloc(&e->xflags, 2 * (size_t)N * 8) != cudaSuccess) mine.ok = 0;
+  if (mine.ok) {
+    cudaMemset(e->xbuf, 0, 2 * T * sizeof(double));
+    cudaMemset(e->xflags, 0, 2 * (size_t)N * 8);
+    if (cudaIpcGetMemHandle(&mine.ps, e->xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, e->xflags) != cudaSuccess) mine.ok = 0;
+  }
+  cudaGetLastError();
+  DevBuf d_cards;
+  SQ_CUDA(e, d_cards.ensure(sizeof(Card) * (size_t)(N + 1)));
+  Card* d_all = d_cards.as<Card>();
+  SQ_CUDA(e, cudaMemcpyAsync(d_all + N, &mine, sizeof(Card), cudaMemcpyHostToDevice, e->stream));
+  ncclResult_t r = g_nccl.AllGather(d_all + N, d_all, sizeof(Card), ncclChar, e->comm, e->stream);
+  if (r != ncclSuccess) { d_cards.release(); return fail(e, SQ_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); }
+  std::vector<Card> all((size_t)N);
+  SQ_CUDA(e, cudaMemcpyAsync(all.data(), d_all, sizeof(Card) * (size_t)N, cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  int ok = mine.ok;
+  for (int i = 0; i < N; ++i) ok &= all[i].ok;
+  std::vector<const double*> ps((size_t)N, nullptr);
+  std::vector<unsigned long long*> fl((size_t)N, nullptr);
+  for (int i = 0; i < N && ok; ++i) {
+    if (i == e->rank) { ps[i] = e->xbuf; fl[i] = e->xflags; continue; }
+    void *a = nullptr, *b = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[i].ps, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    e->peer_mapped.push_back(a);
+    if (cudaIpcOpenMemHandle(&b, all[i].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    e->peer_mapped.push_back(b);
+    ps[i] = static_cast<const double*>(a);
+    fl[i] = static_cast<unsigned long long*>(b);
+  }
+  cudaGetLastError();
+  // everybody or nobody
+  int* d_ok = reinterpret_cast<int*>(d_all);
+  SQ_CUDA(e, cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, e->comm, e->stream);
+  if (r != ncclSuccess) { d_cards.release(); return fail(e, SQ_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"); }
+  SQ_CUDA(e, cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  SQ_CUDA(e, cudaStreamSynchronize(e->stream));
+  d_cards.release();
+  if (!ok) {
+    for (void* m : e->peer_mapped) cudaIpcCloseMemHandle(m);
+    e->peer_mapped.clear();
+    cudaGetLastError();
+    return SQ_OK;
+  }
+  SQ_CUDA(e, e->d_peer_ps.ensure(sizeof(void*) * (size_t)N));
+  SQ_CUDA(e, e->d_peer_flags.ensure(sizeof(void*) * (size_t)N));
+  SQ_CUDA(e, e->d_peer_err.ensure(16));
+  SQ_CUDA(e, cudaMemcpy(e->d_peer_ps.p, ps.data(), sizeof(void*) * (size_t)N, cudaMemcpyHostToDevice));
+  SQ_CUDA(e, cudaMemcpy(e->d_peer_flags.p, fl.data(), sizeof(void*) * (size_t)N, cudaMemcpyHostToDevice));
+  SQ_CUDA(e, cudaMemset(e->d_peer_err.p, 0, 16));
+  e->peer_ok = true;
+  return SQ_OK;
+}
+
 int sq_comm_init(sq_engine* e, int nranks, int rank, const uint8_t id[SQ_NCCL_ID_BYTES]) {
   if (!e) return SQ_ERR_ARG;
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(e, SQ_ERR_ARG, "bad rank %d of %d", rank, nranks);
@@ -1493,7 +1593,7 @@ int sq_comm_init(sq_engine* e, int nranks, int rank, const uint8_t id[SQ_NCCL_ID
   if (r != ncclSuccess) return fail(e, SQ_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error");
   e->nranks = nranks;
   e->rank = rank;
-  return SQ_OK;
+  return setup_peer_exchange(e);
 }
 
 }  // extern "C"

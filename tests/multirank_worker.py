@@ -51,6 +51,11 @@ def main():
         eng.push_reads(*sqb.packing.pack_reads(mine))
     off, tid, score = eng.candidates()
     pi, nr, present, iters = eng.finish(0, 20, 0.01)
+    peer_used = int(eng.stats()["peer_exchange"])
+    # the same pass with ncclAllReduce per iteration instead of the exchange inside the M-step kernel
+    eng.set_option("peer_exchange", 0)
+    pi_n, nr_n, present_n, iters_n = eng.finish(0, 20, 0.01)
+    nccl_used = int(eng.stats()["peer_exchange"]) == 0
     eng.close()
 
     # every rank's vectors must be the same bits
@@ -85,6 +90,9 @@ def main():
             "present_equal": bool(np.array_equal(present, present1)),
             "ranks_bitwise_identical": bool(same_bits),
             "iterations": [int(s[3]) for s in shards], "iterations_one": int(iters1),
+            "peer_exchange": peer_used, "nccl_path_ran": bool(nccl_used),
+            "nccl_vs_peer_pi_max_rel": rel(pi_n, pi), "nccl_vs_peer_numreads_max_rel": rel(nr_n[present > 0], nr[present > 0]),
+            "nccl_vs_peer_same_present_and_iterations": bool(np.array_equal(present_n, present) and iters_n == iters),
         }
         with open(out_path, "w") as f:
             json.dump(res, f)

@@ -50,3 +50,8 @@ def test_ranks_equal_one_engine(gpu_lib, tmp_path, world, klist):
     assert res["present_equal"] and res["ranks_bitwise_identical"], res
     assert res["pi_max_rel"] <= 1e-9 and res["numreads_max_rel"] <= 1e-9, res
     assert res["iterations"] == [res["iterations_one"]] * world, res
+    # separate processes on one box: the EM sums travel over peer memory inside the M-step kernel; the NCCL path
+    # (option peer_exchange = 0) gives the same result up to the order of the N-term sum
+    assert res["peer_exchange"] == 1 and res["nccl_path_ran"], res
+    assert res["nccl_vs_peer_pi_max_rel"] <= 1e-12 and res["nccl_vs_peer_numreads_max_rel"] <= 1e-12, res
+    assert res["nccl_vs_peer_same_present_and_iterations"], res
