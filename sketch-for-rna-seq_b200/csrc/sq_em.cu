@@ -525,53 +525,92 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
 
 // ------------------------------------------------------------------ several GPUs: exchange fused into the M-step
 // Reads are sharded, so every rank holds partial posterior sums of all T transcripts.  Instead of seg_sum ->
-// ncclAllReduce -> update -> converge (a collective and three launches per iteration), every rank writes its sums
-// into a buffer its peers have mapped (CUDA IPC over NVLink / NVSwitch), raises a flag in every peer's memory, and
-// the M-step kernel itself waits for the peers' flags and adds the N vectors in rank order while it updates pi: one
-// pass over peer memory, the same bits on every rank (the order of the sum is the rank order everywhere), no
-// collective.  The buffers are double-buffered by iteration parity: a rank can only be one iteration ahead of the
-// slowest one, because its next M-step waits for everybody's flag.
-__global__ void peer_signal_kernel(unsigned long long* const* __restrict__ peer_flags, uint32_t slot, uint32_t rank,
-                                   uint32_t nranks, unsigned long long epoch) {
-  // the sums were written by the kernels before this one on the stream; make them visible system-wide first
-  __threadfence_system();
-  if (threadIdx.x < nranks) {
-    unsigned long long* f = peer_flags[threadIdx.x] + (size_t)slot * nranks + rank;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+// ncclAllReduce -> update -> converge (a collective and three launches per iteration), the ranks exchange through
+// buffers they have mapped from each other (CUDA IPC over NVLink / NVSwitch), fused into the two kernels that have
+// to run anyway:
+//   1. seg_sum_signal: a rank's per-transcript sums go to its exchange slot; the last block to finish raises the
+//      rank's flag in every peer's memory.
+//   2. em_mstep_peer: waits for everybody's flag, loads the N vectors over the links (eight loads in flight per
+//      thread), adds them in rank order and does the M-step and the convergence test exactly like the one-GPU
+//      kernel: the same bits, hence the same decision, on every rank, and no collective.
+// Every rank reads all of every peer's vector, so the bytes grow with N while NCCL's in-switch reduction does not:
+// measured on 2 MB vectors, this beats ncclAllReduce at N = 2 (EM 1.74 against 1.93 ms per 20 iterations) and
+// loses at N = 8 (2.55 against 2.33 ms; remote loads reached ~250 GB/s).  The engine therefore uses it for two
+// ranks and NCCL beyond.  Also measured and dropped (profiles/r02_notes.md): pushing the sums into every peer
+// with remote stores (1.83 ms at N = 2), and a reduce-scatter + all-gather in two flag rounds (1.97 ms at N = 2:
+// the second round costs more than the bytes it saves).  Slots and flags are double-buffered by iteration
+// parity: nobody can be more than one iteration ahead of the slowest rank, because every M-step waits for
+// everybody's flag; epochs only grow, so a stale flag never matches.
+__device__ __forceinline__ void peer_flag_store(unsigned long long* f, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+}
+// spin until the flag reaches `epoch`; a peer that died must not hang the GPU: after ~4 s the error word is set
+__device__ __forceinline__ void peer_flag_wait(const unsigned long long* f, unsigned long long epoch, uint32_t* err) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    if (v >= epoch) return;
+    if (clock64() - t0 > 8000000000ll) { atomicOr(err, 1u); return; }
   }
 }
-
-__device__ __forceinline__ double ld_peer(const double* p) {
+__device__ __forceinline__ double ld_peer(const double* p) {  // written by another GPU during this kernel's life
   double v;
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
 
-__global__ void __launch_bounds__(256) em_mstep_peer_kernel(const double* const* __restrict__ peer_ps,
-                                                            const unsigned long long* my_flags, uint32_t slot,
-                                                            uint32_t nranks, unsigned long long epoch, double* ps,
-                                                            double* pi, uint32_t T, double add_a, double add_b,
-                                                            double* __restrict__ block_change, double tol,
-                                                            uint32_t* state, double* last_change, uint32_t* err) {
+// a rank's exchange memory: [2 slots][T] doubles; flags: [2 slots][nranks] u64
+struct PeerView {
+  double* const* x;               // every rank's exchange memory (mine included)
+  unsigned long long* const* f;   // every rank's flags
+  uint32_t nranks, rank, slot, T;
+  unsigned long long epoch;
+  uint32_t* err;                  // [0] time-out flag, [1] ticket of seg_sum_signal
+};
+
+__global__ void __launch_bounds__(256) seg_sum_signal_kernel(const uint32_t* __restrict__ seg_off,
+                                                           const double* __restrict__ partial,
+                                                           const uint32_t* __restrict__ state, const PeerView P) {
+  if (state[0]) return;  // converged (on every rank at the same iteration): nobody waits for this flag
+  __shared__ uint32_t s_last;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < P.T) {
+    double s = 0.0;
+    for (uint32_t i = seg_off[t]; i < seg_off[t + 1]; ++i) s += partial[i];
+    P.x[P.rank][(size_t)P.slot * P.T + t] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(P.err + 1, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();  // every block's sums are visible system-wide before the flag is
+  if (threadIdx.x < P.nranks) peer_flag_store(P.f[threadIdx.x] + (size_t)P.slot * P.nranks + P.rank, P.epoch);
+  if (threadIdx.x == 0) P.err[1] = 0;
+}
+
+__global__ void __launch_bounds__(256) em_mstep_peer_kernel(const PeerView P, double* ps, double* pi, double add_a,
+                                                            double add_b, double* __restrict__ block_change, double tol,
+                                                            uint32_t* state, double* last_change) {
   if (state[0]) return;
   __shared__ double sh[8], sh2[8];
   __shared__ uint32_t s_last;
-  if (threadIdx.x < nranks) {  // every peer's sums of this iteration have landed (a dead peer must not hang the GPU)
-    const unsigned long long* f = my_flags + (size_t)slot * nranks + threadIdx.x;
-    const long long t0 = clock64();
-    for (;;) {
-      unsigned long long v;
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v >= epoch) break;
-      if (clock64() - t0 > 8000000000ll) { atomicOr(err, 1u); break; }  // ~4 s
-    }
-  }
+  if (threadIdx.x < P.nranks)
+    peer_flag_wait(P.f[P.rank] + (size_t)P.slot * P.nranks + threadIdx.x, P.epoch, P.err);
   __syncthreads();
   const uint32_t t = blockIdx.x * 256 + threadIdx.x;
   double ch = 0.0;
-  if (t < T) {
+  if (t < P.T) {
     double sum = 0.0;
-    for (uint32_t r = 0; r < nranks; ++r) sum += ld_peer(peer_ps[r] + (size_t)slot * T + t);  // rank order everywhere
+    for (uint32_t r0 = 0; r0 < P.nranks; r0 += 8) {  // eight remote loads in flight, added in rank order (everywhere)
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = r0 + u < P.nranks ? ld_peer(P.x[r0 + u] + (size_t)P.slot * P.T + t) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < P.nranks) sum += v[u];
+    }
     ps[t] = sum;
     const double np = (sum + add_a) + add_b;
     ch = fabs(np - pi[t]);
@@ -726,19 +765,22 @@ void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double t
   if (launches) ++*launches;
 }
 
-// per-transcript sums of this rank into `out` (the peer-visible exchange slot)
-void launch_seg_sum(const EmView& v, double* out, cudaStream_t s, uint64_t* launches) {
-  seg_sum_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.T, v.partial, out, v.state);
-  if (launches) ++*launches;
-}
-
-void launch_em_mstep_peer(const EmView& v, const double* const* peer_ps, unsigned long long* const* peer_flags,
-                          const unsigned long long* my_flags, uint32_t slot, uint32_t rank, uint32_t nranks,
-                          unsigned long long epoch, double add_a, double add_b, double tol, uint32_t* err, cudaStream_t s,
-                          uint64_t* launches) {
-  peer_signal_kernel<<<1, 32, 0, s>>>(peer_flags, slot, rank, nranks, epoch);
-  em_mstep_peer_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(peer_ps, my_flags, slot, nranks, epoch, v.ps, v.pi, v.T, add_a,
-                                                        add_b, v.block_change, tol, v.state, v.last_change, err);
+// the exchange + M-step of one iteration (see above)
+void launch_em_mstep_peer(const EmView& v, double* const* peer_x, unsigned long long* const* peer_flags, uint32_t rank,
+                          uint32_t nranks, unsigned long long epoch, double add_a, double add_b, double tol, uint32_t* err,
+                          cudaStream_t s, uint64_t* launches) {
+  PeerView P;
+  P.x = peer_x;
+  P.f = peer_flags;
+  P.nranks = nranks;
+  P.rank = rank;
+  P.slot = (uint32_t)(epoch & 1);
+  P.T = v.T;
+  P.epoch = epoch;
+  P.err = err;
+  seg_sum_signal_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(v.seg_off, v.partial, v.state, P);
+  em_mstep_peer_kernel<<<(v.T + 255) / 256, 256, 0, s>>>(P, v.ps, v.pi, add_a, add_b, v.block_change, tol, v.state,
+                                                        v.last_change);
   if (launches) *launches += 2;
 }
 

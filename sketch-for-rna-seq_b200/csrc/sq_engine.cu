@@ -168,10 +168,11 @@ struct sq_engine {
   // NCCL
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
-  // EM exchange over peer memory (see sq_em.cu): this rank's two slots of T sums and 2 x nranks flags, the peers'
-  // mappings of theirs (CUDA IPC), the same as device arrays of pointers; epoch counts iterations over the
-  // engine's life (slot = epoch & 1, flags only ever grow)
-  bool peer_ok = false, peer_wanted = true, peer_used = false;
+  // EM exchange over peer memory (see sq_em.cu): this rank's exchange memory ([2 slots][T] sums) and
+  // flags ([2][nranks]), the peers' mappings of theirs (CUDA IPC), the same as device arrays of pointers; epoch
+  // counts iterations over the engine's life (slot = epoch & 1, flags only ever grow)
+  bool peer_ok = false, peer_used = false;
+  int peer_wanted = 1;  // option peer_exchange: 0 never, 1 where it was measured faster (two ranks), 2 whenever possible
   double* xbuf = nullptr;
   unsigned long long* xflags = nullptr;
   std::vector<void*> peer_mapped;  // what cudaIpcOpenMemHandle returned (closed in sq_destroy)
@@ -728,7 +729,7 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "exact_classes") { e->exact_classes = value != 0; return SQ_OK; }
   if (n == "vote_tier") { e->vote_tier = (uint32_t)value; return SQ_OK; }
-  if (n == "peer_exchange") { e->peer_wanted = value != 0; return SQ_OK; }
+  if (n == "peer_exchange") { e->peer_wanted = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return SQ_OK; }
   if (e->n_batches) return fail(e, SQ_ERR_STATE, "options must be set before the first push");
   if (value <= 0) return fail(e, SQ_ERR_ARG, "option %s needs a positive value", name);
   if (n == "batch_bases") e->batch_bases = std::min<uint64_t>((uint64_t)value, 0xF0000000ull);
@@ -1406,6 +1407,10 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   v.seg = e->em_seg;
   v.n_pairs = n_cpairs;
   v.T = T;
+  // measured: the one-shot exchange beats ncclAllReduce for two ranks and loses for eight (every rank reads every
+  // peer's whole vector); option peer_exchange = 2 forces it for any number of ranks
+  const bool peer = e->comm && e->peer_ok && (e->peer_wanted == 2 || (e->peer_wanted == 1 && e->nranks == 2));
+  e->peer_used = peer;
   v.pi = e->pi.as<double>();
   v.ps = e->ps.as<double>();
   v.read_tmp = e->read_tmp.as<double>();
@@ -1421,18 +1426,13 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   {
     StageScope sc(e, 4);
     launch_em_init(v.pi, T, state, st, &e->launches);
-    const bool peer = e->comm && e->peer_ok && e->peer_wanted;
-    e->peer_used = peer;
     for (int it = 0; it < em_iters; ++it) {
       if (peer) {
         // this rank's sums go to its exchange slot; the M-step kernel adds all ranks' slots over peer memory
-        const unsigned long long epoch = ++e->epoch;
-        const uint32_t slot = (uint32_t)(epoch & 1);
         launch_em_estep(v, st, &e->launches, false);
-        launch_seg_sum(v, e->xbuf + (size_t)slot * T, st, &e->launches);
-        launch_em_mstep_peer(v, e->d_peer_ps.as<const double*>(), e->d_peer_flags.as<unsigned long long*>(), e->xflags, slot,
-                             (uint32_t)e->rank, (uint32_t)e->nranks, epoch, add_a, add_b, em_tol,
-                             e->d_peer_err.as<uint32_t>(), st, &e->launches);
+        launch_em_mstep_peer(v, e->d_peer_ps.as<double*>(), e->d_peer_flags.as<unsigned long long*>(), (uint32_t)e->rank,
+                             (uint32_t)e->nranks, ++e->epoch, add_a, add_b, em_tol, e->d_peer_err.as<uint32_t>(), st,
+                             &e->launches);
       } else if (e->comm) {
         launch_em_estep(v, st, &e->launches, true);
         SQ_TRY(allreduce(e, v.ps, T, ncclDouble));
@@ -1525,10 +1525,11 @@ static int setup_peer_exchange(sq_engine* e) {
   Card mine;
   memset(&mine, 0, sizeof(mine));
   mine.ok = 1;
-  if (cudaMalloc(&e->xbuf, 2 * T * sizeof(double)) != cudaSuccess || cudaMalloc(&e->xflags, 2 * (size_t)N * 8) != cudaSuccess) mine.ok = 0;
+  const size_t x_bytes = 2 * T * sizeof(double), f_bytes = 2 * (size_t)N * 8;
+  if (cudaMalloc(&e->xbuf, x_bytes) != cudaSuccess || cudaMalloc(&e->xflags, f_bytes) != cudaSuccess) mine.ok = 0;
   if (mine.ok) {
-    cudaMemset(e->xbuf, 0, 2 * T * sizeof(double));
-    cudaMemset(e->xflags, 0, 2 * (size_t)N * 8);
+    cudaMemset(e->xbuf, 0, x_bytes);
+    cudaMemset(e->xflags, 0, f_bytes);
     if (cudaIpcGetMemHandle(&mine.ps, e->xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, e->xflags) != cudaSuccess) mine.ok = 0;
   }
   cudaGetLastError();
@@ -1543,7 +1544,7 @@ static int setup_peer_exchange(sq_engine* e) {
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));
   int ok = mine.ok;
   for (int i = 0; i < N; ++i) ok &= all[i].ok;
-  std::vector<const double*> ps((size_t)N, nullptr);
+  std::vector<double*> ps((size_t)N, nullptr);
   std::vector<unsigned long long*> fl((size_t)N, nullptr);
   for (int i = 0; i < N && ok; ++i) {
     if (i == e->rank) { ps[i] = e->xbuf; fl[i] = e->xflags; continue; }
@@ -1552,7 +1553,7 @@ static int setup_peer_exchange(sq_engine* e) {
     e->peer_mapped.push_back(a);
     if (cudaIpcOpenMemHandle(&b, all[i].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
     e->peer_mapped.push_back(b);
-    ps[i] = static_cast<const double*>(a);
+    ps[i] = static_cast<double*>(a);
     fl[i] = static_cast<unsigned long long*>(b);
   }
   cudaGetLastError();

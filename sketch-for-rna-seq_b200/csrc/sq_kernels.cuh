@@ -67,11 +67,9 @@ void launch_em_init(double* pi, uint32_t T, uint32_t* state, cudaStream_t s, uin
 void launch_em_estep(const EmView& v, cudaStream_t s, uint64_t* launches, bool with_sum);
 void launch_em_mstep_fused(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches);
 void launch_em_mstep(const EmView& v, double add_a, double add_b, double tol, cudaStream_t s, uint64_t* launches);
-void launch_seg_sum(const EmView& v, double* out, cudaStream_t s, uint64_t* launches);
-void launch_em_mstep_peer(const EmView& v, const double* const* peer_ps, unsigned long long* const* peer_flags,
-                          const unsigned long long* my_flags, uint32_t slot, uint32_t rank, uint32_t nranks,
-                          unsigned long long epoch, double add_a, double add_b, double tol, uint32_t* err, cudaStream_t s,
-                          uint64_t* launches);
+void launch_em_mstep_peer(const EmView& v, double* const* peer_x, unsigned long long* const* peer_flags, uint32_t rank,
+                          uint32_t nranks, unsigned long long epoch, double add_a, double add_b, double tol, uint32_t* err,
+                          cudaStream_t s, uint64_t* launches);
 void launch_assign(const EmView& v, double* numreads, uint32_t* present_u32, cudaStream_t s, uint64_t* launches);
 
 }  // namespace sq

@@ -50,6 +50,7 @@ def main():
     if mine:
         eng.push_reads(*sqb.packing.pack_reads(mine))
     off, tid, score = eng.candidates()
+    eng.set_option("peer_exchange", 2)  # at any number of ranks (the default takes it only where it is faster: two)
     pi, nr, present, iters = eng.finish(0, 20, 0.01)
     peer_used = int(eng.stats()["peer_exchange"])
     # the same pass with ncclAllReduce per iteration instead of the exchange inside the M-step kernel
