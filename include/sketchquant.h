@@ -52,7 +52,7 @@ typedef struct sq_stats {
                             * 0: one GPU, or ncclAllReduce per iteration */
   /* device time of the kernels of each stage, ms, accumulated over batches (CUDA events on the engine stream;
    * only filled when profiling was enabled with sq_set_profiling) */
-  float ms_sketch, ms_vote, ms_compact, ms_sort, ms_em, ms_assign;
+  float ms_sketch, ms_vote, ms_compact /* always 0: nothing is compacted any more */, ms_sort, ms_em, ms_assign;
   uint64_t launches;       /* kernels launched by this engine so far */
   /* vote-kernel work counters (for the roofline's algorithmic bytes) */
   uint64_t queries;        /* (item, k, hash) looked up in the index table */
@@ -90,7 +90,7 @@ void sq_destroy(sq_engine* e);
  * engine with events on its own stream. */
 int sq_set_stream(sq_engine* e, void* cuda_stream);
 int sq_set_profiling(sq_engine* e, int enabled);
-/* Tunables: "batch_bases" (max bases per internal batch), "cand_per_read" (initial staging slots per read),
+/* Tunables: "batch_bases" (max bases per internal batch), "cand_per_read" (candidate pairs per read the store makes room for ahead of the first batches),
  * "overflow_workers", "max_read_len", "em_segment", "sub_batch_reads" (reads per internal batch of
  * sq_push_reads_fixed, default 2^20): set before the first push.  "exact_classes" (any time):
  * 1 = reads are merged into one EM term only after comparing their candidate lists element by element,
