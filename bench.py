@@ -450,7 +450,8 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     b_vote = (12 + 6 * nk) * n_reads + 4 * st["queries"] + 4 * st["postings"] + 8 * st["pairs"] + (8 + 24) * n_reads
     # EM: per iteration the class CSR and its transcript-major copy are read once each (12 B + 8 B gathered per
     # class pair, twice) plus the per-class and per-transcript vectors
-    b_em = iters * (40 * st["em_class_pairs"] + 20 * st["em_classes"] + 16 * T)
+    # (short reads: scores fit 8 bits, a pair is ONE word in both copies: 4 B + 8 B gathered, twice)
+    b_em = iters * ((24 if kind != "long" else 40) * st["em_class_pairs"] + 20 * st["em_classes"] + 16 * T)
     S = steps
     n_batches = max(int(st["batches"]), 1)
     kern = {
