@@ -151,7 +151,7 @@ struct sq_engine {
   // EM scratch
   DevBuf keys_a, keys_b, vals_a, vals_b, sort_tmp, toff, tm_read, nseg, seg_off, seg_tid, seg_begin, pi, ps,
       read_tmp, partial, block_change, misc, numreads, present, scan_tmp, em_off, em_cnt, em_tid, em_score, em_pack,
-      cls_head, cls_id, cls_read, cls_pos, cls_weight, cls_fp, out_pi, out_nr, out_present;
+      cls_head, cls_id, cls_read, cls_pos, cls_weight, out_pi, out_nr, out_present;
   uint64_t n_classes_last = 0, n_cpairs_last = 0;
   int em_iterations = 0;
   // sq_sketch / sq_build_postings scratch
@@ -693,7 +693,7 @@ void sq_destroy(sq_engine* e) {
                    &e->vals_a, &e->vals_b, &e->sort_tmp, &e->toff, &e->tm_read, &e->nseg, &e->seg_off, &e->seg_tid,
                    &e->seg_begin, &e->pi, &e->ps, &e->read_tmp, &e->partial, &e->block_change, &e->misc,
                    &e->numreads, &e->present, &e->scan_tmp, &e->em_off, &e->em_cnt, &e->em_tid, &e->em_score, &e->em_pack,
-                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->cls_fp, &e->out_pi,
+                   &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->out_pi,
                    &e->out_nr, &e->out_present};
   for (DevBuf* b : all) b->release();
   if (e->cand_tid) cudaFree(e->cand_tid);
