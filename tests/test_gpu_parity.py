@@ -479,3 +479,39 @@ def test_device_push_alignment_contract(gpu_lib, sqb, port):
     _, ooff, otid, oscore, _ = port.chain_batch(ks, thr, 0.9, postings, reads)
     assert off_g.tolist() == ooff.tolist()
     assert tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
+
+
+def test_store_grows_and_vote_reruns(gpu_lib, sqb, port):
+    """The vote writes into the free tail of the candidate store; when a batch has more pairs than the room made for
+    it (cand_per_read = 1; a first batch of reads that hit nothing, so "twice the rate so far" is tiny), the store
+    grows and the batch's vote is run again: same candidates, same EM result"""
+    d = dataset(n_genes=60, n_reads=3000, seed=29)
+    ks = [21, 31]
+    thr = port.threshold(SKETCH)
+    postings = port.postings_from_sequences(d["tseqs"], ks, thr)
+    rng = np.random.default_rng(11)
+    junk = [bytes(b"ACGT"[c] for c in rng.integers(0, 4, 150)) for _ in range(4200)]
+    real = d["reads"]
+    assert len(real) >= 1000
+    reads = junk + real
+    T = len(d["names"])
+    with sqb.Engine(ks, T) as e:
+        e.set_option("cand_per_read", 1)
+        e.set_option("batch_bases", 1 << 18)  # ~1700 reads per batch: junk batches first, then the real ones
+        for i, k in enumerate(ks):
+            e.load_index(i, *postings[k])
+        e.push_reads(*sqb.packing.pack_reads(reads))
+        off_g, tid_g, score_g = e.candidates()
+        pi, nr, present, it = e.finish(0, 20, 0.01)
+        st = e.stats()
+    assert st["batches"] >= 4
+    _, ooff, otid, oscore, R = port.chain_batch(ks, thr, 0.9, postings, reads)
+    assert int(ooff[-1]) > 2 * len(real)  # several pairs per real read: more than one per read was needed
+    assert off_g.tolist() == ooff.tolist()
+    assert tid_g.tolist() == otid.tolist() and score_g.tolist() == oscore.tolist()
+    opi, oit = port.em(ooff, otid, oscore, R, T)
+    onr, opres = port.assign(ooff, otid, oscore, T, opi)
+    assert it == oit
+    np.testing.assert_allclose(pi, opi, rtol=RTOL)
+    np.testing.assert_allclose(nr, onr, rtol=RTOL, atol=1e-12)
+    assert present.tolist() == opres.tolist()
