@@ -471,6 +471,9 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
         if dom in tj and kern[dom]["launches"]:
             traffic = tj[dom] * (n_reads / kern[dom]["launches"]) / tj["reads_per_launch"]
             traffic_src = "from profile: %s, scaled to this launch size (not measured in this run)" % tj.get("source", "profiles/traffic.json")
+    pipes = None
+    if os.path.exists(tpath) and kind == "short" and nk == 1:
+        pipes = json.load(open(tpath)).get("pipes", {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": kern[dom]["ms"] / max(kern[dom]["launches"], 1),
@@ -478,6 +481,8 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
                 "kernels": {n: {"ms_per_step": round(v["ms"], 4), "GBps": v["gbs"] and round(v["gbs"], 1),
                                 "frac": v["frac"] and round(v["frac"], 4)} for n, v in kern.items()},
                 "traffic_source": traffic_src,
+                # what actually bounds a kernel that is not memory-bound (from the committed ncu capture, not this run)
+                "pipes_from_profile": pipes,
                 "stage_ms_per_step": {k2: round(v / S, 4) for k2, v in stage.items() if k2.startswith("ms_")},
                 "profiled_ms_per_step": ms_prof / steps,
                 "sketch_gkmers_per_s": n_kmers / (kern["sketch_kernel"]["ms"] / 1e3) / 1e9

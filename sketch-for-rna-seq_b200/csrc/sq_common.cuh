@@ -59,6 +59,8 @@ struct SketchParams {
   uint16_t* cnt;               // [nk][n_items_ub] hashes of the item; SQ_CNT_RAW set: not de-duplicated
   uint32_t* cursor;            // [nk] words used so far (zeroed by the caller)
   uint32_t cap;                // staging entries per lane in shared memory (a lane that selects more re-rolls)
+  uint32_t stage_words;        // packed words a warp can stage in shared memory (a multiple of 4; a warp whose span is
+                               // longer reads from global memory)
   uint32_t dedup;              // 1: an item's equal hashes are stored once (the sketch is a set, include/sketch.h:15)
   unsigned long long* stats;   // optional: += selected hashes of the launch before de-duplication (one atomic per block)
   KLut lut[SQ_MAXK];
@@ -179,6 +181,7 @@ void launch_items(const uint32_t* len, uint32_t n_reads, uint32_t* nit, uint32_t
                   unsigned long long* stats);
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches);
 cudaError_t sketch_configure();  // per device
+uint32_t sketch_stage_words_max();
 // list descriptor (see IndexTable) of every selected hash of the batch, one k-index at a time
 struct VoteDeviceCfg;
 void launch_lookup(const VoteParams& p, const VoteDeviceCfg& cfg, uint32_t ki, cudaStream_t s, uint64_t* launches);

@@ -259,7 +259,24 @@ uint32_t item_hash_bound(const sq_engine* e, uint64_t n_bases, uint32_t n_reads)
   const double b = windows * scale * 2.0 + 8.0;
   return (uint32_t)std::min<double>(b, (double)SQ_CHUNK);
 }
-uint32_t sketch_cap(uint32_t bound) { return std::min<uint32_t>(SQ_CHUNK, std::max<uint32_t>(8, (bound + 7) & ~7u)); }
+// Shared memory of the sketch kernel, sized for the batch: `cap` entries per lane for the selected hashes of an item
+// (mean + 4 sigma of a binomial count, plus the 16 entries of head room the kernel's unrolled block wants; a lane
+// that selects more rolls a second time, straight to global memory, and its read is voted by the window kernel) and `stage_words` packed words per warp for the reads
+// themselves (a warp whose 32 items span more reads from global memory).  Both are upper ends, not limits.
+void sketch_smem_plan(const sq_engine* e, uint64_t n_bases, uint32_t n_reads, uint32_t* cap, uint32_t* stage_words) {
+  const double scale = ((double)e->threshold + 1.0) / 4294967296.0;
+  const uint64_t mean_len = n_reads ? (n_bases + n_reads - 1) / n_reads : 0;
+  const double item_bases = (double)std::min<uint64_t>(mean_len + 8, SQ_CHUNK);
+  const double windows = mean_len + 8 <= SQ_CHUNK ? std::max(item_bases - (double)e->kmin + 1.0, 1.0) : (double)SQ_CHUNK;
+  const double m = windows * scale;
+  // the unrolled 16-step block of the kernel runs only while 16 more entries fit: that much head room on top
+  const uint32_t bound = (uint32_t)std::min<double>(m + 4.0 * std::sqrt(m) + 1.0, (double)SQ_CHUNK);
+  *cap = std::min<uint32_t>(SQ_CHUNK, ((bound + 7) & ~7u) + 16);
+  // a lane touches its item's bases plus kmax - 1 before them; 32 lanes, one word of slack each, 16-byte rounding
+  const uint64_t lane_bases = std::min<uint64_t>(mean_len + 3, SQ_CHUNK) + (mean_len > SQ_CHUNK ? e->kmax : 0);
+  const uint64_t w = 32 * ((lane_bases + 15) / 16 + 1) + 8;
+  *stage_words = (uint32_t)std::min<uint64_t>(sketch_stage_words_max(), (w + 3) & ~3ull);
+}
 
 int check_flags(sq_engine* e) {
   uint32_t flags = 0;
@@ -508,7 +525,7 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
     sp.hoff = s.hoff.as<uint32_t>();
     sp.cnt = s.cnt.as<uint16_t>();
     sp.cursor = e->d_hcur + 8 * s.id;
-    sp.cap = sketch_cap(item_hash_bound(e, n_bases, n_reads));
+    sketch_smem_plan(e, n_bases, n_reads, &sp.cap, &sp.stage_words);
     sp.dedup = 1;
     sp.stats = e->d_totals;  // [0] += sketch hashes
     SQ_CUDA(e, cudaMemsetAsync(sp.cursor, 0, 32, e->stream));
@@ -1663,7 +1680,7 @@ int tap_sketch(sq_engine* e, uint32_t k0, uint32_t nk, const uint32_t* packed_wo
   sp.hoff = s.hoff.as<uint32_t>();
   sp.cnt = s.cnt.as<uint16_t>();
   sp.cursor = e->d_hcur + 16;
-  sp.cap = sketch_cap(item_hash_bound(e, nb, n_reads));
+  sketch_smem_plan(e, nb, n_reads, &sp.cap, &sp.stage_words);
   sp.dedup = 0;  // the tap hands out the multiset, the postings build removes repeats after its sort
   sp.stats = nullptr;
   SQ_CUDA(e, cudaMemsetAsync(sp.cursor, 0, 32, st));

@@ -18,7 +18,7 @@
 namespace sq {
 
 static constexpr int kSketchBlock = 128;
-static constexpr int kStageWordsPerWarp = 32 * 24;  // 32 lanes x (256+~100 bases)/16 words + slack
+static constexpr int kStageWordsMax = 32 * 24;  // per warp: 32 lanes x (256+~100 bases)/16 words + slack
 
 __device__ __forceinline__ uint32_t items_of(uint32_t L) { return L == 0 ? 1u : (L + SQ_CHUNK - 1) / SQ_CHUNK; }
 
@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   uint2* lut = reinterpret_cast<uint2*>(smem);
   for (uint32_t i = threadIdx.x; i < p.nk * 48; i += blockDim.x) lut[i] = p.lut[i / 48].e[i % 48];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-  uint32_t* stage = smem + p.nk * kLutWords + warp * kStageWordsPerWarp;
-  uint32_t* ostage = smem + p.nk * kLutWords + (kSketchBlock / 32) * kStageWordsPerWarp + warp * (p.cap * 32);
+  // both areas are sized by the launch for the batch at hand (mean read length, scale factor): what a block does not
+  // take lets more blocks live on the SM, and this kernel needs the warps to keep its integer pipe fed
+  uint32_t* stage = smem + p.nk * kLutWords + warp * p.stage_words;
+  uint32_t* ostage = smem + p.nk * kLutWords + (kSketchBlock / 32) * p.stage_words + warp * (p.cap * 32);
   // statistics: warps add their selected-hash counts here, the last one to arrive flushes (no exit barrier)
   __shared__ uint32_t s_sel, s_arrived;
   __shared__ __align__(8) unsigned long long s_bar[kSketchBlock / 32];  // one mbarrier per warp (used once: phase 0)
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   if (wmin != 0xFFFFFFFFu) {
     const uint32_t base4 = wmin & ~3u;
     const uint32_t nw = wmax - base4 + 1;
-    if (nw <= (uint32_t)kStageWordsPerWarp) {
+    if (((nw + 3) & ~3u) <= p.stage_words) {
       const uint32_t n4 = (nw + 3) >> 2;
       const uint4* src = reinterpret_cast<const uint4*>(p.packed + base4);
       if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
@@ -290,22 +292,48 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
     // A read of several items is voted through a per-read set of hashes anyway (the same hash may sit in two of
     // its items): its items keep their repeats.
     if (p.dedup && !raw && c > 1 && nit == 1) {
-      uint32_t m1 = 0, m2 = 0;
-      for (uint32_t i = 0; i < c; ++i) {
-        const uint32_t h = lds_u32(col + 128 * i);
-        const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
-        if ((m1 & b1) && (m2 & b2)) {
+      if (c <= 32) {
+        // pass 1, the same for every lane: which entries MAY repeat an earlier one (both filter bits already set)
+        uint32_t m1 = 0, m2 = 0, sus = 0;
+        for (uint32_t i = 0; i < c; ++i) {
+          const uint32_t h = lds_u32(col + 128 * i);
+          const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
+          if ((m1 & b1) && (m2 & b2)) sus |= 1u << i;
+          m1 |= b1;
+          m2 |= b2;
+        }
+        // pass 2: the few suspects are compared with their predecessors, last suspect first, so that the entry a
+        // removal moves down (the last one) is already settled.  The warp runs this loop as often as its worst lane
+        // has suspects (about once), not once per position at which some lane has one.
+        while (sus) {
+          const uint32_t i = 31u - (uint32_t)__clz((int)sus);
+          sus &= ~(1u << i);
+          const uint32_t h = lds_u32(col + 128 * i);
           bool dup = false;
           for (uint32_t j = 0; j < i; ++j) dup |= lds_u32(col + 128 * j) == h;
           if (dup) {  // the last entry takes its place (order inside a set does not matter)
             --c;
             if (i < c) sts_u32(col + 128 * i, lds_u32(col + 128 * c));
-            --i;
-            continue;
           }
         }
-        m1 |= b1;
-        m2 |= b2;
+      } else {
+        uint32_t m1 = 0, m2 = 0;
+        for (uint32_t i = 0; i < c; ++i) {
+          const uint32_t h = lds_u32(col + 128 * i);
+          const uint32_t b1 = 1u << (h & 31), b2 = 1u << ((h >> 5) & 31);
+          if ((m1 & b1) && (m2 & b2)) {
+            bool dup = false;
+            for (uint32_t j = 0; j < i; ++j) dup |= lds_u32(col + 128 * j) == h;
+            if (dup) {
+              --c;
+              if (i < c) sts_u32(col + 128 * i, lds_u32(col + 128 * c));
+              --i;
+              continue;
+            }
+          }
+          m1 |= b1;
+          m2 |= b2;
+        }
       }
     }
     // ---- one region of the dense output per warp, the 32 items back to back
@@ -337,19 +365,21 @@ __global__ void __launch_bounds__(kSketchBlock) sketch_kernel(const __grid_const
   }
 }
 
-size_t sketch_smem_bytes(uint32_t nk, uint32_t cap) {
-  return (nk * kLutWords + (kSketchBlock / 32) * (kStageWordsPerWarp + cap * 32)) * sizeof(uint32_t);
+uint32_t sketch_stage_words_max() { return kStageWordsMax; }
+
+size_t sketch_smem_bytes(uint32_t nk, uint32_t cap, uint32_t stage_words) {
+  return (nk * kLutWords + (kSketchBlock / 32) * (stage_words + cap * 32)) * sizeof(uint32_t);
 }
 
 cudaError_t sketch_configure() {  // per device (sq_create): the staging area may pass the default 48 KB
   return cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)sketch_smem_bytes(SQ_MAXK, SQ_CHUNK));
+                              (int)sketch_smem_bytes(SQ_MAXK, SQ_CHUNK, kStageWordsMax));
 }
 
 void launch_sketch(const SketchParams& p, cudaStream_t s, uint64_t* launches) {
   if (p.n_items_ub == 0) return;
   const uint32_t grid = (p.n_items_ub + kSketchBlock - 1) / kSketchBlock;
-  sketch_kernel<<<grid, kSketchBlock, sketch_smem_bytes(p.nk, p.cap), s>>>(p);
+  sketch_kernel<<<grid, kSketchBlock, sketch_smem_bytes(p.nk, p.cap, p.stage_words), s>>>(p);
   if (launches) ++*launches;
 }
 
