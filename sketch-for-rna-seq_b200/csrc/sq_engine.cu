@@ -271,7 +271,7 @@ void sketch_smem_plan(const sq_engine* e, uint64_t n_bases, uint32_t n_reads, ui
   const double m = windows * scale;
   // the unrolled 16-step block of the kernel runs only while 16 more entries fit: that much head room on top
   const uint32_t bound = (uint32_t)std::min<double>(m + 4.0 * std::sqrt(m) + 1.0, (double)SQ_CHUNK);
-  *cap = std::min<uint32_t>(SQ_CHUNK, ((bound + 7) & ~7u) + 16);
+  *cap = std::min<uint32_t>(SQ_CHUNK, ((bound + 1) & ~1u) + 16);
   // a lane touches its item's bases plus kmax - 1 before them; 32 lanes, one word of slack each, 16-byte rounding
   const uint64_t lane_bases = std::min<uint64_t>(mean_len + 3, SQ_CHUNK) + (mean_len > SQ_CHUNK ? e->kmax : 0);
   const uint64_t w = 32 * ((lane_bases + 15) / 16 + 1) + 8;
