@@ -1,4 +1,4 @@
-// Index-table construction, candidate compaction, and the EM / assignment kernels.
+// Read classes over the candidate store, the EM / assignment kernels and their exchange between GPUs.
 //
 // EM follows estimate_isoform_abundance_em (reference src/isoform_assignment.cpp:9-68) and
 // assign_reads_to_isoforms (:70-97) on a flat CSR of (read -> candidates).  Every reduction has a fixed
@@ -225,7 +225,7 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
   weight[c] = (double)(class_pos[c + 1] - class_pos[c]);
 }
 
-// heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + class table (read, position, count)
+// heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + per class: (first read, position, count)
 void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
                         const void* fp, const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,

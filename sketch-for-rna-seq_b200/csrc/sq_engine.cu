@@ -162,7 +162,7 @@ struct sq_engine {
   const void* bp_sig = nullptr;
   // profiling
   std::vector<StageEvent> events;
-  float ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // sketch, vote, compact, sort, em, assign, items, vote main kernel, lookup
+  float ms[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // sketch, vote, (unused), sort, em, assign, items, vote main kernel, lookup
   uint32_t n_stage[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
   // NCCL
@@ -455,7 +455,7 @@ int acquire_slot(sq_engine* e, Slot** out) {
   return SQ_OK;
 }
 
-// enqueue sketch + vote + compaction for one batch whose inputs are in device memory
+// enqueue sketch + lookup + vote for one batch whose inputs are in device memory
 int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words, const uint32_t* d_boff, uint32_t bias,
               const uint32_t* d_len, uint32_t n_reads, uint64_t n_bases, cudaEvent_t inputs_ready,
               uint32_t* derive_boff = nullptr, uint32_t fixed_len = 0) {
@@ -475,10 +475,10 @@ int run_batch(sq_engine* e, Slot& s, const uint32_t* d_packed, uint64_t n_words,
   SQ_CUDA(e, s.slow_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.mid_list.ensure((size_t)n_reads * 4));
   SQ_CUDA(e, s.scan_tmp.ensure(scan_tmp_words(std::max(n_reads, items_ub)) * 4));
-  // The batch before this one (other slot) must be finalized (host waits for its vote, then enqueues its
-  // compaction).  Host batches: now, before the engine stream starts waiting for our copy, so the compaction
-  // is not held up behind that wait (its vote has been overlapping our copies).  Device batches: after our
-  // sketch is enqueued (below), so the sketch runs while the previous vote's tail kernels finish.
+  // The batch before this one (other slot) must be finalized: the host waits for its vote and learns its exact
+  // pair count, which fixes where in the store this batch's vote writes.  Host batches: now (its vote has been
+  // overlapping our copies).  Device batches: after our sketch is enqueued (below), so the sketch runs while the
+  // previous vote's tail kernels finish.
   if (inputs_ready) {
     SQ_TRY(finalize_slot(e, e->slot[s.id ^ 1]));
     SQ_CUDA(e, cudaStreamWaitEvent(e->stream, inputs_ready, 0));
@@ -1154,7 +1154,7 @@ int sq_sync(sq_engine* e) {
   if (!e) return SQ_ERR_ARG;
   SQ_CUDA(e, cudaSetDevice(e->device));
   SQ_CUDA(e, cudaStreamSynchronize(e->copy_stream));
-  // at most one batch is waiting for its compaction; finalize in age order anyway
+  // at most one batch is waiting for its candidate count; finalize in age order anyway
   SQ_TRY(finalize_slot(e, e->slot[e->next_slot]));
   SQ_TRY(finalize_slot(e, e->slot[e->next_slot ^ 1]));
   SQ_CUDA(e, cudaStreamSynchronize(e->stream));

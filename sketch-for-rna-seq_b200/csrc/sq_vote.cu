@@ -13,7 +13,7 @@
 //   vote_overflow_kernel  the same on a per-worker global-memory scratch sized for every transcript of the index.
 // Every tier produces, per read: per-k maximum over the transcripts seen, the double-precision
 // `count < fraction*max` filter for every k, integer score = sum of counts, candidates ordered by (score desc,
-// transcript asc), appended to the batch staging area.
+// transcript asc), appended to the candidate store (its free tail; see sq_engine.cu).
 #include <algorithm>
 
 #include "sq_common.cuh"
@@ -341,12 +341,12 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
     }
     __syncwarp();
   }
-  // append to the batch staging area
+  // append to the candidate store
   unsigned long long sbase = 0;
   if (lane == 0) {
     sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
     uint32_t kept = nc;
-    if (sbase + nc > P.stage_cap) kept = 0;  // the host re-runs the vote with a staging area of the reported size
+    if (sbase + nc > P.stage_cap) kept = 0;  // the host grows the store to the reported size and re-runs the vote
     P.read_soff[r] = P.stage_base + (uint32_t)sbase;
     P.read_cnt[r] = kept;
     ListHash lh;  // rare tier: one lane folds the ordered list
@@ -1006,7 +1006,7 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
     if (lane == 0) {
       sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
       P.read_soff[r] = P.stage_base + (uint32_t)sbase;
-      P.read_cnt[r] = sbase + nc <= P.stage_cap ? nc : 0u;  // the host re-runs the vote with a staging area of the reported size
+      P.read_cnt[r] = sbase + nc <= P.stage_cap ? nc : 0u;  // the host grows the store and re-runs the vote
     }
     sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
     __syncwarp();
