@@ -352,12 +352,16 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
     nr = torch.empty(T, dtype=torch.float64, pin_memory=True)
     pres = torch.empty(T, dtype=torch.uint8, pin_memory=True)
 
+    # R of the M-step (isoform_assignment.cpp:54-57) = reads of the whole job: the caller knows it (every rank pushes
+    # n_reads), so the engine need not all-reduce its local counts
+    R_all = n_reads * world
+
     def step_device():
         eng.reset_reads()
         for c in chunks:
             eng.push_reads_device(c["words"].data_ptr(), c["words"].numel(), c["boff"].data_ptr(),
                                   c["len"].data_ptr(), c["n"], c["bases"] + 4 * c["n"])
-        return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), 0, 20, 0.01)
+        return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), R_all, 20, 0.01)
 
     # equal-length reads (the short-read workloads): sq_push_reads_fixed, only the packed words travel;
     # otherwise the lengths travel too (base_off = NULL, offsets derived on the GPU)
@@ -370,7 +374,7 @@ def run_workload(cx, kind, ks, scale, chunks, steps, warmup, cpu_kind, cpu_sampl
                 eng.push_reads_fixed_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), fixed_len, c["n"])
             else:
                 eng.push_reads_ptr(c["h_words"].data_ptr(), c["h_words"].numel(), 0, c["h_len"].data_ptr(), c["n"])
-        return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), 0, 20, 0.01)
+        return eng.finish_into(pi.data_ptr(), nr.data_ptr(), pres.data_ptr(), R_all, 20, 0.01)
 
     # the same pinned buffers copied to the device and nothing else: the host->device ceiling of `e2e` on this box
     # (with N ranks: all ranks copy at the same time, as they do in the e2e leg)
