@@ -1443,6 +1443,13 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   {
     StageScope sc(e, 4);
     launch_em_init(v.pi, T, state, st, &e->launches);
+    // The exchange kernels spin on their peers' flags with a time-out (a dead peer must not hang the GPU).  Ranks
+    // may arrive here seconds apart (uneven shards, slower hosts): one small all-reduce lines them up first -- NCCL
+    // waits as long as it takes -- and from there on the iterations run in lock-step.
+    if (peer) {
+      SQ_CUDA(e, cudaMemsetAsync(d_R, 0, 8, st));
+      SQ_TRY(allreduce(e, d_R, 1, ncclUint64));
+    }
     for (int it = 0; it < em_iters; ++it) {
       if (peer) {
         // this rank's sums go to its exchange slot; the M-step kernel adds all ranks' slots over peer memory
