@@ -157,9 +157,16 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint64_t
   h[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+  uint64_t k[kSortItems];  // all loads of the thread in flight before the first shared-memory atomic
+#pragma unroll
   for (int i = 0; i < kSortItems; ++i) {
     const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255], 1u);
+    k[i] = idx < n ? keys[idx] : 0ull;
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint64_t idx = base + (uint64_t)i * kSortThreads + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(k[i] >> shift) & 255], 1u);
   }
   __syncthreads();
   hist[(uint64_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
