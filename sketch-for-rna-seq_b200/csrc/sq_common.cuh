@@ -143,8 +143,7 @@ struct VoteParams {
   uint32_t force_tier;               // tests: 0 = automatic, 1 = every read to the window kernel, 2 = every read to the general kernel
   IndexTable tab[SQ_MAXK];
   // output: the free tail of the engine's candidate store (no staging: what the vote writes is final)
-  uint32_t* stage_tid;               // store + stage_base
-  int32_t* stage_score;
+  uint2* stage;                      // store + stage_base: a pair = {transcript, score} in one 8-byte word
   uint64_t stage_cap;                // free pairs behind stage_base
   uint32_t stage_base;               // pairs of the earlier batches
   unsigned long long* stage_cursor;  // device counter: pairs of this batch

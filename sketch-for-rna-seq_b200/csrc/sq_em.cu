@@ -82,8 +82,7 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
 // multiplication by w: a re-association only.
 __global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restrict__ rd_start,
                                                         const uint32_t* __restrict__ rd_cnt, uint64_t r0, uint32_t n,
-                                                        const uint32_t* __restrict__ cand_tid,
-                                                        const int32_t* __restrict__ cand_score, uint32_t T,
+                                                        const uint2* __restrict__ cand, uint32_t T,
                                                         uint32_t hash_bits, uint64_t* __restrict__ rkey,
                                                         ulonglong2* __restrict__ rfp) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,14 +92,15 @@ __global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restri
   ListHash lh;
   lh.init(c);
   uint32_t top = T;  // reads without candidates go last (one empty class)
-  // blocks of 4 candidates: the eight loads go out together (the kernel waits on latency, the fold is serial)
+  // blocks of 4 candidates: the four loads go out together (the kernel waits on latency, the fold is serial)
   for (uint32_t i0 = 0; i0 < c; i0 += 4) {
     uint32_t t[4];
     int32_t sc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      t[u] = i0 + u < c ? cand_tid[so + i0 + u] : 0u;
-      sc[u] = i0 + u < c ? cand_score[so + i0 + u] : 0;
+      const uint2 pr = i0 + u < c ? cand[so + i0 + u] : make_uint2(0u, 0u);
+      t[u] = pr.x;
+      sc[u] = (int32_t)pr.y;
     }
     if (i0 == 0) top = t[0];
 #pragma unroll
@@ -111,63 +111,70 @@ __global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restri
   rfp[r] = make_ulonglong2(lh.h, lh.g);
 }
 
-void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n,
-                      const uint32_t* cand_tid, const int32_t* cand_score, uint32_t T, uint32_t hash_bits, uint64_t* rkey,
-                      void* rfp, cudaStream_t s, uint64_t* launches) {
+void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n, const uint2* cand,
+                      uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches) {
   if (!n) return;
-  read_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, r0, (uint32_t)n, cand_tid, cand_score, T,
-                                                               hash_bits, rkey, static_cast<ulonglong2*>(rfp));
+  read_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, r0, (uint32_t)n, cand, T, hash_bits, rkey,
+                                                               static_cast<ulonglong2*>(rfp));
   if (launches) ++*launches;
 }
 
 // the store in read order (sq_get_candidates): off = exclusive scan of rd_cnt
 __global__ void csr_gather_kernel(const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
                                   const uint32_t* __restrict__ off, uint64_t n_reads,
-                                  const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                  uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score) {
+                                  const uint2* __restrict__ cand, uint32_t* __restrict__ out_tid,
+                                  int32_t* __restrict__ out_score) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
   const uint32_t b = rd_start[r], n = rd_cnt[r], d = off[r];
   for (uint32_t j = 0; j < n; ++j) {
-    out_tid[d + j] = cand_tid[b + j];
-    out_score[d + j] = cand_score[b + j];
+    const uint2 pr = cand[b + j];
+    out_tid[d + j] = pr.x;
+    out_score[d + j] = (int32_t)pr.y;
   }
 }
 
 void launch_csr_gather(const uint32_t* rd_start, const uint32_t* rd_cnt, uint32_t* off, uint64_t n_reads,
-                       uint32_t* scan_tmp, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid,
-                       int32_t* out_score, cudaStream_t s, uint64_t* launches) {
+                       uint32_t* scan_tmp, const uint2* cand, uint32_t* out_tid, int32_t* out_score, cudaStream_t s,
+                       uint64_t* launches) {
   launch_exclusive_scan(rd_cnt, off, (uint32_t)n_reads, scan_tmp, s, launches);
   if (!n_reads) return;
-  csr_gather_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, off, n_reads, cand_tid, cand_score,
-                                                                      out_tid, out_score);
+  csr_gather_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, off, n_reads, cand, out_tid,
+                                                                      out_score);
   if (launches) ++*launches;
 }
 
-__global__ void class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
-                                  const ulonglong2* __restrict__ fp, uint32_t* __restrict__ head) {
-  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const bool valid = i < n_reads;
-  const uint64_t k = valid ? keys[i] : 0;
-  ulonglong2 mine = make_ulonglong2(0, 0);
-  if (valid) mine = fp[(uint32_t)k];
-  // the predecessor's key and fingerprint come from the neighbouring lane; lane 0 fetches them itself
-  uint64_t pk = __shfl_up_sync(0xFFFFFFFFu, k, 1);
-  unsigned long long px = __shfl_up_sync(0xFFFFFFFFu, mine.x, 1), py = __shfl_up_sync(0xFFFFFFFFu, mine.y, 1);
-  if (lane_id() == 0 && valid && i > 0) {
-    pk = keys[i - 1];
-    const ulonglong2 p = fp[(uint32_t)pk];
-    px = p.x;
-    py = p.y;
+// Four sorted positions per thread: the four fingerprint gathers (random 16-byte reads, the cost of this kernel) are
+// in flight together, and so is the one extra (key, fingerprint) the warp's first lane needs for the position before
+// its own; positions compare with their left neighbour in registers, the first one across lanes.
+__global__ void __launch_bounds__(256) class_head_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
+                                                         const ulonglong2* __restrict__ fp, uint32_t* __restrict__ head) {
+  const uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 4;
+  uint64_t k[4], pk = 0;
+  ulonglong2 f[4], pf = make_ulonglong2(0, 0);
+  const bool first_lane = lane_id() == 0 && i0 > 0 && i0 < n_reads;
+  if (first_lane) pk = keys[i0 - 1];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) k[u] = i0 + u < n_reads ? keys[i0 + u] : 0ull;
+  if (first_lane) pf = fp[(uint32_t)pk];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) f[u] = i0 + u < n_reads ? fp[(uint32_t)k[u]] : make_ulonglong2(0, 0);
+  const uint64_t sk = __shfl_up_sync(0xFFFFFFFFu, k[3], 1);
+  const unsigned long long sx = __shfl_up_sync(0xFFFFFFFFu, f[3].x, 1), sy = __shfl_up_sync(0xFFFFFFFFu, f[3].y, 1);
+  if (lane_id() != 0) { pk = sk; pf.x = sx; pf.y = sy; }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (i0 + u < n_reads)
+      head[i0 + u] = (i0 + u == 0 || (k[u] >> 32) != (pk >> 32) || f[u].x != pf.x || f[u].y != pf.y) ? 1u : 0u;
+    pk = k[u];
+    pf = f[u];
   }
-  if (valid) head[i] = (i == 0 || (k >> 32) != (pk >> 32) || mine.x != px || mine.y != py) ? 1u : 0u;
 }
 
 // exact variant (option exact_classes): equal key AND element-wise equal lists; ~10 random sectors per read
 __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
                                         const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
-                                        const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                        uint32_t* __restrict__ head) {
+                                        const uint2* __restrict__ cand, uint32_t* __restrict__ head) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   uint32_t h = 1;
@@ -176,8 +183,10 @@ __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint6
     const uint32_t b = rd_start[r], n = rd_cnt[r], bq = rd_start[q];
     if (rd_cnt[q] == n) {
       h = 0;
-      for (uint32_t j = 0; j < n; ++j)
-        if (cand_tid[b + j] != cand_tid[bq + j] || cand_score[b + j] != cand_score[bq + j]) { h = 1; break; }
+      for (uint32_t j = 0; j < n; ++j) {
+        const uint2 x = cand[b + j], y = cand[bq + j];
+        if (x.x != y.x || x.y != y.y) { h = 1; break; }
+      }
     }
   }
   head[i] = h;
@@ -202,8 +211,8 @@ __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint3
 __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, const uint32_t* __restrict__ class_pos,
                                     const uint32_t* __restrict__ class_off, uint32_t n_classes,
                                     const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
-                                    const uint32_t* __restrict__ cand_tid, const int32_t* __restrict__ cand_score,
-                                    uint32_t* __restrict__ out_tid, int32_t* __restrict__ out_score,
+                                    const uint2* __restrict__ cand, uint32_t* __restrict__ out_tid,
+                                    int32_t* __restrict__ out_score,
                                     uint32_t* __restrict__ out_pack,
                                     uint32_t* __restrict__ pack_bad, double* __restrict__ weight) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,8 +221,9 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
   const uint32_t b = rd_start[r], n = rd_cnt[r], d = class_off[c];
   bool bad = false;
   for (uint32_t j = 0; j < n; ++j) {
-    const uint32_t t = cand_tid[b + j];
-    const int32_t sc = cand_score[b + j];
+    const uint2 pr = cand[b + j];
+    const uint32_t t = pr.x;
+    const int32_t sc = (int32_t)pr.y;
     out_tid[d + j] = t;
     out_score[d + j] = sc;
     // packed copy for the EM iterations: transcript in 24 bits, score in 8 (half the bytes per pair: the 20 x 2
@@ -227,13 +237,13 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
 
 // heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + per class: (first read, position, count)
 void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
-                        const void* fp, const uint32_t* cand_tid, const int32_t* cand_score, bool exact, uint32_t* head, uint32_t* cid,
+                        const void* fp, const uint2* cand, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, rd_start, rd_cnt, cand_tid, cand_score, head);
-  else class_head_kernel<<<grid, 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
+  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, rd_start, rd_cnt, cand, head);
+  else class_head_kernel<<<(uint32_t)((n_reads + 1023) / 1024), 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
   launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
   class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, rd_cnt, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;
@@ -241,13 +251,13 @@ void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* 
 
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
                          uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* rd_start,
-                         const uint32_t* rd_cnt, const uint32_t* cand_tid, const int32_t* cand_score, uint32_t* out_tid, int32_t* out_score,
+                         const uint32_t* rd_cnt, const uint2* cand, uint32_t* out_tid, int32_t* out_score,
                          uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches) {
   launch_exclusive_scan(class_cnt, class_off, n_classes, scan_tmp, s, launches);
   cudaMemsetAsync(pack_bad, 0, 4, s);
   if (!n_classes) return;
   class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, rd_start, rd_cnt,
-                                                              cand_tid, cand_score, out_tid, out_score, out_pack, pack_bad,
+                                                              cand, out_tid, out_score, out_pack, pack_bad,
                                                               weight);
   if (launches) ++*launches;
 }

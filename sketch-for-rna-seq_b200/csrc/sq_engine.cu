@@ -138,8 +138,7 @@ struct sq_engine {
   bool big_ready = false;
   // candidate store over all pushed reads: the vote kernels append a read's list at an atomic cursor (read r:
   // cand_*[rd_start[r] .. +rd_cnt[r])), so the lists of a batch are contiguous but not in read order
-  uint32_t* cand_tid = nullptr;
-  int32_t* cand_score = nullptr;
+  uint2* cand = nullptr;  // a pair = {transcript, score}: one 8-byte word, one sector where two arrays would touch two
   uint32_t* rd_start = nullptr;
   uint32_t* rd_cnt = nullptr;
   uint64_t* rkey = nullptr;              // per read: class sort key and 128-bit list fingerprint (see sq_em.cu), written
@@ -324,19 +323,12 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
   if (need_pairs > e->cand_cap) {
     uint64_t cap = std::max<uint64_t>(need_pairs + need_pairs / 2, 1 << 20);
     if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
-    uint32_t* t = nullptr;
-    int32_t* sc = nullptr;
-    SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint32_t)));
-    SQ_CUDA(e, cudaMalloc(&sc, cap * sizeof(int32_t)));
-    if (e->cand_tid && e->P) {
-      SQ_CUDA(e, cudaMemcpyAsync(t, e->cand_tid, e->P * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
-      SQ_CUDA(e, cudaMemcpyAsync(sc, e->cand_score, e->P * sizeof(int32_t), cudaMemcpyDeviceToDevice, cs));
-    }
+    uint2* t = nullptr;
+    SQ_CUDA(e, cudaMalloc(&t, cap * sizeof(uint2)));
+    if (e->cand && e->P) SQ_CUDA(e, cudaMemcpyAsync(t, e->cand, e->P * sizeof(uint2), cudaMemcpyDeviceToDevice, cs));
     SQ_CUDA(e, cudaStreamSynchronize(cs));
-    if (e->cand_tid) SQ_CUDA(e, cudaFree(e->cand_tid));
-    if (e->cand_score) SQ_CUDA(e, cudaFree(e->cand_score));
-    e->cand_tid = t;
-    e->cand_score = sc;
+    if (e->cand) SQ_CUDA(e, cudaFree(e->cand));
+    e->cand = t;
     e->cand_cap = cap;
   }
   return SQ_OK;
@@ -344,8 +336,7 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
 
 // point a batch's vote at the free tail of the store (called with the exact P of all earlier batches)
 void aim_vote_at_store(sq_engine* e, Slot& s) {
-  s.vp.stage_tid = e->cand_tid + e->P;
-  s.vp.stage_score = e->cand_score + e->P;
+  s.vp.stage = e->cand + e->P;
   s.vp.stage_cap = e->cand_cap - e->P;
   s.vp.stage_base = (uint32_t)e->P;
   s.vp.read_soff = e->rd_start + s.read_base;
@@ -713,8 +704,7 @@ void sq_destroy(sq_engine* e) {
                    &e->cls_head, &e->cls_id, &e->cls_read, &e->cls_pos, &e->cls_weight, &e->out_pi,
                    &e->out_nr, &e->out_present};
   for (DevBuf* b : all) b->release();
-  if (e->cand_tid) cudaFree(e->cand_tid);
-  if (e->cand_score) cudaFree(e->cand_score);
+  if (e->cand) cudaFree(e->cand);
   if (e->rd_start) cudaFree(e->rd_start);
   if (e->rd_cnt) cudaFree(e->rd_cnt);
   if (e->rkey) cudaFree(e->rkey);
@@ -1198,8 +1188,8 @@ int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* 
   SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
   SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)(R + 1)) * 4));
   if (R) {
-    launch_csr_gather(e->rd_start, e->rd_cnt, e->em_off.as<uint32_t>(), R, e->scan_tmp.as<uint32_t>(), e->cand_tid,
-                      e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->stream, &e->launches);
+    launch_csr_gather(e->rd_start, e->rd_cnt, e->em_off.as<uint32_t>(), R, e->scan_tmp.as<uint32_t>(), e->cand,
+                      e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->stream, &e->launches);
     SQ_CUDA(e, cudaMemcpyAsync(tmp.data(), e->em_off.p, R * 4, cudaMemcpyDeviceToHost, e->stream));
     SQ_CUDA(e, cudaStreamSynchronize(e->stream));
     tmp[R] = (uint32_t)P;
@@ -1261,14 +1251,9 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
     SQ_CUDA(e, cudaMemcpy(e->rd_cnt, cnt32.data(), n_reads * 4, cudaMemcpyHostToDevice));
   }
   if (P) {
-    if (e->perm_identity) {
-      SQ_CUDA(e, cudaMemcpy(e->cand_tid, tid, P * 4, cudaMemcpyHostToDevice));
-    } else {
-      std::vector<uint32_t> itid(P);
-      for (uint64_t i = 0; i < P; ++i) itid[i] = e->int_of[tid[i]];
-      SQ_CUDA(e, cudaMemcpy(e->cand_tid, itid.data(), P * 4, cudaMemcpyHostToDevice));
-    }
-    SQ_CUDA(e, cudaMemcpy(e->cand_score, score, P * 4, cudaMemcpyHostToDevice));
+    std::vector<uint2> pairs(P);
+    for (uint64_t i = 0; i < P; ++i) pairs[i] = make_uint2(e->perm_identity ? tid[i] : e->int_of[tid[i]], (uint32_t)score[i]);
+    SQ_CUDA(e, cudaMemcpy(e->cand, pairs.data(), P * sizeof(uint2), cudaMemcpyHostToDevice));
   }
   e->P = P;
   e->n_reads = n_reads;
@@ -1350,22 +1335,22 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       const void* fp = e->rfp;
       // keys and fingerprints were produced batch by batch behind the votes (sq_set_candidates: here)
       if (!e->keys_valid)
-        launch_read_keys(e->rd_start, e->rd_cnt, 0, R, e->cand_tid, e->cand_score, T, hash_bits, e->rkey, e->rfp, st,
+        launch_read_keys(e->rd_start, e->rd_cnt, 0, R, e->cand, T, hash_bits, e->rkey, e->rfp, st,
                          &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));  // the sort works on a copy
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
                         (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
-      launch_class_heads(skeys, R, e->rd_start, e->rd_cnt, fp, e->cand_tid, e->cand_score, e->exact_classes,
+      launch_class_heads(skeys, R, e->rd_start, e->rd_cnt, fp, e->cand, e->exact_classes,
                          e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
       SQ_CUDA(e, cudaStreamSynchronize(st));
       launch_class_gather(e->cls_read.as<uint32_t>(), e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(),
-                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->rd_start, e->rd_cnt, e->cand_tid,
-                          e->cand_score, e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(),
+                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->rd_start, e->rd_cnt, e->cand,
+                          e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(),
                           d_pack_bad, e->cls_weight.as<double>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_cpairs, e->em_off.as<uint32_t>() + n_classes, 4, cudaMemcpyDeviceToHost, st));
       SQ_CUDA(e, cudaMemcpyAsync(&pack_bad, d_pack_bad, 4, cudaMemcpyDeviceToHost, st));

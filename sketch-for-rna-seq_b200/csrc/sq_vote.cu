@@ -361,8 +361,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
   if (sbase + nc <= P.stage_cap)
     for (uint32_t i = lane; i < nc; i += 32) {
       const unsigned long long key = S.cand[i];
-      P.stage_tid[sbase + i] = (uint32_t)key;
-      P.stage_score[sbase + i] = (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32));
+      P.stage[sbase + i] = make_uint2((uint32_t)key, 0x7FFFFFFFu - (uint32_t)(key >> 32));
     }
   __syncwarp();
   // the candidate buffer aliases the dedup set in the shared-memory tier: restore the empty pattern
@@ -721,8 +720,7 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
         while (e1) {
           const uint32_t p = (uint32_t)__ffs((int)e1) - 1;
           e1 &= e1 - 1;
-          P.stage_tid[sbase] = A.base + p;
-          P.stage_score[sbase] = (int32_t)c;
+          P.stage[sbase] = make_uint2(A.base + p, c);
           lh.add(A.base + p, (int32_t)c);
           if (top == 0xFFFFFFFFu) top = A.base + p;
           ++sbase;
@@ -1018,8 +1016,7 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
       for (uint32_t j = 0; j < nc; ++j) rank += S.cand[j] < key ? 1u : 0u;
       sorted[rank] = key;
       if (fits) {
-        P.stage_tid[sbase + rank] = (uint32_t)key;
-        P.stage_score[sbase + rank] = (int32_t)(0x7FFFFFFFu - (uint32_t)(key >> 32));
+        P.stage[sbase + rank] = make_uint2((uint32_t)key, 0x7FFFFFFFu - (uint32_t)(key >> 32));
       }
     }
     __syncwarp();
