@@ -147,8 +147,7 @@ struct VoteParams {
   uint64_t stage_cap;                // free pairs behind stage_base
   uint32_t stage_base;               // pairs of the earlier batches
   unsigned long long* stage_cursor;  // device counter: pairs of this batch
-  uint32_t* read_soff;               // per read of the batch: start of its list in the store (absolute)
-  uint32_t* read_cnt;                // per read of the batch: candidates
+  uint2* read_loc;                   // per read of the batch: {start of its list in the store (absolute), candidates}
   // per read of the batch: class sort key and 128-bit list fingerprint, folded by whichever kernel emits the list
   uint64_t* rkey;
   void* rfp;                         // ulonglong2

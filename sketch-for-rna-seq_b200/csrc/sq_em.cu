@@ -69,7 +69,7 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
 }
 
 // ------------------------------------------------------------------ candidate store and read classes
-// The vote kernels write a read's candidates straight into the engine's store (one atomic cursor; rd_start / rd_cnt
+// The vote kernels write a read's candidates straight into the engine's store (one atomic cursor; rd[r] = {start, count}
 // say where): nothing is staged, scanned or moved afterwards.  EM does not care which read is which: reads with
 // the same candidate list (same transcripts, same scores) contribute identical terms, so they are collapsed into
 // one class with a weight.  Behind every batch's vote a kernel folds a 128-bit fingerprint of each
@@ -80,15 +80,14 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
 // sectors per read, 2.8 ms at 20 M reads).  Ordering by best candidate keeps the classes of one gene adjacent,
 // which makes the 1/den gathers of the transcript-major pass local.  Summing w identical terms becomes one
 // multiplication by w: a re-association only.
-__global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restrict__ rd_start,
-                                                        const uint32_t* __restrict__ rd_cnt, uint64_t r0, uint32_t n,
+__global__ void __launch_bounds__(256) read_keys_kernel(const uint2* __restrict__ rd, uint64_t r0, uint32_t n,
                                                         const uint2* __restrict__ cand, uint32_t T,
                                                         uint32_t hash_bits, uint64_t* __restrict__ rkey,
                                                         ulonglong2* __restrict__ rfp) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t r = r0 + i;
-  const uint32_t c = rd_cnt[r], so = rd_start[r];
+  const uint32_t c = rd[r].y, so = rd[r].x;
   ListHash lh;
   lh.init(c);
   uint32_t top = T;  // reads without candidates go last (one empty class)
@@ -111,22 +110,27 @@ __global__ void __launch_bounds__(256) read_keys_kernel(const uint32_t* __restri
   rfp[r] = make_ulonglong2(lh.h, lh.g);
 }
 
-void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n, const uint2* cand,
+void launch_read_keys(const uint2* rd, uint64_t r0, uint64_t n, const uint2* cand,
                       uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp, cudaStream_t s, uint64_t* launches) {
   if (!n) return;
-  read_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, r0, (uint32_t)n, cand, T, hash_bits, rkey,
+  read_keys_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(rd, r0, (uint32_t)n, cand, T, hash_bits, rkey,
                                                                static_cast<ulonglong2*>(rfp));
   if (launches) ++*launches;
 }
 
-// the store in read order (sq_get_candidates): off = exclusive scan of rd_cnt
-__global__ void csr_gather_kernel(const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
+// the store in read order (sq_get_candidates): off = exclusive scan of the counts
+__global__ void rd_counts_kernel(const uint2* __restrict__ rd, uint64_t n_reads, uint32_t* __restrict__ cnt) {
+  const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (r < n_reads) cnt[r] = rd[r].y;
+}
+
+__global__ void csr_gather_kernel(const uint2* __restrict__ rd,
                                   const uint32_t* __restrict__ off, uint64_t n_reads,
                                   const uint2* __restrict__ cand, uint32_t* __restrict__ out_tid,
                                   int32_t* __restrict__ out_score) {
   const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (r >= n_reads) return;
-  const uint32_t b = rd_start[r], n = rd_cnt[r], d = off[r];
+  const uint32_t b = rd[r].x, n = rd[r].y, d = off[r];
   for (uint32_t j = 0; j < n; ++j) {
     const uint2 pr = cand[b + j];
     out_tid[d + j] = pr.x;
@@ -134,12 +138,13 @@ __global__ void csr_gather_kernel(const uint32_t* __restrict__ rd_start, const u
   }
 }
 
-void launch_csr_gather(const uint32_t* rd_start, const uint32_t* rd_cnt, uint32_t* off, uint64_t n_reads,
+void launch_csr_gather(const uint2* rd, uint32_t* cnt_tmp, uint32_t* off, uint64_t n_reads,
                        uint32_t* scan_tmp, const uint2* cand, uint32_t* out_tid, int32_t* out_score, cudaStream_t s,
                        uint64_t* launches) {
-  launch_exclusive_scan(rd_cnt, off, (uint32_t)n_reads, scan_tmp, s, launches);
+  if (n_reads) rd_counts_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd, n_reads, cnt_tmp);
+  launch_exclusive_scan(cnt_tmp, off, (uint32_t)n_reads, scan_tmp, s, launches);
   if (!n_reads) return;
-  csr_gather_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd_start, rd_cnt, off, n_reads, cand, out_tid,
+  csr_gather_kernel<<<(uint32_t)((n_reads + 255) / 256), 256, 0, s>>>(rd, off, n_reads, cand, out_tid,
                                                                       out_score);
   if (launches) ++*launches;
 }
@@ -173,15 +178,15 @@ __global__ void __launch_bounds__(256) class_head_kernel(const uint64_t* __restr
 
 // exact variant (option exact_classes): equal key AND element-wise equal lists; ~10 random sectors per read
 __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint64_t n_reads,
-                                        const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
-                                        const uint2* __restrict__ cand, uint32_t* __restrict__ head) {
+                                        const uint2* __restrict__ rd, const uint2* __restrict__ cand,
+                                        uint32_t* __restrict__ head) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   uint32_t h = 1;
   if (i > 0 && (keys[i] >> 32) == (keys[i - 1] >> 32)) {
     const uint32_t r = (uint32_t)keys[i], q = (uint32_t)keys[i - 1];
-    const uint32_t b = rd_start[r], n = rd_cnt[r], bq = rd_start[q];
-    if (rd_cnt[q] == n) {
+    const uint32_t b = rd[r].x, n = rd[r].y, bq = rd[q].x;
+    if (rd[q].y == n) {
       h = 0;
       for (uint32_t j = 0; j < n; ++j) {
         const uint2 x = cand[b + j], y = cand[bq + j];
@@ -195,7 +200,7 @@ __global__ void class_head_exact_kernel(const uint64_t* __restrict__ keys, uint6
 // class c = run of sorted positions starting at a head: its list is the head's, its weight the run length
 __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint32_t* __restrict__ cid,
                                   const uint64_t* __restrict__ keys, uint64_t n_reads,
-                                  const uint32_t* __restrict__ rd_cnt, uint32_t* __restrict__ class_read,
+                                  const uint2* __restrict__ rd, uint32_t* __restrict__ class_read,
                                   uint32_t* __restrict__ class_pos, uint32_t* __restrict__ class_cnt) {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
@@ -203,22 +208,23 @@ __global__ void class_fill_kernel(const uint32_t* __restrict__ head, const uint3
     const uint32_t c = cid[i], r = (uint32_t)keys[i];
     class_read[c] = r;
     class_pos[c] = (uint32_t)i;
-    class_cnt[c] = rd_cnt[r];
+    class_cnt[c] = rd[r].y;
   }
   if (i == n_reads - 1) class_pos[cid[n_reads]] = (uint32_t)n_reads;  // cid[n_reads] = number of classes
 }
 
 __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, const uint32_t* __restrict__ class_pos,
                                     const uint32_t* __restrict__ class_off, uint32_t n_classes,
-                                    const uint32_t* __restrict__ rd_start, const uint32_t* __restrict__ rd_cnt,
-                                    const uint2* __restrict__ cand, uint32_t* __restrict__ out_tid,
+                                    const uint2* __restrict__ rd, const uint2* __restrict__ cand,
+                                    uint32_t* __restrict__ out_tid,
                                     int32_t* __restrict__ out_score,
                                     uint32_t* __restrict__ out_pack,
                                     uint32_t* __restrict__ pack_bad, double* __restrict__ weight) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_classes) return;
   const uint32_t r = class_read[c];
-  const uint32_t b = rd_start[r], n = rd_cnt[r], d = class_off[c];
+  const uint2 loc = rd[r];  // one sector says where the class's list is and how long
+  const uint32_t b = loc.x, n = loc.y, d = class_off[c];
   bool bad = false;
   for (uint32_t j = 0; j < n; ++j) {
     const uint2 pr = cand[b + j];
@@ -236,27 +242,26 @@ __global__ void class_gather_kernel(const uint32_t* __restrict__ class_read, con
 }
 
 // heads + class ids (cid = exclusive scan of head, n_reads+1 entries) + per class: (first read, position, count)
-void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint2* rd,
                         const void* fp, const uint2* cand, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches) {
   if (!n_reads) return;
   const uint32_t grid = (uint32_t)((n_reads + 255) / 256);
-  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, rd_start, rd_cnt, cand, head);
+  if (exact) class_head_exact_kernel<<<grid, 256, 0, s>>>(keys, n_reads, rd, cand, head);
   else class_head_kernel<<<(uint32_t)((n_reads + 1023) / 1024), 256, 0, s>>>(keys, n_reads, static_cast<const ulonglong2*>(fp), head);
   launch_exclusive_scan(head, cid, (uint32_t)n_reads, scan_tmp, s, launches);
-  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, rd_cnt, class_read, class_pos, class_cnt);
+  class_fill_kernel<<<grid, 256, 0, s>>>(head, cid, keys, n_reads, rd, class_read, class_pos, class_cnt);
   if (launches) *launches += 2;
 }
 
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
-                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* rd_start,
-                         const uint32_t* rd_cnt, const uint2* cand, uint32_t* out_tid, int32_t* out_score,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint2* rd, const uint2* cand, uint32_t* out_tid, int32_t* out_score,
                          uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches) {
   launch_exclusive_scan(class_cnt, class_off, n_classes, scan_tmp, s, launches);
   cudaMemsetAsync(pack_bad, 0, 4, s);
   if (!n_classes) return;
-  class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, rd_start, rd_cnt,
+  class_gather_kernel<<<(n_classes + 255) / 256, 256, 0, s>>>(class_read, class_pos, class_off, n_classes, rd,
                                                               cand, out_tid, out_score, out_pack, pack_bad,
                                                               weight);
   if (launches) ++*launches;

@@ -137,10 +137,9 @@ struct sq_engine {
   uint32_t big_cap_log2 = 0, big_set_log2 = 0;
   bool big_ready = false;
   // candidate store over all pushed reads: the vote kernels append a read's list at an atomic cursor (read r:
-  // cand_*[rd_start[r] .. +rd_cnt[r])), so the lists of a batch are contiguous but not in read order
+  // cand[rd[r].x .. + rd[r].y)), so the lists of a batch are contiguous but not in read order
   uint2* cand = nullptr;  // a pair = {transcript, score}: one 8-byte word, one sector where two arrays would touch two
-  uint32_t* rd_start = nullptr;
-  uint32_t* rd_cnt = nullptr;
+  uint2* rd = nullptr;  // per read: {start of its list in cand, candidates}
   uint64_t* rkey = nullptr;              // per read: class sort key and 128-bit list fingerprint (see sq_em.cu), written
   void* rfp = nullptr;                   // behind every batch's vote
   bool keys_valid = true;                // false: the store was filled by sq_set_candidates
@@ -294,26 +293,22 @@ int ensure_store(sq_engine* e, uint64_t read_base, uint64_t reads, uint64_t pair
   const uint64_t need_reads = read_base + reads + 1;
   if (need_reads > e->read_cap) {
     const uint64_t cap = std::max<uint64_t>(need_reads + need_reads / 2, 1 << 16);
-    uint32_t *ps = nullptr, *pc = nullptr;
+    uint2* ps = nullptr;
     uint64_t* pk = nullptr;
     void* pf = nullptr;
-    SQ_CUDA(e, cudaMalloc(&ps, cap * sizeof(uint32_t)));
-    SQ_CUDA(e, cudaMalloc(&pc, cap * sizeof(uint32_t)));
+    SQ_CUDA(e, cudaMalloc(&ps, cap * sizeof(uint2)));
     SQ_CUDA(e, cudaMalloc(&pk, cap * sizeof(uint64_t)));
     SQ_CUDA(e, cudaMalloc(&pf, cap * 16));
-    if (e->rd_start && read_base) {
-      SQ_CUDA(e, cudaMemcpyAsync(ps, e->rd_start, read_base * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
-      SQ_CUDA(e, cudaMemcpyAsync(pc, e->rd_cnt, read_base * sizeof(uint32_t), cudaMemcpyDeviceToDevice, cs));
+    if (e->rd && read_base) {
+      SQ_CUDA(e, cudaMemcpyAsync(ps, e->rd, read_base * sizeof(uint2), cudaMemcpyDeviceToDevice, cs));
       SQ_CUDA(e, cudaMemcpyAsync(pk, e->rkey, read_base * sizeof(uint64_t), cudaMemcpyDeviceToDevice, cs));
       SQ_CUDA(e, cudaMemcpyAsync(pf, e->rfp, read_base * 16, cudaMemcpyDeviceToDevice, cs));
     }
     SQ_CUDA(e, cudaStreamSynchronize(cs));
-    if (e->rd_start) SQ_CUDA(e, cudaFree(e->rd_start));
-    if (e->rd_cnt) SQ_CUDA(e, cudaFree(e->rd_cnt));
+    if (e->rd) SQ_CUDA(e, cudaFree(e->rd));
     if (e->rkey) SQ_CUDA(e, cudaFree(e->rkey));
     if (e->rfp) SQ_CUDA(e, cudaFree(e->rfp));
-    e->rd_start = ps;
-    e->rd_cnt = pc;
+    e->rd = ps;
     e->rkey = pk;
     e->rfp = pf;
     e->read_cap = cap;
@@ -339,8 +334,7 @@ void aim_vote_at_store(sq_engine* e, Slot& s) {
   s.vp.stage = e->cand + e->P;
   s.vp.stage_cap = e->cand_cap - e->P;
   s.vp.stage_base = (uint32_t)e->P;
-  s.vp.read_soff = e->rd_start + s.read_base;
-  s.vp.read_cnt = e->rd_cnt + s.read_base;
+  s.vp.read_loc = e->rd + s.read_base;
   s.vp.rkey = e->rkey;
   s.vp.rfp = e->rfp;
   s.vp.read_base = s.read_base;
@@ -705,8 +699,7 @@ void sq_destroy(sq_engine* e) {
                    &e->out_nr, &e->out_present};
   for (DevBuf* b : all) b->release();
   if (e->cand) cudaFree(e->cand);
-  if (e->rd_start) cudaFree(e->rd_start);
-  if (e->rd_cnt) cudaFree(e->rd_cnt);
+  if (e->rd) cudaFree(e->rd);
   if (e->rkey) cudaFree(e->rkey);
   if (e->rfp) cudaFree(e->rfp);
   if (e->d_totals) cudaFree(e->d_totals);
@@ -1188,7 +1181,8 @@ int sq_get_candidates(sq_engine* e, uint64_t* read_off, uint32_t* tid, int32_t* 
   SQ_CUDA(e, e->em_score.ensure((P + 1) * 4));
   SQ_CUDA(e, e->scan_tmp.ensure(scan_tmp_words((uint32_t)(R + 1)) * 4));
   if (R) {
-    launch_csr_gather(e->rd_start, e->rd_cnt, e->em_off.as<uint32_t>(), R, e->scan_tmp.as<uint32_t>(), e->cand,
+    SQ_CUDA(e, e->em_cnt.ensure((R + 2) * 4));
+    launch_csr_gather(e->rd, e->em_cnt.as<uint32_t>(), e->em_off.as<uint32_t>(), R, e->scan_tmp.as<uint32_t>(), e->cand,
                       e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->stream, &e->launches);
     SQ_CUDA(e, cudaMemcpyAsync(tmp.data(), e->em_off.p, R * 4, cudaMemcpyDeviceToHost, e->stream));
     SQ_CUDA(e, cudaStreamSynchronize(e->stream));
@@ -1247,8 +1241,9 @@ int sq_set_candidates(sq_engine* e, uint64_t n_reads, const uint64_t* read_off, 
     cnt32[i] = (uint32_t)(read_off[i + 1] - read_off[i]);
   }
   if (n_reads) {
-    SQ_CUDA(e, cudaMemcpy(e->rd_start, start32.data(), n_reads * 4, cudaMemcpyHostToDevice));
-    SQ_CUDA(e, cudaMemcpy(e->rd_cnt, cnt32.data(), n_reads * 4, cudaMemcpyHostToDevice));
+    std::vector<uint2> loc(n_reads);
+    for (uint64_t i = 0; i < n_reads; ++i) loc[i] = make_uint2(start32[i], cnt32[i]);
+    SQ_CUDA(e, cudaMemcpy(e->rd, loc.data(), n_reads * sizeof(uint2), cudaMemcpyHostToDevice));
   }
   if (P) {
     std::vector<uint2> pairs(P);
@@ -1335,21 +1330,21 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
       const void* fp = e->rfp;
       // keys and fingerprints were produced batch by batch behind the votes (sq_set_candidates: here)
       if (!e->keys_valid)
-        launch_read_keys(e->rd_start, e->rd_cnt, 0, R, e->cand, T, hash_bits, e->rkey, e->rfp, st,
+        launch_read_keys(e->rd, 0, R, e->cand, T, hash_bits, e->rkey, e->rfp, st,
                          &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(e->keys_a.p, e->rkey, R * 8, cudaMemcpyDeviceToDevice, st));  // the sort works on a copy
       uint64_t* skeys = nullptr;
       uint32_t* dummy = nullptr;
       launch_radix_sort(e->keys_a.as<uint64_t>(), e->keys_b.as<uint64_t>(), nullptr, nullptr, R,
                         (int)(hash_bits + top_bits), e->sort_tmp.as<uint32_t>(), &skeys, &dummy, st, &e->launches, 32);
-      launch_class_heads(skeys, R, e->rd_start, e->rd_cnt, fp, e->cand, e->exact_classes,
+      launch_class_heads(skeys, R, e->rd, fp, e->cand, e->exact_classes,
                          e->cls_head.as<uint32_t>(),
                          e->cls_id.as<uint32_t>(), e->scan_tmp.as<uint32_t>(), e->cls_read.as<uint32_t>(),
                          e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_classes, e->cls_id.as<uint32_t>() + R, 4, cudaMemcpyDeviceToHost, st));
       SQ_CUDA(e, cudaStreamSynchronize(st));
       launch_class_gather(e->cls_read.as<uint32_t>(), e->cls_pos.as<uint32_t>(), e->em_cnt.as<uint32_t>(),
-                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->rd_start, e->rd_cnt, e->cand,
+                          e->em_off.as<uint32_t>(), n_classes, e->scan_tmp.as<uint32_t>(), e->rd, e->cand,
                           e->em_tid.as<uint32_t>(), e->em_score.as<int32_t>(), e->em_pack.as<uint32_t>(),
                           d_pack_bad, e->cls_weight.as<double>(), st, &e->launches);
       SQ_CUDA(e, cudaMemcpyAsync(&n_cpairs, e->em_off.as<uint32_t>() + n_classes, 4, cudaMemcpyDeviceToHost, st));

@@ -43,19 +43,18 @@ void launch_permute_out(const double* pi, const double* numreads, const uint32_t
                         uint64_t* launches);
 
 // candidate store: per-read class keys + fingerprints behind a batch's vote; the store in read order (taps)
-void launch_read_keys(const uint32_t* rd_start, const uint32_t* rd_cnt, uint64_t r0, uint64_t n,
+void launch_read_keys(const uint2* rd, uint64_t r0, uint64_t n,
                       const uint2* cand, uint32_t T, uint32_t hash_bits, uint64_t* rkey, void* rfp, cudaStream_t s,
                       uint64_t* launches);
-void launch_csr_gather(const uint32_t* rd_start, const uint32_t* rd_cnt, uint32_t* off, uint64_t n_reads,
+void launch_csr_gather(const uint2* rd, uint32_t* cnt_tmp, uint32_t* off, uint64_t n_reads,
                        uint32_t* scan_tmp, const uint2* cand, uint32_t* out_tid, int32_t* out_score, cudaStream_t s,
                        uint64_t* launches);
-void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint32_t* rd_start, const uint32_t* rd_cnt,
+void launch_class_heads(const uint64_t* keys, uint64_t n_reads, const uint2* rd,
                         const void* fp, const uint2* cand, bool exact, uint32_t* head, uint32_t* cid,
                         uint32_t* scan_tmp, uint32_t* class_read, uint32_t* class_pos, uint32_t* class_cnt,
                         cudaStream_t s, uint64_t* launches);
 void launch_class_gather(const uint32_t* class_read, const uint32_t* class_pos, const uint32_t* class_cnt,
-                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint32_t* rd_start,
-                         const uint32_t* rd_cnt, const uint2* cand, uint32_t* out_tid, int32_t* out_score,
+                         uint32_t* class_off, uint32_t n_classes, uint32_t* scan_tmp, const uint2* rd, const uint2* cand, uint32_t* out_tid, int32_t* out_score,
                          uint32_t* out_pack, uint32_t* pack_bad, double* weight, cudaStream_t s, uint64_t* launches);
 void launch_make_sort_keys(const uint32_t* read_off, uint64_t n_reads, const uint32_t* cand_tid, bool packed,
                            uint64_t* keys, cudaStream_t s, uint64_t* launches);

@@ -347,8 +347,7 @@ __device__ int vote_read(const VoteParams& P, const Scratch& S, uint32_t r, uint
     sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
     uint32_t kept = nc;
     if (sbase + nc > P.stage_cap) kept = 0;  // the host grows the store to the reported size and re-runs the vote
-    P.read_soff[r] = P.stage_base + (uint32_t)sbase;
-    P.read_cnt[r] = kept;
+    P.read_loc[r] = make_uint2(P.stage_base + (uint32_t)sbase, kept);
     ListHash lh;  // rare tier: one lane folds the ordered list
     lh.init(nc);
     for (uint32_t i = 0; i < nc; ++i) {
@@ -402,8 +401,7 @@ __global__ void __launch_bounds__(kVoteWarps * 32) vote_kernel(const __grid_cons
       if (lane == 0) {
         const uint32_t pos = atomicAdd(P.ovf_count, 1u);
         P.ovf_list[pos] = r;
-        P.read_cnt[r] = 0;
-        P.read_soff[r] = 0;
+        P.read_loc[r] = make_uint2(0u, 0u);
       }
     }
   }
@@ -701,8 +699,7 @@ __global__ void __launch_bounds__(kBitsBlock, NK * NP <= 10 ? 8 : 5) vote_bits_k
   const bool fits = sbase + wtot <= P.stage_cap;
   sbase += incl - nc;
   if (valid) {
-    P.read_soff[r] = P.stage_base + (uint32_t)sbase;
-    P.read_cnt[r] = (fits && !defer) ? nc : 0u;  // deferred reads are rewritten by the next kernel
+    P.read_loc[r] = make_uint2(P.stage_base + (uint32_t)sbase, (fits && !defer) ? nc : 0u);  // deferred reads are rewritten by the next kernel
     ListHash lh;
     lh.init(nc);
     uint32_t top = P.key_T;
@@ -989,8 +986,7 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
     if (defer) {
       if (lane == 0) {
         P.slow_list[atomicAdd(P.slow_count, 1u)] = r;
-        P.read_cnt[r] = 0;
-        P.read_soff[r] = 0;
+        P.read_loc[r] = make_uint2(0u, 0u);
       }
       __syncwarp();
       continue;
@@ -1003,8 +999,8 @@ __global__ void __launch_bounds__(kLongWarps * 32) vote_long_kernel(const __grid
     unsigned long long sbase = 0;
     if (lane == 0) {
       sbase = nc ? atomicAdd(P.stage_cursor, (unsigned long long)nc) : 0ull;
-      P.read_soff[r] = P.stage_base + (uint32_t)sbase;
-      P.read_cnt[r] = sbase + nc <= P.stage_cap ? nc : 0u;  // the host grows the store and re-runs the vote
+      // (a list that does not fit: the host grows the store and re-runs the vote)
+      P.read_loc[r] = make_uint2(P.stage_base + (uint32_t)sbase, sbase + nc <= P.stage_cap ? nc : 0u);
     }
     sbase = __shfl_sync(0xFFFFFFFFu, sbase, 0);
     __syncwarp();
@@ -1066,8 +1062,7 @@ __global__ void __launch_bounds__(32) vote_overflow_kernel(const __grid_constant
     if (vote_read(P, S, r, work)) {
       if (lane_id() == 0) {
         atomicOr(P.flags, 2u);
-        P.read_cnt[r] = 0;
-        P.read_soff[r] = 0;
+        P.read_loc[r] = make_uint2(0u, 0u);
       }
     }
   }
