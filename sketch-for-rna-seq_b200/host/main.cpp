@@ -231,6 +231,16 @@ struct PinnedBatch {
 void quantification(const std::string& index_path, const std::string& reads_path, const std::string& output_path,
                     std::vector<unsigned>& kmer_lengths, const Options& opt) {
   const double t_start = now();
+  // The CUDA driver and the first context take longer to come up than a cached index takes to read: start them now,
+  // beside the index file, instead of when the first engine is created (a page-locked allocation is the lightest
+  // call of the ABI that needs a context).  Without a device this does nothing; the error comes from sq_create.
+  std::thread cuda_warmup([] {
+    if (sq_device_count() > 0) {
+      void* p = sq_host_alloc(4096);
+      if (p) sq_host_free(p);
+    }
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } warmup_joiner{cuda_warmup};
   IndexData idx;
   const bool have_index = read_index(index_path, &idx, false, opt.index_cache);
   if (have_index) kmer_lengths.assign(idx.ks.begin(), idx.ks.end());  // load_index overwrites the -k list (main.cpp:174)
