@@ -97,7 +97,7 @@ int sq_set_profiling(sq_engine* e, int enabled);
  * 0 (default) = when the 128-bit fingerprints of the lists agree (~2.5 ms faster per 20 M reads).
  * "peer_exchange" (any time, every rank alike): with a communicator the ranks' EM sums can be exchanged over peer memory
  * inside the M-step kernel (when all ranks could map each other's buffers) instead of one ncclAllReduce per iteration:
- * 0 = never, 1 (default) = where that was measured faster (two ranks), 2 = whenever possible.
+ * 0 = never, 1 (default) = where that was measured faster (up to four ranks), 2 = whenever possible.
  * "vote_tier" (any time, tests): 0 = automatic, 1 = every read through the warp-per-read window kernel, 2 = every
  * read through the general warp-per-read kernel; the results do not depend on it. */
 int sq_set_option(sq_engine* e, const char* name, int64_t value);

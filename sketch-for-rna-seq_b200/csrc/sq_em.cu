@@ -549,9 +549,9 @@ __global__ void __launch_bounds__(256) em_mstep_fused_kernel(const uint32_t* __r
 //      thread), adds them in rank order and does the M-step and the convergence test exactly like the one-GPU
 //      kernel: the same bits, hence the same decision, on every rank, and no collective.
 // Every rank reads all of every peer's vector, so the bytes grow with N while NCCL's in-switch reduction does not:
-// measured on 2 MB vectors, this beats ncclAllReduce at N = 2 (EM 1.74 against 1.93 ms per 20 iterations) and
-// loses at N = 8 (2.55 against 2.33 ms; remote loads reached ~250 GB/s).  The engine therefore uses it for two
-// ranks and NCCL beyond.  Also measured and dropped (profiles/r02_notes.md): pushing the sums into every peer
+// measured on 2 MB vectors, this beats ncclAllReduce at N = 2 (EM 1.74 against 1.93 ms per 20 iterations) and N = 4
+// (1.97 against 2.06 ms) and loses at N = 8 (2.55 against 2.33 ms; remote loads reached ~250 GB/s).  The engine
+// therefore uses it up to four ranks and NCCL beyond.  Also measured and dropped (profiles/r02_notes.md): pushing the sums into every peer
 // with remote stores (1.83 ms at N = 2), and a reduce-scatter + all-gather in two flag rounds (1.97 ms at N = 2:
 // the second round costs more than the bytes it saves).  Slots and flags are double-buffered by iteration
 // parity: nobody can be more than one iteration ahead of the slowest rank, because every M-step waits for

@@ -170,7 +170,7 @@ struct sq_engine {
   // flags ([2][nranks]), the peers' mappings of theirs (CUDA IPC), the same as device arrays of pointers; epoch
   // counts iterations over the engine's life (slot = epoch & 1, flags only ever grow)
   bool peer_ok = false, peer_used = false;
-  int peer_wanted = 1;  // option peer_exchange: 0 never, 1 where it was measured faster (two ranks), 2 whenever possible
+  int peer_wanted = 1;  // option peer_exchange: 0 never, 1 where it was measured faster (up to four ranks), 2 whenever possible
   double* xbuf = nullptr;
   unsigned long long* xflags = nullptr;
   std::vector<void*> peer_mapped;  // what cudaIpcOpenMemHandle returned (closed in sq_destroy)
@@ -1404,9 +1404,9 @@ int sq_finish(sq_engine* e, uint64_t R_total, int em_iters, double em_tol, doubl
   v.seg = e->em_seg;
   v.n_pairs = n_cpairs;
   v.T = T;
-  // measured: the one-shot exchange beats ncclAllReduce for two ranks and loses for eight (every rank reads every
-  // peer's whole vector); option peer_exchange = 2 forces it for any number of ranks
-  const bool peer = e->comm && e->peer_ok && (e->peer_wanted == 2 || (e->peer_wanted == 1 && e->nranks == 2));
+  // measured: the one-shot exchange beats ncclAllReduce for two and four ranks and loses for eight (every rank reads
+  // every peer's whole vector); option peer_exchange = 2 forces it for any number of ranks
+  const bool peer = e->comm && e->peer_ok && (e->peer_wanted == 2 || (e->peer_wanted == 1 && e->nranks <= 4));
   e->peer_used = peer;
   v.pi = e->pi.as<double>();
   v.ps = e->ps.as<double>();
