@@ -5,7 +5,12 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -250,14 +255,122 @@ bool FastqScanner::next(size_t max_records, uint64_t max_seq_bytes, RawChunk* ou
   return !out->recs.empty() || pos_ < n;
 }
 
+// ---- parallel scanning (see fastx.hpp)
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static uint64_t count_newlines_avx2(const char* p, size_t n) {
+  uint64_t c = 0;
+  size_t i = 0;
+  const __m256i nl = _mm256_set1_epi8('\n');
+  for (; i + 32 <= n; i += 32)
+    c += (uint64_t)__builtin_popcount((unsigned)_mm256_movemask_epi8(
+        _mm256_cmpeq_epi8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(p + i)), nl)));
+  for (; i < n; ++i) c += p[i] == '\n';
+  return c;
+}
+#endif
+static uint64_t count_newlines(const char* p, size_t n) {
+#if defined(__x86_64__)
+  if (__builtin_cpu_supports("avx2")) return count_newlines_avx2(p, n);
+#endif
+  uint64_t c = 0;
+  for (size_t i = 0; i < n; ++i) c += p[i] == '\n';
+  return c;
+}
+
+std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads) {
+  const char* d = f.data();
+  const size_t n = f.size();
+  const size_t S = std::max<size_t>(1, (n + std::max<size_t>(target_bytes, 1) - 1) / std::max<size_t>(target_bytes, 1));
+  std::vector<FastqSegment> seg(S);
+  // boundaries: the first line start at or after i * n / S
+  std::vector<size_t> cut(S + 1, n);
+  cut[0] = 0;
+  for (size_t i = 1; i < S; ++i) {
+    size_t o = (size_t)((unsigned __int128)n * i / S);
+    if (o <= cut[i - 1]) o = cut[i - 1];
+    if (o == 0 || d[o - 1] == '\n') { cut[i] = o; continue; }
+    const void* q = memchr(d + o, '\n', n - o);
+    cut[i] = q ? (size_t)(static_cast<const char*>(q) - d) + 1 : n;
+  }
+  for (size_t i = 1; i <= S; ++i) cut[i] = std::max(cut[i], cut[i - 1]);
+  std::vector<uint64_t> lines(S, 0);
+  const unsigned nt = (unsigned)std::max(1, std::min<int>(n_threads, (int)S));
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (size_t i; (i = next++) < S;) lines[i] = count_newlines(d + cut[i], cut[i + 1] - cut[i]);
+    });
+  for (auto& t : th) t.join();
+  uint64_t before = 0;
+  for (size_t i = 0; i < S; ++i) {
+    seg[i].begin = cut[i];
+    seg[i].end = cut[i + 1];
+    seg[i].first_line = before;
+    before += lines[i];  // every segment but the last ends behind a newline: whole lines only
+  }
+  return seg;
+}
+
+FastqSegmentScanner::FastqSegmentScanner(const FastqFile& f, const FastqSegment& seg)
+    : d_(f.data()), n_(f.size()), pos_(seg.begin), end_(seg.end) {
+  // lines 4i+1 .. 4i+3 at the head of the segment belong to a record whose header is in the segment before
+  for (uint64_t phase = seg.first_line & 3; phase != 0 && pos_ < end_; phase = (phase + 1) & 3) {
+    const void* q = memchr(d_ + pos_, '\n', n_ - pos_);
+    pos_ = q ? (size_t)(static_cast<const char*>(q) - d_) + 1 : n_;
+  }
+}
+
+bool FastqSegmentScanner::next(size_t max_records, uint64_t max_seq_bytes, RawChunk* out) {
+  out->recs.clear();
+  out->seq_bytes = 0;
+  const char* d = d_;
+  const size_t n = n_;
+  auto line_end = [&](size_t p) {  // position of the line's '\n', or n
+    const void* q = p < n ? memchr(d + p, '\n', n - p) : nullptr;
+    return q ? (size_t)(static_cast<const char*>(q) - d) : n;
+  };
+  while (regular_ && pos_ < end_ && out->recs.size() < max_records && out->seq_bytes < max_seq_bytes) {
+    const size_t b = pos_, e = line_end(b);
+    if (e == b || d[b] != '@') {  // a header position without a header: not a regular four-line FASTQ
+      regular_ = false;
+      break;
+    }
+    pos_ = e + 1;
+    FastqFile::Rec r;
+    r.id_off = b + 1;
+    r.id_len = (uint32_t)(e - b - 1);
+    if (pos_ < n) {
+      const size_t se = line_end(pos_);
+      r.seq_off = pos_;
+      r.seq_len = (uint32_t)(se - pos_);
+      pos_ = se + 1;
+    } else {
+      r.seq_off = n;
+      r.seq_len = 0;  // getline on EOF leaves an empty sequence
+    }
+    for (int skip = 0; skip < 2 && pos_ < n; ++skip) pos_ = line_end(pos_) + 1;  // '+', quality
+    out->recs.push_back(r);
+    out->seq_bytes += r.seq_len;
+    ++seen_;
+  }
+  if (pos_ > n) pos_ = n;
+  return regular_ && (!out->recs.empty() || pos_ < end_);
+}
+
+// The fill level is kept per 1/64 of the table (64 counters, a cache line each): one shared counter would be the
+// one line every inserting thread fights for.
 IdSet::IdSet(uint64_t expected) {
-  uint64_t cap = 1024;
+  uint64_t cap = 1 << 16;
   while (cap < expected * 2 + 16) cap <<= 1;
   mask_ = cap - 1;
-  limit_ = cap - cap / 4;
+  limit_ = (cap - cap / 4) / 64;  // per stripe
+  stripe_shift_ = 0;
+  while ((cap >> stripe_shift_) > 64) ++stripe_shift_;
   slots_ = calloc(cap, sizeof(uint64_t));
-  count_ = calloc(1, sizeof(uint64_t));
+  count_ = aligned_alloc(64, 64 * 64);
   if (!slots_ || !count_) throw std::runtime_error("IdSet: out of memory");
+  memset(count_, 0, 64 * 64);
 }
 IdSet::~IdSet() {
   free(slots_);
@@ -270,9 +383,10 @@ void IdSet::prefetch(uint64_t h) const {
 bool IdSet::insert(uint64_t h) {
   if (h == 0) h = 0x9E3779B97F4A7C15ull;  // 0 marks a free slot
   uint64_t* slots = static_cast<uint64_t*>(slots_);
-  uint64_t* count = static_cast<uint64_t*>(count_);
+  const uint64_t s0 = ((h * 0x9E3779B97F4A7C15ull) >> 20) & mask_;
+  uint64_t* count = static_cast<uint64_t*>(count_) + (s0 >> stripe_shift_) * 8;
   if (__atomic_load_n(count, __ATOMIC_RELAXED) >= limit_) return false;
-  for (uint64_t s = (h * 0x9E3779B97F4A7C15ull) >> 20;; ++s) {
+  for (uint64_t s = s0;; ++s) {
     uint64_t* slot = slots + (s & mask_);
     uint64_t cur = __atomic_load_n(slot, __ATOMIC_RELAXED);
     if (cur == 0) {
@@ -286,7 +400,6 @@ bool IdSet::insert(uint64_t h) {
 }
 
 #if defined(__x86_64__)
-#include <immintrin.h>
 // 32 bases -> 8 packed bytes; returns false when a byte is not one of A C G T.  code = x ^ (x >> 1) with
 // x = (c >> 1) & 3 maps A C G T to 0 1 2 3; maddubs / madd fold four 2-bit codes into one byte.
 __attribute__((target("avx2"))) static inline bool pack32_avx2(const unsigned char* s, uint8_t* dst) {

@@ -63,6 +63,38 @@ class FastqScanner {
   uint64_t seen_ = 0;
 };
 
+// ---- scanning in parallel.  One sequential scanner tops out at ~3 GB/s (10 M reads/s), far below what the
+// packing workers and the GPU take.  The file is therefore cut into segments at line starts; the number of lines
+// before each segment is counted in parallel, and a segment is scanned on its own ASSUMING the file is a regular
+// FASTQ: every record four lines, i.e. every line whose index is a multiple of 4 is a non-empty line starting
+// with '@'.  Under that assumption upstream's state machine (main.cpp:107-151: skip lines until one starts with
+// '@', take the next line as the sequence, skip two more) consumes exactly four lines per record, so the record
+// at lines 4i .. 4i+3 is what it produces.  A segment scanner that meets a header position without a header
+// reports the file as irregular, and the caller falls back to the sequential scan of the whole file (the same
+// fall-back that duplicate read ids take): the assumption is checked, never trusted.
+struct FastqSegment {
+  size_t begin = 0, end = 0;  // bytes; begin is the start of a line, end the start of the next segment's first line (or EOF)
+  uint64_t first_line = 0;    // index of the line that starts at `begin`
+};
+// segments of about target_bytes (at least one, even for an empty file), line counts taken by n_threads threads
+std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads);
+
+class FastqSegmentScanner {
+ public:
+  FastqSegmentScanner(const FastqFile& f, const FastqSegment& seg);
+  // next chunk of the records whose header line starts inside the segment; false when the segment is exhausted
+  // (or the file turned out irregular: check regular())
+  bool next(size_t max_records, uint64_t max_seq_bytes, RawChunk* out);
+  uint64_t records_seen() const { return seen_; }
+  bool regular() const { return regular_; }
+
+ private:
+  const char* d_;
+  size_t n_, pos_, end_;
+  uint64_t seen_ = 0;
+  bool regular_ = true;
+};
+
 // concurrent set of 64-bit id hashes (open addressing, lock-free)
 class IdSet {
  public:
@@ -76,6 +108,7 @@ class IdSet {
  private:
   void* slots_;
   uint64_t mask_, limit_;
+  unsigned stripe_shift_;
   void* count_;
 };
 

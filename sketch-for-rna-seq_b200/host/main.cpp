@@ -284,53 +284,50 @@ void quantification(const std::string& index_path, const std::string& reads_path
     if (G > 1) SQ(nullptr, sq_nccl_unique_id(uid));
     FastqFile fq(reads_path);  // an unopenable file throws like upstream
 
-    // ---- pipeline: one scanner cuts the file into chunks of records (by reads AND by bases: a chunk of long
-    // reads stays far below the engine's batch limits); workers admit + pack each chunk into a page-locked
-    // buffer; one pusher per GPU creates its engine and index replica, then hands ready chunks to sq_push_reads
-    // while scanning and packing go on.
+    // ---- pipeline: the file is cut into segments at line starts (line counts taken in parallel, fastx.hpp); every
+    // worker scans segments into chunks of records (by reads AND by bases: a chunk of long reads stays far below
+    // the engine's batch limits), admits + packs each chunk into a page-locked buffer; one pusher per GPU creates
+    // its engine and index replica, then hands ready chunks to sq_push_reads while scanning and packing go on.
+    // A file that is not a regular four-line FASTQ is redone through the sequential scan, like one with duplicate ids.
     const size_t chunk_reads = 1u << 18;
     const uint64_t chunk_bases = 1ull << 26;
     const int W = std::max(1, threads - 1);
-    Channel<RawChunk> raw((size_t)W + 2);
     Channel<PinnedBatch*> ready((size_t)2 * G + 2);
     Channel<PinnedBatch*> pool((size_t)W + 2 * G + 4);
     std::vector<PinnedBatch> buffers((size_t)W + 2 * G + 2);
     for (auto& bf : buffers) pool.push(&bf);
     IdSet ids(fq.size() / 150 + 1024);
-    std::atomic<bool> ids_unique{true};
+    std::atomic<bool> ids_unique{true}, regular{true};
     std::atomic<uint64_t> admitted{0}, seen{0};
+    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W);
+    std::atomic<size_t> next_seg{0};
     std::mutex err_mu;
     std::string first_error;
     auto fail_all = [&](const std::string& what) {
       { std::lock_guard<std::mutex> lk(err_mu); if (first_error.empty()) first_error = what; }
-      raw.abort(); ready.abort(); pool.abort();
+      ready.abort(); pool.abort();
     };
-    std::thread scanner([&] {
-      try {
-        FastqScanner sc(fq);
-        RawChunk c;
-        while (sc.next(chunk_reads, chunk_bases, &c)) {
-          if (!c.recs.empty() && !raw.push(std::move(c))) break;
-          c = RawChunk();
-        }
-        seen = sc.records_seen();
-      } catch (const std::exception& ex) { fail_all(ex.what()); }
-      raw.close();
-    });
     std::atomic<int> workers_left{W};
     std::vector<std::thread> workers;
     for (int w = 0; w < W; ++w)
       workers.emplace_back([&] {
         try {
           RawChunk c;
-          while (raw.pop(&c)) {
-            PinnedBatch* bf = nullptr;
-            if (!pool.pop(&bf)) break;
-            bf->ensure(c.seq_bytes, c.recs.size());
-            if (!admit_and_pack(fq.data(), c, kmax, &ids, &bf->v)) ids_unique = false;
-            admitted += bf->v.n_reads;
-            if (bf->v.n_reads == 0) { pool.push(bf); continue; }
-            if (!ready.push(bf)) break;
+          bool go = true;
+          for (size_t si; go && regular && (si = next_seg++) < segs.size();) {
+            FastqSegmentScanner sc(fq, segs[si]);
+            while (go && sc.next(chunk_reads, chunk_bases, &c)) {
+              if (c.recs.empty()) continue;
+              PinnedBatch* bf = nullptr;
+              if (!pool.pop(&bf)) { go = false; break; }
+              bf->ensure(c.seq_bytes, c.recs.size());
+              if (!admit_and_pack(fq.data(), c, kmax, &ids, &bf->v)) ids_unique = false;
+              admitted += bf->v.n_reads;
+              if (bf->v.n_reads == 0) { pool.push(bf); continue; }
+              if (!ready.push(bf)) go = false;
+            }
+            seen += sc.records_seen();
+            if (!sc.regular()) regular = false;
           }
         } catch (const std::exception& ex) { fail_all(ex.what()); }
         if (--workers_left == 0) ready.close();
@@ -358,7 +355,6 @@ void quantification(const std::string& index_path, const std::string& reads_path
           pool.push(bf);
         }
       });
-    scanner.join();
     for (auto& w : workers) w.join();
     for (auto& p : pushers) p.join();
     if (!first_error.empty()) throw std::runtime_error(first_error);
@@ -371,11 +367,12 @@ void quantification(const std::string& index_path, const std::string& reads_path
       for (int g = 0; g < G; ++g) th.emplace_back([&, g] { fn(g); });
       for (auto& t : th) t.join();
     };
-    if (!ids_unique) {
+    if (!ids_unique || !regular) {
       // some read id came twice (or the id set overflowed): later duplicates replace earlier ones
-      // (read_sketches[read.id] = ..., main.cpp:147), a whole-file rule -- redo the reads through the exact scan
+      // (read_sketches[read.id] = ..., main.cpp:147), a whole-file rule -- or the file is not a regular four-line
+      // FASTQ, so the segments could not be scanned on their own: redo the reads through the exact sequential scan
       exact_path = true;
-      if (trace) fprintf(stderr, "[sq trace] duplicate read ids: exact path\n");
+      if (trace) fprintf(stderr, "[sq trace] %s: exact path\n", regular ? "duplicate read ids" : "irregular FASTQ");
       std::vector<FastqFile::Rec> recs = fq.admitted_records(kmax, threads, &n_seen);
       R = recs.size();
       on_all_gpus([&](int g) {
@@ -544,49 +541,81 @@ int main(int argc, char* argv[]) {
       }
     }
     std::cout << "records " << sc.records_seen() << " admitted " << admitted << " unique " << (unique ? 1 : 0) << "\n" << body.str();
+  } else if (mode == "selftest-segments" && optind + 2 <= argc) {
+    // the parallel scan of quant mode (segments at line starts, scanned independently), segment by segment in file
+    // order: prints what selftest-stream prints when the file is a regular four-line FASTQ, "regular 0" otherwise
+    FastqFile fq(argv[optind]);
+    const size_t target = (size_t)std::max(1L, atol(argv[optind + 1]));
+    const std::vector<FastqSegment> segs = split_fastq(fq, target, opt.threads > 0 ? opt.threads : 4);
+    IdSet ids(fq.size() / 150 + 1024);
+    const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
+    RawChunk c;
+    bool unique = true, regular = true;
+    uint64_t admitted = 0, seen = 0;
+    std::ostringstream body;
+    for (const FastqSegment& sg : segs) {
+      FastqSegmentScanner sc(fq, sg);
+      while (sc.next(3, 200, &c)) {
+        if (c.recs.empty()) continue;
+        std::vector<uint32_t> mem((c.seq_bytes + 4 * c.recs.size()) / 16 + 16 + 2 * c.recs.size());
+        PackedView v;
+        v.words = mem.data();
+        v.base_off = mem.data() + (c.seq_bytes + 4 * c.recs.size()) / 16 + 16;
+        v.len = v.base_off + c.recs.size();
+        unique &= admit_and_pack(fq.data(), c, kmax, &ids, &v);
+        admitted += v.n_reads;
+        for (uint32_t i = 0; i < v.n_reads; ++i) {
+          std::string sq(v.len[i], '?');
+          for (uint32_t j = 0; j < v.len[i]; ++j) {
+            const uint64_t b = (uint64_t)v.base_off[i] + j;
+            sq[j] = "ACGT"[(v.words[b >> 4] >> (2 * (b & 15))) & 3];
+          }
+          body << sq << "\n";
+        }
+      }
+      seen += sc.records_seen();
+      regular &= sc.regular();
+    }
+    std::cout << "segments " << segs.size() << " regular " << (regular ? 1 : 0) << "\n";
+    if (regular) std::cout << "records " << seen << " admitted " << admitted << " unique " << (unique ? 1 : 0) << "\n" << body.str();
   } else if (mode == "selftest-ingest" && optind + 1 <= argc) {
     // host side of quant mode's ingest pipeline alone (scan -> admit + pack in workers, batches dropped): reads/s
     const double t0 = now();
     FastqFile fq(argv[optind]);
     const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
     const int W = std::max(1, (opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency()) - 1);
-    Channel<RawChunk> raw((size_t)W + 2);
     IdSet ids(fq.size() / 150 + 1024);
-    std::atomic<uint64_t> admitted{0}, bases{0};
-    std::atomic<bool> unique{true};
-    uint64_t seen = 0;
-    std::thread scanner([&] {
-      FastqScanner sc(fq);
-      RawChunk c;
-      while (sc.next(1u << 18, 1ull << 26, &c)) {
-        if (!c.recs.empty()) raw.push(std::move(c));
-        c = RawChunk();
-      }
-      seen = sc.records_seen();
-      raw.close();
-    });
+    std::atomic<uint64_t> admitted{0}, bases{0}, seen{0};
+    std::atomic<bool> unique{true}, regular{true};
+    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W);
+    std::atomic<size_t> next_seg{0};
     std::vector<std::thread> workers;
     for (int w = 0; w < W; ++w)
       workers.emplace_back([&] {
         RawChunk c;
         std::vector<uint32_t> mem;
-        while (raw.pop(&c)) {
-          if (getenv("SQ_SCAN_ONLY")) { admitted += c.recs.size(); continue; }
-          const size_t words = (c.seq_bytes + 4 * c.recs.size()) / 16 + 16;
-          mem.resize(words + 2 * c.recs.size());
-          PackedView v;
-          v.words = mem.data();
-          v.base_off = mem.data() + words;
-          v.len = v.base_off + c.recs.size();
-          if (!admit_and_pack(fq.data(), c, kmax, &ids, &v)) unique = false;
-          admitted += v.n_reads;
-          bases += v.n_bases;
+        for (size_t si; (si = next_seg++) < segs.size();) {
+          FastqSegmentScanner sc(fq, segs[si]);
+          while (sc.next(1u << 18, 1ull << 26, &c)) {
+            if (c.recs.empty()) continue;
+            if (getenv("SQ_SCAN_ONLY")) { admitted += c.recs.size(); continue; }
+            const size_t words = (c.seq_bytes + 4 * c.recs.size()) / 16 + 16;
+            mem.resize(words + 2 * c.recs.size());
+            PackedView v;
+            v.words = mem.data();
+            v.base_off = mem.data() + words;
+            v.len = v.base_off + c.recs.size();
+            if (!admit_and_pack(fq.data(), c, kmax, &ids, &v)) unique = false;
+            admitted += v.n_reads;
+            bases += v.n_bases;
+          }
+          seen += sc.records_seen();
+          if (!sc.regular()) regular = false;
         }
       });
-    scanner.join();
     for (auto& w : workers) w.join();
     const double dt = now() - t0;
-    std::cout << "records " << seen << " admitted " << admitted << " unique " << (unique ? 1 : 0) << " threads " << (W + 1)
+    std::cout << "records " << seen << " admitted " << admitted << " unique " << (unique ? 1 : 0) << " regular " << (regular ? 1 : 0) << " threads " << W
               << " seconds " << dt << " reads_per_s " << (admitted / dt) << " MB_per_s " << (fq.size() / dt / 1e6) << "\n";
   } else if (mode == "selftest-fasta" && optind + 1 <= argc) {
     for (auto& r : load_fasta(argv[optind])) std::cout << r.id << "\t" << r.sequence << "\n";

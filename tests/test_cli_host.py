@@ -138,3 +138,39 @@ def test_streaming_scan_equals_whole_file_scan(tmp_path):
     fq.write_bytes(TRICKY_FASTQ)
     rc3, out3, _ = run(OURS, "-k", "21,31", "-o", "selftest-stream", str(fq))
     assert rc3 == 0 and out3.split("\n")[0].endswith("unique 0")
+
+
+def test_parallel_segment_scan_equals_sequential_scan(tmp_path):
+    """quant mode scans the FASTQ in segments cut at line starts (line counts taken in parallel); on a regular
+    four-line file every segmentation gives the records of the sequential scan, an irregular file is reported"""
+    rng = np.random.default_rng(21)
+    recs = []
+    for i in range(700):
+        n = int(rng.integers(1, 400))
+        s = bytes(rng.choice(list(b"ACGT"), n).tolist())
+        if i % 13 == 0:
+            s = s[: n // 2] + b"N" + s[n // 2 + 1:]
+        q = bytes(rng.choice(list(b"@+IJ#"), n).tolist())  # quality lines that start with '@' or '+'
+        recs.append(b"@r%d/1 x\n" % i + s + b"\n+anything\n" + q + b"\n")
+    fq = tmp_path / "p.fq"
+    for tail in (b"", b"@last\nACGTACGTACGTACGTACGTACGTACGTACGTACGT", b"@cut\n"):  # complete, no final newline, header only
+        fq.write_bytes(b"".join(recs) + tail)
+        rc, seq_out, _ = run(OURS, "-k", "21,31", "-o", "selftest-stream", str(fq))
+        assert rc == 0
+        for target in (1, 97, 1000, 50_000, 10_000_000):
+            rc2, out2, _ = run(OURS, "-k", "21,31", "-o", "selftest-segments", str(fq), str(target))
+            assert rc2 == 0
+            first, rest = out2.split("\n", 1)
+            assert first.endswith("regular 1"), (target, first)
+            assert rest == seq_out, target
+    # irregular files: a blank line between records, a header that lost its '@', a three-line record
+    for bad in (b"".join(recs[:300]) + b"\n" + b"".join(recs[300:]),
+                b"".join(recs[:300]) + recs[300][1:] + b"".join(recs[301:]),
+                b"".join(recs[:300]) + b"@x\nACGT\n+\n" + b"".join(recs[300:])):
+        fq.write_bytes(bad)
+        flagged = 0
+        for target in (1000, 10_000_000):
+            rc3, out3, _ = run(OURS, "-k", "21,31", "-o", "selftest-segments", str(fq), str(target))
+            assert rc3 == 0
+            flagged += out3.split("\n")[0].endswith("regular 0")
+        assert flagged == 2
