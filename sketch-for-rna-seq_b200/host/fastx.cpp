@@ -277,7 +277,7 @@ static uint64_t count_newlines(const char* p, size_t n) {
   return c;
 }
 
-std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads) {
+std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads, uint64_t* total_lines) {
   const char* d = f.data();
   const size_t n = f.size();
   const size_t S = std::max<size_t>(1, (n + std::max<size_t>(target_bytes, 1) - 1) / std::max<size_t>(target_bytes, 1));
@@ -309,6 +309,7 @@ std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, i
     seg[i].first_line = before;
     before += lines[i];  // every segment but the last ends behind a newline: whole lines only
   }
+  if (total_lines) *total_lines = before + (n > 0 && d[n - 1] != '\n' ? 1 : 0);
   return seg;
 }
 

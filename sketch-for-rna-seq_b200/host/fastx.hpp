@@ -77,7 +77,8 @@ struct FastqSegment {
   uint64_t first_line = 0;    // index of the line that starts at `begin`
 };
 // segments of about target_bytes (at least one, even for an empty file), line counts taken by n_threads threads
-std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads);
+// (total_lines, optional: newlines in the file + 1 for an unterminated last line -- four per record of a regular file)
+std::vector<FastqSegment> split_fastq(const FastqFile& f, size_t target_bytes, int n_threads, uint64_t* total_lines = nullptr);
 
 class FastqSegmentScanner {
  public:

@@ -296,10 +296,11 @@ void quantification(const std::string& index_path, const std::string& reads_path
     Channel<PinnedBatch*> pool((size_t)W + 2 * G + 4);
     std::vector<PinnedBatch> buffers((size_t)W + 2 * G + 2);
     for (auto& bf : buffers) pool.push(&bf);
-    IdSet ids(fq.size() / 150 + 1024);
+    uint64_t fq_lines = 0;
+    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W, &fq_lines);
+    IdSet ids(fq_lines / 4 + 1024);  // sized from the line count: a regular file has exactly lines / 4 records
     std::atomic<bool> ids_unique{true}, regular{true};
     std::atomic<uint64_t> admitted{0}, seen{0};
-    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W);
     std::atomic<size_t> next_seg{0};
     std::mutex err_mu;
     std::string first_error;
@@ -584,10 +585,11 @@ int main(int argc, char* argv[]) {
     FastqFile fq(argv[optind]);
     const uint32_t kmax = *std::max_element(kmer_lengths.begin(), kmer_lengths.end());
     const int W = std::max(1, (opt.threads > 0 ? opt.threads : (int)std::thread::hardware_concurrency()) - 1);
-    IdSet ids(fq.size() / 150 + 1024);
+    uint64_t fq_lines = 0;
+    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W, &fq_lines);
+    IdSet ids(fq_lines / 4 + 1024);
     std::atomic<uint64_t> admitted{0}, bases{0}, seen{0};
     std::atomic<bool> unique{true}, regular{true};
-    const std::vector<FastqSegment> segs = split_fastq(fq, (size_t)32 << 20, W);
     std::atomic<size_t> next_seg{0};
     std::vector<std::thread> workers;
     for (int w = 0; w < W; ++w)
