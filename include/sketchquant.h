@@ -105,7 +105,7 @@ int sq_set_option(sq_engine* e, const char* name, int64_t value);
 /* Replaces the TranscriptMapping for k-index kidx that load_index() fills (src/data_io.cpp:274-300,
  * include/sketch.h:23): nkeys distinct hashes, CSR offsets post_off[nkeys+1], dense transcript ids
  * post_tid[post_off[nkeys]] (< n_transcripts, each at most once per key).  Host arrays.  Builds the
- * GPU-resident bucketed open-addressing table.  A k-index that is never loaded behaves like a missing map
+ * GPU-resident index (key bitmap with ranks, list descriptors, de-duplicated posting lists).  A k-index that is never loaded behaves like a missing map
  * (src/sparse_chaining.cpp:51-53). */
 int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* keys, const uint64_t* post_off,
                   const uint32_t* post_tid);
@@ -122,7 +122,9 @@ int sq_push_reads(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, 
  * next multiple of 4 bases: only the packed words travel, lengths and offsets are written on the GPU. */
 int sq_push_reads_fixed(sq_engine* e, const uint32_t* packed_words, uint64_t n_words, uint32_t read_len,
                         uint32_t n_reads);
-/* Same with the batch already resident in DEVICE memory (the buffers must stay valid until sq_sync). */
+/* Same with the batch already resident in DEVICE memory (the buffers must stay valid until sq_sync).  The packed
+ * words must start on a 16-byte boundary and the allocation must be readable up to the next multiple of 4 words
+ * behind n_words (any cudaMalloc'ed buffer is): the sketch kernel stages them with 16-byte bulk copies. */
 int sq_push_reads_device(sq_engine* e, const uint32_t* d_packed_words, uint64_t n_words,
                          const uint32_t* d_base_off, const uint32_t* d_len, uint32_t n_reads,
                          uint64_t n_bases_hint);
