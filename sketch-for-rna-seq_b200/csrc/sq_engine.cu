@@ -813,16 +813,33 @@ int sq_load_index(sq_engine* e, uint32_t kidx, uint64_t nkeys, const uint32_t* k
   std::vector<std::vector<uint32_t>> rep(nth), support(nth);
   std::vector<uint32_t> loc(nkeys, SQ_EMPTY);  // distinct-list number inside the partition
   auto part_of = [&](uint64_t h) { return (unsigned)(((h >> 40) * nth) >> 24); };
+  // the keys of every partition, in key order (a counting sort): a thread then walks its own keys only instead of
+  // filtering all of them
+  std::vector<uint64_t> pstart(nth + 1, 0);
+  std::vector<uint32_t> pkeys;
+  {
+    std::vector<uint8_t> part(nkeys);
+    run([&](unsigned x) {
+      const uint64_t i0 = nkeys * x / nth, i1 = nkeys * (x + 1) / nth;
+      for (uint64_t i = i0; i < i1; ++i) part[i] = post_off[i + 1] > post_off[i] ? (uint8_t)part_of(lh[i]) : (uint8_t)0xFF;
+    });
+    for (uint64_t i = 0; i < nkeys; ++i)
+      if (part[i] != 0xFF) ++pstart[part[i] + 1];
+    for (unsigned x = 0; x < nth; ++x) pstart[x + 1] += pstart[x];
+    pkeys.resize(pstart[nth]);
+    std::vector<uint64_t> cur(pstart.begin(), pstart.end() - 1);
+    for (uint64_t i = 0; i < nkeys; ++i)
+      if (part[i] != 0xFF) pkeys[cur[part[i]]++] = (uint32_t)i;
+  }
   run([&](unsigned x) {
-    uint64_t mine = 0;
-    for (uint64_t i = 0; i < nkeys; ++i) mine += post_off[i + 1] > post_off[i] && part_of(lh[i]) == x;
+    const uint64_t mine = pstart[x + 1] - pstart[x];
     uint64_t cap = 16;
     while (cap < mine * 2 + 2) cap <<= 1;
     std::vector<uint64_t> hkey(cap, 0);
     std::vector<uint32_t> hval(cap, SQ_EMPTY);
-    for (uint64_t i = 0; i < nkeys; ++i) {
+    for (uint64_t pi = pstart[x]; pi < pstart[x + 1]; ++pi) {
+      const uint64_t i = pkeys[pi];
       const uint64_t b0 = post_off[i], b1 = post_off[i + 1], h = lh[i];
-      if (b1 <= b0 || part_of(h) != x) continue;
       uint64_t slot = (h * 0x9E3779B97F4A7C15ull) & (cap - 1);
       for (;;) {
         if (hval[slot] == SQ_EMPTY) {
